@@ -1,0 +1,160 @@
+/* loamgpu.h — C-ABI of the B200-native LOAM hot path (libloamgpu.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.
+ * The host-side C++ templates in include/loam/ (same signatures as the reference's
+ * loam/features.h:108-111,119-122,166-169 and loam/registration.h:128-131) call only
+ * these entry points; INTEGRATION.md shows the binding a maintainer of the reference
+ * would add.  Every entry point runs hand-written sm_100a CUDA kernels; there is no
+ * CPU fallback — without a CUDA device loamgpu_create() fails with LOAMGPU_ERR_CUDA.
+ *
+ * Conventions
+ *   - return value 0 = OK, otherwise a loamgpu_status; loamgpu_last_error() has the text.
+ *   - poses are 7 doubles: qx qy qz qw tx ty tz  (Eigen coeffs() order, geometry.h:27-50).
+ *   - point clouds: dtype LOAMGPU_F32 (x,y,z floats at byte offsets 0/4/8 of each
+ *     `stride_bytes` record, e.g. 16 for a float4/PCL point) or LOAMGPU_F64 (x,y,z doubles
+ *     at offsets 0/8/16, e.g. stride 24 for Eigen::Vector3d).  Arithmetic is always IEEE
+ *     fp64 after widening, exactly as the reference's accessors do (common.h:55-78).
+ *   - feature / correspondence indices are uint32.
+ *   - a context is bound to one device and one stream; use one context per thread/GPU
+ *     (the reference is stateless and re-entrant; contexts give the same property).
+ */
+#ifndef LOAMGPU_H
+#define LOAMGPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct loamgpu_ctx loamgpu_ctx;
+
+typedef enum {
+  LOAMGPU_OK = 0,
+  LOAMGPU_ERR_SIZE_MISMATCH = 1, /* scan size != scan_lines*points_per_line (common.h:104-113 -> std::runtime_error) */
+  LOAMGPU_ERR_INVALID = 2,       /* bad argument (null pointer, number_sectors == 0, capacity too small ...) */
+  LOAMGPU_ERR_CUDA = 3,          /* CUDA runtime failure / no device */
+  LOAMGPU_ERR_UNSUPPORTED = 4    /* outside kernel limits (points_per_line or neighbour count too large) */
+} loamgpu_status;
+
+enum { LOAMGPU_F32 = 0, LOAMGPU_F64 = 1 };
+
+/* replaces loam::LidarParams, common.h:29-41 */
+typedef struct {
+  uint64_t scan_lines;
+  uint64_t points_per_line;
+  double min_range;
+  double max_range;
+} loamgpu_lidar_params;
+
+/* replaces loam::FeatureExtractionParams, features.h:37-66 (same defaults via loamgpu_default_fe_params) */
+typedef struct {
+  uint64_t neighbor_points;
+  uint64_t number_sectors;
+  uint64_t max_edge_feats_per_sector;
+  uint64_t max_planar_feats_per_sector;
+  double edge_feat_threshold;
+  double planar_feat_threshold;
+  double occlusion_thresh;
+  double parallel_thresh;
+} loamgpu_fe_params;
+
+/* replaces loam::RegistrationParams, registration.h:40-75 */
+typedef struct {
+  uint64_t num_edge_neighbors;
+  double max_edge_neighbor_dist;
+  uint64_t min_line_fit_points;
+  double min_line_condition_number;
+  uint64_t num_plane_neighbors;
+  double max_plane_neighbor_dist;
+  uint64_t min_plane_fit_points;
+  double max_avg_point_plane_dist;
+  uint64_t max_iterations;
+  double rotation_convergence_thresh;
+  double position_convergence_thresh;
+  uint64_t min_associations;
+} loamgpu_reg_params;
+
+/* replaces loam::RegistrationDetail, registration.h:79-109, flattened.  All buffers are
+ * caller-allocated host memory; any pointer may be NULL to skip that output. */
+typedef struct {
+  uint32_t max_iters_cap;  /* in : rows available in the per-iteration buffers */
+  uint32_t n_src_edge;     /* in : row stride (in pairs) of edge_assoc  */
+  uint32_t n_src_planar;   /* in : row stride (in pairs) of plane_assoc */
+  uint32_t n_iters;        /* out: iteration_info.size() */
+  int32_t termination;     /* out: 0 CONVERGED, 1 MAX_ITER, 2 INSUFFICIENT_ASSOCIATIONS */
+  double* iter_est;        /* [cap][7] target_T_source_init of each iteration */
+  double* iter_update;     /* [cap][7] estimate_update */
+  uint32_t* n_edge_assoc;  /* [cap] */
+  uint32_t* n_plane_assoc; /* [cap] */
+  uint32_t* edge_assoc;    /* [cap][n_src_edge][2]   (source idx, nearest target idx), source-idx order */
+  uint32_t* plane_assoc;   /* [cap][n_src_planar][2] */
+  uint32_t* lm_iters;      /* [cap] LM iterations of each inner solve */
+  double* lm_cost;         /* [cap][2] initial / final cost of each inner solve */
+} loamgpu_detail;
+
+/* ---------------------------------------------------------------- lifecycle */
+int loamgpu_create(int device, loamgpu_ctx** out);
+void loamgpu_destroy(loamgpu_ctx* ctx);
+/* text of the last error on this context (ctx == NULL: last loamgpu_create failure of this thread) */
+const char* loamgpu_last_error(const loamgpu_ctx* ctx);
+/* run subsequent calls on an externally owned cudaStream_t (NULL = the context's own stream) */
+int loamgpu_set_stream(loamgpu_ctx* ctx, void* cuda_stream);
+void loamgpu_default_fe_params(loamgpu_fe_params* p);
+void loamgpu_default_reg_params(loamgpu_reg_params* p);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t loamgpu_launch_count(const loamgpu_ctx* ctx);
+
+/* ------------------------------------------------- feature extraction (host buffers) */
+/* replaces loam::extractFeatures, features.h:108-111 / features-inl.h:11-50.  Writes the
+ * indices (into the input scan) of the selected edge / planar points, in the reference's
+ * output order (line-major, sector-major, selection order); the C++ wrapper gathers the
+ * point copies.  Capacities needed: scan_lines*number_sectors*(max_*_feats_per_sector+1). */
+int loamgpu_extract(loamgpu_ctx* ctx, const void* pts, int dtype, size_t stride_bytes, uint64_t n_points,
+                    const loamgpu_lidar_params* lidar, const loamgpu_fe_params* fe, uint32_t* edge_idx,
+                    uint64_t edge_cap, uint64_t* n_edge, uint32_t* planar_idx, uint64_t planar_cap,
+                    uint64_t* n_planar);
+/* replaces loam::computeCurvature, features.h:119-122 / features-inl.h:53-87 (curvature[i] for point i) */
+int loamgpu_curvature(loamgpu_ctx* ctx, const void* pts, int dtype, size_t stride_bytes, uint64_t n_points,
+                      const loamgpu_lidar_params* lidar, const loamgpu_fe_params* fe, double* curvature);
+/* replaces loam::computeValidPoints, features.h:166-169 / features-inl.h:90-124 (1 = valid) */
+int loamgpu_valid_mask(loamgpu_ctx* ctx, const void* pts, int dtype, size_t stride_bytes, uint64_t n_points,
+                       const loamgpu_lidar_params* lidar, const loamgpu_fe_params* fe, uint8_t* mask);
+
+/* ---------------------------------------------------- registration (host buffers) */
+/* replaces loam::registerFeatures, registration.h:128-131 / registration-inl.h:11-78.
+ * Feature clouds are n x 3 contiguous doubles (the reference widens with featuresToEigen,
+ * features.h:188-198). */
+int loamgpu_register(loamgpu_ctx* ctx, const double* src_edge, uint64_t n_src_edge, const double* src_planar,
+                     uint64_t n_src_planar, const double* tgt_edge, uint64_t n_tgt_edge, const double* tgt_planar,
+                     uint64_t n_tgt_planar, const double init_pose[7], const loamgpu_reg_params* params,
+                     double out_pose[7], loamgpu_detail* detail);
+/* replaces kdtree_internal::knnSearch, kdtree.cpp:10-28, batched: for each query the k nearest
+ * targets (ascending squared distance, ties by ascending index) that lie strictly inside
+ * max_dist (max_dist <= 0: unbounded).  idx_out is [n_queries][k] (unused slots 0xFFFFFFFF). */
+int loamgpu_knn(loamgpu_ctx* ctx, const double* targets, uint64_t n_targets, const double* queries,
+                uint64_t n_queries, uint32_t k, double max_dist, uint32_t* idx_out, uint32_t* count_out);
+
+/* ------------------------------------------------------- sequence odometry (batched) */
+/* extract + scan-to-scan register over a sequence of organised float4 scans
+ * ({x,y,z,unused} floats, n_scans * scan_lines*points_per_line records): every scan is
+ * extracted once; pair k registers source = scan k+1 onto target = scan k from an identity
+ * initial estimate (the loop of the reference's README.md:46-59).  Features never leave the
+ * device.  Outputs per pair: pose [7], termination, outer iterations run, and the feature
+ * counts of every scan (n_edge/n_planar, may be NULL).
+ *   _host  : scans/outputs in host memory (pinned or pageable); H2D/D2H inside the call.
+ *   _device: scans/outputs already resident in device memory. */
+int loamgpu_odometry_host(loamgpu_ctx* ctx, const float* scans, uint64_t n_scans, const loamgpu_lidar_params* lidar,
+                          const loamgpu_fe_params* fe, const loamgpu_reg_params* reg, double* poses,
+                          int32_t* termination, uint32_t* iterations, uint32_t* n_edge, uint32_t* n_planar);
+int loamgpu_odometry_device(loamgpu_ctx* ctx, const float* scans_dev, uint64_t n_scans,
+                            const loamgpu_lidar_params* lidar, const loamgpu_fe_params* fe,
+                            const loamgpu_reg_params* reg, double* poses_dev, int32_t* termination_dev,
+                            uint32_t* iterations_dev, uint32_t* n_edge_dev, uint32_t* n_planar_dev);
+/* pairs processed per internal chunk by the odometry calls (default 256) */
+int loamgpu_set_chunk_pairs(loamgpu_ctx* ctx, uint32_t pairs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LOAMGPU_H */

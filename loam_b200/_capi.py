@@ -1,0 +1,258 @@
+"""ctypes binding of libloamgpu.so (the C-ABI declared in include/loamgpu.h).
+
+There is no CPU fallback: if the shared library is missing it is built with nvcc, and if no CUDA
+device is present `Context()` raises (loamgpu_create fails with LOAMGPU_ERR_CUDA).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+u64, f64, u32, i32 = C.c_uint64, C.c_double, C.c_uint32, C.c_int32
+PD = C.POINTER(C.c_double)
+PU32 = C.POINTER(C.c_uint32)
+
+OK, ERR_SIZE_MISMATCH, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = range(5)
+F32, F64 = 0, 1
+
+# every symbol include/loamgpu.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "loamgpu_create", "loamgpu_destroy", "loamgpu_last_error", "loamgpu_set_stream", "loamgpu_default_fe_params",
+    "loamgpu_default_reg_params", "loamgpu_launch_count", "loamgpu_extract", "loamgpu_curvature",
+    "loamgpu_valid_mask", "loamgpu_register", "loamgpu_knn", "loamgpu_odometry_host", "loamgpu_odometry_device",
+    "loamgpu_set_chunk_pairs",
+]
+
+
+class CLidarParams(C.Structure):
+    _fields_ = [("scan_lines", u64), ("points_per_line", u64), ("min_range", f64), ("max_range", f64)]
+
+
+class CFeParams(C.Structure):
+    _fields_ = [("neighbor_points", u64), ("number_sectors", u64), ("max_edge_feats_per_sector", u64),
+                ("max_planar_feats_per_sector", u64), ("edge_feat_threshold", f64), ("planar_feat_threshold", f64),
+                ("occlusion_thresh", f64), ("parallel_thresh", f64)]
+
+
+class CRegParams(C.Structure):
+    _fields_ = [("num_edge_neighbors", u64), ("max_edge_neighbor_dist", f64), ("min_line_fit_points", u64),
+                ("min_line_condition_number", f64), ("num_plane_neighbors", u64), ("max_plane_neighbor_dist", f64),
+                ("min_plane_fit_points", u64), ("max_avg_point_plane_dist", f64), ("max_iterations", u64),
+                ("rotation_convergence_thresh", f64), ("position_convergence_thresh", f64), ("min_associations", u64)]
+
+
+class CDetail(C.Structure):
+    _fields_ = [("max_iters_cap", u32), ("n_src_edge", u32), ("n_src_planar", u32), ("n_iters", u32),
+                ("termination", i32), ("iter_est", PD), ("iter_update", PD), ("n_edge_assoc", PU32),
+                ("n_plane_assoc", PU32), ("edge_assoc", PU32), ("plane_assoc", PU32), ("lm_iters", PU32),
+                ("lm_cost", PD)]
+
+
+class LoamGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(msg)
+        self.code = code
+
+
+_lib = None
+
+
+def load_library(build_if_missing: bool = True) -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if build_if_missing and _build.needs_build():
+        _build.build()
+    if not os.path.exists(path):
+        raise ImportError(f"{path} not found: build it with `python -m loam_b200.build` (needs nvcc)")
+    lib = C.CDLL(path)
+    lib.loamgpu_last_error.restype = C.c_char_p
+    lib.loamgpu_last_error.argtypes = [C.c_void_p]
+    lib.loamgpu_launch_count.restype = u64
+    lib.loamgpu_launch_count.argtypes = [C.c_void_p]
+    lib.loamgpu_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.loamgpu_destroy.argtypes = [C.c_void_p]
+    lib.loamgpu_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    lib.loamgpu_set_chunk_pairs.argtypes = [C.c_void_p, u32]
+    vp = C.c_void_p
+    lib.loamgpu_extract.argtypes = [vp, vp, C.c_int, C.c_size_t, u64, vp, vp, vp, u64, vp, vp, u64, vp]
+    lib.loamgpu_curvature.argtypes = [vp, vp, C.c_int, C.c_size_t, u64, vp, vp, vp]
+    lib.loamgpu_valid_mask.argtypes = [vp, vp, C.c_int, C.c_size_t, u64, vp, vp, vp]
+    lib.loamgpu_register.argtypes = [vp, vp, u64, vp, u64, vp, u64, vp, u64, vp, vp, vp, vp]
+    lib.loamgpu_knn.argtypes = [vp, vp, u64, vp, u64, u32, f64, vp, vp]
+    lib.loamgpu_odometry_host.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.loamgpu_odometry_device.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, vp, vp, vp]
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _cloud(points):
+    """Return (array, dtype code, stride) for an (N,>=3) float32/float64 array without changing values."""
+    a = np.asarray(points)
+    if a.size == 0:
+        return np.zeros((0, 3), dtype=np.float64), F64, 24
+    if a.ndim != 2 or a.shape[1] < 3:
+        raise ValueError("point cloud must be an (N, >=3) array")
+    if a.dtype == np.float32:
+        a = np.ascontiguousarray(a)
+        return a, F32, a.strides[0]
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, F64, a.strides[0]
+
+
+def _xyz64(points):
+    a = np.asarray(points, dtype=np.float64)
+    if a.size == 0:
+        return np.zeros((0, 3), dtype=np.float64)
+    return np.ascontiguousarray(a.reshape(len(a), -1)[:, :3])
+
+
+class Context:
+    """One loamgpu context = one device + one stream + its device buffers."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.loamgpu_create(device, C.byref(h))
+        if rc != OK:
+            raise LoamGpuError(rc, "loamgpu_create failed: " + self.lib.loamgpu_last_error(None).decode())
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.loamgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != OK:
+            raise LoamGpuError(rc, self.lib.loamgpu_last_error(self.h).decode())
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.loamgpu_launch_count(self.h))
+
+    def set_stream(self, cuda_stream: int | None):
+        self._check(self.lib.loamgpu_set_stream(self.h, C.c_void_p(cuda_stream or 0)))
+
+    def set_chunk_pairs(self, n: int):
+        self._check(self.lib.loamgpu_set_chunk_pairs(self.h, n))
+
+    # ---------------------------------------------------------------- features
+    def extract(self, points, lp: CLidarParams, fe: CFeParams):
+        a, dt, stride = _cloud(points)
+        n = len(a)
+        e = np.empty(max(n, 1), dtype=np.uint32)
+        p = np.empty(max(n, 1), dtype=np.uint32)
+        ne, npl = u64(0), u64(0)
+        self._check(self.lib.loamgpu_extract(self.h, _ptr(a), dt, stride, n, C.addressof(lp), C.addressof(fe),
+                                             _ptr(e), len(e), C.addressof(ne), _ptr(p), len(p), C.addressof(npl)))
+        return e[:ne.value].copy(), p[:npl.value].copy()
+
+    def curvature(self, points, lp, fe):
+        a, dt, stride = _cloud(points)
+        out = np.empty(len(a), dtype=np.float64)
+        self._check(self.lib.loamgpu_curvature(self.h, _ptr(a), dt, stride, len(a), C.addressof(lp), C.addressof(fe),
+                                               _ptr(out)))
+        return out
+
+    def valid_mask(self, points, lp, fe):
+        a, dt, stride = _cloud(points)
+        out = np.empty(len(a), dtype=np.uint8)
+        self._check(self.lib.loamgpu_valid_mask(self.h, _ptr(a), dt, stride, len(a), C.addressof(lp),
+                                                C.addressof(fe), _ptr(out)))
+        return out.astype(bool)
+
+    # ---------------------------------------------------------------- registration
+    def register(self, src_edge, src_planar, tgt_edge, tgt_planar, init_pose, rp: CRegParams, want_detail=False):
+        se, sp, te, tp = (_xyz64(x) for x in (src_edge, src_planar, tgt_edge, tgt_planar))
+        init = np.ascontiguousarray(init_pose, dtype=np.float64)
+        out = np.empty(7, dtype=np.float64)
+        det = None
+        bufs = None
+        if want_detail:
+            cap = max(int(rp.max_iterations), 1)
+            bufs = dict(
+                iter_est=np.zeros((cap, 7)), iter_update=np.zeros((cap, 7)),
+                n_edge_assoc=np.zeros(cap, dtype=np.uint32), n_plane_assoc=np.zeros(cap, dtype=np.uint32),
+                edge_assoc=np.zeros((cap, max(len(se), 1), 2), dtype=np.uint32),
+                plane_assoc=np.zeros((cap, max(len(sp), 1), 2), dtype=np.uint32),
+                lm_iters=np.zeros(cap, dtype=np.uint32), lm_cost=np.zeros((cap, 2)))
+            det = CDetail(cap, max(len(se), 1), max(len(sp), 1), 0, 1,
+                          bufs["iter_est"].ctypes.data_as(PD), bufs["iter_update"].ctypes.data_as(PD),
+                          bufs["n_edge_assoc"].ctypes.data_as(PU32), bufs["n_plane_assoc"].ctypes.data_as(PU32),
+                          bufs["edge_assoc"].ctypes.data_as(PU32), bufs["plane_assoc"].ctypes.data_as(PU32),
+                          bufs["lm_iters"].ctypes.data_as(PU32), bufs["lm_cost"].ctypes.data_as(PD))
+        self._check(self.lib.loamgpu_register(self.h, _ptr(se), len(se), _ptr(sp), len(sp), _ptr(te), len(te),
+                                              _ptr(tp), len(tp), _ptr(init), C.addressof(rp), _ptr(out),
+                                              C.addressof(det) if det is not None else None))
+        if not want_detail:
+            return out
+        n = det.n_iters
+        info = dict(n_iters=n, termination=det.termination, iter_est=bufs["iter_est"][:n].copy(),
+                    iter_update=bufs["iter_update"][:n].copy(), lm_iters=bufs["lm_iters"][:n].copy(),
+                    lm_cost=bufs["lm_cost"][:n].copy(),
+                    edge_assoc=[bufs["edge_assoc"][i, :bufs["n_edge_assoc"][i]].copy() for i in range(n)],
+                    plane_assoc=[bufs["plane_assoc"][i, :bufs["n_plane_assoc"][i]].copy() for i in range(n)])
+        return out, info
+
+    def knn(self, targets, queries, k: int, max_dist: float):
+        t, q = _xyz64(targets), _xyz64(queries)
+        idx = np.full((len(q), k), 0xFFFFFFFF, dtype=np.uint32)
+        cnt = np.zeros(len(q), dtype=np.uint32)
+        self._check(self.lib.loamgpu_knn(self.h, _ptr(t), len(t), _ptr(q), len(q), k, max_dist, _ptr(idx), _ptr(cnt)))
+        return idx, cnt
+
+    # ---------------------------------------------------------------- sequence odometry
+    def odometry_host(self, scans: np.ndarray, lp, fe, rp):
+        """scans: float32 [n_scans, R*P, 4] host array.  Returns poses[n-1,7], termination, iterations, n_edge, n_planar."""
+        s = np.ascontiguousarray(scans, dtype=np.float32)
+        n = s.shape[0]
+        poses = np.zeros((max(n - 1, 0), 7))
+        term = np.zeros(max(n - 1, 0), dtype=np.int32)
+        its = np.zeros(max(n - 1, 0), dtype=np.uint32)
+        ne = np.zeros(n, dtype=np.uint32)
+        npl = np.zeros(n, dtype=np.uint32)
+        self._check(self.lib.loamgpu_odometry_host(self.h, _ptr(s), n, C.addressof(lp), C.addressof(fe),
+                                                   C.addressof(rp), _ptr(poses), _ptr(term), _ptr(its), _ptr(ne),
+                                                   _ptr(npl)))
+        return poses, term, its, ne, npl
+
+    def odometry_host_ptr(self, scans_ptr: int, n_scans: int, lp, fe, rp, poses_ptr, term_ptr, iters_ptr, ne_ptr,
+                          np_ptr):
+        self._check(self.lib.loamgpu_odometry_host(self.h, scans_ptr, n_scans, C.addressof(lp), C.addressof(fe),
+                                                   C.addressof(rp), poses_ptr, term_ptr, iters_ptr, ne_ptr, np_ptr))
+
+    def odometry_device_ptr(self, scans_ptr: int, n_scans: int, lp, fe, rp, poses_ptr, term_ptr, iters_ptr, ne_ptr,
+                            np_ptr):
+        """All pointers are device addresses (e.g. torch tensor .data_ptr()); asynchronous on the context stream."""
+        self._check(self.lib.loamgpu_odometry_device(self.h, scans_ptr, n_scans, C.addressof(lp), C.addressof(fe),
+                                                     C.addressof(rp), poses_ptr, term_ptr, iters_ptr, ne_ptr,
+                                                     np_ptr))
+
+
+def default_fe_params() -> CFeParams:
+    p = CFeParams()
+    load_library().loamgpu_default_fe_params(C.byref(p))
+    return p
+
+
+def default_reg_params() -> CRegParams:
+    p = CRegParams()
+    load_library().loamgpu_default_reg_params(C.byref(p))
+    return p

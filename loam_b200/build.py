@@ -1,0 +1,54 @@
+"""Build libloamgpu.so (hand-written sm_100a kernels + C-ABI) in-tree with nvcc.
+
+-fmad=false : the reference is built for baseline x86-64 (no FMA); feature and correspondence
+              indices must be bit-exact, so no multiply-add is ever contracted.
+-lineinfo   : ncu source pages map to the .cu files.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SRC = [os.path.join(HERE, "csrc", f) for f in ("extract.cu", "register.cu", "capi.cu")]
+DEPS = SRC + [os.path.join(HERE, "csrc", f) for f in ("common.cuh", "kernels.h")] + [
+    os.path.join(ROOT, "include", "loamgpu.h")]
+LIB = os.path.join(HERE, "lib", "libloamgpu.so")
+
+
+def nvcc_path() -> str:
+    for p in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if p and (os.path.isabs(p) and os.path.exists(p) or not os.path.isabs(p)):
+            return p
+    return "nvcc"
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(d) > t for d in DEPS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    cmd = [nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+           "-fmad=false", "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"),
+           "-I", os.path.join(HERE, "csrc"), "-o", LIB] + SRC
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed building libloamgpu.so")
+    if verbose:
+        print(r.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

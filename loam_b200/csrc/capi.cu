@@ -1,0 +1,789 @@
+// C-ABI entry points of libloamgpu.so (declared in include/loamgpu.h) and the host-side context:
+// device buffers, streams, chunked sequence pipeline.  Host code only packs buffers and launches
+// kernels; every number in the results is produced by the CUDA kernels in extract.cu / register.cu.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "loamgpu.h"
+
+using namespace loamgpu;
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+thread_local std::string g_create_err;
+
+}  // namespace
+
+struct loamgpu_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+  std::string err;
+  uint64_t launches = 0;
+  uint32_t chunk_pairs = 256;
+  int max_smem_optin = 0;
+
+  DevBuf scan_in[2];                       // H2D staging of scans
+  DevBuf ring_edge, ring_planar, ring_counts;
+  DevBuf edge_idx, planar_idx, edge_pts, planar_pts, feat_counts;
+  DevBuf ge_hdr, ge_cells, ge_sorted, ge_rank, gp_hdr, gp_cells, gp_sorted, gp_rank;
+  DevBuf state, rec_p, rec_a, rec_b, nearest;
+  DevBuf misc, out_pose, out_term, out_iters, out_ne, out_np;
+  DevBuf det_est, det_upd, det_assoc_n, det_lm_iters, det_lm_cost, init_pose;
+};
+
+namespace {
+
+int fail(loamgpu_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+int cuda_fail(loamgpu_ctx* c, cudaError_t e, const char* what) {
+  return fail(c, LOAMGPU_ERR_CUDA, std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e));
+}
+#define CU(call)                                              \
+  do {                                                        \
+    cudaError_t _e = (call);                                  \
+    if (_e != cudaSuccess) return cuda_fail(ctx, _e, #call);  \
+  } while (0)
+
+// geometry of one extraction problem, validated
+struct ExtractPlan {
+  uint32_t R, P, N, S, maxE, maxP, capE_ring, capP_ring, capE_scan, capP_scan;
+  size_t smem;
+};
+
+int plan_extract(loamgpu_ctx* ctx, int dtype, size_t stride, uint64_t n_points, const loamgpu_lidar_params* lp,
+                 const loamgpu_fe_params* fe, ExtractPlan* pl) {
+  if (!lp || !fe) return fail(ctx, LOAMGPU_ERR_INVALID, "null parameter struct");
+  if (dtype != LOAMGPU_F32 && dtype != LOAMGPU_F64) return fail(ctx, LOAMGPU_ERR_INVALID, "unknown dtype");
+  if (stride < (dtype == LOAMGPU_F32 ? 12u : 24u) || stride % (dtype == LOAMGPU_F32 ? 4u : 8u))
+    return fail(ctx, LOAMGPU_ERR_INVALID, "stride_bytes too small / misaligned for dtype");
+  if (n_points != lp->scan_lines * lp->points_per_line) {
+    // exact text of the reference's std::runtime_error (common.h:106-111)
+    char buf[256];
+    snprintf(buf, sizeof buf, "LOAM: provided lidar scan size ( %llu)  does not match provided lidar parameters (%llu x %llu)",
+             (unsigned long long)n_points, (unsigned long long)lp->scan_lines,
+             (unsigned long long)lp->points_per_line);
+    return fail(ctx, LOAMGPU_ERR_SIZE_MISMATCH, buf);
+  }
+  if (n_points == 0) {
+    memset(pl, 0, sizeof *pl);
+    return LOAMGPU_OK;
+  }
+  if (fe->number_sectors == 0)
+    return fail(ctx, LOAMGPU_ERR_INVALID, "number_sectors must be >= 1 (the reference divides by it)");
+  if (fe->neighbor_points == 0)
+    return fail(ctx, LOAMGPU_ERR_INVALID,
+                "neighbor_points must be >= 1 (the reference indexes point idx-1 and throws std::out_of_range)");
+  if (lp->points_per_line > 65535 || lp->scan_lines > 0xFFFFFFu || n_points > 0xFFFFFFFFull)
+    return fail(ctx, LOAMGPU_ERR_UNSUPPORTED, "scan too large (points_per_line <= 65535, total points < 2^32)");
+  const uint64_t P = lp->points_per_line;
+  pl->R = (uint32_t)lp->scan_lines;
+  pl->P = (uint32_t)P;
+  pl->N = (uint32_t)std::min<uint64_t>(fe->neighbor_points, P);
+  pl->S = (uint32_t)std::min<uint64_t>(fe->number_sectors, 0xFFFFFFFFull);
+  if (fe->number_sectors > 65536) return fail(ctx, LOAMGPU_ERR_UNSUPPORTED, "number_sectors > 65536");
+  pl->maxE = (uint32_t)std::min<uint64_t>(fe->max_edge_feats_per_sector, P);
+  pl->maxP = (uint32_t)std::min<uint64_t>(fe->max_planar_feats_per_sector, P);
+  pl->capE_ring = (uint32_t)std::min<uint64_t>((uint64_t)pl->S * ((uint64_t)pl->maxE + 1), P);
+  pl->capP_ring = (uint32_t)std::min<uint64_t>((uint64_t)pl->S * ((uint64_t)pl->maxP + 1), P);
+  pl->capE_scan = pl->R * pl->capE_ring;
+  pl->capP_scan = pl->R * pl->capP_ring;
+  pl->smem = extract_smem_bytes(dtype, pl->P, pl->S);
+  if (pl->smem > (size_t)ctx->max_smem_optin)
+    return fail(ctx, LOAMGPU_ERR_UNSUPPORTED, "points_per_line too large for one CTA's shared memory");
+  return LOAMGPU_OK;
+}
+
+void fill_extract_args(ExtractArgs& a, const ExtractPlan& pl, const void* dev_pts, int dtype, size_t stride,
+                       const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe) {
+  memset(&a, 0, sizeof a);
+  a.pts = (const unsigned char*)dev_pts;
+  a.scan_stride_bytes = (uint64_t)pl.R * pl.P * stride;
+  a.stride = (uint32_t)stride;
+  a.dtype = dtype;
+  const size_t rec = dtype == LOAMGPU_F32 ? 16 : 24;
+  a.use_bulk = (stride == rec) && (((size_t)pl.P * rec) % 16 == 0) && (((uintptr_t)dev_pts) % 16 == 0) &&
+               (a.scan_stride_bytes % 16 == 0);
+  a.R = pl.R;
+  a.P = pl.P;
+  a.N = pl.N;
+  a.S = pl.S;
+  a.maxE = pl.maxE;
+  a.maxP = pl.maxP;
+  a.edge_thr = fe->edge_feat_threshold;
+  a.planar_thr = fe->planar_feat_threshold;
+  a.occ = fe->occlusion_thresh;
+  a.par = fe->parallel_thresh;
+  a.min_range = lp->min_range;
+  a.max_range = lp->max_range;
+  a.capE_ring = pl.capE_ring;
+  a.capP_ring = pl.capP_ring;
+}
+
+int reserve_extract(loamgpu_ctx* ctx, const ExtractPlan& pl, uint32_t n_scans, uint32_t n_slots) {
+  CU(ctx->ring_edge.reserve((size_t)n_scans * pl.R * pl.capE_ring * 4));
+  CU(ctx->ring_planar.reserve((size_t)n_scans * pl.R * pl.capP_ring * 4));
+  CU(ctx->ring_counts.reserve((size_t)n_scans * pl.R * 8));
+  CU(ctx->edge_idx.reserve((size_t)n_slots * pl.capE_scan * 4));
+  CU(ctx->planar_idx.reserve((size_t)n_slots * pl.capP_scan * 4));
+  CU(ctx->edge_pts.reserve((size_t)n_slots * pl.capE_scan * 32));
+  CU(ctx->planar_pts.reserve((size_t)n_slots * pl.capP_scan * 32));
+  CU(ctx->feat_counts.reserve((size_t)n_slots * 8));
+  return LOAMGPU_OK;
+}
+
+// Extract `n_scans` device-resident scans into feature slots (scan0 + i) % n_slots.
+int run_extract(loamgpu_ctx* ctx, const ExtractPlan& pl, const void* dev_pts, int dtype, size_t stride,
+                const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe, uint32_t n_scans, uint64_t scan0,
+                uint32_t n_slots, uint32_t* n_edge_out, uint32_t* n_planar_out) {
+  ExtractArgs a;
+  fill_extract_args(a, pl, dev_pts, dtype, stride, lp, fe);
+  a.ring_edge = ctx->ring_edge.as<uint32_t>();
+  a.ring_planar = ctx->ring_planar.as<uint32_t>();
+  a.ring_counts = ctx->ring_counts.as<uint32_t>();
+  CU(launch_extract(a, n_scans, ctx->stream));
+  ctx->launches++;
+  PackArgs p;
+  memset(&p, 0, sizeof p);
+  p.pts = a.pts;
+  p.scan_stride_bytes = a.scan_stride_bytes;
+  p.stride = a.stride;
+  p.dtype = dtype;
+  p.R = pl.R;
+  p.capE_ring = pl.capE_ring;
+  p.capP_ring = pl.capP_ring;
+  p.capE_scan = pl.capE_scan;
+  p.capP_scan = pl.capP_scan;
+  p.ring_edge = a.ring_edge;
+  p.ring_planar = a.ring_planar;
+  p.ring_counts = a.ring_counts;
+  p.scan0 = scan0;
+  p.n_slots = n_slots;
+  p.edge_idx = ctx->edge_idx.as<uint32_t>();
+  p.planar_idx = ctx->planar_idx.as<uint32_t>();
+  p.edge_pts = ctx->edge_pts.as<double4>();
+  p.planar_pts = ctx->planar_pts.as<double4>();
+  p.feat_counts = ctx->feat_counts.as<uint32_t>();
+  p.n_edge_out = n_edge_out;
+  p.n_planar_out = n_planar_out;
+  CU(launch_pack(p, n_scans, ctx->stream));
+  ctx->launches++;
+  return LOAMGPU_OK;
+}
+
+int make_regp(loamgpu_ctx* ctx, const loamgpu_reg_params* rp, RegP* out) {
+  if (!rp) return fail(ctx, LOAMGPU_ERR_INVALID, "null registration params");
+  if (rp->num_edge_neighbors == 0 || rp->num_plane_neighbors == 0)
+    return fail(ctx, LOAMGPU_ERR_INVALID, "num_*_neighbors must be >= 1");
+  if (rp->num_edge_neighbors > (uint64_t)kKnnMax || rp->num_plane_neighbors > (uint64_t)kKnnMax)
+    return fail(ctx, LOAMGPU_ERR_UNSUPPORTED, "num_*_neighbors > 32 not supported");
+  out->ke = (int)rp->num_edge_neighbors;
+  out->kp = (int)rp->num_plane_neighbors;
+  out->re = rp->max_edge_neighbor_dist;
+  out->rp = rp->max_plane_neighbor_dist;
+  out->min_line = (int)std::min<uint64_t>(rp->min_line_fit_points, 1u << 30);
+  out->min_plane = (int)std::min<uint64_t>(rp->min_plane_fit_points, 1u << 30);
+  out->min_cond = rp->min_line_condition_number;
+  out->max_avg = rp->max_avg_point_plane_dist;
+  out->max_iterations = (int)std::min<uint64_t>(rp->max_iterations, 1u << 20);
+  out->rot_thr = rp->rotation_convergence_thresh;
+  out->pos_thr = rp->position_convergence_thresh;
+  out->min_assoc = rp->min_associations;
+  return LOAMGPU_OK;
+}
+
+uint32_t cell_cap_for(uint32_t pt_cap) { return std::max<uint32_t>(4096u, 8u * pt_cap); }
+
+int reserve_register(loamgpu_ctx* ctx, uint32_t n_pairs, uint32_t capE, uint32_t capP, uint32_t detail_iters) {
+  const uint32_t ccE = cell_cap_for(capE), ccP = cell_cap_for(capP);
+  CU(ctx->ge_hdr.reserve((size_t)n_pairs * sizeof(GridHdr)));
+  CU(ctx->gp_hdr.reserve((size_t)n_pairs * sizeof(GridHdr)));
+  CU(ctx->ge_cells.reserve((size_t)n_pairs * (ccE + 1) * 4));
+  CU(ctx->gp_cells.reserve((size_t)n_pairs * (ccP + 1) * 4));
+  CU(ctx->ge_sorted.reserve((size_t)n_pairs * capE * 32));
+  CU(ctx->gp_sorted.reserve((size_t)n_pairs * capP * 32));
+  CU(ctx->ge_rank.reserve((size_t)n_pairs * capE * 4));
+  CU(ctx->gp_rank.reserve((size_t)n_pairs * capP * 4));
+  CU(ctx->state.reserve((size_t)n_pairs * sizeof(PairState)));
+  CU(ctx->rec_p.reserve((size_t)n_pairs * (capE + capP) * 32));
+  CU(ctx->rec_a.reserve((size_t)n_pairs * (capE + capP) * 32));
+  CU(ctx->rec_b.reserve((size_t)n_pairs * capE * 32));
+  if (detail_iters) CU(ctx->nearest.reserve((size_t)detail_iters * n_pairs * (capE + capP) * 4));
+  return LOAMGPU_OK;
+}
+
+GridSetArrays grid_arrays(loamgpu_ctx* ctx, bool planar, uint32_t cap) {
+  GridSetArrays g;
+  g.hdr = (planar ? ctx->gp_hdr : ctx->ge_hdr).as<GridHdr>();
+  g.cell_start = (planar ? ctx->gp_cells : ctx->ge_cells).as<uint32_t>();
+  g.sorted = (planar ? ctx->gp_sorted : ctx->ge_sorted).as<double4>();
+  g.rank = (planar ? ctx->gp_rank : ctx->ge_rank).as<uint32_t>();
+  g.cell_cap = cell_cap_for(cap);
+  g.pt_cap = cap;
+  return g;
+}
+
+// Register n_pairs pairs whose features sit in slots: tgt = (pair0+p) % n_slots, src = (pair0+p+src_offset) % n_slots.
+int run_register(loamgpu_ctx* ctx, const RegP& rp, uint32_t n_pairs, uint64_t pair0, uint32_t n_slots, int src_offset,
+                 uint32_t capE, uint32_t capP, const double* init_pose_dev, bool detail) {
+  GridBuildArgs gb;
+  memset(&gb, 0, sizeof gb);
+  gb.counts = ctx->feat_counts.as<uint32_t>();
+  gb.slot0 = pair0;
+  gb.n_slots = n_slots;
+  gb.pts = ctx->edge_pts.as<double4>();
+  gb.pt_stride = capE;
+  gb.kind = 0;
+  gb.k_nominal = rp.ke;
+  gb.g = grid_arrays(ctx, false, capE);
+  CU(launch_grid_build(gb, n_pairs, ctx->stream));
+  gb.pts = ctx->planar_pts.as<double4>();
+  gb.pt_stride = capP;
+  gb.kind = 1;
+  gb.k_nominal = rp.kp;
+  gb.g = grid_arrays(ctx, true, capP);
+  CU(launch_grid_build(gb, n_pairs, ctx->stream));
+  CU(launch_init_pairs(ctx->state.as<PairState>(), n_pairs, init_pose_dev, ctx->stream));
+  ctx->launches += 3;
+
+  AssocArgs aa;
+  memset(&aa, 0, sizeof aa);
+  aa.edge_pts = ctx->edge_pts.as<double4>();
+  aa.planar_pts = ctx->planar_pts.as<double4>();
+  aa.feat_counts = ctx->feat_counts.as<uint32_t>();
+  aa.capE_scan = capE;
+  aa.capP_scan = capP;
+  aa.pair0 = pair0;
+  aa.n_slots = n_slots;
+  aa.src_offset = src_offset;
+  aa.ge = grid_arrays(ctx, false, capE);
+  aa.gp = grid_arrays(ctx, true, capP);
+  aa.state = ctx->state.as<PairState>();
+  aa.rec_p = ctx->rec_p.as<double4>();
+  aa.rec_a = ctx->rec_a.as<double4>();
+  aa.rec_b = ctx->rec_b.as<double4>();
+  aa.nearest = detail ? ctx->nearest.as<int32_t>() : nullptr;
+  aa.rp = rp;
+  LmArgs la;
+  memset(&la, 0, sizeof la);
+  la.state = aa.state;
+  la.rec_p = aa.rec_p;
+  la.rec_a = aa.rec_a;
+  la.rec_b = aa.rec_b;
+  la.feat_counts = aa.feat_counts;
+  la.capE_scan = capE;
+  la.capP_scan = capP;
+  la.pair0 = pair0;
+  la.n_slots = n_slots;
+  la.src_offset = src_offset;
+  la.rp = rp;
+  if (detail) {
+    la.d_iter_est = ctx->det_est.as<double>();
+    la.d_iter_update = ctx->det_upd.as<double>();
+    la.d_assoc_n = ctx->det_assoc_n.as<uint32_t>();
+    la.d_lm_iters = ctx->det_lm_iters.as<uint32_t>();
+    la.d_lm_cost = ctx->det_lm_cost.as<double>();
+  }
+  for (int it = 0; it < rp.max_iterations; it++) {
+    CU(launch_assoc(aa, n_pairs, it, ctx->stream));
+    la.outer_iter = it;
+    CU(launch_lm(la, n_pairs, ctx->stream));
+    ctx->launches += 2;
+  }
+  return LOAMGPU_OK;
+}
+
+}  // namespace
+
+// =============================================================================================== C ABI
+
+extern "C" {
+
+int loamgpu_create(int device, loamgpu_ctx** out) {
+  if (!out) return LOAMGPU_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    g_create_err = std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                   "); libloamgpu has no CPU fallback";
+    return LOAMGPU_ERR_CUDA;
+  }
+  if (device < 0 || device >= count) {
+    g_create_err = "device index out of range";
+    return LOAMGPU_ERR_INVALID;
+  }
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    g_create_err = cudaGetErrorString(e);
+    return LOAMGPU_ERR_CUDA;
+  }
+  loamgpu_ctx* c = new loamgpu_ctx();
+  c->device = device;
+  cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    g_create_err = "cudaStreamCreate failed";
+    delete c;
+    return LOAMGPU_ERR_CUDA;
+  }
+  for (int i = 0; i < 2; i++) {
+    cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming);
+  }
+  c->stream = c->own_stream;
+  *out = c;
+  return LOAMGPU_OK;
+}
+
+void loamgpu_destroy(loamgpu_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  DevBuf* bufs[] = {&c->scan_in[0], &c->scan_in[1], &c->ring_edge, &c->ring_planar, &c->ring_counts, &c->edge_idx,
+                    &c->planar_idx, &c->edge_pts, &c->planar_pts, &c->feat_counts, &c->ge_hdr, &c->ge_cells,
+                    &c->ge_sorted, &c->ge_rank, &c->gp_hdr, &c->gp_cells, &c->gp_sorted, &c->gp_rank, &c->state,
+                    &c->rec_p, &c->rec_a, &c->rec_b, &c->nearest, &c->misc, &c->out_pose, &c->out_term,
+                    &c->out_iters, &c->out_ne, &c->out_np, &c->det_est, &c->det_upd, &c->det_assoc_n,
+                    &c->det_lm_iters, &c->det_lm_cost, &c->init_pose};
+  for (DevBuf* b : bufs) b->release();
+  for (int i = 0; i < 2; i++) {
+    if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
+    if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]);
+  }
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  delete c;
+}
+
+const char* loamgpu_last_error(const loamgpu_ctx* c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+
+int loamgpu_set_stream(loamgpu_ctx* c, void* s) {
+  if (!c) return LOAMGPU_ERR_INVALID;
+  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  return LOAMGPU_OK;
+}
+
+void loamgpu_default_fe_params(loamgpu_fe_params* p) {  // features.h:37-66
+  p->neighbor_points = 3;
+  p->number_sectors = 6;
+  p->max_edge_feats_per_sector = 10;
+  p->max_planar_feats_per_sector = 50;
+  p->edge_feat_threshold = 100.0;
+  p->planar_feat_threshold = 1.0;
+  p->occlusion_thresh = 0.5;
+  p->parallel_thresh = 1.0;
+}
+
+void loamgpu_default_reg_params(loamgpu_reg_params* p) {  // registration.h:40-75
+  p->num_edge_neighbors = 5;
+  p->max_edge_neighbor_dist = 1.0;
+  p->min_line_fit_points = 3;
+  p->min_line_condition_number = 10;
+  p->num_plane_neighbors = 5;
+  p->max_plane_neighbor_dist = 2.0;
+  p->min_plane_fit_points = 4;
+  p->max_avg_point_plane_dist = 0.1;
+  p->max_iterations = 10;
+  p->rotation_convergence_thresh = 1e-3;
+  p->position_convergence_thresh = 1e-2;
+  p->min_associations = 100;
+}
+
+uint64_t loamgpu_launch_count(const loamgpu_ctx* c) { return c ? c->launches : 0; }
+
+int loamgpu_set_chunk_pairs(loamgpu_ctx* c, uint32_t pairs) {
+  if (!c || pairs == 0) return LOAMGPU_ERR_INVALID;
+  c->chunk_pairs = pairs;
+  return LOAMGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------ extraction
+
+int loamgpu_extract(loamgpu_ctx* ctx, const void* pts, int dtype, size_t stride, uint64_t n_points,
+                    const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe, uint32_t* edge_idx,
+                    uint64_t edge_cap, uint64_t* n_edge, uint32_t* planar_idx, uint64_t planar_cap,
+                    uint64_t* n_planar) {
+  if (!ctx) return LOAMGPU_ERR_INVALID;
+  if (!n_edge || !n_planar) return fail(ctx, LOAMGPU_ERR_INVALID, "null count pointer");
+  CU(cudaSetDevice(ctx->device));
+  ExtractPlan pl;
+  int rc = plan_extract(ctx, dtype, stride, n_points, lp, fe, &pl);
+  if (rc) return rc;
+  *n_edge = 0;
+  *n_planar = 0;
+  if (n_points == 0) return LOAMGPU_OK;
+  if (!pts) return fail(ctx, LOAMGPU_ERR_INVALID, "null point buffer");
+  const size_t bytes = (size_t)n_points * stride;
+  CU(ctx->scan_in[0].reserve(bytes));
+  rc = reserve_extract(ctx, pl, 1, 1);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(ctx->scan_in[0].p, pts, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  rc = run_extract(ctx, pl, ctx->scan_in[0].p, dtype, stride, lp, fe, 1, 0, 1, nullptr, nullptr);
+  if (rc) return rc;
+  uint32_t counts[2];
+  CU(cudaMemcpyAsync(counts, ctx->feat_counts.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (counts[0] > edge_cap || counts[1] > planar_cap || (counts[0] && !edge_idx) || (counts[1] && !planar_idx))
+    return fail(ctx, LOAMGPU_ERR_INVALID, "output index buffers too small");
+  if (counts[0]) CU(cudaMemcpyAsync(edge_idx, ctx->edge_idx.p, 4 * (size_t)counts[0], cudaMemcpyDeviceToHost, ctx->stream));
+  if (counts[1])
+    CU(cudaMemcpyAsync(planar_idx, ctx->planar_idx.p, 4 * (size_t)counts[1], cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  *n_edge = counts[0];
+  *n_planar = counts[1];
+  return LOAMGPU_OK;
+}
+
+static int curvature_or_mask(loamgpu_ctx* ctx, const void* pts, int dtype, size_t stride, uint64_t n_points,
+                             const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe, double* curv,
+                             uint8_t* mask) {
+  if (!ctx) return LOAMGPU_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  ExtractPlan pl;
+  int rc = plan_extract(ctx, dtype, stride, n_points, lp, fe, &pl);
+  if (rc) return rc;
+  if (n_points == 0) return LOAMGPU_OK;
+  if (!pts || (!curv && !mask)) return fail(ctx, LOAMGPU_ERR_INVALID, "null buffer");
+  const size_t bytes = (size_t)n_points * stride;
+  CU(ctx->scan_in[0].reserve(bytes));
+  CU(ctx->misc.reserve((size_t)n_points * 9));
+  CU(cudaMemcpyAsync(ctx->scan_in[0].p, pts, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  ExtractArgs a;
+  fill_extract_args(a, pl, ctx->scan_in[0].p, dtype, stride, lp, fe);
+  double* d_curv = ctx->misc.as<double>();
+  uint8_t* d_mask = ctx->misc.as<uint8_t>() + (size_t)n_points * 8;
+  a.curv_out = curv ? d_curv : nullptr;
+  a.mask_out = mask ? d_mask : nullptr;
+  CU(launch_extract(a, 1, ctx->stream));
+  ctx->launches++;
+  if (curv) CU(cudaMemcpyAsync(curv, d_curv, (size_t)n_points * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (mask) CU(cudaMemcpyAsync(mask, d_mask, (size_t)n_points, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return LOAMGPU_OK;
+}
+
+int loamgpu_curvature(loamgpu_ctx* ctx, const void* pts, int dtype, size_t stride, uint64_t n_points,
+                      const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe, double* curvature) {
+  return curvature_or_mask(ctx, pts, dtype, stride, n_points, lp, fe, curvature, nullptr);
+}
+
+int loamgpu_valid_mask(loamgpu_ctx* ctx, const void* pts, int dtype, size_t stride, uint64_t n_points,
+                       const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe, uint8_t* mask) {
+  return curvature_or_mask(ctx, pts, dtype, stride, n_points, lp, fe, nullptr, mask);
+}
+
+// ------------------------------------------------------------------------------------------ registration
+
+static void widen(const double* src, uint64_t n, std::vector<double>& dst, size_t off_pts) {
+  for (uint64_t i = 0; i < n; i++) {
+    double* d = dst.data() + (off_pts + i) * 4;
+    d[0] = src[3 * i];
+    d[1] = src[3 * i + 1];
+    d[2] = src[3 * i + 2];
+    d[3] = 0.0;
+  }
+}
+
+int loamgpu_register(loamgpu_ctx* ctx, const double* src_edge, uint64_t n_se, const double* src_planar, uint64_t n_sp,
+                     const double* tgt_edge, uint64_t n_te, const double* tgt_planar, uint64_t n_tp,
+                     const double init_pose[7], const loamgpu_reg_params* params, double out_pose[7],
+                     loamgpu_detail* detail) {
+  if (!ctx) return LOAMGPU_ERR_INVALID;
+  if (!init_pose || !out_pose) return fail(ctx, LOAMGPU_ERR_INVALID, "null pose pointer");
+  if ((n_se && !src_edge) || (n_sp && !src_planar) || (n_te && !tgt_edge) || (n_tp && !tgt_planar))
+    return fail(ctx, LOAMGPU_ERR_INVALID, "null feature buffer");
+  if (std::max(std::max(n_se, n_sp), std::max(n_te, n_tp)) > 0x7FFFFFFFull)
+    return fail(ctx, LOAMGPU_ERR_UNSUPPORTED, "feature set too large");
+  CU(cudaSetDevice(ctx->device));
+  RegP rp;
+  int rc = make_regp(ctx, params, &rp);
+  if (rc) return rc;
+  const uint32_t capE = (uint32_t)std::max<uint64_t>(std::max(n_se, n_te), 1);
+  const uint32_t capP = (uint32_t)std::max<uint64_t>(std::max(n_sp, n_tp), 1);
+  const bool want_detail = detail != nullptr;
+  const uint32_t det_iters = want_detail ? (uint32_t)std::max(rp.max_iterations, 1) : 0;
+  // slots: 0 = target, 1 = source
+  CU(ctx->edge_pts.reserve((size_t)2 * capE * 32));
+  CU(ctx->planar_pts.reserve((size_t)2 * capP * 32));
+  CU(ctx->feat_counts.reserve(16));
+  rc = reserve_register(ctx, 1, capE, capP, det_iters);
+  if (rc) return rc;
+  CU(ctx->init_pose.reserve(7 * 8));
+  CU(ctx->out_pose.reserve(7 * 8));
+  CU(ctx->out_term.reserve(4));
+  CU(ctx->out_iters.reserve(4));
+  if (want_detail) {
+    CU(ctx->det_est.reserve((size_t)det_iters * 7 * 8));
+    CU(ctx->det_upd.reserve((size_t)det_iters * 7 * 8));
+    CU(ctx->det_assoc_n.reserve((size_t)det_iters * 8));
+    CU(ctx->det_lm_iters.reserve((size_t)det_iters * 4));
+    CU(ctx->det_lm_cost.reserve((size_t)det_iters * 16));
+    CU(cudaMemsetAsync(ctx->det_assoc_n.p, 0, (size_t)det_iters * 8, ctx->stream));
+  }
+  std::vector<double> he((size_t)2 * capE * 4), hp((size_t)2 * capP * 4);
+  widen(tgt_edge, n_te, he, 0);
+  widen(src_edge, n_se, he, capE);
+  widen(tgt_planar, n_tp, hp, 0);
+  widen(src_planar, n_sp, hp, capP);
+  const uint32_t counts[4] = {(uint32_t)n_te, (uint32_t)n_tp, (uint32_t)n_se, (uint32_t)n_sp};
+  CU(cudaMemcpyAsync(ctx->edge_pts.p, he.data(), he.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->planar_pts.p, hp.data(), hp.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->feat_counts.p, counts, 16, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->init_pose.p, init_pose, 56, cudaMemcpyHostToDevice, ctx->stream));
+  rc = run_register(ctx, rp, 1, 0, 2, 1, capE, capP, ctx->init_pose.as<double>(), want_detail);
+  if (rc) return rc;
+  CU(launch_finish_pairs(ctx->state.as<PairState>(), 1, ctx->out_pose.as<double>(), ctx->out_term.as<int32_t>(),
+                         ctx->out_iters.as<uint32_t>(), ctx->stream));
+  ctx->launches++;
+  int32_t term = 1;
+  uint32_t iters = 0;
+  CU(cudaMemcpyAsync(out_pose, ctx->out_pose.p, 56, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(&term, ctx->out_term.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(&iters, ctx->out_iters.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (want_detail) {
+    detail->n_iters = iters;
+    detail->termination = term;
+    const uint32_t rows = std::min<uint32_t>(iters, detail->max_iters_cap);
+    std::vector<uint32_t> assoc_n((size_t)std::max<uint32_t>(rows, 1) * 2);
+    if (rows) {
+      if (detail->iter_est) CU(cudaMemcpy(detail->iter_est, ctx->det_est.p, (size_t)rows * 56, cudaMemcpyDeviceToHost));
+      if (detail->iter_update)
+        CU(cudaMemcpy(detail->iter_update, ctx->det_upd.p, (size_t)rows * 56, cudaMemcpyDeviceToHost));
+      if (detail->lm_iters)
+        CU(cudaMemcpy(detail->lm_iters, ctx->det_lm_iters.p, (size_t)rows * 4, cudaMemcpyDeviceToHost));
+      if (detail->lm_cost) CU(cudaMemcpy(detail->lm_cost, ctx->det_lm_cost.p, (size_t)rows * 16, cudaMemcpyDeviceToHost));
+      CU(cudaMemcpy(assoc_n.data(), ctx->det_assoc_n.p, (size_t)rows * 8, cudaMemcpyDeviceToHost));
+      const size_t cap_src = (size_t)capE + capP;
+      std::vector<int32_t> nearest((size_t)rows * cap_src);
+      CU(cudaMemcpy(nearest.data(), ctx->nearest.p, nearest.size() * 4, cudaMemcpyDeviceToHost));
+      for (uint32_t it = 0; it < rows; it++) {
+        // association lists in source-index order (registration.cpp:59,100)
+        uint32_t ne = 0, np = 0;
+        const int32_t* row = nearest.data() + (size_t)it * cap_src;
+        for (uint64_t i = 0; i < n_se; i++)
+          if (row[i] >= 0) {
+            if (detail->edge_assoc && ne < detail->n_src_edge) {
+              uint32_t* o = detail->edge_assoc + ((size_t)it * detail->n_src_edge + ne) * 2;
+              o[0] = (uint32_t)i;
+              o[1] = (uint32_t)row[i];
+            }
+            ne++;
+          }
+        for (uint64_t i = 0; i < n_sp; i++)
+          if (row[capE + i] >= 0) {
+            if (detail->plane_assoc && np < detail->n_src_planar) {
+              uint32_t* o = detail->plane_assoc + ((size_t)it * detail->n_src_planar + np) * 2;
+              o[0] = (uint32_t)i;
+              o[1] = (uint32_t)row[capE + i];
+            }
+            np++;
+          }
+        if (detail->n_edge_assoc) detail->n_edge_assoc[it] = ne;
+        if (detail->n_plane_assoc) detail->n_plane_assoc[it] = np;
+      }
+    }
+  }
+  return LOAMGPU_OK;
+}
+
+int loamgpu_knn(loamgpu_ctx* ctx, const double* targets, uint64_t n_t, const double* queries, uint64_t n_q, uint32_t k,
+                double max_dist, uint32_t* idx_out, uint32_t* count_out) {
+  if (!ctx) return LOAMGPU_ERR_INVALID;
+  if (k == 0 || k > (uint32_t)kKnnMax) return fail(ctx, LOAMGPU_ERR_UNSUPPORTED, "k must be in [1, 32]");
+  if ((n_t && !targets) || (n_q && (!queries || !idx_out || !count_out)))
+    return fail(ctx, LOAMGPU_ERR_INVALID, "null buffer");
+  if (n_t > 0x7FFFFFFFull) return fail(ctx, LOAMGPU_ERR_UNSUPPORTED, "target set too large");
+  if (n_q == 0) return LOAMGPU_OK;
+  CU(cudaSetDevice(ctx->device));
+  const uint32_t cap = (uint32_t)std::max<uint64_t>(n_t, 1);
+  CU(ctx->planar_pts.reserve((size_t)cap * 32));
+  CU(ctx->feat_counts.reserve(8));
+  int rc = reserve_register(ctx, 1, 1, cap, 0);
+  if (rc) return rc;
+  CU(ctx->misc.reserve((size_t)n_q * (24 + 4 * (size_t)k + 4)));
+  std::vector<double> hp((size_t)cap * 4);
+  widen(targets, n_t, hp, 0);
+  const uint32_t counts[2] = {0, (uint32_t)n_t};
+  CU(cudaMemcpyAsync(ctx->planar_pts.p, hp.data(), hp.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->feat_counts.p, counts, 8, cudaMemcpyHostToDevice, ctx->stream));
+  GridBuildArgs gb;
+  memset(&gb, 0, sizeof gb);
+  gb.counts = ctx->feat_counts.as<uint32_t>();
+  gb.slot0 = 0;
+  gb.n_slots = 1;
+  gb.pts = ctx->planar_pts.as<double4>();
+  gb.pt_stride = cap;
+  gb.kind = 1;
+  gb.k_nominal = (int)k;
+  gb.g = grid_arrays(ctx, true, cap);
+  CU(launch_grid_build(gb, 1, ctx->stream));
+  double* dq = ctx->misc.as<double>();
+  uint32_t* didx = reinterpret_cast<uint32_t*>(dq + 3 * n_q);
+  uint32_t* dcnt = didx + (size_t)n_q * k;
+  CU(cudaMemcpyAsync(dq, queries, (size_t)n_q * 24, cudaMemcpyHostToDevice, ctx->stream));
+  KnnArgs ka;
+  ka.queries = dq;
+  ka.n_queries = n_q;
+  ka.g = gb.g;
+  ka.k = (int)k;
+  ka.max_dist = max_dist;
+  ka.idx_out = didx;
+  ka.count_out = dcnt;
+  CU(launch_knn(ka, ctx->stream));
+  ctx->launches += 2;
+  CU(cudaMemcpyAsync(idx_out, didx, (size_t)n_q * k * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(count_out, dcnt, (size_t)n_q * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return LOAMGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------ sequence odometry
+
+}  // extern "C"
+
+// Core of both odometry entry points.  `fetch(c0, n, buf)` must make scans [c0, c0+n) available on the device and
+// return their device pointer (the _device variant just offsets; the _host variant copies on the copy stream).
+template <typename Fetch>
+static int odometry_core(loamgpu_ctx* ctx, uint64_t n_scans, const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe,
+                         const loamgpu_reg_params* reg, double* poses_dev, int32_t* term_dev, uint32_t* iters_dev,
+                         uint32_t* ne_dev, uint32_t* np_dev, Fetch fetch) {
+  ExtractPlan pl;
+  const uint64_t n_per = lp->scan_lines * lp->points_per_line;
+  int rc = plan_extract(ctx, LOAMGPU_F32, 16, n_per, lp, fe, &pl);
+  if (rc) return rc;
+  if (n_per == 0) return fail(ctx, LOAMGPU_ERR_INVALID, "empty scans");
+  RegP rp;
+  rc = make_regp(ctx, reg, &rp);
+  if (rc) return rc;
+  const uint32_t chunk = (uint32_t)std::min<uint64_t>(ctx->chunk_pairs, std::max<uint64_t>(n_scans, 2) - 1);
+  const uint32_t n_slots = chunk + 1;
+  rc = reserve_extract(ctx, pl, chunk + 1, n_slots);
+  if (rc) return rc;
+  rc = reserve_register(ctx, chunk, pl.capE_scan, pl.capP_scan, 0);
+  if (rc) return rc;
+  if (n_scans == 1) {  // no pair: just the feature counts
+    const float* d = nullptr;
+    rc = fetch(0, 1, 0, &d);
+    if (rc) return rc;
+    return run_extract(ctx, pl, d, LOAMGPU_F32, 16, lp, fe, 1, 0, n_slots, ne_dev, np_dev);
+  }
+  const uint64_t n_pairs = n_scans - 1;
+  int buf = 0;
+  for (uint64_t p0 = 0; p0 < n_pairs; p0 += chunk, buf ^= 1) {
+    const uint32_t np = (uint32_t)std::min<uint64_t>(chunk, n_pairs - p0);
+    // scans needed: p0 .. p0+np ; scan p0 is already in its slot except for the first chunk
+    const uint64_t s0 = p0 == 0 ? 0 : p0 + 1;
+    const uint32_t ns = (uint32_t)(p0 + np + 1 - s0);
+    const float* d = nullptr;
+    rc = fetch(s0, ns, buf, &d);
+    if (rc) return rc;
+    rc = run_extract(ctx, pl, d, LOAMGPU_F32, 16, lp, fe, ns, s0, n_slots, ne_dev, np_dev);
+    if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev_consumed[buf], ctx->stream));
+    rc = run_register(ctx, rp, np, p0, n_slots, 1, pl.capE_scan, pl.capP_scan, nullptr, false);
+    if (rc) return rc;
+    CU(launch_finish_pairs(ctx->state.as<PairState>(), np, poses_dev ? poses_dev + 7 * p0 : nullptr,
+                           term_dev ? term_dev + p0 : nullptr, iters_dev ? iters_dev + p0 : nullptr, ctx->stream));
+    ctx->launches++;
+  }
+  return LOAMGPU_OK;
+}
+
+extern "C" {
+
+int loamgpu_odometry_device(loamgpu_ctx* ctx, const float* scans_dev, uint64_t n_scans, const loamgpu_lidar_params* lp,
+                            const loamgpu_fe_params* fe, const loamgpu_reg_params* reg, double* poses_dev,
+                            int32_t* term_dev, uint32_t* iters_dev, uint32_t* ne_dev, uint32_t* np_dev) {
+  if (!ctx) return LOAMGPU_ERR_INVALID;
+  if (!lp || !fe || !reg) return fail(ctx, LOAMGPU_ERR_INVALID, "null parameter struct");
+  if (n_scans == 0) return LOAMGPU_OK;
+  if (!scans_dev) return fail(ctx, LOAMGPU_ERR_INVALID, "null scan buffer");
+  CU(cudaSetDevice(ctx->device));
+  const uint64_t n_per = lp->scan_lines * lp->points_per_line;
+  auto fetch = [&](uint64_t s0, uint32_t, int, const float** out) {
+    *out = scans_dev + s0 * n_per * 4;
+    return (int)LOAMGPU_OK;
+  };
+  return odometry_core(ctx, n_scans, lp, fe, reg, poses_dev, term_dev, iters_dev, ne_dev, np_dev, fetch);
+}
+
+int loamgpu_odometry_host(loamgpu_ctx* ctx, const float* scans, uint64_t n_scans, const loamgpu_lidar_params* lp,
+                          const loamgpu_fe_params* fe, const loamgpu_reg_params* reg, double* poses, int32_t* termination,
+                          uint32_t* iterations, uint32_t* n_edge, uint32_t* n_planar) {
+  if (!ctx) return LOAMGPU_ERR_INVALID;
+  if (!lp || !fe || !reg) return fail(ctx, LOAMGPU_ERR_INVALID, "null parameter struct");
+  if (n_scans == 0) return LOAMGPU_OK;
+  if (!scans) return fail(ctx, LOAMGPU_ERR_INVALID, "null scan buffer");
+  CU(cudaSetDevice(ctx->device));
+  const uint64_t n_per = lp->scan_lines * lp->points_per_line;
+  const size_t scan_bytes = (size_t)n_per * 16;
+  const uint64_t n_pairs = n_scans - 1;
+  const uint32_t chunk = (uint32_t)std::min<uint64_t>(ctx->chunk_pairs, std::max<uint64_t>(n_scans, 2) - 1);
+  for (int b = 0; b < 2; b++) CU(ctx->scan_in[b].reserve((size_t)(chunk + 1) * scan_bytes));
+  CU(ctx->out_pose.reserve(std::max<uint64_t>(n_pairs, 1) * 56));
+  CU(ctx->out_term.reserve(std::max<uint64_t>(n_pairs, 1) * 4));
+  CU(ctx->out_iters.reserve(std::max<uint64_t>(n_pairs, 1) * 4));
+  CU(ctx->out_ne.reserve(n_scans * 4));
+  CU(ctx->out_np.reserve(n_scans * 4));
+  // make sure earlier work on the compute stream no longer reads the staging buffers
+  CU(cudaEventRecord(ctx->ev_consumed[0], ctx->stream));
+  CU(cudaEventRecord(ctx->ev_consumed[1], ctx->stream));
+  auto fetch = [&](uint64_t s0, uint32_t ns, int buf, const float** out) {
+    // copy stream: wait until the previous user of this staging buffer is done, copy, signal the compute stream
+    cudaError_t e = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[buf], 0);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(ctx->scan_in[buf].p, scans + s0 * n_per * 4, (size_t)ns * scan_bytes,
+                          cudaMemcpyHostToDevice, ctx->copy_stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_copied[buf], ctx->copy_stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[buf], 0);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "odometry_host fetch");
+    *out = ctx->scan_in[buf].as<float>();
+    return (int)LOAMGPU_OK;
+  };
+  int rc = odometry_core(ctx, n_scans, lp, fe, reg, ctx->out_pose.as<double>(), ctx->out_term.as<int32_t>(),
+                         ctx->out_iters.as<uint32_t>(), ctx->out_ne.as<uint32_t>(), ctx->out_np.as<uint32_t>(), fetch);
+  if (rc) return rc;
+  if (poses && n_pairs) CU(cudaMemcpyAsync(poses, ctx->out_pose.p, n_pairs * 56, cudaMemcpyDeviceToHost, ctx->stream));
+  if (termination && n_pairs)
+    CU(cudaMemcpyAsync(termination, ctx->out_term.p, n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (iterations && n_pairs)
+    CU(cudaMemcpyAsync(iterations, ctx->out_iters.p, n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (n_edge) CU(cudaMemcpyAsync(n_edge, ctx->out_ne.p, n_scans * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (n_planar) CU(cudaMemcpyAsync(n_planar, ctx->out_np.p, n_scans * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return LOAMGPU_OK;
+}
+
+}  // extern "C"

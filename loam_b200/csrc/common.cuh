@@ -1,0 +1,95 @@
+// Shared device/host helpers for the loamgpu kernels (sm_100a).
+// All arithmetic that decides an index (curvature, range, squared distance) is written with
+// explicit round-to-nearest intrinsics so it can never be contracted into an FMA: the reference
+// is built for baseline x86-64 (no FMA), and feature / correspondence indices must be bit-exact.
+// The whole library is additionally compiled with -fmad=false.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "loamgpu.h"
+
+namespace loamgpu {
+
+// ------------------------------------------------------------------ fp64, never fused
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+
+// common.h:81-86 : sqrt((x*x + y*y) + z*z)
+__device__ __forceinline__ double point_range(double x, double y, double z) {
+  return __dsqrt_rn(dadd(dadd(dmul(x, x), dmul(y, y)), dmul(z, z)));
+}
+// nanoflann L2_Simple_Adaptor::evalMetric : diff = query - point ; ((d0^2) + d1^2) + d2^2
+__device__ __forceinline__ double sqdist(double qx, double qy, double qz, double px, double py, double pz) {
+  const double d0 = dsub(qx, px), d1 = dsub(qy, py), d2 = dsub(qz, pz);
+  return dadd(dadd(dmul(d0, d0), dmul(d1, d1)), dmul(d2, d2));
+}
+
+struct V3 {
+  double x, y, z;
+};
+__device__ __forceinline__ V3 cross(const V3& a, const V3& b) {
+  return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+__device__ __forceinline__ double dot(const V3& a, const V3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ double norm(const V3& a) { return sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
+
+// Pose = (qx qy qz qw tx ty tz).  Eigen QuaternionBase::_transformVector, no normalisation
+// (geometry.cpp:21): uv = 2 (u x v) ; v + w uv + u x uv
+__device__ __forceinline__ V3 quat_rotate(const double* q, const V3& v) {
+  const V3 u{q[0], q[1], q[2]};
+  V3 uv = cross(u, v);
+  uv.x += uv.x;
+  uv.y += uv.y;
+  uv.z += uv.z;
+  const V3 uuv = cross(u, uv);
+  return V3{v.x + q[3] * uv.x + uuv.x, v.y + q[3] * uv.y + uuv.y, v.z + q[3] * uv.z + uuv.z};
+}
+__device__ __forceinline__ V3 pose_act(const double* pose, const V3& p) {
+  const V3 r = quat_rotate(pose, p);
+  return V3{r.x + pose[4], r.y + pose[5], r.z + pose[6]};
+}
+// Eigen quaternion product a*b with (x,y,z,w) storage
+__device__ __forceinline__ void quat_mul(const double* a, const double* b, double* o) {
+  const double w = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+  const double x = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+  const double y = a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2];
+  const double z = a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0];
+  o[0] = x;
+  o[1] = y;
+  o[2] = z;
+  o[3] = w;
+}
+
+// ------------------------------------------------------------------ uniform-grid NN structure
+struct GridHdr {
+  double ox, oy, oz;  // origin (bbox min)
+  double h, inv_h;    // cell size
+  int nx, ny, nz;     // dims
+  uint32_t n;         // points
+  uint32_t ncells;
+  uint32_t pad;
+};
+
+// ------------------------------------------------------------------ per-pair ICF state
+struct PairState {
+  double est[7];       // target_T_source_est
+  int32_t status;      // -1 active ; 0 CONVERGED ; 1 MAX_ITER ; 2 INSUFFICIENT_ASSOCIATIONS
+  uint32_t iters;      // outer iterations recorded (iteration_info.size())
+  uint32_t n_edge_assoc, n_plane_assoc;  // of the current outer iteration
+};
+
+// flattened parameter block handed to the registration kernels
+struct RegP {
+  int ke, kp;                // neighbours
+  double re, rp;             // max neighbour distance (<=0: unbounded)
+  int min_line, min_plane;   // fit guards
+  double min_cond, max_avg;  // fit quality guards
+  int max_iterations;
+  double rot_thr, pos_thr;
+  uint64_t min_assoc;
+};
+
+}  // namespace loamgpu

@@ -1,0 +1,344 @@
+// Feature extraction kernels (replaces loam/features-inl.h + src/features.cpp of the reference).
+//
+// K1+K2 fused: one CTA per scan ring.  The ring is staged once into shared memory (a single
+// TMA bulk copy when the layout allows it), then range / curvature / validity mask / per-sector
+// ordering / greedy selection all run out of shared memory; the scan is read from HBM exactly once.
+//
+//   phase A  stage ring (cp.async.bulk + mbarrier, or strided loads for odd layouts)
+//   phase B  range r[j] = sqrt((x^2+y^2)+z^2)                         common.h:81-86
+//   phase C  curvature stencil (2N+1 taps, fp64, unfused)             features-inl.h:53-87
+//            validity mask (4 checks, idempotent "set false" scatter) features-inl.h:90-124, features.cpp:20-68
+//   phase D  candidate keys:  planar candidates (valid && c < planar_thr), edge candidates (valid && c > edge_thr)
+//   phase E  per-sector rank sort on (curvature, index) — total order, tie-break = ascending index
+//            (the reference's std::sort is unstable and compares curvature only: features.h:91, features-inl.h:38)
+//   phase F  greedy walk, sectors in order (suppression spills into the next sector, features-inl.h:148-151),
+//            edge walk (descending) then planar walk (ascending) per sector    features-inl.h:137-180
+//
+// Filtering to candidates before ordering is exact: the walks only ever act on points that pass the
+// (static) threshold and are valid, and the mask only ever changes true -> false.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace loamgpu {
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+template <typename T>
+struct Rec;  // packed staging record in shared memory
+template <>
+struct Rec<float> {
+  static constexpr int kBytes = 16;  // float4-shaped
+  static constexpr int kElems = 4;
+};
+template <>
+struct Rec<double> {
+  static constexpr int kBytes = 24;  // Eigen::Vector3d-shaped
+  static constexpr int kElems = 3;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kExtractThreads) extract_ring_kernel(ExtractArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t P = a.P, N = a.N, S = a.S;
+  const uint32_t ring = blockIdx.x, scan = blockIdx.y;
+  const uint32_t tid = threadIdx.x, nthr = blockDim.x;
+
+  // ---- shared memory carve-up (see extract_smem_bytes) ----
+  T* stage = reinterpret_cast<T*>(smem);                                    // P * Rec<T>::kBytes
+  double* rng = reinterpret_cast<double*>(smem + (size_t)P * Rec<T>::kBytes);  // P doubles  (later: planar keys, then pick lists)
+  double* cur = rng + P;                                                     // P doubles  (later: edge keys)
+  uint8_t* mask = reinterpret_cast<uint8_t*>(cur + P);                       // P bytes
+  uint32_t* nPs = reinterpret_cast<uint32_t*>(mask + ((P + 15) & ~15u));     // S counters
+  uint32_t* nEs = nPs + S;                                                   // S counters
+  uint64_t* bar = reinterpret_cast<uint64_t*>(nEs + S + ((2 * S) & 1));      // 8-byte aligned mbarrier
+  uint16_t* sortedP = reinterpret_cast<uint16_t*>(smem);                     // aliases stage (dead after phase C)
+  uint16_t* sortedE = sortedP + P;
+
+  const unsigned char* ring_src =
+      a.pts + (size_t)scan * a.scan_stride_bytes + (size_t)ring * P * a.stride;
+
+  // ---- phase A: stage the ring ----
+  if (a.use_bulk) {
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+      const uint32_t bytes = P * Rec<T>::kBytes;
+      mbar_expect_tx(bar, bytes);
+      bulk_g2s(stage, ring_src, bytes, bar);
+    }
+    mbar_wait(bar, 0);
+  } else {
+    for (uint32_t j = tid; j < P; j += nthr) {
+      const T* src = reinterpret_cast<const T*>(ring_src + (size_t)j * a.stride);
+      stage[j * Rec<T>::kElems + 0] = src[0];
+      stage[j * Rec<T>::kElems + 1] = src[1];
+      stage[j * Rec<T>::kElems + 2] = src[2];
+    }
+    __syncthreads();
+  }
+
+  // ---- phase B: ranges ----
+  for (uint32_t j = tid; j < P; j += nthr) {
+    const double x = (double)stage[j * Rec<T>::kElems + 0];
+    const double y = (double)stage[j * Rec<T>::kElems + 1];
+    const double z = (double)stage[j * Rec<T>::kElems + 2];
+    rng[j] = point_range(x, y, z);
+  }
+  for (uint32_t s = tid; s < 2 * S; s += nthr) nPs[s] = 0;
+  __syncthreads();
+
+  // ---- phase C: curvature + mask ----
+  // P - N wraps exactly like the reference's size_t arithmetic when P < N (features-inl.h:66-67)
+  const uint64_t hi_edge = (uint64_t)P - (uint64_t)N;
+  const double m2n = -(2.0 * (double)N);
+  for (uint32_t j = tid; j < P; j += nthr) {
+    const bool ring_edge = (j < N) || ((uint64_t)j >= hi_edge);
+    double c = -1.0;
+    if (!ring_edge) {
+      double dx = dmul(m2n, (double)stage[j * Rec<T>::kElems + 0]);
+      double dy = dmul(m2n, (double)stage[j * Rec<T>::kElems + 1]);
+      double dz = dmul(m2n, (double)stage[j * Rec<T>::kElems + 2]);
+      for (uint32_t k = 1; k <= N; k++) {
+        const T* lo = stage + (size_t)(j - k) * Rec<T>::kElems;
+        const T* hi = stage + (size_t)(j + k) * Rec<T>::kElems;
+        dx = dadd(dadd(dx, (double)lo[0]), (double)hi[0]);
+        dy = dadd(dadd(dy, (double)lo[1]), (double)hi[1]);
+        dz = dadd(dadd(dz, (double)lo[2]), (double)hi[2]);
+      }
+      c = dadd(dadd(dmul(dx, dx), dmul(dy, dy)), dmul(dz, dz));
+    }
+    cur[j] = c;
+    mask[j] = ring_edge ? 0 : 1;
+  }
+  __syncthreads();
+  for (uint32_t j = tid; j < P; j += nthr) {
+    if ((j < N) || ((uint64_t)j >= hi_edge)) continue;  // CHECK 1 handled above
+    const double r = rng[j], rn = rng[j + 1], rp = rng[j - 1];
+    if (r < a.min_range || r > a.max_range) {  // CHECK 2
+      mask[j] = 0;
+      for (uint32_t k = 1; k <= N; k++) {
+        mask[j + k] = 0;
+        mask[j - k] = 0;
+      }
+    } else if (dsub(rn, r) > a.occ) {  // CHECK 3 case 1
+      for (uint32_t k = 1; k <= N; k++) mask[j + k] = 0;
+    } else if (dsub(r, rn) > a.occ) {  // CHECK 3 case 2
+      for (uint32_t k = 0; k < N; k++) mask[j - k] = 0;
+    } else {  // CHECK 4
+      const double diff_next = fabs(dsub(rp, r));
+      const double diff_prev = fabs(dsub(rn, r));
+      const double lim = dmul(a.par, r);
+      if (diff_next > lim && diff_prev > lim) mask[j] = 0;
+    }
+  }
+  __syncthreads();
+
+  if (a.curv_out != nullptr || a.mask_out != nullptr) {  // secondary entry points stop here
+    const size_t base = (size_t)scan * a.R * P + (size_t)ring * P;
+    for (uint32_t j = tid; j < P; j += nthr) {
+      if (a.curv_out) a.curv_out[base + j] = cur[j];
+      if (a.mask_out) a.mask_out[base + j] = mask[j];
+    }
+    return;
+  }
+
+  // ---- phase D: candidate keys (planar keys overwrite rng, edge keys overwrite cur) ----
+  const double inf = CUDART_INF;
+  for (uint32_t j = tid; j < P; j += nthr) {
+    const double c = cur[j];
+    const bool ok = mask[j] != 0;
+    rng[j] = (ok && c < a.planar_thr) ? c : inf;
+    cur[j] = (ok && c > a.edge_thr) ? c : -inf;
+  }
+  __syncthreads();
+
+  // ---- phase E: per-sector rank sort ----
+  const uint32_t pps = P / S;
+  for (uint32_t j = tid; j < P; j += nthr) {
+    uint32_t s = pps ? j / pps : S - 1;
+    if (s > S - 1) s = S - 1;
+    const uint32_t b = s * pps;
+    const uint32_t e = (s == S - 1) ? P : b + pps;
+    const double kp = rng[j], ke = cur[j];
+    const bool candP = kp < inf, candE = ke > -inf;
+    if (!candP && !candE) continue;
+    uint32_t rp = 0, re = 0;
+    for (uint32_t t = b; t < e; t++) {
+      const double tp = rng[t], te = cur[t];
+      rp += (tp < kp || (tp == kp && t < j)) ? 1u : 0u;
+      re += (te > ke || (te == ke && t > j)) ? 1u : 0u;
+    }
+    if (candP) {
+      sortedP[b + rp] = (uint16_t)j;
+      atomicAdd(&nPs[s], 1u);
+    }
+    if (candE) {
+      sortedE[b + re] = (uint16_t)j;
+      atomicAdd(&nEs[s], 1u);
+    }
+  }
+  __syncthreads();
+
+  // ---- phase F: greedy walk (sequential by construction) ----
+  uint16_t* outE = reinterpret_cast<uint16_t*>(rng);  // keys are dead now; rng+cur hold >= 16P bytes
+  uint16_t* outP = outE + a.capE_ring;
+  __shared__ uint32_t s_cnt[2];
+  if (tid == 0) {
+    uint32_t ne = 0, np = 0;
+    for (uint32_t s = 0; s < S; s++) {
+      const uint32_t b = s * pps;
+      uint32_t cnt = 0;
+      const uint32_t mE = nEs[s];
+      for (uint32_t r = 0; r < mE; r++) {
+        const uint32_t i = sortedE[b + r];
+        if (mask[i]) {
+          outE[ne++] = (uint16_t)i;
+          for (uint32_t k = 0; k < N; k++) {
+            mask[i + k] = 0;
+            mask[i - k] = 0;
+          }
+          cnt++;
+        }
+        if (cnt > a.maxE) break;
+      }
+      cnt = 0;
+      const uint32_t mP = nPs[s];
+      for (uint32_t r = 0; r < mP; r++) {
+        const uint32_t i = sortedP[b + r];
+        if (mask[i]) {
+          outP[np++] = (uint16_t)i;
+          for (uint32_t k = 0; k < N; k++) {
+            mask[i + k] = 0;
+            mask[i - k] = 0;
+          }
+          cnt++;
+        }
+        if (cnt > a.maxP) break;
+      }
+    }
+    s_cnt[0] = ne;
+    s_cnt[1] = np;
+  }
+  __syncthreads();
+
+  const size_t ring_id = (size_t)scan * a.R + ring;
+  const uint32_t ne = s_cnt[0], np = s_cnt[1];
+  uint32_t* ge = a.ring_edge + ring_id * a.capE_ring;
+  uint32_t* gp = a.ring_planar + ring_id * a.capP_ring;
+  for (uint32_t i = tid; i < ne; i += nthr) ge[i] = ring * P + outE[i];
+  for (uint32_t i = tid; i < np; i += nthr) gp[i] = ring * P + outP[i];
+  if (tid == 0) {
+    a.ring_counts[ring_id * 2 + 0] = ne;
+    a.ring_counts[ring_id * 2 + 1] = np;
+  }
+}
+
+// Pack per-ring pick lists into the scan-level feature arrays (reference output order:
+// line-major, sector-major, selection order) and gather the widened feature points
+// (featuresToEigen, features.h:188-198).  One CTA per scan.
+__global__ void __launch_bounds__(256) pack_features_kernel(PackArgs a) {
+  extern __shared__ uint32_t offs[];  // [R+1][2]
+  const uint32_t scan = blockIdx.x, R = a.R;
+  const uint32_t slot = (uint32_t)((a.scan0 + scan) % a.n_slots);
+  if (threadIdx.x == 0) {
+    uint32_t e = 0, p = 0;
+    for (uint32_t r = 0; r < R; r++) {
+      offs[2 * r] = e;
+      offs[2 * r + 1] = p;
+      e += a.ring_counts[((size_t)scan * R + r) * 2];
+      p += a.ring_counts[((size_t)scan * R + r) * 2 + 1];
+    }
+    offs[2 * R] = e;
+    offs[2 * R + 1] = p;
+    a.feat_counts[slot * 2] = e;
+    a.feat_counts[slot * 2 + 1] = p;
+    if (a.n_edge_out) a.n_edge_out[a.scan0 + scan] = e;
+    if (a.n_planar_out) a.n_planar_out[a.scan0 + scan] = p;
+  }
+  __syncthreads();
+  const unsigned char* base = a.pts + (size_t)scan * a.scan_stride_bytes;
+  for (uint32_t r = 0; r < R; r++) {
+    for (int kind = 0; kind < 2; kind++) {
+      const uint32_t n = offs[2 * (r + 1) + kind] - offs[2 * r + kind];
+      const uint32_t cap_ring = kind ? a.capP_ring : a.capE_ring;
+      const uint32_t cap_scan = kind ? a.capP_scan : a.capE_scan;
+      const uint32_t* src = (kind ? a.ring_planar : a.ring_edge) + ((size_t)scan * R + r) * cap_ring;
+      uint32_t* dst_idx = (kind ? a.planar_idx : a.edge_idx) + (size_t)slot * cap_scan + offs[2 * r + kind];
+      double4* dst_pt = (kind ? a.planar_pts : a.edge_pts) + (size_t)slot * cap_scan + offs[2 * r + kind];
+      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t id = src[i];
+        dst_idx[i] = id;
+        const unsigned char* rec = base + (size_t)id * a.stride;
+        double4 v;
+        if (a.dtype == LOAMGPU_F32) {
+          const float* f = reinterpret_cast<const float*>(rec);
+          v = make_double4((double)f[0], (double)f[1], (double)f[2], 0.0);
+        } else {
+          const double* d = reinterpret_cast<const double*>(rec);
+          v = make_double4(d[0], d[1], d[2], 0.0);
+        }
+        dst_pt[i] = v;
+      }
+    }
+  }
+}
+
+}  // namespace
+
+size_t extract_smem_bytes(int dtype, uint32_t P, uint32_t S) {
+  const size_t rec = dtype == LOAMGPU_F32 ? 16 : 24;
+  size_t b = (size_t)P * rec + 16 * (size_t)P + ((P + 15) & ~15u) + 8 * (size_t)S + 8 + 16;
+  return (b + 127) & ~(size_t)127;
+}
+
+cudaError_t launch_extract(const ExtractArgs& a, uint32_t n_scans, cudaStream_t st) {
+  const size_t smem = extract_smem_bytes(a.dtype, a.P, a.S);
+  dim3 grid(a.R, n_scans);
+  cudaError_t err;
+  if (a.dtype == LOAMGPU_F32) {
+    err = cudaFuncSetAttribute(extract_ring_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    extract_ring_kernel<float><<<grid, kExtractThreads, smem, st>>>(a);
+  } else {
+    err = cudaFuncSetAttribute(extract_ring_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    extract_ring_kernel<double><<<grid, kExtractThreads, smem, st>>>(a);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack(const PackArgs& a, uint32_t n_scans, cudaStream_t st) {
+  pack_features_kernel<<<n_scans, 256, (size_t)(a.R + 1) * 2 * sizeof(uint32_t), st>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace loamgpu

@@ -1,0 +1,139 @@
+// Host-visible launch interface of the loamgpu kernels (internal to libloamgpu.so).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace loamgpu {
+
+constexpr int kExtractThreads = 256;
+constexpr int kAssocThreads = 128;
+constexpr int kLmThreads = 512;
+constexpr int kGridThreads = 1024;
+constexpr int kKnnRegMax = 8;    // neighbour counts up to this stay in registers
+constexpr int kKnnMax = 32;      // hard limit on num_*_neighbors
+
+struct ExtractArgs {
+  const unsigned char* pts;     // first scan of this launch
+  uint64_t scan_stride_bytes;   // bytes between scans
+  uint32_t stride;              // bytes between points
+  int dtype;
+  int use_bulk;                 // ring can be staged with one cp.async.bulk
+  uint32_t R, P, N, S;
+  uint32_t maxE, maxP;          // max_*_feats_per_sector clipped to P
+  double edge_thr, planar_thr, occ, par, min_range, max_range;
+  uint32_t capE_ring, capP_ring;
+  uint32_t* ring_edge;          // [scan][R][capE_ring] scan-level point index
+  uint32_t* ring_planar;        // [scan][R][capP_ring]
+  uint32_t* ring_counts;        // [scan][R][2]
+  double* curv_out;             // optional [scan][R*P]  (computeCurvature)
+  uint8_t* mask_out;            // optional [scan][R*P]  (computeValidPoints)
+};
+
+struct PackArgs {
+  const unsigned char* pts;
+  uint64_t scan_stride_bytes;
+  uint32_t stride;
+  int dtype;
+  uint32_t R;
+  uint32_t capE_ring, capP_ring, capE_scan, capP_scan;
+  const uint32_t* ring_edge;
+  const uint32_t* ring_planar;
+  const uint32_t* ring_counts;
+  uint64_t scan0;               // global index of the first scan of this launch
+  uint32_t n_slots;             // feature slots form a ring buffer: slot = scan % n_slots
+  uint32_t* edge_idx;           // [slot][capE_scan]
+  uint32_t* planar_idx;         // [slot][capP_scan]
+  double4* edge_pts;            // [slot][capE_scan]  (x,y,z,0)
+  double4* planar_pts;          // [slot][capP_scan]
+  uint32_t* feat_counts;        // [slot][2]
+  uint32_t* n_edge_out;         // optional [global scan] feature counts for the caller
+  uint32_t* n_planar_out;
+};
+
+size_t extract_smem_bytes(int dtype, uint32_t P, uint32_t S);
+cudaError_t launch_extract(const ExtractArgs& a, uint32_t n_scans, cudaStream_t st);
+cudaError_t launch_pack(const PackArgs& a, uint32_t n_scans, cudaStream_t st);
+
+// One NN structure ("grid set") = header + cell_start + cell-sorted points.
+struct GridSetArrays {
+  GridHdr* hdr;          // [n_sets]
+  uint32_t* cell_start;  // [n_sets][cell_cap + 1]
+  double4* sorted;       // [n_sets][pt_cap]   (x,y,z, bits(original index))
+  uint32_t* rank;        // [n_sets][pt_cap]   build scratch: rank of each point inside its cell
+  uint32_t cell_cap;
+  uint32_t pt_cap;
+};
+
+// Build NN structures for `n_sets` point sets.  Set s reads points
+// pts[(slot0 + s) % n_slots][0 .. counts[((slot0+s) % n_slots)*2 + kind]).
+struct GridBuildArgs {
+  const double4* pts;      // [slot][pt_stride]
+  const uint32_t* counts;  // [slot][2]
+  uint32_t pt_stride;
+  int kind;                // 0 edge, 1 planar
+  uint64_t slot0;
+  uint32_t n_slots;
+  int k_nominal;           // neighbour count the cell size is tuned for
+  GridSetArrays g;
+};
+cudaError_t launch_grid_build(const GridBuildArgs& a, uint32_t n_sets, cudaStream_t st);
+
+struct AssocArgs {
+  // source / target feature slots of pair p: src = (pair0 + p + 1) % n_slots, tgt = (pair0 + p) % n_slots
+  const double4* edge_pts;
+  const double4* planar_pts;
+  const uint32_t* feat_counts;
+  uint32_t capE_scan, capP_scan;
+  uint64_t pair0;
+  uint32_t n_slots;
+  int src_offset;          // 1 for sequence odometry; explicit-pair calls use slots 1 (src) / 0 (tgt)
+  GridSetArrays ge, gp;    // target grids, set index = pair
+  PairState* state;        // [pair]
+  double4* rec_p;          // [pair][capE+capP]  transformed point, w = 0 invalid / 1 edge / 2 plane
+  double4* rec_a;          // [pair][capE+capP]  edge: line point a ; plane: normal, w = d
+  double4* rec_b;          // [pair][capE]       edge: line point b
+  int32_t* nearest;        // optional [outer_iter][pair][capE+capP] nearest target index or -1 (detail)
+  RegP rp;
+};
+cudaError_t launch_assoc(const AssocArgs& a, uint32_t n_pairs, int outer_iter, cudaStream_t st);
+
+struct LmArgs {
+  PairState* state;
+  const double4* rec_p;
+  const double4* rec_a;
+  const double4* rec_b;
+  const uint32_t* feat_counts;
+  uint32_t capE_scan, capP_scan;
+  uint64_t pair0;
+  uint32_t n_slots;
+  int src_offset;
+  int outer_iter;
+  RegP rp;
+  // optional detail (single-pair API): per outer iteration rows
+  double* d_iter_est;      // [cap][7]
+  double* d_iter_update;   // [cap][7]
+  uint32_t* d_assoc_n;     // [cap][2]
+  uint32_t* d_lm_iters;    // [cap]
+  double* d_lm_cost;       // [cap][2]
+};
+cudaError_t launch_lm(const LmArgs& a, uint32_t n_pairs, cudaStream_t st);
+
+struct KnnArgs {
+  const double* queries;  // [n][3]
+  uint64_t n_queries;
+  GridSetArrays g;        // set 0
+  int k;
+  double max_dist;
+  uint32_t* idx_out;      // [n][k]
+  uint32_t* count_out;    // [n]
+};
+cudaError_t launch_knn(const KnnArgs& a, cudaStream_t st);
+
+cudaError_t launch_init_pairs(PairState* st, uint32_t n_pairs, const double* init_pose_or_null, cudaStream_t s);
+// Copy per-pair results to flat output arrays (device pointers; any may be null) and finalise MAX_ITER.
+cudaError_t launch_finish_pairs(const PairState* st, uint32_t n_pairs, double* poses, int32_t* term, uint32_t* iters,
+                                cudaStream_t s);
+
+}  // namespace loamgpu

@@ -1,0 +1,1092 @@
+// Registration kernels (replaces loam/registration-inl.h, src/registration.cpp, src/kdtree.cpp,
+// src/geometry.cpp:42-73 of the reference, plus the Ceres 2.2.0 trust-region solve it delegates to).
+//
+//   K3  grid_build_kernel   uniform-grid NN structure over one target feature set (replaces the
+//                           nanoflann KD-tree build, registration-inl.h:20-23); cell size tuned from a
+//                           measured surface density so a 3x3x3 block holds a few dozen candidates
+//   K4  knn_grid()          exact k-NN with shell expansion + strict radius filter (kdtree.cpp:10-28)
+//   K5  fit_line/fit_plane  per-query PCA line / column-pivoted-QR plane (geometry.cpp:42-73)
+//   K45 assoc_kernel        transform + K4 + K5 + guards for every source feature of every active pair
+//                           (associateEdges/associatePlanes, registration.cpp:23-103)
+//   K6/K7 lm_kernel         one CTA per pair: residuals + analytic SE(3) Jacobians + Huber corrector,
+//                           6x6 J^T J / J^T r / cost reduced warp-shuffle -> shared memory, and the
+//                           Levenberg-Marquardt controller (Ceres TrustRegionMinimizer semantics) entirely
+//                           on the device; then the ICF update / convergence test (registration-inl.h:59-73)
+//
+// Tie-break (documented, deterministic): equal squared distances resolve by ascending target index
+// (nanoflann resolves them by tree-traversal order, i.e. unpinned in the reference).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace loamgpu {
+
+namespace {
+
+// ============================================================================ grid build (K3)
+
+__device__ __forceinline__ int cell_coord(double v, double o, double inv_h, int n) {
+  int c = (int)floor(dmul(dsub(v, o), inv_h));
+  c = c < 0 ? 0 : c;
+  return c >= n ? n - 1 : c;
+}
+
+__device__ double block_reduce_minmax(double v, bool is_max, double* s_red) {
+  for (int o = 16; o > 0; o >>= 1) {
+    const double t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmax(v, t) : fmin(v, t);
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = s_red[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); w++) r = is_max ? fmax(r, s_red[w]) : fmin(r, s_red[w]);
+  return r;
+}
+
+__device__ uint32_t block_reduce_sum_u32(uint32_t v, uint32_t* s_red) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  uint32_t r = 0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); w++) r += s_red[w];
+  return r;
+}
+
+constexpr int kTrialCells = 32768;
+
+__global__ void __launch_bounds__(kGridThreads) grid_build_kernel(GridBuildArgs a) {
+  __shared__ double s_red[32];
+  __shared__ uint32_t s_redu[32];
+  __shared__ uint32_t s_bitmap[kTrialCells / 32];
+  __shared__ uint32_t s_scan[kGridThreads / 32];
+
+  const uint32_t set = blockIdx.x;
+  const uint32_t slot = (uint32_t)((a.slot0 + set) % a.n_slots);
+  const uint32_t n = a.counts[slot * 2 + a.kind];
+  const double4* pts = a.pts + (size_t)slot * a.pt_stride;
+  GridHdr* hdr = a.g.hdr + set;
+  uint32_t* cs = a.g.cell_start + (size_t)set * (a.g.cell_cap + 1);
+  double4* sorted = a.g.sorted + (size_t)set * a.g.pt_cap;
+  const uint32_t tid = threadIdx.x, nthr = blockDim.x;
+
+  if (n == 0) {
+    if (tid == 0) {
+      GridHdr h;
+      h.ox = h.oy = h.oz = 0;
+      h.h = 1;
+      h.inv_h = 1;
+      h.nx = h.ny = h.nz = 0;
+      h.n = 0;
+      h.ncells = 0;
+      h.pad = 0;
+      *hdr = h;
+    }
+    return;
+  }
+
+  // ---- bounding box
+  double lo[3] = {CUDART_INF, CUDART_INF, CUDART_INF}, hi[3] = {-CUDART_INF, -CUDART_INF, -CUDART_INF};
+  for (uint32_t i = tid; i < n; i += nthr) {
+    const double4 p = pts[i];
+    lo[0] = fmin(lo[0], p.x);
+    lo[1] = fmin(lo[1], p.y);
+    lo[2] = fmin(lo[2], p.z);
+    hi[0] = fmax(hi[0], p.x);
+    hi[1] = fmax(hi[1], p.y);
+    hi[2] = fmax(hi[2], p.z);
+  }
+  for (int d = 0; d < 3; d++) {
+    lo[d] = block_reduce_minmax(lo[d], false, s_red);
+    hi[d] = block_reduce_minmax(hi[d], true, s_red);
+  }
+  double ext[3];
+  double emax = 0;
+  for (int d = 0; d < 3; d++) {
+    ext[d] = hi[d] - lo[d];
+    emax = fmax(emax, ext[d]);
+  }
+  const double emin = fmax(emax * 1e-3, 1e-6);
+  double extc[3];
+  for (int d = 0; d < 3; d++) extc[d] = fmax(ext[d], emin);
+
+  // ---- trial occupancy at a coarse resolution -> surface density -> cell size
+  double ht = cbrt(extc[0] * extc[1] * extc[2] / (double)kTrialCells);
+  int tx, ty, tz;
+  for (;;) {
+    tx = (int)floor(ext[0] / ht) + 1;
+    ty = (int)floor(ext[1] / ht) + 1;
+    tz = (int)floor(ext[2] / ht) + 1;
+    if ((double)tx * (double)ty * (double)tz <= (double)kTrialCells) break;
+    ht *= 1.25;
+  }
+  for (uint32_t i = tid; i < kTrialCells / 32; i += nthr) s_bitmap[i] = 0;
+  __syncthreads();
+  {
+    const double inv = 1.0 / ht;
+    for (uint32_t i = tid; i < n; i += nthr) {
+      const double4 p = pts[i];
+      const int cx = cell_coord(p.x, lo[0], inv, tx), cy = cell_coord(p.y, lo[1], inv, ty),
+                cz = cell_coord(p.z, lo[2], inv, tz);
+      const uint32_t c = ((uint32_t)cz * ty + cy) * tx + cx;
+      atomicOr(&s_bitmap[c >> 5], 1u << (c & 31));
+    }
+  }
+  __syncthreads();
+  uint32_t occ = 0;
+  for (uint32_t i = tid; i < kTrialCells / 32; i += nthr) occ += __popc(s_bitmap[i]);
+  occ = block_reduce_sum_u32(occ, s_redu);
+  // points on 2-D surfaces: area ~ occupied cells * ht^2 ; expected k-NN radius sqrt(k / (pi rho))
+  const double rho = (double)n / ((double)occ * ht * ht);
+  double h = 1.5 * sqrt((double)(a.k_nominal > 0 ? a.k_nominal : 1) / (3.141592653589793 * rho));
+  h = fmax(h, emax * 1e-6 + 1e-9);
+  int nx, ny, nz;
+  for (;;) {
+    nx = (int)floor(ext[0] / h) + 1;
+    ny = (int)floor(ext[1] / h) + 1;
+    nz = (int)floor(ext[2] / h) + 1;
+    if ((double)nx * (double)ny * (double)nz <= (double)a.g.cell_cap) break;
+    h *= 1.1;
+  }
+  const double inv_h = 1.0 / h;
+  const uint32_t ncells = (uint32_t)nx * (uint32_t)ny * (uint32_t)nz;
+  if (tid == 0) {
+    GridHdr g;
+    g.ox = lo[0];
+    g.oy = lo[1];
+    g.oz = lo[2];
+    g.h = h;
+    g.inv_h = inv_h;
+    g.nx = nx;
+    g.ny = ny;
+    g.nz = nz;
+    g.n = n;
+    g.ncells = ncells;
+    g.pad = 0;
+    *hdr = g;
+  }
+
+  // ---- counting sort by cell
+  for (uint32_t c = tid; c <= ncells; c += nthr) cs[c] = 0;
+  __syncthreads();
+  uint32_t* rank = a.g.rank + (size_t)set * a.g.pt_cap;
+  for (uint32_t i = tid; i < n; i += nthr) {
+    const double4 p = pts[i];
+    const uint32_t c = ((uint32_t)cell_coord(p.z, lo[2], inv_h, nz) * ny + cell_coord(p.y, lo[1], inv_h, ny)) * nx +
+                       cell_coord(p.x, lo[0], inv_h, nx);
+    rank[i] = atomicAdd(&cs[c], 1u);
+  }
+  __syncthreads();
+  // exclusive scan of cs[0..ncells] (thread-contiguous chunks + block scan of the chunk sums)
+  {
+    const uint32_t total = ncells + 1;
+    const uint32_t chunk = (total + nthr - 1) / nthr;
+    const uint32_t b = tid * chunk, e = min(b + chunk, total);
+    uint32_t sum = 0;
+    for (uint32_t c = b; c < e; c++) sum += cs[c];
+    // inclusive warp scan
+    uint32_t inc = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if ((int)(tid & 31) >= o) inc += t;
+    }
+    if ((tid & 31) == 31) s_scan[tid >> 5] = inc;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (uint32_t w = 0; w < (tid >> 5); w++) woff += s_scan[w];
+    uint32_t run = woff + inc - sum;
+    for (uint32_t c = b; c < e; c++) {
+      const uint32_t v = cs[c];
+      cs[c] = run;
+      run += v;
+    }
+  }
+  __syncthreads();
+  for (uint32_t i = tid; i < n; i += nthr) {
+    const double4 p = pts[i];
+    const uint32_t c = ((uint32_t)cell_coord(p.z, lo[2], inv_h, nz) * ny + cell_coord(p.y, lo[1], inv_h, ny)) * nx +
+                       cell_coord(p.x, lo[0], inv_h, nx);
+    sorted[cs[c] + rank[i]] = make_double4(p.x, p.y, p.z, __longlong_as_double((long long)i));
+  }
+}
+
+// ============================================================================ exact k-NN (K4)
+
+template <int KMAX>
+struct TopK {
+  double d[KMAX];
+  uint32_t id[KMAX];
+  double worst_d;
+  uint32_t worst_id;
+  int k;
+
+  __device__ __forceinline__ void init(int k_) {
+    k = k_;
+#pragma unroll
+    for (int i = 0; i < KMAX; i++) {
+      d[i] = CUDART_INF;
+      id[i] = 0xFFFFFFFFu;
+    }
+    worst_d = CUDART_INF;
+    worst_id = 0xFFFFFFFFu;
+  }
+  static __device__ __forceinline__ bool lt(double da, uint32_t ia, double db, uint32_t ib) {
+    return da < db || (da == db && ia < ib);
+  }
+  // sorted insertion by (d, id); caller guarantees lt(new, worst)
+  __device__ __forceinline__ void insert(double dn, uint32_t in) {
+#pragma unroll
+    for (int i = KMAX - 1; i > 0; --i) {
+      if (i < k) {
+        if (lt(dn, in, d[i - 1], id[i - 1])) {
+          d[i] = d[i - 1];
+          id[i] = id[i - 1];
+        } else if (lt(dn, in, d[i], id[i])) {
+          d[i] = dn;
+          id[i] = in;
+        }
+      }
+    }
+    if (lt(dn, in, d[0], id[0])) {
+      d[0] = dn;
+      id[0] = in;
+    }
+#pragma unroll
+    for (int i = 0; i < KMAX; i++)
+      if (i == k - 1) {
+        worst_d = d[i];
+        worst_id = id[i];
+      }
+  }
+};
+
+// Exact k nearest neighbours of (qx,qy,qz) among the points of one grid set, restricted to points that can
+// pass the radius filter.  Shell expansion: after all cells with Chebyshev cell distance <= r are visited,
+// every unvisited point is farther than (r + mf) * h, mf = the query's smallest distance (in cells) to a
+// face of its own cell; stop once the k-th best is closer than that, or that bound passes the radius.
+template <int KMAX>
+__device__ __forceinline__ void knn_grid(const GridHdr& g, const uint32_t* __restrict__ cs,
+                                         const double4* __restrict__ sorted, double qx, double qy, double qz, int k,
+                                         double max_dist, TopK<KMAX>& tk) {
+  tk.init(k);
+  if (g.n == 0) return;
+  const double SAFE = 1.0 - 1e-9;
+  // squared-distance bound above which a candidate certainly fails sqrt(d2) < max_dist
+  const double d2_cut = max_dist > 0 ? max_dist * max_dist * (1.0 + 1e-12) : CUDART_INF;
+  double fc[3] = {dmul(dsub(qx, g.ox), g.inv_h), dmul(dsub(qy, g.oy), g.inv_h), dmul(dsub(qz, g.oz), g.inv_h)};
+  int ic[3];
+  double mf = 1.0;
+  const int dims[3] = {g.nx, g.ny, g.nz};
+  int r_lo = 0, r_cover = 0;
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    double f = fmin(fmax(fc[a], -1.0e9), 1.0e9);
+    const double fl = floor(f);
+    ic[a] = (int)fl;
+    const double fr = f - fl;
+    mf = fmin(mf, fmin(fr, 1.0 - fr));
+    const int below = -ic[a], above = ic[a] - (dims[a] - 1);
+    r_lo = max(r_lo, max(below, above));
+    r_cover = max(r_cover, max(ic[a], dims[a] - 1 - ic[a]));
+  }
+  r_lo = max(r_lo, 0);
+
+  auto scan_cells = [&](uint32_t b, uint32_t e) {
+    for (uint32_t p = b; p < e; p++) {
+      const double4 t = sorted[p];
+      const double d2 = sqdist(qx, qy, qz, t.x, t.y, t.z);
+      if (d2 <= d2_cut) {
+        const uint32_t id = (uint32_t)__double_as_longlong(t.w);
+        if (TopK<KMAX>::lt(d2, id, tk.worst_d, tk.worst_id)) tk.insert(d2, id);
+      }
+    }
+  };
+  // visit cells with Chebyshev distance exactly r (or <= r when full == true)
+  auto visit = [&](int r, bool full) {
+    const int z0 = max(ic[2] - r, 0), z1 = min(ic[2] + r, g.nz - 1);
+    const int y0 = max(ic[1] - r, 0), y1 = min(ic[1] + r, g.ny - 1);
+    const int x0 = max(ic[0] - r, 0), x1 = min(ic[0] + r, g.nx - 1);
+    if (x0 > x1) return;
+    for (int z = z0; z <= z1; z++) {
+      const bool zface = (z == ic[2] - r) || (z == ic[2] + r);
+      for (int y = y0; y <= y1; y++) {
+        const uint32_t row = ((uint32_t)z * g.ny + y) * g.nx;
+        if (full || zface || y == ic[1] - r || y == ic[1] + r) {
+          scan_cells(cs[row + x0], cs[row + x1 + 1]);
+        } else {
+          if (ic[0] - r >= 0 && ic[0] - r < g.nx) scan_cells(cs[row + ic[0] - r], cs[row + ic[0] - r + 1]);
+          if (ic[0] + r >= 0 && ic[0] + r < g.nx) scan_cells(cs[row + ic[0] + r], cs[row + ic[0] + r + 1]);
+        }
+      }
+    }
+  };
+
+  int r = max(1, r_lo);
+  visit(r, true);
+  for (;;) {
+    const double guard = ((double)r + mf) * g.h * SAFE;
+    if (tk.worst_d < guard * guard) break;           // k found, all closer than any unvisited point
+    if (max_dist > 0 && guard >= max_dist) break;    // everything inside the radius has been visited
+    if (r >= r_cover) break;                         // whole grid visited
+    r++;
+    visit(r, false);
+  }
+}
+
+// kdtree.cpp:24-26 : keep neighbours with max_dist <= 0 || sqrt(d2) < max_dist (strict). Sorted => prefix.
+template <int KMAX>
+__device__ __forceinline__ int radius_count(const TopK<KMAX>& tk, double max_dist) {
+  int m = 0;
+#pragma unroll
+  for (int i = 0; i < KMAX; i++) {
+    if (i < tk.k && tk.id[i] != 0xFFFFFFFFu && (max_dist <= 0 || sqrt(tk.d[i]) < max_dist)) m++;
+  }
+  return m;
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(128) knn_kernel(KnnArgs a) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n_queries) return;
+  const GridHdr g = a.g.hdr[0];
+  TopK<KMAX> tk;
+  knn_grid<KMAX>(g, a.g.cell_start, a.g.sorted, a.queries[3 * i], a.queries[3 * i + 1], a.queries[3 * i + 2], a.k,
+                 a.max_dist, tk);
+  const int m = radius_count(tk, a.max_dist);
+  a.count_out[i] = (uint32_t)m;
+#pragma unroll
+  for (int j = 0; j < KMAX; j++)
+    if (j < a.k) a.idx_out[i * a.k + j] = j < m ? tk.id[j] : 0xFFFFFFFFu;
+}
+
+// ============================================================================ fits (K5)
+
+// Cyclic Jacobi on a symmetric 3x3; returns the eigenvector of the largest eigenvalue
+// (stands in for Eigen::SelfAdjointEigenSolver<Matrix3d>, geometry.cpp:49-51).
+__device__ __forceinline__ V3 principal_axis(double A[3][3]) {
+  double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  for (int sweep = 0; sweep < 12; sweep++) {
+    const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+    const double tr = fabs(A[0][0]) + fabs(A[1][1]) + fabs(A[2][2]);
+    if (off <= 1e-20 * tr) break;
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+#pragma unroll
+      for (int q = p + 1; q < 3; q++) {
+        const double apq = A[p][q];
+        if (apq == 0.0) continue;
+        const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0);
+        const double s = t * c;
+        A[p][p] = A[p][p] - t * apq;
+        A[q][q] = A[q][q] + t * apq;
+        A[p][q] = 0.0;
+        A[q][p] = 0.0;
+        const int r = 3 - p - q;
+        const double arp = A[r][p], arq = A[r][q];
+        A[r][p] = c * arp - s * arq;
+        A[p][r] = A[r][p];
+        A[r][q] = s * arp + c * arq;
+        A[q][r] = A[r][q];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          const double vkp = V[k][p], vkq = V[k][q];
+          V[k][p] = c * vkp - s * vkq;
+          V[k][q] = s * vkp + c * vkq;
+        }
+      }
+    }
+  }
+  int big = 0;
+  if (A[1][1] > A[big][big]) big = 1;
+  if (A[2][2] > A[big][big]) big = 2;
+  return V3{V[0][big], V[1][big], V[2][big]};
+}
+
+// geometry.cpp:42-59.  The condition number is never produced (the reference computes and discards it,
+// leaving DBL_MAX), so the min_line_condition_number guard can only fire for a threshold above DBL_MAX.
+template <int KMAX>
+__device__ __forceinline__ void fit_line(const double (&P)[KMAX][3], int K, V3& la, V3& lb) {
+  double c[3] = {0, 0, 0};
+  for (int k = 0; k < K; k++) {
+    c[0] += P[k][0];
+    c[1] += P[k][1];
+    c[2] += P[k][2];
+  }
+  c[0] /= (double)K;
+  c[1] /= (double)K;
+  c[2] /= (double)K;
+  double S[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  for (int k = 0; k < K; k++) {
+    const double v[3] = {P[k][0] - c[0], P[k][1] - c[1], P[k][2] - c[2]};
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) S[i][j] += v[i] * v[j];
+  }
+  const V3 dir = principal_axis(S);
+  la = V3{c[0] + 0.1 * dir.x, c[1] + 0.1 * dir.y, c[2] + 0.1 * dir.z};
+  lb = V3{c[0] - 0.1 * dir.x, c[1] - 0.1 * dir.y, c[2] - 0.1 * dir.z};
+}
+
+// geometry.cpp:62-73 : column-pivoted Householder QR least squares of  points * abc = 1  (Eigen
+// ColPivHouseholderQR semantics incl. its rank threshold), then normal = abc/|abc|, d = 1/|abc| and the
+// SIGNED mean distance.
+template <int KMAX>
+__device__ __forceinline__ double fit_plane(const double (&P)[KMAX][3], int K, V3& nrm, double& dist) {
+  double A[KMAX][3], c[KMAX];
+  int perm[3] = {0, 1, 2};
+  for (int k = 0; k < K; k++) {
+    A[k][0] = P[k][0];
+    A[k][1] = P[k][1];
+    A[k][2] = P[k][2];
+    c[k] = 1.0;
+  }
+  const int size = K < 3 ? K : 3;
+  double maxnorm = 0.0;
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    double s = 0;
+    for (int k = 0; k < K; k++) s += A[k][j] * A[k][j];
+    s = sqrt(s);
+    if (s > maxnorm) maxnorm = s;
+  }
+  const double th = maxnorm * 2.220446049250313e-16 / (double)K;
+  const double threshold_helper = th * th;
+  int nonzero = size;
+  for (int k = 0; k < size; k++) {
+    int big = k;
+    double bigsq = -1.0;
+    for (int j = k; j < 3; j++) {
+      double s = 0;
+      for (int r = k; r < K; r++) s += A[r][j] * A[r][j];
+      if (s > bigsq) {
+        bigsq = s;
+        big = j;
+      }
+    }
+    if (nonzero == size && bigsq < threshold_helper * (double)(K - k)) nonzero = k;
+    if (big != k) {
+      for (int r = 0; r < K; r++) {
+        const double t = A[r][k];
+        A[r][k] = A[r][big];
+        A[r][big] = t;
+      }
+      const int t = perm[k];
+      perm[k] = perm[big];
+      perm[big] = t;
+    }
+    double tail = 0;
+    for (int r = k + 1; r < K; r++) tail += A[r][k] * A[r][k];
+    const double c0 = A[k][k];
+    double tau, beta;
+    if (tail <= 2.2250738585072014e-308) {
+      tau = 0;
+      beta = c0;
+      for (int r = k + 1; r < K; r++) A[r][k] = 0;
+    } else {
+      beta = sqrt(c0 * c0 + tail);
+      if (c0 >= 0) beta = -beta;
+      for (int r = k + 1; r < K; r++) A[r][k] = A[r][k] / (c0 - beta);
+      tau = (beta - c0) / beta;
+    }
+    A[k][k] = beta;
+    for (int j = k + 1; j < 3; j++) {
+      double w = A[k][j];
+      for (int r = k + 1; r < K; r++) w += A[r][k] * A[r][j];
+      w *= tau;
+      A[k][j] -= w;
+      for (int r = k + 1; r < K; r++) A[r][j] -= w * A[r][k];
+    }
+    {
+      double w = c[k];
+      for (int r = k + 1; r < K; r++) w += A[r][k] * c[r];
+      w *= tau;
+      c[k] -= w;
+      for (int r = k + 1; r < K; r++) c[r] -= w * A[r][k];
+    }
+  }
+  double y[3] = {0, 0, 0};
+  for (int i = nonzero - 1; i >= 0; i--) {
+    double s = c[i];
+    for (int j = i + 1; j < nonzero; j++) s -= A[i][j] * y[j];
+    y[i] = s / A[i][i];
+  }
+  double abc[3] = {0, 0, 0};
+  for (int i = 0; i < nonzero; i++) abc[perm[i]] = y[i];
+  const double nn = sqrt(abc[0] * abc[0] + abc[1] * abc[1] + abc[2] * abc[2]);
+  nrm = V3{abc[0] / nn, abc[1] / nn, abc[2] / nn};
+  dist = 1.0 / nn;
+  double sum = 0;
+  for (int k = 0; k < K; k++) sum += (P[k][0] * nrm.x + P[k][1] * nrm.y + P[k][2] * nrm.z) - dist;
+  return sum / (double)K;
+}
+
+// ============================================================================ association (K45)
+
+template <int KMAX>
+__global__ void __launch_bounds__(kAssocThreads) assoc_kernel(AssocArgs a, int outer_iter) {
+  const uint32_t pair = blockIdx.y;
+  PairState* ps = a.state + pair;
+  if (ps->status != -1) return;
+  const uint32_t tgt_slot = (uint32_t)((a.pair0 + pair) % a.n_slots);
+  const uint32_t src_slot = (uint32_t)((a.pair0 + pair + a.src_offset) % a.n_slots);
+  const uint32_t nE = a.feat_counts[src_slot * 2], nP = a.feat_counts[src_slot * 2 + 1];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blockIdx.x * blockDim.x >= nE + nP) return;  // whole block beyond the source features
+  const bool active = i < nE + nP;
+  const bool is_plane = active && i >= nE;
+  bool ok = false;
+  if (active) {
+    double est[7];
+#pragma unroll
+    for (int j = 0; j < 7; j++) est[j] = ps->est[j];
+    const uint32_t li = is_plane ? i - nE : i;
+    const size_t cap_src = (size_t)a.capE_scan + a.capP_scan;
+    const size_t rec = (size_t)pair * cap_src + (is_plane ? a.capE_scan + li : li);
+    const double4 sp = is_plane ? a.planar_pts[(size_t)src_slot * a.capP_scan + li]
+                                : a.edge_pts[(size_t)src_slot * a.capE_scan + li];
+    const V3 q = pose_act(est, V3{sp.x, sp.y, sp.z});  // registration.cpp:34,75
+    const GridSetArrays& gs = is_plane ? a.gp : a.ge;
+    const GridHdr g = gs.hdr[pair];
+    const int k = is_plane ? a.rp.kp : a.rp.ke;
+    const double md = is_plane ? a.rp.rp : a.rp.re;
+    TopK<KMAX> tk;
+    knn_grid<KMAX>(g, gs.cell_start + (size_t)pair * (gs.cell_cap + 1), gs.sorted + (size_t)pair * gs.pt_cap, q.x,
+                   q.y, q.z, k, md, tk);
+    const int m = radius_count(tk, md);
+    const int need = is_plane ? a.rp.min_plane : a.rp.min_line;
+    double4 rp4 = make_double4(q.x, q.y, q.z, 0.0);
+    if (m >= need && m > 0) {
+      const double4* tp = is_plane ? a.planar_pts + (size_t)tgt_slot * a.capP_scan
+                                   : a.edge_pts + (size_t)tgt_slot * a.capE_scan;
+      double N[KMAX][3];
+#pragma unroll
+      for (int j = 0; j < KMAX; j++) {
+        if (j < m) {
+          const double4 t = tp[tk.id[j]];
+          N[j][0] = t.x;
+          N[j][1] = t.y;
+          N[j][2] = t.z;
+        }
+      }
+      if (!is_plane) {
+        V3 la, lb;
+        fit_line<KMAX>(N, m, la, lb);
+        // registration.cpp:49: condition_number is always DBL_MAX in the reference (geometry.cpp:55-56)
+        if (!(1.7976931348623157e308 < a.rp.min_cond)) {
+          ok = true;
+          rp4.w = 1.0;
+          a.rec_a[rec] = make_double4(la.x, la.y, la.z, 0.0);
+          a.rec_b[(size_t)pair * a.capE_scan + li] = make_double4(lb.x, lb.y, lb.z, 0.0);
+        }
+      } else {
+        V3 nrm;
+        double dist;
+        const double avg = fit_plane<KMAX>(N, m, nrm, dist);
+        if (!(avg > a.rp.max_avg)) {  // registration.cpp:90
+          ok = true;
+          rp4.w = 2.0;
+          a.rec_a[rec] = make_double4(nrm.x, nrm.y, nrm.z, dist);
+        }
+      }
+    }
+    a.rec_p[rec] = rp4;
+    if (a.nearest) a.nearest[((size_t)outer_iter * gridDim.y + pair) * cap_src + (is_plane ? a.capE_scan + li : li)] =
+        ok ? (int32_t)tk.id[0] : -1;
+  }
+  const unsigned be = __ballot_sync(0xffffffffu, ok && !is_plane);
+  const unsigned bp = __ballot_sync(0xffffffffu, ok && is_plane);
+  if ((threadIdx.x & 31) == 0) {
+    if (be) atomicAdd(&ps->n_edge_assoc, (uint32_t)__popc(be));
+    if (bp) atomicAdd(&ps->n_plane_assoc, (uint32_t)__popc(bp));
+  }
+}
+
+// ============================================================================ LM solve + ICF update (K6/K7)
+
+struct Eval {
+  double H[21];  // upper triangle of J^T J (tangent 6x6, loss-corrected, unscaled)
+  double g[6];   // J^T r
+  double cost;   // 1/2 sum rho(s)
+};
+
+// ceres::QuaternionManifold (w-first) applied literally to Eigen's (x,y,z,w) memory — SURVEY §8a-notes
+__device__ __forceinline__ void manifold_plus(const double* x, const double* delta, double* out) {
+  const double nd = sqrt(delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2]);
+  if (nd == 0.0) {
+    out[0] = x[0];
+    out[1] = x[1];
+    out[2] = x[2];
+    out[3] = x[3];
+  } else {
+    const double sbd = sin(nd) / nd;
+    const double q0 = cos(nd), q1 = sbd * delta[0], q2 = sbd * delta[1], q3 = sbd * delta[2];
+    out[0] = q0 * x[0] - q1 * x[1] - q2 * x[2] - q3 * x[3];
+    out[1] = q0 * x[1] + q1 * x[0] + q2 * x[3] - q3 * x[2];
+    out[2] = q0 * x[2] - q1 * x[3] + q2 * x[0] + q3 * x[1];
+    out[3] = q0 * x[3] + q1 * x[2] - q2 * x[1] + q3 * x[0];
+  }
+  out[4] = x[4] + delta[3];
+  out[5] = x[5] + delta[4];
+  out[6] = x[6] + delta[5];
+}
+
+// One residual: value, tangent Jacobian row (6), Huber corrector; accumulates into e.
+__device__ __forceinline__ void accumulate_residual(const double4& rp, const double4& ra, const double4& rb,
+                                                    const double* x, const double (&PJ)[4][3], Eval& e) {
+  const V3 p{rp.x, rp.y, rp.z};
+  const V3 u{x[0], x[1], x[2]};
+  const double w = x[3];
+  V3 uv = cross(u, p);
+  uv.x += uv.x;
+  uv.y += uv.y;
+  uv.z += uv.z;
+  const V3 uuv = cross(u, uv);
+  const V3 pt{p.x + w * uv.x + uuv.x + x[4], p.y + w * uv.y + uuv.y + x[5], p.z + w * uv.z + uuv.z + x[6]};
+  double r;
+  V3 g;
+  if (rp.w == 1.0) {  // point-to-line, geometry-inl.h:21-27
+    const V3 a{ra.x, ra.y, ra.z}, b{rb.x, rb.y, rb.z};
+    const V3 d1{pt.x - a.x, pt.y - a.y, pt.z - a.z}, d2{pt.x - b.x, pt.y - b.y, pt.z - b.z};
+    const V3 ab{a.x - b.x, a.y - b.y, a.z - b.z};
+    const V3 c = cross(d1, d2);
+    const double num = norm(c), den = norm(ab);
+    r = num / den;
+    if (num > 0) {
+      const V3 ch{c.x / num, c.y / num, c.z / num};
+      g = cross(ab, ch);
+      g.x /= den;
+      g.y /= den;
+      g.z /= den;
+    } else {
+      g = V3{0, 0, 0};
+    }
+  } else {  // point-to-plane, geometry-inl.h:30-33
+    const double s = ra.x * pt.x + ra.y * pt.y + ra.z * pt.z - ra.w;
+    r = fabs(s);
+    const double sg = copysign(1.0, s);
+    g = V3{sg * ra.x, sg * ra.y, sg * ra.z};
+  }
+  // ambient Jacobian wrt (qx qy qz qw): d pt/d u_i = w*2(e_i x p) + e_i x uv + u x 2(e_i x p) ; d pt/d w = uv
+  double J4[4];
+  {
+    const V3 e0{1, 0, 0}, e1{0, 1, 0}, e2{0, 0, 1};
+    const V3 es[3] = {e0, e1, e2};
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      V3 Ai = cross(es[i], p);
+      Ai.x += Ai.x;
+      Ai.y += Ai.y;
+      Ai.z += Ai.z;
+      const V3 t1 = cross(es[i], uv), t2 = cross(u, Ai);
+      J4[i] = g.x * (w * Ai.x + t1.x + t2.x) + g.y * (w * Ai.y + t1.y + t2.y) + g.z * (w * Ai.z + t1.z + t2.z);
+    }
+    J4[3] = g.x * uv.x + g.y * uv.y + g.z * uv.z;
+  }
+  // Huber(1.0) + corrector (rho'' <= 0 branch): scale residual and Jacobian row by sqrt(rho')
+  const double s2 = r * r;
+  double rho0, sr1;
+  if (s2 > 1.0) {
+    const double rr = sqrt(s2);
+    const double rho1 = fmax(2.2250738585072014e-308, 1.0 / rr);
+    rho0 = 2.0 * rr - 1.0;
+    sr1 = sqrt(rho1);
+  } else {
+    rho0 = s2;
+    sr1 = 1.0;
+  }
+  double J[6];
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    double acc = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) acc += J4[k] * PJ[k][j];
+    J[j] = acc * sr1;
+  }
+  J[3] = g.x * sr1;
+  J[4] = g.y * sr1;
+  J[5] = g.z * sr1;
+  const double rc = r * sr1;
+  e.cost += 0.5 * rho0;
+  int t = 0;
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    e.g[i] += J[i] * rc;
+#pragma unroll
+    for (int j = i; j < 6; j++) e.H[t++] += J[i] * J[j];
+  }
+}
+
+// Evaluate the whole problem of this pair at x; deterministic fixed-order reduction
+// (per-thread strided partial -> warp shuffle tree -> per-warp shared partials summed in warp order).
+__device__ void evaluate_problem(const double4* __restrict__ rec_p, const double4* __restrict__ rec_a,
+                                 const double4* __restrict__ rec_b, uint32_t nE, uint32_t nP, uint32_t capE,
+                                 const double* x, double* s_part /*[nwarps][28]*/, double* s_tot /*[28]*/, Eval& out) {
+  double PJ[4][3];
+  PJ[0][0] = -x[1]; PJ[0][1] = -x[2]; PJ[0][2] = -x[3];
+  PJ[1][0] = x[0];  PJ[1][1] = x[3];  PJ[1][2] = -x[2];
+  PJ[2][0] = -x[3]; PJ[2][1] = x[0];  PJ[2][2] = x[1];
+  PJ[3][0] = x[2];  PJ[3][1] = -x[1]; PJ[3][2] = x[0];
+  Eval e;
+#pragma unroll
+  for (int i = 0; i < 21; i++) e.H[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 6; i++) e.g[i] = 0;
+  e.cost = 0;
+  const uint32_t total = nE + nP;
+  for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+    const uint32_t ri = i < nE ? i : capE + (i - nE);
+    const double4 rp = rec_p[ri];
+    if (rp.w == 0.0) continue;
+    const double4 ra = rec_a[ri];
+    double4 rb = make_double4(0, 0, 0, 0);
+    if (i < nE) rb = rec_b[i];
+    accumulate_residual(rp, ra, rb, x, PJ, e);
+  }
+  double v[28];
+#pragma unroll
+  for (int i = 0; i < 21; i++) v[i] = e.H[i];
+#pragma unroll
+  for (int i = 0; i < 6; i++) v[21 + i] = e.g[i];
+  v[27] = e.cost;
+#pragma unroll
+  for (int i = 0; i < 28; i++) {
+    double t = v[i];
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+    v[i] = t;
+  }
+  const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();  // protect s_part / s_tot from the previous evaluation's readers
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int i = 0; i < 28; i++) s_part[warp * 28 + i] = v[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < 28) {
+    double t = 0;
+    for (int wv = 0; wv < nw; wv++) t += s_part[wv * 28 + threadIdx.x];
+    s_tot[threadIdx.x] = t;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 21; i++) out.H[i] = s_tot[i];
+#pragma unroll
+  for (int i = 0; i < 6; i++) out.g[i] = s_tot[21 + i];
+  out.cost = s_tot[27];
+}
+
+__device__ __forceinline__ int hidx(int i, int j) {  // upper-triangle index, i <= j
+  return i * 6 - (i * (i - 1)) / 2 + (j - i);
+}
+
+// Solve (A) y = b for symmetric positive definite 6x6 by Cholesky; returns false if not SPD / not finite.
+__device__ __forceinline__ bool chol6_solve(const double (&A)[6][6], const double (&b)[6], double (&y)[6]) {
+  double L[6][6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+#pragma unroll
+    for (int j = 0; j <= i; j++) {
+      double s = A[i][j];
+#pragma unroll
+      for (int k = 0; k < j; k++) s -= L[i][k] * L[j][k];
+      if (i == j) {
+        if (!(s > 0.0)) return false;
+        L[i][i] = sqrt(s);
+      } else {
+        L[i][j] = s / L[j][j];
+      }
+    }
+  }
+  double z[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    double s = b[i];
+#pragma unroll
+    for (int k = 0; k < i; k++) s -= L[i][k] * z[k];
+    z[i] = s / L[i][i];
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; i--) {
+    double s = z[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; k++) s -= L[k][i] * y[k];
+    y[i] = s / L[i][i];
+  }
+  bool fin = true;
+#pragma unroll
+  for (int i = 0; i < 6; i++) fin = fin && isfinite(y[i]);
+  return fin;
+}
+
+__device__ __forceinline__ double grad_max_norm(const double* x, const double* g) {
+  double ng[6], proj[7];
+#pragma unroll
+  for (int j = 0; j < 6; j++) ng[j] = -g[j];
+  manifold_plus(x, ng, proj);
+  double m = 0;
+#pragma unroll
+  for (int i = 0; i < 7; i++) m = fmax(m, fabs(x[i] - proj[i]));
+  return m;
+}
+
+__device__ __forceinline__ double norm7(const double* x) {
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 7; i++) s += x[i] * x[i];
+  return sqrt(s);
+}
+
+// One CTA per pair.  Every thread runs the (tiny, uniform) controller redundantly on the reduced sums, so
+// no broadcast of the step is needed between evaluations.
+__global__ void __launch_bounds__(kLmThreads) lm_kernel(LmArgs a) {
+  __shared__ double s_part[(kLmThreads / 32) * 28];
+  __shared__ double s_tot[28];
+  const uint32_t pair = blockIdx.x;
+  PairState* ps = a.state + pair;
+  if (ps->status != -1) return;
+  const uint32_t src_slot = (uint32_t)((a.pair0 + pair + a.src_offset) % a.n_slots);
+  const uint32_t nE = a.feat_counts[src_slot * 2], nP = a.feat_counts[src_slot * 2 + 1];
+  const uint32_t n_ea = ps->n_edge_assoc, n_pa = ps->n_plane_assoc;
+  __syncthreads();  // everyone has read the counters before thread 0 resets them
+  if (threadIdx.x == 0) {
+    ps->n_edge_assoc = 0;
+    ps->n_plane_assoc = 0;
+  }
+  if ((uint64_t)n_ea + n_pa < a.rp.min_assoc) {  // registration-inl.h:45-48
+    if (threadIdx.x == 0) ps->status = 2;
+    return;
+  }
+  const size_t cap_src = (size_t)a.capE_scan + a.capP_scan;
+  const double4* rec_p = a.rec_p + (size_t)pair * cap_src;
+  const double4* rec_a = a.rec_a + (size_t)pair * cap_src;
+  const double4* rec_b = a.rec_b + (size_t)pair * a.capE_scan;
+
+  // ---- Ceres TrustRegionMinimizer, LEVENBERG_MARQUARDT, max_num_iterations = 4, defaults otherwise
+  const int max_num_iterations = 4;
+  const double function_tolerance = 1e-6, gradient_tolerance = 1e-10, parameter_tolerance = 1e-8;
+  const double min_relative_decrease = 1e-3, min_radius = 1e-32, max_radius = 1e16;
+  const double min_diag = 1e-6, max_diag = 1e32;
+  double radius = 1e4, decrease_factor = 2.0;
+  bool reuse_diagonal = false;
+
+  double x[7] = {0, 0, 0, 1, 0, 0, 0};
+  double x_norm = norm7(x);
+  Eval ev;
+  double scale[6], diag[6];
+  uint32_t lm_iterations = 0;
+  double cost0 = 0, x_cost = 0;
+  if (n_ea + n_pa > 0) {
+    evaluate_problem(rec_p, rec_a, rec_b, nE, nP, a.capE_scan, x, s_part, s_tot, ev);
+    x_cost = ev.cost;
+    cost0 = x_cost;
+#pragma unroll
+    for (int j = 0; j < 6; j++) scale[j] = 1.0 / (1.0 + sqrt(ev.H[hidx(j, j)]));
+    double gmax = grad_max_norm(x, ev.g);
+    bool step_successful = true, armed = false;
+    int iteration = 0;
+    for (;;) {
+      if (iteration >= max_num_iterations) break;
+      if (step_successful && gmax <= gradient_tolerance) break;
+      if (radius <= min_radius) break;
+      iteration++;
+      // scaled normal equations: Hs = S H S, gs = S g
+      double Hs[6][6], gs[6];
+#pragma unroll
+      for (int i = 0; i < 6; i++) {
+        gs[i] = ev.g[i] * scale[i];
+#pragma unroll
+        for (int j = i; j < 6; j++) {
+          const double v = ev.H[hidx(i, j)] * scale[i] * scale[j];
+          Hs[i][j] = v;
+          Hs[j][i] = v;
+        }
+      }
+      if (!reuse_diagonal) {
+#pragma unroll
+        for (int j = 0; j < 6; j++) diag[j] = fmin(fmax(Hs[j][j], min_diag), max_diag);
+      }
+      double A[6][6], y[6], step[6];
+#pragma unroll
+      for (int i = 0; i < 6; i++) {
+#pragma unroll
+        for (int j = 0; j < 6; j++) A[i][j] = Hs[i][j];
+        A[i][i] += diag[i] / radius;  // (sqrt(diag/radius))^2
+      }
+      const bool solved = chol6_solve(A, gs, y);
+      reuse_diagonal = true;
+      bool valid = false;
+      double model_cost_change = 0;
+      if (solved) {
+        double sg = 0, shs = 0;
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+          step[i] = -y[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+          sg += step[i] * gs[i];
+          double t = 0;
+#pragma unroll
+          for (int j = 0; j < 6; j++) t += Hs[i][j] * step[j];
+          shs += step[i] * t;
+        }
+        model_cost_change = -(sg + 0.5 * shs);
+        valid = model_cost_change > 0.0;
+      }
+      if (!valid) {  // HandleInvalidStep
+        radius *= 0.5;
+        reuse_diagonal = true;
+        step_successful = false;
+        continue;
+      }
+      double delta[6], cand[7];
+#pragma unroll
+      for (int j = 0; j < 6; j++) delta[j] = step[j] * scale[j];
+      manifold_plus(x, delta, cand);
+      Eval ec;
+      evaluate_problem(rec_p, rec_a, rec_b, nE, nP, a.capE_scan, cand, s_part, s_tot, ec);
+      const double cand_cost = ec.cost;
+      if (armed) {
+        double dn = 0;
+#pragma unroll
+        for (int i = 0; i < 7; i++) dn += (x[i] - cand[i]) * (x[i] - cand[i]);
+        if (sqrt(dn) <= parameter_tolerance * (x_norm + parameter_tolerance)) break;
+        if (fabs(x_cost - cand_cost) <= function_tolerance * x_cost) break;
+      }
+      const double rel = (x_cost - cand_cost) / model_cost_change;
+      if (rel > min_relative_decrease) {  // HandleSuccessfulStep (evaluation at cand already holds J, g)
+#pragma unroll
+        for (int i = 0; i < 7; i++) x[i] = cand[i];
+        x_norm = norm7(x);
+        ev = ec;
+        x_cost = cand_cost;
+        gmax = grad_max_norm(x, ev.g);
+        step_successful = true;
+        const double q = 2.0 * rel - 1.0;
+        radius = radius / fmax(1.0 / 3.0, 1.0 - q * q * q);
+        radius = fmin(max_radius, radius);
+        decrease_factor = 2.0;
+        reuse_diagonal = false;
+        armed = true;
+      } else {
+        step_successful = false;
+        radius = radius / decrease_factor;
+        decrease_factor *= 2.0;
+        reuse_diagonal = true;
+      }
+    }
+    lm_iterations = (uint32_t)iteration;
+  }
+
+  // ---- ICF update (registration-inl.h:59-73)
+  if (threadIdx.x == 0) {
+    double est[7], nxt[7];
+#pragma unroll
+    for (int j = 0; j < 7; j++) est[j] = ps->est[j];
+    if (a.d_iter_est && pair == 0) {
+      for (int j = 0; j < 7; j++) {
+        a.d_iter_est[7 * a.outer_iter + j] = est[j];
+        a.d_iter_update[7 * a.outer_iter + j] = x[j];
+      }
+      a.d_assoc_n[2 * a.outer_iter] = n_ea;
+      a.d_assoc_n[2 * a.outer_iter + 1] = n_pa;
+      a.d_lm_iters[a.outer_iter] = lm_iterations;
+      a.d_lm_cost[2 * a.outer_iter] = cost0;
+      a.d_lm_cost[2 * a.outer_iter + 1] = x_cost;
+    }
+    quat_mul(x, est, nxt);  // left composition: est = update.compose(est), geometry.cpp:16-18
+    const V3 rt = quat_rotate(x, V3{est[4], est[5], est[6]});
+    nxt[4] = x[4] + rt.x;
+    nxt[5] = x[5] + rt.y;
+    nxt[6] = x[6] + rt.z;
+#pragma unroll
+    for (int j = 0; j < 7; j++) ps->est[j] = nxt[j];
+    ps->iters = ps->iters + 1;
+    // angularDistance(update.q, Identity) = 2 atan2(|vec|, |w|) ; |t|
+    const double ang = 2.0 * atan2(sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]), fabs(x[3]));
+    const double pos = sqrt(x[4] * x[4] + x[5] * x[5] + x[6] * x[6]);
+    if (ang < a.rp.rot_thr && pos < a.rp.pos_thr) {
+      ps->status = 0;
+    } else if (a.outer_iter + 1 >= a.rp.max_iterations) {
+      ps->status = 1;
+    }
+  }
+}
+
+__global__ void init_pairs_kernel(PairState* st, uint32_t n, const double* init) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  PairState s;
+  const double ident[7] = {0, 0, 0, 1, 0, 0, 0};
+  for (int j = 0; j < 7; j++) s.est[j] = init ? init[j] : ident[j];
+  s.status = -1;
+  s.iters = 0;
+  s.n_edge_assoc = 0;
+  s.n_plane_assoc = 0;
+  st[i] = s;
+}
+
+__global__ void finish_pairs_kernel(const PairState* st, uint32_t n, double* poses, int32_t* term, uint32_t* iters) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const PairState s = st[i];
+  if (poses)
+    for (int j = 0; j < 7; j++) poses[7 * (size_t)i + j] = s.est[j];
+  if (term) term[i] = s.status == -1 ? 1 : s.status;  // never stopped early => MAX_ITER (registration-inl.h:27)
+  if (iters) iters[i] = s.iters;
+}
+
+}  // namespace
+
+// ============================================================================ host launchers
+
+cudaError_t launch_grid_build(const GridBuildArgs& a, uint32_t n_sets, cudaStream_t st) {
+  if (n_sets == 0) return cudaSuccess;
+  grid_build_kernel<<<n_sets, kGridThreads, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_assoc(const AssocArgs& a, uint32_t n_pairs, int outer_iter, cudaStream_t st) {
+  if (n_pairs == 0) return cudaSuccess;
+  const uint32_t cap = a.capE_scan + a.capP_scan;
+  dim3 grid((cap + kAssocThreads - 1) / kAssocThreads, n_pairs);
+  const int kmax = a.rp.ke > a.rp.kp ? a.rp.ke : a.rp.kp;
+  if (kmax <= kKnnRegMax)
+    assoc_kernel<kKnnRegMax><<<grid, kAssocThreads, 0, st>>>(a, outer_iter);
+  else
+    assoc_kernel<kKnnMax><<<grid, kAssocThreads, 0, st>>>(a, outer_iter);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_lm(const LmArgs& a, uint32_t n_pairs, cudaStream_t st) {
+  if (n_pairs == 0) return cudaSuccess;
+  lm_kernel<<<n_pairs, kLmThreads, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_knn(const KnnArgs& a, cudaStream_t st) {
+  if (a.n_queries == 0) return cudaSuccess;
+  const uint32_t blocks = (uint32_t)((a.n_queries + 127) / 128);
+  if (a.k <= kKnnRegMax)
+    knn_kernel<kKnnRegMax><<<blocks, 128, 0, st>>>(a);
+  else
+    knn_kernel<kKnnMax><<<blocks, 128, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_init_pairs(PairState* s, uint32_t n_pairs, const double* init_pose_or_null, cudaStream_t st) {
+  if (n_pairs == 0) return cudaSuccess;
+  init_pairs_kernel<<<(n_pairs + 127) / 128, 128, 0, st>>>(s, n_pairs, init_pose_or_null);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_finish_pairs(const PairState* s, uint32_t n_pairs, double* poses, int32_t* term, uint32_t* iters,
+                                cudaStream_t st) {
+  if (n_pairs == 0) return cudaSuccess;
+  finish_pairs_kernel<<<(n_pairs + 127) / 128, 128, 0, st>>>(s, n_pairs, poses, term, iters);
+  return cudaGetLastError();
+}
+
+}  // namespace loamgpu
