@@ -85,3 +85,15 @@ REG_SCENARIOS = [
 # pose parity tolerance between the CUDA path and the oracle (BASELINE.json north_star)
 POSE_TOL_RAD = 1e-6
 POSE_TOL_M = 1e-5
+
+
+def to_capi(s):
+    """Oracle ctypes struct -> the C-ABI struct of the same layout (LidarParams / FeParams / RegParams)."""
+    import ctypes as C
+
+    from loam_b200 import _capi
+    cls = {"LidarParams": _capi.CLidarParams, "FeParams": _capi.CFeParams, "RegParams": _capi.CRegParams}[type(s).__name__]
+    assert C.sizeof(cls) == C.sizeof(s)
+    c = cls()
+    C.memmove(C.addressof(c), C.addressof(s), C.sizeof(s))
+    return c
