@@ -105,6 +105,22 @@ void loamgpu_default_reg_params(loamgpu_reg_params* p);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t loamgpu_launch_count(const loamgpu_ctx* ctx);
 
+/* Per-kernel-class device time, measured with CUDA events on the launching stream
+ * (bench.py's roofline.achieved).  set_profiling(1) brackets every launch with an event
+ * pair; kernel_times() synchronises the stream, returns accumulated milliseconds and launch
+ * counts per class since the previous call, and resets the accumulators. */
+enum {
+  LOAMGPU_K_EXTRACT = 0, /* extract_ring_kernel  (K1+K2) */
+  LOAMGPU_K_PACK = 1,    /* pack_features_kernel */
+  LOAMGPU_K_GRID = 2,    /* grid_build_kernel    (K3) */
+  LOAMGPU_K_ASSOC = 3,   /* assoc_kernel / knn_kernel (K4+K5) */
+  LOAMGPU_K_LM = 4,      /* lm_kernel            (K6+K7) */
+  LOAMGPU_K_MISC = 5,    /* init/finish pair state */
+  LOAMGPU_K_COUNT = 6
+};
+int loamgpu_set_profiling(loamgpu_ctx* ctx, int on);
+int loamgpu_kernel_times(loamgpu_ctx* ctx, double ms[LOAMGPU_K_COUNT], uint64_t launches[LOAMGPU_K_COUNT]);
+
 /* ------------------------------------------------- feature extraction (host buffers) */
 /* replaces loam::extractFeatures, features.h:108-111 / features-inl.h:11-50.  Writes the
  * indices (into the input scan) of the selected edge / planar points, in the reference's

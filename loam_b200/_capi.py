@@ -24,8 +24,9 @@ SYMBOLS = [
     "loamgpu_create", "loamgpu_destroy", "loamgpu_last_error", "loamgpu_set_stream", "loamgpu_default_fe_params",
     "loamgpu_default_reg_params", "loamgpu_launch_count", "loamgpu_extract", "loamgpu_curvature",
     "loamgpu_valid_mask", "loamgpu_register", "loamgpu_knn", "loamgpu_odometry_host", "loamgpu_odometry_device",
-    "loamgpu_set_chunk_pairs",
+    "loamgpu_set_chunk_pairs", "loamgpu_set_profiling", "loamgpu_kernel_times",
 ]
+KERNEL_CLASSES = ["extract", "pack", "grid_build", "assoc", "lm", "misc"]
 
 
 class CLidarParams(C.Structure):
@@ -79,6 +80,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     lib.loamgpu_destroy.argtypes = [C.c_void_p]
     lib.loamgpu_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     lib.loamgpu_set_chunk_pairs.argtypes = [C.c_void_p, u32]
+    lib.loamgpu_set_profiling.argtypes = [C.c_void_p, C.c_int]
+    lib.loamgpu_kernel_times.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     vp = C.c_void_p
     lib.loamgpu_extract.argtypes = [vp, vp, C.c_int, C.c_size_t, u64, vp, vp, vp, u64, vp, vp, u64, vp]
     lib.loamgpu_curvature.argtypes = [vp, vp, C.c_int, C.c_size_t, u64, vp, vp, vp]
@@ -149,6 +152,16 @@ class Context:
 
     def set_stream(self, cuda_stream: int | None):
         self._check(self.lib.loamgpu_set_stream(self.h, C.c_void_p(cuda_stream or 0)))
+
+    def set_profiling(self, on: bool):
+        self._check(self.lib.loamgpu_set_profiling(self.h, 1 if on else 0))
+
+    def kernel_times(self):
+        """{class: (milliseconds, launches)} since the previous call (synchronises the stream)."""
+        ms = np.zeros(len(KERNEL_CLASSES))
+        n = np.zeros(len(KERNEL_CLASSES), dtype=np.uint64)
+        self._check(self.lib.loamgpu_kernel_times(self.h, _ptr(ms), _ptr(n)))
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(KERNEL_CLASSES)}
 
     def set_chunk_pairs(self, n: int):
         self._check(self.lib.loamgpu_set_chunk_pairs(self.h, n))

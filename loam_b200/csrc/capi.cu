@@ -58,6 +58,17 @@ struct loamgpu_ctx {
   DevBuf state, rec_p, rec_a, rec_b, nearest;
   DevBuf misc, out_pose, out_term, out_iters, out_ne, out_np;
   DevBuf det_est, det_upd, det_assoc_n, det_lm_iters, det_lm_cost, init_pose;
+
+  // optional per-kernel-class timing (CUDA events on the launching stream)
+  struct ProfRec {
+    int kind;
+    cudaEvent_t a, b;
+  };
+  bool profiling = false;
+  std::vector<ProfRec> prof_open;       // recorded, not yet read back
+  std::vector<cudaEvent_t> prof_pool;   // free events
+  double prof_ms[LOAMGPU_K_COUNT] = {};
+  uint64_t prof_n[LOAMGPU_K_COUNT] = {};
 };
 
 namespace {
@@ -73,6 +84,40 @@ int cuda_fail(loamgpu_ctx* c, cudaError_t e, const char* what) {
   do {                                                        \
     cudaError_t _e = (call);                                  \
     if (_e != cudaSuccess) return cuda_fail(ctx, _e, #call);  \
+  } while (0)
+
+// Times one launch when profiling is on: events bracket the launch on the launching stream.
+struct ProfScope {
+  loamgpu_ctx* c;
+  cudaEvent_t a = nullptr, b = nullptr;
+  int kind;
+  static cudaEvent_t get(loamgpu_ctx* c) {
+    if (!c->prof_pool.empty()) {
+      cudaEvent_t e = c->prof_pool.back();
+      c->prof_pool.pop_back();
+      return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+  }
+  ProfScope(loamgpu_ctx* ctx, int k) : c(ctx), kind(k) {
+    c->launches++;
+    if (!c->profiling) return;
+    a = get(c);
+    b = get(c);
+    cudaEventRecord(a, c->stream);
+  }
+  ~ProfScope() {
+    if (!a) return;
+    cudaEventRecord(b, c->stream);
+    c->prof_open.push_back({kind, a, b});
+  }
+};
+#define TIMED(kind, call)          \
+  do {                             \
+    ProfScope _ps(ctx, kind);      \
+    CU(call);                      \
   } while (0)
 
 // geometry of one extraction problem, validated
@@ -171,8 +216,7 @@ int run_extract(loamgpu_ctx* ctx, const ExtractPlan& pl, const void* dev_pts, in
   a.ring_edge = ctx->ring_edge.as<uint32_t>();
   a.ring_planar = ctx->ring_planar.as<uint32_t>();
   a.ring_counts = ctx->ring_counts.as<uint32_t>();
-  CU(launch_extract(a, n_scans, ctx->stream));
-  ctx->launches++;
+  TIMED(LOAMGPU_K_EXTRACT, launch_extract(a, n_scans, ctx->stream));
   PackArgs p;
   memset(&p, 0, sizeof p);
   p.pts = a.pts;
@@ -196,8 +240,7 @@ int run_extract(loamgpu_ctx* ctx, const ExtractPlan& pl, const void* dev_pts, in
   p.feat_counts = ctx->feat_counts.as<uint32_t>();
   p.n_edge_out = n_edge_out;
   p.n_planar_out = n_planar_out;
-  CU(launch_pack(p, n_scans, ctx->stream));
-  ctx->launches++;
+  TIMED(LOAMGPU_K_PACK, launch_pack(p, n_scans, ctx->stream));
   return LOAMGPU_OK;
 }
 
@@ -266,15 +309,14 @@ int run_register(loamgpu_ctx* ctx, const RegP& rp, uint32_t n_pairs, uint64_t pa
   gb.kind = 0;
   gb.k_nominal = rp.ke;
   gb.g = grid_arrays(ctx, false, capE);
-  CU(launch_grid_build(gb, n_pairs, ctx->stream));
+  TIMED(LOAMGPU_K_GRID, launch_grid_build(gb, n_pairs, ctx->stream));
   gb.pts = ctx->planar_pts.as<double4>();
   gb.pt_stride = capP;
   gb.kind = 1;
   gb.k_nominal = rp.kp;
   gb.g = grid_arrays(ctx, true, capP);
-  CU(launch_grid_build(gb, n_pairs, ctx->stream));
-  CU(launch_init_pairs(ctx->state.as<PairState>(), n_pairs, init_pose_dev, ctx->stream));
-  ctx->launches += 3;
+  TIMED(LOAMGPU_K_GRID, launch_grid_build(gb, n_pairs, ctx->stream));
+  TIMED(LOAMGPU_K_MISC, launch_init_pairs(ctx->state.as<PairState>(), n_pairs, init_pose_dev, ctx->stream));
 
   AssocArgs aa;
   memset(&aa, 0, sizeof aa);
@@ -315,10 +357,9 @@ int run_register(loamgpu_ctx* ctx, const RegP& rp, uint32_t n_pairs, uint64_t pa
     la.d_lm_cost = ctx->det_lm_cost.as<double>();
   }
   for (int it = 0; it < rp.max_iterations; it++) {
-    CU(launch_assoc(aa, n_pairs, it, ctx->stream));
+    TIMED(LOAMGPU_K_ASSOC, launch_assoc(aa, n_pairs, it, ctx->stream));
     la.outer_iter = it;
-    CU(launch_lm(la, n_pairs, ctx->stream));
-    ctx->launches += 2;
+    TIMED(LOAMGPU_K_LM, launch_lm(la, n_pairs, ctx->stream));
   }
   return LOAMGPU_OK;
 }
@@ -381,6 +422,11 @@ void loamgpu_destroy(loamgpu_ctx* c) {
     if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
     if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]);
   }
+  for (auto& r : c->prof_open) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   delete c;
@@ -421,6 +467,35 @@ void loamgpu_default_reg_params(loamgpu_reg_params* p) {  // registration.h:40-7
 }
 
 uint64_t loamgpu_launch_count(const loamgpu_ctx* c) { return c ? c->launches : 0; }
+
+int loamgpu_set_profiling(loamgpu_ctx* c, int on) {
+  if (!c) return LOAMGPU_ERR_INVALID;
+  c->profiling = on != 0;
+  return LOAMGPU_OK;
+}
+
+int loamgpu_kernel_times(loamgpu_ctx* ctx, double* ms, uint64_t* launches) {
+  if (!ctx) return LOAMGPU_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (auto& r : ctx->prof_open) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+      ctx->prof_ms[r.kind] += (double)t;
+      ctx->prof_n[r.kind]++;
+    }
+    ctx->prof_pool.push_back(r.a);
+    ctx->prof_pool.push_back(r.b);
+  }
+  ctx->prof_open.clear();
+  for (int k = 0; k < LOAMGPU_K_COUNT; k++) {
+    if (ms) ms[k] = ctx->prof_ms[k];
+    if (launches) launches[k] = ctx->prof_n[k];
+    ctx->prof_ms[k] = 0;
+    ctx->prof_n[k] = 0;
+  }
+  return LOAMGPU_OK;
+}
 
 int loamgpu_set_chunk_pairs(loamgpu_ctx* c, uint32_t pairs) {
   if (!c || pairs == 0) return LOAMGPU_ERR_INVALID;
@@ -485,8 +560,7 @@ static int curvature_or_mask(loamgpu_ctx* ctx, const void* pts, int dtype, size_
   uint8_t* d_mask = ctx->misc.as<uint8_t>() + (size_t)n_points * 8;
   a.curv_out = curv ? d_curv : nullptr;
   a.mask_out = mask ? d_mask : nullptr;
-  CU(launch_extract(a, 1, ctx->stream));
-  ctx->launches++;
+  TIMED(LOAMGPU_K_EXTRACT, launch_extract(a, 1, ctx->stream));
   if (curv) CU(cudaMemcpyAsync(curv, d_curv, (size_t)n_points * 8, cudaMemcpyDeviceToHost, ctx->stream));
   if (mask) CU(cudaMemcpyAsync(mask, d_mask, (size_t)n_points, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
@@ -563,9 +637,8 @@ int loamgpu_register(loamgpu_ctx* ctx, const double* src_edge, uint64_t n_se, co
   CU(cudaMemcpyAsync(ctx->init_pose.p, init_pose, 56, cudaMemcpyHostToDevice, ctx->stream));
   rc = run_register(ctx, rp, 1, 0, 2, 1, capE, capP, ctx->init_pose.as<double>(), want_detail);
   if (rc) return rc;
-  CU(launch_finish_pairs(ctx->state.as<PairState>(), 1, ctx->out_pose.as<double>(), ctx->out_term.as<int32_t>(),
-                         ctx->out_iters.as<uint32_t>(), ctx->stream));
-  ctx->launches++;
+  TIMED(LOAMGPU_K_MISC, launch_finish_pairs(ctx->state.as<PairState>(), 1, ctx->out_pose.as<double>(),
+                                            ctx->out_term.as<int32_t>(), ctx->out_iters.as<uint32_t>(), ctx->stream));
   int32_t term = 1;
   uint32_t iters = 0;
   CU(cudaMemcpyAsync(out_pose, ctx->out_pose.p, 56, cudaMemcpyDeviceToHost, ctx->stream));
@@ -648,7 +721,7 @@ int loamgpu_knn(loamgpu_ctx* ctx, const double* targets, uint64_t n_t, const dou
   gb.kind = 1;
   gb.k_nominal = (int)k;
   gb.g = grid_arrays(ctx, true, cap);
-  CU(launch_grid_build(gb, 1, ctx->stream));
+  TIMED(LOAMGPU_K_GRID, launch_grid_build(gb, 1, ctx->stream));
   double* dq = ctx->misc.as<double>();
   uint32_t* didx = reinterpret_cast<uint32_t*>(dq + 3 * n_q);
   uint32_t* dcnt = didx + (size_t)n_q * k;
@@ -661,8 +734,7 @@ int loamgpu_knn(loamgpu_ctx* ctx, const double* targets, uint64_t n_t, const dou
   ka.max_dist = max_dist;
   ka.idx_out = didx;
   ka.count_out = dcnt;
-  CU(launch_knn(ka, ctx->stream));
-  ctx->launches += 2;
+  TIMED(LOAMGPU_K_ASSOC, launch_knn(ka, ctx->stream));
   CU(cudaMemcpyAsync(idx_out, didx, (size_t)n_q * k * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(count_out, dcnt, (size_t)n_q * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
@@ -714,9 +786,9 @@ static int odometry_core(loamgpu_ctx* ctx, uint64_t n_scans, const loamgpu_lidar
     CU(cudaEventRecord(ctx->ev_consumed[buf], ctx->stream));
     rc = run_register(ctx, rp, np, p0, n_slots, 1, pl.capE_scan, pl.capP_scan, nullptr, false);
     if (rc) return rc;
-    CU(launch_finish_pairs(ctx->state.as<PairState>(), np, poses_dev ? poses_dev + 7 * p0 : nullptr,
-                           term_dev ? term_dev + p0 : nullptr, iters_dev ? iters_dev + p0 : nullptr, ctx->stream));
-    ctx->launches++;
+    TIMED(LOAMGPU_K_MISC,
+          launch_finish_pairs(ctx->state.as<PairState>(), np, poses_dev ? poses_dev + 7 * p0 : nullptr,
+                              term_dev ? term_dev + p0 : nullptr, iters_dev ? iters_dev + p0 : nullptr, ctx->stream));
   }
   return LOAMGPU_OK;
 }
