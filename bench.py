@@ -287,7 +287,10 @@ def ours(a):
     h_np = torch.zeros(n, dtype=torch.int32, pin_memory=True)
     torch.cuda.synchronize()
 
-    stream = torch.cuda.current_stream()
+    # a dedicated non-default stream: the library treats a NULL stream handle as "use the context's own stream",
+    # and the CUDA events below must sit on the stream the kernels are launched on
+    stream = torch.cuda.Stream(device=dev)
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
 
     def step_device():
