@@ -1,0 +1,456 @@
+// GPU nearest-neighbour structure over one target feature set (replaces the nanoflann KD-tree of the
+// reference: kdtree.h:24-41, kdtree.cpp:10-28, built at registration-inl.h:20-23).
+//
+//   K3  bvh_build_kernel  one CTA per set: bounding box -> 30-bit Morton codes -> in-CTA stable LSD radix sort
+//                         (4-bit digits, counters in shared memory) -> Morton-ordered point copy -> binary radix
+//                         tree over the sorted codes (every internal node finds its key range and split with
+//                         count-leading-zeros binary searches, so all nodes are built in parallel) -> boxes
+//                         bottom-up (the second thread to reach a node merges its children)
+//   K4  knn_bvh()         exact k-NN for one query per thread: near-child-first traversal with a short stack,
+//                         subtrees of <= 8 points are scanned as leaves; float32 box lower bounds (boxes rounded
+//                         outward, query rounded both ways, arithmetic rounded down => never above the true fp64
+//                         distance), fp64 point distances in the reference's operation order, branch-free sorted
+//                         insertion on (d2, index)
+//
+// Why a tree and not a uniform grid: LiDAR feature density falls with 1/range^2; a uniform cell sized for the
+// average makes near-sensor queries scan hundreds of candidates (measured: profiles/r1_assoc_v1_hotlines.txt).
+// Why a radix tree and not fixed 8-point runs of the Morton order: runs that straddle a jump of the Z curve get
+// huge boxes; splitting at Morton-prefix boundaries visits ~3 leaves / ~18 points per query instead of ~10 / ~84
+// (CPU simulation on a 64x1024 synthetic pair).
+//
+// Tie-break (documented, deterministic): equal squared distances resolve by ascending target index
+// (nanoflann resolves them by tree-traversal order, i.e. unpinned in the reference).
+#pragma once
+#include "common.cuh"
+#include "kernels.h"
+
+namespace loamgpu {
+namespace {
+
+// ============================================================================ build (K3)
+
+__device__ double block_reduce_minmax(double v, bool is_max, double* s_red) {
+  for (int o = 16; o > 0; o >>= 1) {
+    const double t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmax(v, t) : fmin(v, t);
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = s_red[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); w++) r = is_max ? fmax(r, s_red[w]) : fmin(r, s_red[w]);
+  return r;
+}
+
+__device__ __forceinline__ uint32_t spread10(uint32_t v) {  // 10 bits -> every third bit
+  v &= 0x3FFu;
+  v = (v | (v << 16)) & 0x030000FFu;
+  v = (v | (v << 8)) & 0x0300F00Fu;
+  v = (v | (v << 4)) & 0x030C30C3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+
+constexpr int kRadixBits = 4;
+constexpr int kRadixBins = 1 << kRadixBits;
+constexpr int kMortonBits = 30;
+
+__global__ void __launch_bounds__(kBuildThreads) bvh_build_kernel(BvhBuildArgs a) {
+  extern __shared__ uint32_t s_cnt[];  // [kRadixBins][kBuildThreads]
+  __shared__ double s_red[32];
+  __shared__ uint32_t s_scan[kBuildThreads / 32];
+  __shared__ uint32_t s_wtot[kRadixBins * (kBuildThreads / 32)];
+
+  const uint32_t set = blockIdx.x;
+  const uint32_t slot = (uint32_t)((a.slot0 + set) % a.n_slots);
+  const uint32_t n = a.counts[slot * 2 + a.kind];
+  const double4* pts = a.pts + (size_t)slot * a.pt_stride;
+  BvhHdr* hdr = a.g.hdr + set;
+  BvhNode* nodes = a.g.nodes + (size_t)set * a.g.pt_cap;
+  double4* sorted = a.g.sorted + (size_t)set * a.g.pt_cap;
+  uint2* keyA = a.g.keys + (size_t)set * 2 * a.g.pt_cap;
+  uint2* keyB = keyA + a.g.pt_cap;
+  const uint32_t tid = threadIdx.x, nthr = blockDim.x;
+
+  if (tid == 0) {
+    BvhHdr h;
+    h.n = n;
+    h.pad[0] = h.pad[1] = h.pad[2] = 0;
+    *hdr = h;
+  }
+  if (n == 0) return;
+
+  // ---- bounding box
+  double lo[3] = {CUDART_INF, CUDART_INF, CUDART_INF}, hi[3] = {-CUDART_INF, -CUDART_INF, -CUDART_INF};
+  for (uint32_t i = tid; i < n; i += nthr) {
+    const double4 p = pts[i];
+    lo[0] = fmin(lo[0], p.x);
+    lo[1] = fmin(lo[1], p.y);
+    lo[2] = fmin(lo[2], p.z);
+    hi[0] = fmax(hi[0], p.x);
+    hi[1] = fmax(hi[1], p.y);
+    hi[2] = fmax(hi[2], p.z);
+  }
+  double emax = 0;
+  for (int d = 0; d < 3; d++) {
+    lo[d] = block_reduce_minmax(lo[d], false, s_red);
+    hi[d] = block_reduce_minmax(hi[d], true, s_red);
+    emax = fmax(emax, hi[d] - lo[d]);
+  }
+  // one scale for all axes (cubic cells); the ordering only has to be spatially coherent, not exact
+  const double scale = emax > 0 ? 1023.999 / emax : 0.0;
+
+  // ---- Morton keys (thread-contiguous chunks: the radix passes below need a fixed item -> thread map)
+  const uint32_t chunk = (n + nthr - 1) / nthr;
+  const uint32_t c0 = min(tid * chunk, n), c1 = min(c0 + chunk, n);
+  for (uint32_t i = c0; i < c1; i++) {
+    const double4 p = pts[i];
+    const uint32_t ix = (uint32_t)fmin(fmax((p.x - lo[0]) * scale, 0.0), 1023.0);
+    const uint32_t iy = (uint32_t)fmin(fmax((p.y - lo[1]) * scale, 0.0), 1023.0);
+    const uint32_t iz = (uint32_t)fmin(fmax((p.z - lo[2]) * scale, 0.0), 1023.0);
+    keyA[i] = make_uint2(spread10(ix) | (spread10(iy) << 1) | (spread10(iz) << 2), i);
+  }
+  __syncthreads();
+
+  // ---- stable LSD radix sort, 4 bits per pass.  Rank of an item = items with a smaller digit + items with the
+  // same digit owned by earlier threads + earlier items of the same digit in this thread's own chunk.
+  uint2* src = keyA;
+  uint2* dst = keyB;
+  const uint32_t lane = tid & 31, warp = tid >> 5;
+  for (int shift = 0; shift < kMortonBits; shift += kRadixBits) {
+#pragma unroll
+    for (int b = 0; b < kRadixBins; b++) s_cnt[b * kBuildThreads + tid] = 0;
+    for (uint32_t i = c0; i < c1; i++) s_cnt[((src[i].x >> shift) & (kRadixBins - 1)) * kBuildThreads + tid]++;
+    // per-bin inclusive scan across the warp's 32 threads; warp totals -> s_wtot[bin][warp]
+    uint32_t cnt[kRadixBins], inc[kRadixBins];
+#pragma unroll
+    for (int b = 0; b < kRadixBins; b++) {
+      cnt[b] = s_cnt[b * kBuildThreads + tid];
+      uint32_t v = cnt[b];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if ((int)lane >= o) v += t;
+      }
+      inc[b] = v;
+      if (lane == 31) s_wtot[b * (kBuildThreads / 32) + warp] = v;
+    }
+    __syncthreads();
+    // exclusive scan of the 16 x 32 warp totals (flattened bin-major) by the first 512 threads
+    if (tid < kRadixBins * (kBuildThreads / 32)) {
+      const uint32_t mine = s_wtot[tid];
+      uint32_t v = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if ((int)lane >= o) v += t;
+      }
+      if (lane == 31) s_scan[warp] = v;
+      s_wtot[tid] = v - mine;  // exclusive within this group of 32
+    }
+    __syncthreads();
+    if (tid < kRadixBins * (kBuildThreads / 32)) {
+      uint32_t off = 0;
+      for (uint32_t w = 0; w < warp; w++) off += s_scan[w];
+      s_wtot[tid] += off;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < kRadixBins; b++)
+      s_cnt[b * kBuildThreads + tid] = s_wtot[b * (kBuildThreads / 32) + warp] + inc[b] - cnt[b];
+    // (each thread reads back only its own column below, so no barrier is needed here)
+    for (uint32_t i = c0; i < c1; i++) {
+      const uint2 kv = src[i];
+      const uint32_t pos = s_cnt[((kv.x >> shift) & (kRadixBins - 1)) * kBuildThreads + tid]++;
+      dst[pos] = kv;
+    }
+    __syncthreads();
+    uint2* t = src;
+    src = dst;
+    dst = t;
+  }
+
+  // ---- Morton-ordered point copy
+  for (uint32_t i = tid; i < n; i += nthr) {
+    const uint32_t id = src[i].y;
+    const double4 p = pts[id];
+    sorted[i] = make_double4(p.x, p.y, p.z, __longlong_as_double((long long)id));
+  }
+  __syncthreads();
+
+  if (n < 2) return;  // a single point has no internal node; knn_bvh scans it directly
+
+  // ---- binary radix tree over the sorted (code, position) keys.  Internal node i covers the key range [first, last]
+  // with i == first or i == last; its children are node/leaf `split` (range [first, split]) and `split + 1`
+  // (range [split + 1, last]).
+  const uint2* key = src;
+  int* parent = reinterpret_cast<int*>(a.g.aux + (size_t)set * 3 * a.g.pt_cap);  // internal node -> parent
+  int* leaf_parent = parent + a.g.pt_cap;                                         // sorted point -> parent
+  int* arrived = leaf_parent + a.g.pt_cap;                                        // per internal node
+  auto delta = [&](int i, int j) -> int {  // common-prefix length of keys i and j, -1 outside the array
+    if (j < 0 || j >= (int)n) return -1;
+    const uint32_t ci = key[i].x, cj = key[j].x;
+    return ci != cj ? __clz(ci ^ cj) : 32 + __clz((uint32_t)i ^ (uint32_t)j);
+  };
+  if (tid == 0) parent[0] = -1;
+  for (uint32_t t = tid; t + 1 < n; t += nthr) {
+    const int i = (int)t;
+    const int d = delta(i, i + 1) - delta(i, i - 1) >= 0 ? 1 : -1;
+    const int dmin = delta(i, i - d);
+    int lmax = 2;
+    while (delta(i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int st = lmax >> 1; st >= 1; st >>= 1)
+      if (delta(i, i + (l + st) * d) > dmin) l += st;
+    const int j = i + l * d;
+    const int dnode = delta(i, j);
+    int sp = 0;
+    for (int div = 2;; div <<= 1) {
+      const int st = (l + div - 1) / div;
+      if (delta(i, i + (sp + st) * d) > dnode) sp += st;
+      if (st <= 1) break;
+    }
+    const int split = i + sp * d + min(d, 0);
+    const int first = min(i, j), last = max(i, j);
+    uint32_t w = (uint32_t)split;
+    if (first == split) {
+      w |= kLeftLeaf;
+      leaf_parent[split] = i;
+    } else {
+      parent[split] = i;
+    }
+    if (last == split + 1) {
+      w |= kRightLeaf;
+      leaf_parent[split + 1] = i;
+    } else {
+      parent[split + 1] = i;
+    }
+    nodes[i].split = w;
+    arrived[i] = 0;
+  }
+  __syncthreads();
+
+  // ---- boxes, bottom-up: every point climbs; the first thread to reach a node stops, the second merges the children
+  for (uint32_t pidx = tid; pidx < n; pidx += nthr) {
+    int node = leaf_parent[pidx];
+    while (node >= 0) {
+      __threadfence();  // publish this thread's box writes before announcing arrival
+      if (atomicAdd(&arrived[node], 1) == 0) break;
+      const uint32_t w = nodes[node].split;
+      const uint32_t sp = w & kSplitMask;
+      float lo[3], hi[3];
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+        float clo[3], chi[3];
+        if (w & (c == 0 ? kLeftLeaf : kRightLeaf)) {
+          const double4 pt = sorted[sp + c];
+          clo[0] = __double2float_rd(pt.x); chi[0] = __double2float_ru(pt.x);
+          clo[1] = __double2float_rd(pt.y); chi[1] = __double2float_ru(pt.y);
+          clo[2] = __double2float_rd(pt.z); chi[2] = __double2float_ru(pt.z);
+        } else {
+          const float4* f = reinterpret_cast<const float4*>(nodes + sp + c);
+          const float4 va = __ldcg(f), vb = __ldcg(f + 1);
+          clo[0] = va.x; clo[1] = va.y; clo[2] = va.z;
+          chi[0] = vb.x; chi[1] = vb.y; chi[2] = vb.z;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          lo[k] = c == 0 ? clo[k] : fminf(lo[k], clo[k]);
+          hi[k] = c == 0 ? chi[k] : fmaxf(hi[k], chi[k]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        nodes[node].lo[k] = lo[k];
+        nodes[node].hi[k] = hi[k];
+      }
+      node = parent[node];
+    }
+  }
+}
+
+// ============================================================================ exact k-NN (K4)
+
+// K best (d2, id) pairs, sorted ascending, in registers.  insert() is a branch-free shifting network:
+// every lane of a warp executes the same instructions whatever its data.
+template <int K>
+struct TopK {
+  double d[K];
+  uint32_t id[K];
+
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int i = 0; i < K; i++) {
+      d[i] = CUDART_INF;
+      id[i] = 0xFFFFFFFFu;
+    }
+  }
+  static __device__ __forceinline__ bool lt(double da, uint32_t ia, double db, uint32_t ib) {
+    return da < db || (da == db && ia < ib);
+  }
+  __device__ __forceinline__ void insert(double dn, uint32_t in) {
+    bool c[K];
+#pragma unroll
+    for (int i = 0; i < K; i++) c[i] = lt(dn, in, d[i], id[i]);
+#pragma unroll
+    for (int i = K - 1; i > 0; --i) {
+      // c[i-1] implies c[i] (the array is sorted)
+      d[i] = c[i] ? (c[i - 1] ? d[i - 1] : dn) : d[i];
+      id[i] = c[i] ? (c[i - 1] ? id[i - 1] : in) : id[i];
+    }
+    d[0] = c[0] ? dn : d[0];
+    id[0] = c[0] ? in : id[0];
+  }
+  // k-th best distance (k <= K, runtime)
+  __device__ __forceinline__ double kth(int k) const {
+    double v = d[K - 1];
+#pragma unroll
+    for (int i = 0; i < K - 1; i++)
+      if (i == k - 1) v = d[i];
+    return v;
+  }
+};
+
+struct QueryF {  // the query rounded down / up to float, for conservative box tests
+  float lo[3], hi[3];
+};
+
+// Lower bound (never above the true value) of the squared distance from the query to any point inside the box.
+__device__ __forceinline__ float box_lower_bound(const BvhNode& b, const QueryF& q) {
+  float s = 0.f;
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    const float below = __fsub_rd(b.lo[d], q.hi[d]);  // > 0 when the query is below the box
+    const float above = __fsub_rd(q.lo[d], b.hi[d]);  // > 0 when the query is above the box
+    const float g = fmaxf(fmaxf(below, above), 0.f);
+    s = __fadd_rd(s, __fmul_rd(g, g));
+  }
+  return s;  // empty boxes (lo = +inf, hi = -inf) give +inf
+}
+
+__device__ __forceinline__ BvhNode load_node(const BvhNode* __restrict__ p) {
+  const float4* f = reinterpret_cast<const float4*>(p);
+  const float4 a = __ldg(f), b = __ldg(f + 1);
+  BvhNode n;
+  n.lo[0] = a.x; n.lo[1] = a.y; n.lo[2] = a.z; n.split = __float_as_uint(a.w);
+  n.hi[0] = b.x; n.hi[1] = b.y; n.hi[2] = b.z; n.pad = 0;
+  return n;
+}
+
+// Exact k nearest neighbours of (qx,qy,qz) among the points of one set, restricted to candidates that can pass the
+// strict radius filter of kdtree.cpp:24-26 (d2 <= d2_cut is a superset of sqrt(d2) < max_dist; radius_count() applies
+// the exact test afterwards).  A subtree is skipped only when its box lower bound is STRICTLY above the current k-th
+// best (or the radius cut), so candidates that tie the k-th distance are still seen and resolved by index.
+constexpr int kBvhStack = 64;  // >= tree depth: 30 Morton bits + 32 position bits for duplicate codes
+
+template <int K>
+__device__ __forceinline__ void knn_bvh(const BvhHdr& h, const BvhNode* __restrict__ nodes,
+                                        const double4* __restrict__ sorted, double qx, double qy, double qz, int k,
+                                        double max_dist, TopK<K>& tk) {
+  tk.init();
+  if (h.n == 0) return;
+  const double d2_cut = max_dist > 0 ? max_dist * max_dist * (1.0 + 1e-12) : CUDART_INF;
+  QueryF q;
+  q.lo[0] = __double2float_rd(qx); q.hi[0] = __double2float_ru(qx);
+  q.lo[1] = __double2float_rd(qy); q.hi[1] = __double2float_ru(qy);
+  q.lo[2] = __double2float_rd(qz); q.hi[2] = __double2float_ru(qz);
+  float bound = __double2float_ru(d2_cut);  // a subtree is pruned when its lower bound > bound
+
+  // pending subtrees: (node index, key range, lower bound); a subtree of <= kBvhLeaf points is scanned as a leaf
+  uint32_t st_node[kBvhStack], st_first[kBvhStack], st_last[kBvhStack];
+  float st_lb[kBvhStack];
+  int sp = 0;
+  uint32_t node = 0, first = 0, last = h.n - 1;
+  bool have = true, done = false;
+  if (h.n > (uint32_t)kBvhLeaf && box_lower_bound(load_node(nodes), q) > bound) return;
+
+  // All lanes advance their own traversal one node per step until each stands on a leaf it must scan (or is done);
+  // then the warp scans the leaves together — the scan is ~10x the cost of a step, so it must run converged.
+  while (true) {
+    bool at_leaf = false;
+    while (!done && !at_leaf) {
+      if (!have) {
+        if (sp == 0) {
+          done = true;
+        } else {
+          --sp;
+          if (st_lb[sp] <= bound) {
+            node = st_node[sp];
+            first = st_first[sp];
+            last = st_last[sp];
+            have = true;
+          }
+        }
+      } else if (last - first < (uint32_t)kBvhLeaf) {
+        at_leaf = true;
+      } else {
+        const uint32_t w = __ldg(&nodes[node].split);
+        const uint32_t s = w & kSplitMask;
+        // a single-point child has no box of its own: bound 0 (it is scanned as a one-point leaf)
+        const float dl = (w & kLeftLeaf) ? 0.f : box_lower_bound(load_node(nodes + s), q);
+        const float dr = (w & kRightLeaf) ? 0.f : box_lower_bound(load_node(nodes + s + 1), q);
+        const bool right_first = dr < dl;
+        const float dn = right_first ? dr : dl, df = right_first ? dl : dr;
+        const uint32_t l_first = first, l_last = s, r_first = s + 1, r_last = last;
+        if (df <= bound) {  // far child stays pending
+          st_node[sp] = right_first ? s : s + 1;
+          st_first[sp] = right_first ? l_first : r_first;
+          st_last[sp] = right_first ? l_last : r_last;
+          st_lb[sp] = df;
+          sp++;
+        }
+        if (dn <= bound) {
+          node = right_first ? s + 1 : s;
+          first = right_first ? r_first : l_first;
+          last = right_first ? r_last : l_last;
+        } else {
+          have = false;
+        }
+      }
+    }
+    if (!at_leaf) break;  // done
+    // ---- leaf: fp64 distances in nanoflann's L2_Simple order, branch-free insertion
+#pragma unroll
+    for (int j = 0; j < kBvhLeaf; j++) {
+      const uint32_t p = first + j;
+      const double4 t = sorted[min(p, last)];
+      double d2 = sqdist(qx, qy, qz, t.x, t.y, t.z);
+      uint32_t id = (uint32_t)__double_as_longlong(t.w);
+      const bool ok = p <= last && d2 <= d2_cut;
+      d2 = ok ? d2 : CUDART_INF;
+      id = ok ? id : 0xFFFFFFFFu;
+      tk.insert(d2, id);
+    }
+    bound = __double2float_ru(fmin(tk.kth(k), d2_cut));
+    have = false;
+  }
+}
+
+// kdtree.cpp:24-26 : keep neighbours with max_dist <= 0 || sqrt(d2) < max_dist (strict). Sorted => prefix.
+template <int K>
+__device__ __forceinline__ int radius_count(const TopK<K>& tk, int k, double max_dist) {
+  int m = 0;
+#pragma unroll
+  for (int i = 0; i < K; i++) {
+    if (i < k && tk.id[i] != 0xFFFFFFFFu && (max_dist <= 0 || sqrt(tk.d[i]) < max_dist)) m++;
+  }
+  return m;
+}
+
+template <int K>
+__global__ void __launch_bounds__(128) knn_kernel(KnnArgs a) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n_queries) return;
+  const BvhHdr h = a.g.hdr[0];
+  TopK<K> tk;
+  knn_bvh<K>(h, a.g.nodes, a.g.sorted, a.queries[3 * i], a.queries[3 * i + 1], a.queries[3 * i + 2], a.k, a.max_dist,
+             tk);
+  const int m = radius_count(tk, a.k, a.max_dist);
+  a.count_out[i] = (uint32_t)m;
+#pragma unroll
+  for (int j = 0; j < K; j++)
+    if (j < a.k) a.idx_out[i * a.k + j] = j < m ? tk.id[j] : 0xFFFFFFFFu;
+}
+
+}  // namespace
+}  // namespace loamgpu

@@ -54,7 +54,7 @@ struct loamgpu_ctx {
   DevBuf scan_in[2];                       // H2D staging of scans
   DevBuf ring_edge, ring_planar, ring_counts;
   DevBuf edge_idx, planar_idx, edge_pts, planar_pts, feat_counts;
-  DevBuf ge_hdr, ge_cells, ge_sorted, ge_rank, gp_hdr, gp_cells, gp_sorted, gp_rank;
+  DevBuf ge_hdr, ge_nodes, ge_sorted, ge_keys, ge_aux, gp_hdr, gp_nodes, gp_sorted, gp_keys, gp_aux;
   DevBuf state, rec_p, rec_a, rec_b, nearest;
   DevBuf misc, out_pose, out_term, out_iters, out_ne, out_np;
   DevBuf det_est, det_upd, det_assoc_n, det_lm_iters, det_lm_cost, init_pose;
@@ -265,18 +265,17 @@ int make_regp(loamgpu_ctx* ctx, const loamgpu_reg_params* rp, RegP* out) {
   return LOAMGPU_OK;
 }
 
-uint32_t cell_cap_for(uint32_t pt_cap) { return std::max<uint32_t>(4096u, 8u * pt_cap); }
-
 int reserve_register(loamgpu_ctx* ctx, uint32_t n_pairs, uint32_t capE, uint32_t capP, uint32_t detail_iters) {
-  const uint32_t ccE = cell_cap_for(capE), ccP = cell_cap_for(capP);
-  CU(ctx->ge_hdr.reserve((size_t)n_pairs * sizeof(GridHdr)));
-  CU(ctx->gp_hdr.reserve((size_t)n_pairs * sizeof(GridHdr)));
-  CU(ctx->ge_cells.reserve((size_t)n_pairs * (ccE + 1) * 4));
-  CU(ctx->gp_cells.reserve((size_t)n_pairs * (ccP + 1) * 4));
+  CU(ctx->ge_hdr.reserve((size_t)n_pairs * sizeof(BvhHdr)));
+  CU(ctx->gp_hdr.reserve((size_t)n_pairs * sizeof(BvhHdr)));
+  CU(ctx->ge_nodes.reserve((size_t)n_pairs * capE * sizeof(BvhNode)));
+  CU(ctx->gp_nodes.reserve((size_t)n_pairs * capP * sizeof(BvhNode)));
+  CU(ctx->ge_aux.reserve((size_t)n_pairs * capE * 12));
+  CU(ctx->gp_aux.reserve((size_t)n_pairs * capP * 12));
   CU(ctx->ge_sorted.reserve((size_t)n_pairs * capE * 32));
   CU(ctx->gp_sorted.reserve((size_t)n_pairs * capP * 32));
-  CU(ctx->ge_rank.reserve((size_t)n_pairs * capE * 4));
-  CU(ctx->gp_rank.reserve((size_t)n_pairs * capP * 4));
+  CU(ctx->ge_keys.reserve((size_t)n_pairs * capE * 16));
+  CU(ctx->gp_keys.reserve((size_t)n_pairs * capP * 16));
   CU(ctx->state.reserve((size_t)n_pairs * sizeof(PairState)));
   CU(ctx->rec_p.reserve((size_t)n_pairs * (capE + capP) * 32));
   CU(ctx->rec_a.reserve((size_t)n_pairs * (capE + capP) * 32));
@@ -285,13 +284,13 @@ int reserve_register(loamgpu_ctx* ctx, uint32_t n_pairs, uint32_t capE, uint32_t
   return LOAMGPU_OK;
 }
 
-GridSetArrays grid_arrays(loamgpu_ctx* ctx, bool planar, uint32_t cap) {
-  GridSetArrays g;
-  g.hdr = (planar ? ctx->gp_hdr : ctx->ge_hdr).as<GridHdr>();
-  g.cell_start = (planar ? ctx->gp_cells : ctx->ge_cells).as<uint32_t>();
+BvhSetArrays bvh_arrays(loamgpu_ctx* ctx, bool planar, uint32_t cap) {
+  BvhSetArrays g;
+  g.hdr = (planar ? ctx->gp_hdr : ctx->ge_hdr).as<BvhHdr>();
+  g.nodes = (planar ? ctx->gp_nodes : ctx->ge_nodes).as<BvhNode>();
   g.sorted = (planar ? ctx->gp_sorted : ctx->ge_sorted).as<double4>();
-  g.rank = (planar ? ctx->gp_rank : ctx->ge_rank).as<uint32_t>();
-  g.cell_cap = cell_cap_for(cap);
+  g.keys = (planar ? ctx->gp_keys : ctx->ge_keys).as<uint2>();
+  g.aux = (planar ? ctx->gp_aux : ctx->ge_aux).as<int>();
   g.pt_cap = cap;
   return g;
 }
@@ -299,7 +298,7 @@ GridSetArrays grid_arrays(loamgpu_ctx* ctx, bool planar, uint32_t cap) {
 // Register n_pairs pairs whose features sit in slots: tgt = (pair0+p) % n_slots, src = (pair0+p+src_offset) % n_slots.
 int run_register(loamgpu_ctx* ctx, const RegP& rp, uint32_t n_pairs, uint64_t pair0, uint32_t n_slots, int src_offset,
                  uint32_t capE, uint32_t capP, const double* init_pose_dev, bool detail) {
-  GridBuildArgs gb;
+  BvhBuildArgs gb;
   memset(&gb, 0, sizeof gb);
   gb.counts = ctx->feat_counts.as<uint32_t>();
   gb.slot0 = pair0;
@@ -307,15 +306,13 @@ int run_register(loamgpu_ctx* ctx, const RegP& rp, uint32_t n_pairs, uint64_t pa
   gb.pts = ctx->edge_pts.as<double4>();
   gb.pt_stride = capE;
   gb.kind = 0;
-  gb.k_nominal = rp.ke;
-  gb.g = grid_arrays(ctx, false, capE);
-  TIMED(LOAMGPU_K_GRID, launch_grid_build(gb, n_pairs, ctx->stream));
+  gb.g = bvh_arrays(ctx, false, capE);
+  TIMED(LOAMGPU_K_GRID, launch_bvh_build(gb, n_pairs, ctx->stream));
   gb.pts = ctx->planar_pts.as<double4>();
   gb.pt_stride = capP;
   gb.kind = 1;
-  gb.k_nominal = rp.kp;
-  gb.g = grid_arrays(ctx, true, capP);
-  TIMED(LOAMGPU_K_GRID, launch_grid_build(gb, n_pairs, ctx->stream));
+  gb.g = bvh_arrays(ctx, true, capP);
+  TIMED(LOAMGPU_K_GRID, launch_bvh_build(gb, n_pairs, ctx->stream));
   TIMED(LOAMGPU_K_MISC, launch_init_pairs(ctx->state.as<PairState>(), n_pairs, init_pose_dev, ctx->stream));
 
   AssocArgs aa;
@@ -328,8 +325,8 @@ int run_register(loamgpu_ctx* ctx, const RegP& rp, uint32_t n_pairs, uint64_t pa
   aa.pair0 = pair0;
   aa.n_slots = n_slots;
   aa.src_offset = src_offset;
-  aa.ge = grid_arrays(ctx, false, capE);
-  aa.gp = grid_arrays(ctx, true, capP);
+  aa.ge = bvh_arrays(ctx, false, capE);
+  aa.gp = bvh_arrays(ctx, true, capP);
   aa.state = ctx->state.as<PairState>();
   aa.rec_p = ctx->rec_p.as<double4>();
   aa.rec_a = ctx->rec_a.as<double4>();
@@ -412,8 +409,8 @@ void loamgpu_destroy(loamgpu_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   DevBuf* bufs[] = {&c->scan_in[0], &c->scan_in[1], &c->ring_edge, &c->ring_planar, &c->ring_counts, &c->edge_idx,
-                    &c->planar_idx, &c->edge_pts, &c->planar_pts, &c->feat_counts, &c->ge_hdr, &c->ge_cells,
-                    &c->ge_sorted, &c->ge_rank, &c->gp_hdr, &c->gp_cells, &c->gp_sorted, &c->gp_rank, &c->state,
+                    &c->planar_idx, &c->edge_pts, &c->planar_pts, &c->feat_counts, &c->ge_hdr, &c->ge_nodes,
+                    &c->ge_sorted, &c->ge_keys, &c->ge_aux, &c->gp_hdr, &c->gp_nodes, &c->gp_sorted, &c->gp_keys, &c->gp_aux, &c->state,
                     &c->rec_p, &c->rec_a, &c->rec_b, &c->nearest, &c->misc, &c->out_pose, &c->out_term,
                     &c->out_iters, &c->out_ne, &c->out_np, &c->det_est, &c->det_upd, &c->det_assoc_n,
                     &c->det_lm_iters, &c->det_lm_cost, &c->init_pose};
@@ -711,7 +708,7 @@ int loamgpu_knn(loamgpu_ctx* ctx, const double* targets, uint64_t n_t, const dou
   const uint32_t counts[2] = {0, (uint32_t)n_t};
   CU(cudaMemcpyAsync(ctx->planar_pts.p, hp.data(), hp.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->feat_counts.p, counts, 8, cudaMemcpyHostToDevice, ctx->stream));
-  GridBuildArgs gb;
+  BvhBuildArgs gb;
   memset(&gb, 0, sizeof gb);
   gb.counts = ctx->feat_counts.as<uint32_t>();
   gb.slot0 = 0;
@@ -719,9 +716,8 @@ int loamgpu_knn(loamgpu_ctx* ctx, const double* targets, uint64_t n_t, const dou
   gb.pts = ctx->planar_pts.as<double4>();
   gb.pt_stride = cap;
   gb.kind = 1;
-  gb.k_nominal = (int)k;
-  gb.g = grid_arrays(ctx, true, cap);
-  TIMED(LOAMGPU_K_GRID, launch_grid_build(gb, 1, ctx->stream));
+  gb.g = bvh_arrays(ctx, true, cap);
+  TIMED(LOAMGPU_K_GRID, launch_bvh_build(gb, 1, ctx->stream));
   double* dq = ctx->misc.as<double>();
   uint32_t* didx = reinterpret_cast<uint32_t*>(dq + 3 * n_q);
   uint32_t* dcnt = didx + (size_t)n_q * k;

@@ -63,13 +63,22 @@ __device__ __forceinline__ void quat_mul(const double* a, const double* b, doubl
   o[3] = w;
 }
 
-// ------------------------------------------------------------------ uniform-grid NN structure
-struct GridHdr {
-  double ox, oy, oz;  // origin (bbox min)
-  double h, inv_h;    // cell size
-  int nx, ny, nz;     // dims
-  uint32_t n;         // points
-  uint32_t ncells;
+// ------------------------------------------------------------------ NN structure: LBVH (binary radix tree)
+// Points are sorted by 30-bit Morton code; a binary radix tree over the sorted (code, position) keys has n - 1
+// internal nodes, root = node 0.  Node i covers a key range [first, last] (derived top-down during traversal) and
+// splits it into [first, split] / [split + 1, last]; its children are nodes `split` and `split + 1` — adjacent
+// records — unless the child range is a single point (flag bits).  Boxes are float32 rounded outward, so box tests
+// run on the fp32 pipe and still give a true lower bound on the fp64 point distances.
+constexpr int kBvhLeaf = 8;  // subtrees of at most this many points are scanned, not descended
+constexpr uint32_t kLeftLeaf = 0x80000000u, kRightLeaf = 0x40000000u, kSplitMask = 0x3FFFFFFFu;
+struct BvhHdr {
+  uint32_t n;  // points
+  uint32_t pad[3];
+};
+struct __align__(32) BvhNode {
+  float lo[3];
+  uint32_t split;  // split position | kLeftLeaf | kRightLeaf
+  float hi[3];
   uint32_t pad;
 };
 

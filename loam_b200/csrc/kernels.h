@@ -10,8 +10,9 @@ namespace loamgpu {
 constexpr int kExtractThreads = 256;
 constexpr int kAssocThreads = 128;
 constexpr int kLmThreads = 512;
-constexpr int kGridThreads = 1024;
-constexpr int kKnnRegMax = 8;    // neighbour counts up to this stay in registers
+constexpr int kBuildThreads = 1024;
+constexpr int kKnnSmall = 5;     // neighbour counts up to this use the 5-slot register top-k
+constexpr int kKnnRegMax = 8;    // ... up to this the 8-slot one
 constexpr int kKnnMax = 32;      // hard limit on num_*_neighbors
 
 struct ExtractArgs {
@@ -56,29 +57,28 @@ size_t extract_smem_bytes(int dtype, uint32_t P, uint32_t S);
 cudaError_t launch_extract(const ExtractArgs& a, uint32_t n_scans, cudaStream_t st);
 cudaError_t launch_pack(const PackArgs& a, uint32_t n_scans, cudaStream_t st);
 
-// One NN structure ("grid set") = header + cell_start + cell-sorted points.
-struct GridSetArrays {
-  GridHdr* hdr;          // [n_sets]
-  uint32_t* cell_start;  // [n_sets][cell_cap + 1]
-  double4* sorted;       // [n_sets][pt_cap]   (x,y,z, bits(original index))
-  uint32_t* rank;        // [n_sets][pt_cap]   build scratch: rank of each point inside its cell
-  uint32_t cell_cap;
+// One NN structure ("set") = header + node records + Morton-sorted points (+ build scratch).
+struct BvhSetArrays {
+  BvhHdr* hdr;        // [n_sets]
+  BvhNode* nodes;     // [n_sets][pt_cap]     internal nodes 0 .. n-2, root = 0
+  double4* sorted;    // [n_sets][pt_cap]     (x,y,z, bits(original index)), Morton order
+  uint2* keys;        // [n_sets][2][pt_cap]  radix-sort ping-pong scratch: (morton, original index)
+  int* aux;           // [n_sets][3][pt_cap]  build scratch: node parent, point parent, arrival counter
   uint32_t pt_cap;
 };
 
 // Build NN structures for `n_sets` point sets.  Set s reads points
 // pts[(slot0 + s) % n_slots][0 .. counts[((slot0+s) % n_slots)*2 + kind]).
-struct GridBuildArgs {
+struct BvhBuildArgs {
   const double4* pts;      // [slot][pt_stride]
   const uint32_t* counts;  // [slot][2]
   uint32_t pt_stride;
   int kind;                // 0 edge, 1 planar
   uint64_t slot0;
   uint32_t n_slots;
-  int k_nominal;           // neighbour count the cell size is tuned for
-  GridSetArrays g;
+  BvhSetArrays g;
 };
-cudaError_t launch_grid_build(const GridBuildArgs& a, uint32_t n_sets, cudaStream_t st);
+cudaError_t launch_bvh_build(const BvhBuildArgs& a, uint32_t n_sets, cudaStream_t st);
 
 struct AssocArgs {
   // source / target feature slots of pair p: src = (pair0 + p + 1) % n_slots, tgt = (pair0 + p) % n_slots
@@ -89,7 +89,7 @@ struct AssocArgs {
   uint64_t pair0;
   uint32_t n_slots;
   int src_offset;          // 1 for sequence odometry; explicit-pair calls use slots 1 (src) / 0 (tgt)
-  GridSetArrays ge, gp;    // target grids, set index = pair
+  BvhSetArrays ge, gp;     // target NN structures, set index = pair
   PairState* state;        // [pair]
   double4* rec_p;          // [pair][capE+capP]  transformed point, w = 0 invalid / 1 edge / 2 plane
   double4* rec_a;          // [pair][capE+capP]  edge: line point a ; plane: normal, w = d
@@ -123,7 +123,7 @@ cudaError_t launch_lm(const LmArgs& a, uint32_t n_pairs, cudaStream_t st);
 struct KnnArgs {
   const double* queries;  // [n][3]
   uint64_t n_queries;
-  GridSetArrays g;        // set 0
+  BvhSetArrays g;         // set 0
   int k;
   double max_dist;
   uint32_t* idx_out;      // [n][k]

@@ -1,10 +1,9 @@
 // Registration kernels (replaces loam/registration-inl.h, src/registration.cpp, src/kdtree.cpp,
 // src/geometry.cpp:42-73 of the reference, plus the Ceres 2.2.0 trust-region solve it delegates to).
 //
-//   K3  grid_build_kernel   uniform-grid NN structure over one target feature set (replaces the
-//                           nanoflann KD-tree build, registration-inl.h:20-23); cell size tuned from a
-//                           measured surface density so a 3x3x3 block holds a few dozen candidates
-//   K4  knn_grid()          exact k-NN with shell expansion + strict radius filter (kdtree.cpp:10-28)
+//   K3  bvh_build_kernel    implicit LBVH over one target feature set (bvh.cuh; replaces the nanoflann
+//                           KD-tree build, registration-inl.h:20-23)
+//   K4  knn_bvh()           exact k-NN + strict radius filter (bvh.cuh; kdtree.cpp:10-28)
 //   K5  fit_line/fit_plane  per-query PCA line / column-pivoted-QR plane (geometry.cpp:42-73)
 //   K45 assoc_kernel        transform + K4 + K5 + guards for every source feature of every active pair
 //                           (associateEdges/associatePlanes, registration.cpp:23-103)
@@ -15,349 +14,13 @@
 //
 // Tie-break (documented, deterministic): equal squared distances resolve by ascending target index
 // (nanoflann resolves them by tree-traversal order, i.e. unpinned in the reference).
+#include "bvh.cuh"
 #include "common.cuh"
 #include "kernels.h"
 
 namespace loamgpu {
 
 namespace {
-
-// ============================================================================ grid build (K3)
-
-__device__ __forceinline__ int cell_coord(double v, double o, double inv_h, int n) {
-  int c = (int)floor(dmul(dsub(v, o), inv_h));
-  c = c < 0 ? 0 : c;
-  return c >= n ? n - 1 : c;
-}
-
-__device__ double block_reduce_minmax(double v, bool is_max, double* s_red) {
-  for (int o = 16; o > 0; o >>= 1) {
-    const double t = __shfl_xor_sync(0xffffffffu, v, o);
-    v = is_max ? fmax(v, t) : fmin(v, t);
-  }
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  double r = s_red[0];
-  for (int w = 1; w < (int)(blockDim.x >> 5); w++) r = is_max ? fmax(r, s_red[w]) : fmin(r, s_red[w]);
-  return r;
-}
-
-__device__ uint32_t block_reduce_sum_u32(uint32_t v, uint32_t* s_red) {
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  uint32_t r = 0;
-  for (int w = 0; w < (int)(blockDim.x >> 5); w++) r += s_red[w];
-  return r;
-}
-
-constexpr int kTrialCells = 32768;
-
-__global__ void __launch_bounds__(kGridThreads) grid_build_kernel(GridBuildArgs a) {
-  __shared__ double s_red[32];
-  __shared__ uint32_t s_redu[32];
-  __shared__ uint32_t s_bitmap[kTrialCells / 32];
-  __shared__ uint32_t s_scan[kGridThreads / 32];
-
-  const uint32_t set = blockIdx.x;
-  const uint32_t slot = (uint32_t)((a.slot0 + set) % a.n_slots);
-  const uint32_t n = a.counts[slot * 2 + a.kind];
-  const double4* pts = a.pts + (size_t)slot * a.pt_stride;
-  GridHdr* hdr = a.g.hdr + set;
-  uint32_t* cs = a.g.cell_start + (size_t)set * (a.g.cell_cap + 1);
-  double4* sorted = a.g.sorted + (size_t)set * a.g.pt_cap;
-  const uint32_t tid = threadIdx.x, nthr = blockDim.x;
-
-  if (n == 0) {
-    if (tid == 0) {
-      GridHdr h;
-      h.ox = h.oy = h.oz = 0;
-      h.h = 1;
-      h.inv_h = 1;
-      h.nx = h.ny = h.nz = 0;
-      h.n = 0;
-      h.ncells = 0;
-      h.pad = 0;
-      *hdr = h;
-    }
-    return;
-  }
-
-  // ---- bounding box
-  double lo[3] = {CUDART_INF, CUDART_INF, CUDART_INF}, hi[3] = {-CUDART_INF, -CUDART_INF, -CUDART_INF};
-  for (uint32_t i = tid; i < n; i += nthr) {
-    const double4 p = pts[i];
-    lo[0] = fmin(lo[0], p.x);
-    lo[1] = fmin(lo[1], p.y);
-    lo[2] = fmin(lo[2], p.z);
-    hi[0] = fmax(hi[0], p.x);
-    hi[1] = fmax(hi[1], p.y);
-    hi[2] = fmax(hi[2], p.z);
-  }
-  for (int d = 0; d < 3; d++) {
-    lo[d] = block_reduce_minmax(lo[d], false, s_red);
-    hi[d] = block_reduce_minmax(hi[d], true, s_red);
-  }
-  double ext[3];
-  double emax = 0;
-  for (int d = 0; d < 3; d++) {
-    ext[d] = hi[d] - lo[d];
-    emax = fmax(emax, ext[d]);
-  }
-  const double emin = fmax(emax * 1e-3, 1e-6);
-  double extc[3];
-  for (int d = 0; d < 3; d++) extc[d] = fmax(ext[d], emin);
-
-  // ---- trial occupancy at a coarse resolution -> surface density -> cell size
-  double ht = cbrt(extc[0] * extc[1] * extc[2] / (double)kTrialCells);
-  int tx, ty, tz;
-  for (;;) {
-    tx = (int)floor(ext[0] / ht) + 1;
-    ty = (int)floor(ext[1] / ht) + 1;
-    tz = (int)floor(ext[2] / ht) + 1;
-    if ((double)tx * (double)ty * (double)tz <= (double)kTrialCells) break;
-    ht *= 1.25;
-  }
-  for (uint32_t i = tid; i < kTrialCells / 32; i += nthr) s_bitmap[i] = 0;
-  __syncthreads();
-  {
-    const double inv = 1.0 / ht;
-    for (uint32_t i = tid; i < n; i += nthr) {
-      const double4 p = pts[i];
-      const int cx = cell_coord(p.x, lo[0], inv, tx), cy = cell_coord(p.y, lo[1], inv, ty),
-                cz = cell_coord(p.z, lo[2], inv, tz);
-      const uint32_t c = ((uint32_t)cz * ty + cy) * tx + cx;
-      atomicOr(&s_bitmap[c >> 5], 1u << (c & 31));
-    }
-  }
-  __syncthreads();
-  uint32_t occ = 0;
-  for (uint32_t i = tid; i < kTrialCells / 32; i += nthr) occ += __popc(s_bitmap[i]);
-  occ = block_reduce_sum_u32(occ, s_redu);
-  // points on 2-D surfaces: area ~ occupied cells * ht^2 ; expected k-NN radius sqrt(k / (pi rho))
-  const double rho = (double)n / ((double)occ * ht * ht);
-  double h = 1.5 * sqrt((double)(a.k_nominal > 0 ? a.k_nominal : 1) / (3.141592653589793 * rho));
-  h = fmax(h, emax * 1e-6 + 1e-9);
-  int nx, ny, nz;
-  for (;;) {
-    nx = (int)floor(ext[0] / h) + 1;
-    ny = (int)floor(ext[1] / h) + 1;
-    nz = (int)floor(ext[2] / h) + 1;
-    if ((double)nx * (double)ny * (double)nz <= (double)a.g.cell_cap) break;
-    h *= 1.1;
-  }
-  const double inv_h = 1.0 / h;
-  const uint32_t ncells = (uint32_t)nx * (uint32_t)ny * (uint32_t)nz;
-  if (tid == 0) {
-    GridHdr g;
-    g.ox = lo[0];
-    g.oy = lo[1];
-    g.oz = lo[2];
-    g.h = h;
-    g.inv_h = inv_h;
-    g.nx = nx;
-    g.ny = ny;
-    g.nz = nz;
-    g.n = n;
-    g.ncells = ncells;
-    g.pad = 0;
-    *hdr = g;
-  }
-
-  // ---- counting sort by cell
-  for (uint32_t c = tid; c <= ncells; c += nthr) cs[c] = 0;
-  __syncthreads();
-  uint32_t* rank = a.g.rank + (size_t)set * a.g.pt_cap;
-  for (uint32_t i = tid; i < n; i += nthr) {
-    const double4 p = pts[i];
-    const uint32_t c = ((uint32_t)cell_coord(p.z, lo[2], inv_h, nz) * ny + cell_coord(p.y, lo[1], inv_h, ny)) * nx +
-                       cell_coord(p.x, lo[0], inv_h, nx);
-    rank[i] = atomicAdd(&cs[c], 1u);
-  }
-  __syncthreads();
-  // exclusive scan of cs[0..ncells] (thread-contiguous chunks + block scan of the chunk sums)
-  {
-    const uint32_t total = ncells + 1;
-    const uint32_t chunk = (total + nthr - 1) / nthr;
-    const uint32_t b = tid * chunk, e = min(b + chunk, total);
-    uint32_t sum = 0;
-    for (uint32_t c = b; c < e; c++) sum += cs[c];
-    // inclusive warp scan
-    uint32_t inc = sum;
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-      if ((int)(tid & 31) >= o) inc += t;
-    }
-    if ((tid & 31) == 31) s_scan[tid >> 5] = inc;
-    __syncthreads();
-    uint32_t woff = 0;
-    for (uint32_t w = 0; w < (tid >> 5); w++) woff += s_scan[w];
-    uint32_t run = woff + inc - sum;
-    for (uint32_t c = b; c < e; c++) {
-      const uint32_t v = cs[c];
-      cs[c] = run;
-      run += v;
-    }
-  }
-  __syncthreads();
-  for (uint32_t i = tid; i < n; i += nthr) {
-    const double4 p = pts[i];
-    const uint32_t c = ((uint32_t)cell_coord(p.z, lo[2], inv_h, nz) * ny + cell_coord(p.y, lo[1], inv_h, ny)) * nx +
-                       cell_coord(p.x, lo[0], inv_h, nx);
-    sorted[cs[c] + rank[i]] = make_double4(p.x, p.y, p.z, __longlong_as_double((long long)i));
-  }
-}
-
-// ============================================================================ exact k-NN (K4)
-
-template <int KMAX>
-struct TopK {
-  double d[KMAX];
-  uint32_t id[KMAX];
-  double worst_d;
-  uint32_t worst_id;
-  int k;
-
-  __device__ __forceinline__ void init(int k_) {
-    k = k_;
-#pragma unroll
-    for (int i = 0; i < KMAX; i++) {
-      d[i] = CUDART_INF;
-      id[i] = 0xFFFFFFFFu;
-    }
-    worst_d = CUDART_INF;
-    worst_id = 0xFFFFFFFFu;
-  }
-  static __device__ __forceinline__ bool lt(double da, uint32_t ia, double db, uint32_t ib) {
-    return da < db || (da == db && ia < ib);
-  }
-  // sorted insertion by (d, id); caller guarantees lt(new, worst)
-  __device__ __forceinline__ void insert(double dn, uint32_t in) {
-#pragma unroll
-    for (int i = KMAX - 1; i > 0; --i) {
-      if (i < k) {
-        if (lt(dn, in, d[i - 1], id[i - 1])) {
-          d[i] = d[i - 1];
-          id[i] = id[i - 1];
-        } else if (lt(dn, in, d[i], id[i])) {
-          d[i] = dn;
-          id[i] = in;
-        }
-      }
-    }
-    if (lt(dn, in, d[0], id[0])) {
-      d[0] = dn;
-      id[0] = in;
-    }
-#pragma unroll
-    for (int i = 0; i < KMAX; i++)
-      if (i == k - 1) {
-        worst_d = d[i];
-        worst_id = id[i];
-      }
-  }
-};
-
-// Exact k nearest neighbours of (qx,qy,qz) among the points of one grid set, restricted to points that can
-// pass the radius filter.  Shell expansion: after all cells with Chebyshev cell distance <= r are visited,
-// every unvisited point is farther than (r + mf) * h, mf = the query's smallest distance (in cells) to a
-// face of its own cell; stop once the k-th best is closer than that, or that bound passes the radius.
-template <int KMAX>
-__device__ __forceinline__ void knn_grid(const GridHdr& g, const uint32_t* __restrict__ cs,
-                                         const double4* __restrict__ sorted, double qx, double qy, double qz, int k,
-                                         double max_dist, TopK<KMAX>& tk) {
-  tk.init(k);
-  if (g.n == 0) return;
-  const double SAFE = 1.0 - 1e-9;
-  // squared-distance bound above which a candidate certainly fails sqrt(d2) < max_dist
-  const double d2_cut = max_dist > 0 ? max_dist * max_dist * (1.0 + 1e-12) : CUDART_INF;
-  double fc[3] = {dmul(dsub(qx, g.ox), g.inv_h), dmul(dsub(qy, g.oy), g.inv_h), dmul(dsub(qz, g.oz), g.inv_h)};
-  int ic[3];
-  double mf = 1.0;
-  const int dims[3] = {g.nx, g.ny, g.nz};
-  int r_lo = 0, r_cover = 0;
-#pragma unroll
-  for (int a = 0; a < 3; a++) {
-    double f = fmin(fmax(fc[a], -1.0e9), 1.0e9);
-    const double fl = floor(f);
-    ic[a] = (int)fl;
-    const double fr = f - fl;
-    mf = fmin(mf, fmin(fr, 1.0 - fr));
-    const int below = -ic[a], above = ic[a] - (dims[a] - 1);
-    r_lo = max(r_lo, max(below, above));
-    r_cover = max(r_cover, max(ic[a], dims[a] - 1 - ic[a]));
-  }
-  r_lo = max(r_lo, 0);
-
-  auto scan_cells = [&](uint32_t b, uint32_t e) {
-    for (uint32_t p = b; p < e; p++) {
-      const double4 t = sorted[p];
-      const double d2 = sqdist(qx, qy, qz, t.x, t.y, t.z);
-      if (d2 <= d2_cut) {
-        const uint32_t id = (uint32_t)__double_as_longlong(t.w);
-        if (TopK<KMAX>::lt(d2, id, tk.worst_d, tk.worst_id)) tk.insert(d2, id);
-      }
-    }
-  };
-  // visit cells with Chebyshev distance exactly r (or <= r when full == true)
-  auto visit = [&](int r, bool full) {
-    const int z0 = max(ic[2] - r, 0), z1 = min(ic[2] + r, g.nz - 1);
-    const int y0 = max(ic[1] - r, 0), y1 = min(ic[1] + r, g.ny - 1);
-    const int x0 = max(ic[0] - r, 0), x1 = min(ic[0] + r, g.nx - 1);
-    if (x0 > x1) return;
-    for (int z = z0; z <= z1; z++) {
-      const bool zface = (z == ic[2] - r) || (z == ic[2] + r);
-      for (int y = y0; y <= y1; y++) {
-        const uint32_t row = ((uint32_t)z * g.ny + y) * g.nx;
-        if (full || zface || y == ic[1] - r || y == ic[1] + r) {
-          scan_cells(cs[row + x0], cs[row + x1 + 1]);
-        } else {
-          if (ic[0] - r >= 0 && ic[0] - r < g.nx) scan_cells(cs[row + ic[0] - r], cs[row + ic[0] - r + 1]);
-          if (ic[0] + r >= 0 && ic[0] + r < g.nx) scan_cells(cs[row + ic[0] + r], cs[row + ic[0] + r + 1]);
-        }
-      }
-    }
-  };
-
-  int r = max(1, r_lo);
-  visit(r, true);
-  for (;;) {
-    const double guard = ((double)r + mf) * g.h * SAFE;
-    if (tk.worst_d < guard * guard) break;           // k found, all closer than any unvisited point
-    if (max_dist > 0 && guard >= max_dist) break;    // everything inside the radius has been visited
-    if (r >= r_cover) break;                         // whole grid visited
-    r++;
-    visit(r, false);
-  }
-}
-
-// kdtree.cpp:24-26 : keep neighbours with max_dist <= 0 || sqrt(d2) < max_dist (strict). Sorted => prefix.
-template <int KMAX>
-__device__ __forceinline__ int radius_count(const TopK<KMAX>& tk, double max_dist) {
-  int m = 0;
-#pragma unroll
-  for (int i = 0; i < KMAX; i++) {
-    if (i < tk.k && tk.id[i] != 0xFFFFFFFFu && (max_dist <= 0 || sqrt(tk.d[i]) < max_dist)) m++;
-  }
-  return m;
-}
-
-template <int KMAX>
-__global__ void __launch_bounds__(128) knn_kernel(KnnArgs a) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.n_queries) return;
-  const GridHdr g = a.g.hdr[0];
-  TopK<KMAX> tk;
-  knn_grid<KMAX>(g, a.g.cell_start, a.g.sorted, a.queries[3 * i], a.queries[3 * i + 1], a.queries[3 * i + 2], a.k,
-                 a.max_dist, tk);
-  const int m = radius_count(tk, a.max_dist);
-  a.count_out[i] = (uint32_t)m;
-#pragma unroll
-  for (int j = 0; j < KMAX; j++)
-    if (j < a.k) a.idx_out[i * a.k + j] = j < m ? tk.id[j] : 0xFFFFFFFFu;
-}
 
 // ============================================================================ fits (K5)
 
@@ -548,14 +211,14 @@ __global__ void __launch_bounds__(kAssocThreads) assoc_kernel(AssocArgs a, int o
     const double4 sp = is_plane ? a.planar_pts[(size_t)src_slot * a.capP_scan + li]
                                 : a.edge_pts[(size_t)src_slot * a.capE_scan + li];
     const V3 q = pose_act(est, V3{sp.x, sp.y, sp.z});  // registration.cpp:34,75
-    const GridSetArrays& gs = is_plane ? a.gp : a.ge;
-    const GridHdr g = gs.hdr[pair];
+    const BvhSetArrays& gs = is_plane ? a.gp : a.ge;
+    const BvhHdr g = gs.hdr[pair];
     const int k = is_plane ? a.rp.kp : a.rp.ke;
     const double md = is_plane ? a.rp.rp : a.rp.re;
     TopK<KMAX> tk;
-    knn_grid<KMAX>(g, gs.cell_start + (size_t)pair * (gs.cell_cap + 1), gs.sorted + (size_t)pair * gs.pt_cap, q.x,
-                   q.y, q.z, k, md, tk);
-    const int m = radius_count(tk, md);
+    knn_bvh<KMAX>(g, gs.nodes + (size_t)pair * gs.pt_cap, gs.sorted + (size_t)pair * gs.pt_cap, q.x, q.y, q.z, k,
+                  md, tk);
+    const int m = radius_count(tk, k, md);
     const int need = is_plane ? a.rp.min_plane : a.rp.min_line;
     double4 rp4 = make_double4(q.x, q.y, q.z, 0.0);
     if (m >= need && m > 0) {
@@ -1042,9 +705,12 @@ __global__ void finish_pairs_kernel(const PairState* st, uint32_t n, double* pos
 
 // ============================================================================ host launchers
 
-cudaError_t launch_grid_build(const GridBuildArgs& a, uint32_t n_sets, cudaStream_t st) {
+cudaError_t launch_bvh_build(const BvhBuildArgs& a, uint32_t n_sets, cudaStream_t st) {
   if (n_sets == 0) return cudaSuccess;
-  grid_build_kernel<<<n_sets, kGridThreads, 0, st>>>(a);
+  const size_t smem = (size_t)kRadixBins * kBuildThreads * sizeof(uint32_t);
+  cudaError_t err = cudaFuncSetAttribute(bvh_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  bvh_build_kernel<<<n_sets, kBuildThreads, smem, st>>>(a);
   return cudaGetLastError();
 }
 
@@ -1053,7 +719,9 @@ cudaError_t launch_assoc(const AssocArgs& a, uint32_t n_pairs, int outer_iter, c
   const uint32_t cap = a.capE_scan + a.capP_scan;
   dim3 grid((cap + kAssocThreads - 1) / kAssocThreads, n_pairs);
   const int kmax = a.rp.ke > a.rp.kp ? a.rp.ke : a.rp.kp;
-  if (kmax <= kKnnRegMax)
+  if (kmax <= kKnnSmall)
+    assoc_kernel<kKnnSmall><<<grid, kAssocThreads, 0, st>>>(a, outer_iter);
+  else if (kmax <= kKnnRegMax)
     assoc_kernel<kKnnRegMax><<<grid, kAssocThreads, 0, st>>>(a, outer_iter);
   else
     assoc_kernel<kKnnMax><<<grid, kAssocThreads, 0, st>>>(a, outer_iter);
@@ -1069,7 +737,9 @@ cudaError_t launch_lm(const LmArgs& a, uint32_t n_pairs, cudaStream_t st) {
 cudaError_t launch_knn(const KnnArgs& a, cudaStream_t st) {
   if (a.n_queries == 0) return cudaSuccess;
   const uint32_t blocks = (uint32_t)((a.n_queries + 127) / 128);
-  if (a.k <= kKnnRegMax)
+  if (a.k <= kKnnSmall)
+    knn_kernel<kKnnSmall><<<blocks, 128, 0, st>>>(a);
+  else if (a.k <= kKnnRegMax)
     knn_kernel<kKnnRegMax><<<blocks, 128, 0, st>>>(a);
   else
     knn_kernel<kKnnMax><<<blocks, 128, 0, st>>>(a);
