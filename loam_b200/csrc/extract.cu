@@ -8,14 +8,13 @@
 //   phase B  range r[j] = sqrt((x^2+y^2)+z^2)                         common.h:81-86
 //   phase C  curvature stencil (2N+1 taps, fp64, unfused)             features-inl.h:53-87
 //            validity mask (4 checks, idempotent "set false" scatter) features-inl.h:90-124, features.cpp:20-68
-//   phase D  candidate keys:  planar candidates (valid && c < planar_thr), edge candidates (valid && c > edge_thr)
-//   phase E  per-sector rank sort on (curvature, index) — total order, tie-break = ascending index
-//            (the reference's std::sort is unstable and compares curvature only: features.h:91, features-inl.h:38)
-//   phase F  greedy walk, sectors in order (suppression spills into the next sector, features-inl.h:148-151),
-//            edge walk (descending) then planar walk (ascending) per sector    features-inl.h:137-180
+//   phase D  selection: per (sector, edge|planar) walk in the reference's order, the greedy pick-and-suppress
+//            recursion is resolved in parallel rounds over the sector's columns, picks are ranked by
+//            (curvature, index) and truncated to max+1                         features-inl.h:27-48,137-180
 //
-// Filtering to candidates before ordering is exact: the walks only ever act on points that pass the
-// (static) threshold and are valid, and the mask only ever changes true -> false.
+// Tie-break (documented): the reference's std::sort is unstable and compares curvature only (features.h:91,
+// features-inl.h:38); here equal curvatures order by ascending index in the sorted sector, i.e. the edge walk
+// (which runs from the end) prefers the larger index and the planar walk the smaller one.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -65,6 +64,12 @@ struct Rec<double> {
   static constexpr int kElems = 3;
 };
 
+// the range buffer is reused for the walk state (P bytes, padded to 16) and the pick list (P uint16)
+__host__ __device__ inline uint32_t rng_doubles(uint32_t P) {
+  const uint32_t need = ((P + 15) & ~15u) + 2 * P;
+  return max(P, (need + 7) / 8);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kExtractThreads) extract_ring_kernel(ExtractArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -73,15 +78,11 @@ __global__ void __launch_bounds__(kExtractThreads) extract_ring_kernel(ExtractAr
   const uint32_t tid = threadIdx.x, nthr = blockDim.x;
 
   // ---- shared memory carve-up (see extract_smem_bytes) ----
-  T* stage = reinterpret_cast<T*>(smem);                                    // P * Rec<T>::kBytes
-  double* rng = reinterpret_cast<double*>(smem + (size_t)P * Rec<T>::kBytes);  // P doubles  (later: planar keys, then pick lists)
-  double* cur = rng + P;                                                     // P doubles  (later: edge keys)
-  uint8_t* mask = reinterpret_cast<uint8_t*>(cur + P);                       // P bytes
-  uint32_t* nPs = reinterpret_cast<uint32_t*>(mask + ((P + 15) & ~15u));     // S counters
-  uint32_t* nEs = nPs + S;                                                   // S counters
-  uint64_t* bar = reinterpret_cast<uint64_t*>(nEs + S + ((2 * S) & 1));      // 8-byte aligned mbarrier
-  uint16_t* sortedP = reinterpret_cast<uint16_t*>(smem);                     // aliases stage (dead after phase C)
-  uint16_t* sortedE = sortedP + P;
+  T* stage = reinterpret_cast<T*>(smem);                                       // P * Rec<T>::kBytes
+  double* rng = reinterpret_cast<double*>(smem + (size_t)P * Rec<T>::kBytes);  // ranges; later the walk state + pick list
+  double* cur = rng + rng_doubles(P);                                          // P doubles
+  uint8_t* mask = reinterpret_cast<uint8_t*>(cur + P);                         // P bytes
+  uint64_t* bar = reinterpret_cast<uint64_t*>(mask + ((P + 15) & ~15u));       // 8-byte aligned mbarrier
 
   const unsigned char* ring_src =
       a.pts + (size_t)scan * a.scan_stride_bytes + (size_t)ring * P * a.stride;
@@ -113,7 +114,6 @@ __global__ void __launch_bounds__(kExtractThreads) extract_ring_kernel(ExtractAr
     const double z = (double)stage[j * Rec<T>::kElems + 2];
     rng[j] = point_range(x, y, z);
   }
-  for (uint32_t s = tid; s < 2 * S; s += nthr) nPs[s] = 0;
   __syncthreads();
 
   // ---- phase C: curvature + mask ----
@@ -171,94 +171,102 @@ __global__ void __launch_bounds__(kExtractThreads) extract_ring_kernel(ExtractAr
     return;
   }
 
-  // ---- phase D: candidate keys (planar keys overwrite rng, edge keys overwrite cur) ----
-  const double inf = CUDART_INF;
-  for (uint32_t j = tid; j < P; j += nthr) {
-    const double c = cur[j];
-    const bool ok = mask[j] != 0;
-    rng[j] = (ok && c < a.planar_thr) ? c : inf;
-    cur[j] = (ok && c > a.edge_thr) ? c : -inf;
-  }
-  __syncthreads();
-
-  // ---- phase E: per-sector rank sort ----
+  // ---- phase D: selection.  The reference sorts each sector by curvature and walks it greedily (edge walk from the
+  // largest curvature down, then planar walk from the smallest up; a pick invalidates its +-(N-1) neighbours; a walk
+  // stops after max+1 picks).  The outcome of one walk is fully determined by local comparisons: a candidate is
+  // picked iff no higher-priority candidate within +-(N-1) columns is picked.  That recursion is resolved here in
+  // parallel rounds (decided states are final, so in-place updates are safe), the picks are then ranked by priority
+  // (= the reference's selection order), truncated to max+1, and only the accepted picks invalidate neighbours.
+  // Walks run in the reference's order (sector-major, edge before planar) because each sees the mask left by the
+  // previous ones, including suppression that spills across a sector boundary (features-inl.h:148-151).
+  uint8_t* st = reinterpret_cast<uint8_t*>(rng);                  // walk state per column (rng is dead now)
+  uint16_t* plist = reinterpret_cast<uint16_t*>(st + ((P + 15) & ~15u));  // columns picked in the current walk
+  __shared__ uint32_t s_m, s_base[2];
+  if (tid == 0) s_base[0] = s_base[1] = 0;
   const uint32_t pps = P / S;
-  for (uint32_t j = tid; j < P; j += nthr) {
-    uint32_t s = pps ? j / pps : S - 1;
-    if (s > S - 1) s = S - 1;
-    const uint32_t b = s * pps;
-    const uint32_t e = (s == S - 1) ? P : b + pps;
-    const double kp = rng[j], ke = cur[j];
-    const bool candP = kp < inf, candE = ke > -inf;
-    if (!candP && !candE) continue;
-    uint32_t rp = 0, re = 0;
-    for (uint32_t t = b; t < e; t++) {
-      const double tp = rng[t], te = cur[t];
-      rp += (tp < kp || (tp == kp && t < j)) ? 1u : 0u;
-      re += (te > ke || (te == ke && t > j)) ? 1u : 0u;
-    }
-    if (candP) {
-      sortedP[b + rp] = (uint16_t)j;
-      atomicAdd(&nPs[s], 1u);
-    }
-    if (candE) {
-      sortedE[b + re] = (uint16_t)j;
-      atomicAdd(&nEs[s], 1u);
-    }
-  }
-  __syncthreads();
-
-  // ---- phase F: greedy walk (sequential by construction) ----
-  uint16_t* outE = reinterpret_cast<uint16_t*>(rng);  // keys are dead now; rng+cur hold >= 16P bytes
-  uint16_t* outP = outE + a.capE_ring;
-  __shared__ uint32_t s_cnt[2];
-  if (tid == 0) {
-    uint32_t ne = 0, np = 0;
-    for (uint32_t s = 0; s < S; s++) {
-      const uint32_t b = s * pps;
-      uint32_t cnt = 0;
-      const uint32_t mE = nEs[s];
-      for (uint32_t r = 0; r < mE; r++) {
-        const uint32_t i = sortedE[b + r];
-        if (mask[i]) {
-          outE[ne++] = (uint16_t)i;
-          for (uint32_t k = 0; k < N; k++) {
-            mask[i + k] = 0;
-            mask[i - k] = 0;
-          }
-          cnt++;
-        }
-        if (cnt > a.maxE) break;
-      }
-      cnt = 0;
-      const uint32_t mP = nPs[s];
-      for (uint32_t r = 0; r < mP; r++) {
-        const uint32_t i = sortedP[b + r];
-        if (mask[i]) {
-          outP[np++] = (uint16_t)i;
-          for (uint32_t k = 0; k < N; k++) {
-            mask[i + k] = 0;
-            mask[i - k] = 0;
-          }
-          cnt++;
-        }
-        if (cnt > a.maxP) break;
-      }
-    }
-    s_cnt[0] = ne;
-    s_cnt[1] = np;
-  }
-  __syncthreads();
-
+  const uint32_t reach = N - 1;
   const size_t ring_id = (size_t)scan * a.R + ring;
-  const uint32_t ne = s_cnt[0], np = s_cnt[1];
   uint32_t* ge = a.ring_edge + ring_id * a.capE_ring;
   uint32_t* gp = a.ring_planar + ring_id * a.capP_ring;
-  for (uint32_t i = tid; i < ne; i += nthr) ge[i] = ring * P + outE[i];
-  for (uint32_t i = tid; i < np; i += nthr) gp[i] = ring * P + outP[i];
+  enum : uint8_t { kNone = 0, kOpen = 1, kPicked = 2, kDropped = 3 };
+  for (uint32_t walk = 0; walk < 2 * S; walk++) {
+    const uint32_t sec = walk >> 1;
+    const bool planar = (walk & 1u) != 0;
+    const uint32_t b = sec * pps, e = (sec == S - 1) ? P : b + pps;
+    const uint32_t cap = planar ? a.maxP : a.maxE;  // the walk accepts cap + 1 picks
+    // priority: edge = larger curvature first, ties by larger index (the ascending (c, idx) order walked from the
+    // end); planar = smaller curvature first, ties by smaller index
+    auto before = [&](uint32_t t, uint32_t j) -> bool {
+      const double ct = cur[t], cj = cur[j];
+      return planar ? (ct < cj || (ct == cj && t < j)) : (ct > cj || (ct == cj && t > j));
+    };
+    bool any = false;
+    for (uint32_t j = b + tid; j < e; j += nthr) {
+      const double c = cur[j];
+      const bool cand = mask[j] != 0 && (planar ? c < a.planar_thr : c > a.edge_thr);
+      st[j] = cand ? kOpen : kNone;
+      any |= cand;
+    }
+    if (tid == 0) s_m = 0;
+    if (!__syncthreads_or(any)) continue;  // no candidate in this walk (uniform: every thread sees the same result)
+    for (;;) {
+      bool open_left = false;
+      for (uint32_t j = b + tid; j < e; j += nthr) {
+        if (st[j] != kOpen) continue;
+        bool wait = false, drop = false;
+        for (uint32_t n = 1; n <= reach; n++) {
+          if (j >= b + n) {
+            const uint32_t t = j - n;
+            const uint8_t s = st[t];
+            if ((s == kOpen || s == kPicked) && before(t, j)) {
+              drop |= s == kPicked;
+              wait |= s == kOpen;
+            }
+          }
+          if (j + n < e) {
+            const uint32_t t = j + n;
+            const uint8_t s = st[t];
+            if ((s == kOpen || s == kPicked) && before(t, j)) {
+              drop |= s == kPicked;
+              wait |= s == kOpen;
+            }
+          }
+        }
+        if (drop) {
+          st[j] = kDropped;
+        } else if (!wait) {
+          st[j] = kPicked;
+          plist[atomicAdd(&s_m, 1u)] = (uint16_t)j;
+        } else {
+          open_left = true;
+        }
+      }
+      if (!__syncthreads_or(open_left)) break;
+    }
+    // rank the picks by priority; accept the first cap + 1; only those invalidate their neighbours
+    const uint32_t m = s_m;
+    const uint32_t base = s_base[planar ? 1 : 0];
+    for (uint32_t j = b + tid; j < e; j += nthr) {
+      if (st[j] != kPicked) continue;
+      uint32_t rank = 0;
+      for (uint32_t i = 0; i < m; i++) {
+        const uint32_t t = plist[i];
+        rank += (t != j && before(t, j)) ? 1u : 0u;
+      }
+      if (rank > cap) continue;
+      (planar ? gp : ge)[base + rank] = ring * P + j;
+      for (uint32_t n = 0; n <= reach; n++) {
+        if (j + n < P) mask[j + n] = 0;
+        if (j >= n) mask[j - n] = 0;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) s_base[planar ? 1 : 0] = base + min(m, cap + 1);
+  }
+  __syncthreads();
   if (tid == 0) {
-    a.ring_counts[ring_id * 2 + 0] = ne;
-    a.ring_counts[ring_id * 2 + 1] = np;
+    a.ring_counts[ring_id * 2 + 0] = s_base[0];
+    a.ring_counts[ring_id * 2 + 1] = s_base[1];
   }
 }
 
@@ -315,8 +323,9 @@ __global__ void __launch_bounds__(256) pack_features_kernel(PackArgs a) {
 }  // namespace
 
 size_t extract_smem_bytes(int dtype, uint32_t P, uint32_t S) {
+  (void)S;
   const size_t rec = dtype == LOAMGPU_F32 ? 16 : 24;
-  size_t b = (size_t)P * rec + 16 * (size_t)P + ((P + 15) & ~15u) + 8 * (size_t)S + 8 + 16;
+  size_t b = (size_t)P * rec + 8 * (size_t)rng_doubles(P) + 8 * (size_t)P + ((P + 15) & ~15u) + 8 + 16;
   return (b + 127) & ~(size_t)127;
 }
 
