@@ -227,8 +227,9 @@ def algorithmic_bytes(n_points, ne, npl, iters, k=K_NEIGH):
     return {
         "extract": 16 * n_points * n_scans + 4 * int(F.sum()),
         "pack": (4 + 16) * int(F.sum()),
-        "grid_build": 32 * int(T.sum()),
-        "assoc": int((iters * S).sum()) * (16 + 16 * k + 8),
+        "nn_build": 32 * int(T.sum()),
+        "knn": int((iters * S).sum()) * (16 + 16 * k + 8),
+        "fit": int((iters * S).sum()) * (16 * k + 48),
         "lm": int((iters * S).sum()) * 48,
         "misc": 0,
     }

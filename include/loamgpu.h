@@ -112,11 +112,12 @@ uint64_t loamgpu_launch_count(const loamgpu_ctx* ctx);
 enum {
   LOAMGPU_K_EXTRACT = 0, /* extract_ring_kernel  (K1+K2) */
   LOAMGPU_K_PACK = 1,    /* pack_features_kernel */
-  LOAMGPU_K_GRID = 2,    /* grid_build_kernel    (K3) */
-  LOAMGPU_K_ASSOC = 3,   /* assoc_kernel / knn_kernel (K4+K5) */
+  LOAMGPU_K_GRID = 2,    /* bvh_build_kernel     (K3) */
+  LOAMGPU_K_ASSOC = 3,   /* assoc_knn_kernel / knn_kernel (K4) */
   LOAMGPU_K_LM = 4,      /* lm_kernel            (K6+K7) */
   LOAMGPU_K_MISC = 5,    /* init/finish pair state */
-  LOAMGPU_K_COUNT = 6
+  LOAMGPU_K_FIT = 6,     /* assoc_fit_kernel     (K5) */
+  LOAMGPU_K_COUNT = 7
 };
 int loamgpu_set_profiling(loamgpu_ctx* ctx, int on);
 int loamgpu_kernel_times(loamgpu_ctx* ctx, double ms[LOAMGPU_K_COUNT], uint64_t launches[LOAMGPU_K_COUNT]);

@@ -26,7 +26,7 @@ SYMBOLS = [
     "loamgpu_valid_mask", "loamgpu_register", "loamgpu_knn", "loamgpu_odometry_host", "loamgpu_odometry_device",
     "loamgpu_set_chunk_pairs", "loamgpu_set_profiling", "loamgpu_kernel_times",
 ]
-KERNEL_CLASSES = ["extract", "pack", "grid_build", "assoc", "lm", "misc"]
+KERNEL_CLASSES = ["extract", "pack", "nn_build", "knn", "lm", "misc", "fit"]
 
 
 class CLidarParams(C.Structure):

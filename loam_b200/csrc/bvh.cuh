@@ -5,7 +5,7 @@
 //                         (4-bit digits, counters in shared memory) -> Morton-ordered point copy -> binary radix
 //                         tree over the sorted codes (every internal node finds its key range and split with
 //                         count-leading-zeros binary searches, so all nodes are built in parallel) -> boxes
-//                         bottom-up (the second thread to reach a node merges its children)
+//                         bottom-up in barrier-separated passes (a node merges its children once both are ready)
 //   K4  knn_bvh()         exact k-NN for one query per thread: near-child-first traversal with a short stack,
 //                         subtrees of <= 8 points are scanned as leaves; float32 box lower bounds (boxes rounded
 //                         outward, query rounded both ways, arithmetic rounded down => never above the true fp64
@@ -184,15 +184,12 @@ __global__ void __launch_bounds__(kBuildThreads) bvh_build_kernel(BvhBuildArgs a
   // with i == first or i == last; its children are node/leaf `split` (range [first, split]) and `split + 1`
   // (range [split + 1, last]).
   const uint2* key = src;
-  int* parent = reinterpret_cast<int*>(a.g.aux + (size_t)set * 3 * a.g.pt_cap);  // internal node -> parent
-  int* leaf_parent = parent + a.g.pt_cap;                                         // sorted point -> parent
-  int* arrived = leaf_parent + a.g.pt_cap;                                        // per internal node
+  int* arrived = a.g.aux + (size_t)set * a.g.pt_cap;  // per internal node: 0 pending, 2 merged this pass, 1 ready
   auto delta = [&](int i, int j) -> int {  // common-prefix length of keys i and j, -1 outside the array
     if (j < 0 || j >= (int)n) return -1;
     const uint32_t ci = key[i].x, cj = key[j].x;
     return ci != cj ? __clz(ci ^ cj) : 32 + __clz((uint32_t)i ^ (uint32_t)j);
   };
-  if (tid == 0) parent[0] = -1;
   for (uint32_t t = tid; t + 1 < n; t += nthr) {
     const int i = (int)t;
     const int d = delta(i, i + 1) - delta(i, i - 1) >= 0 ? 1 : -1;
@@ -213,31 +210,31 @@ __global__ void __launch_bounds__(kBuildThreads) bvh_build_kernel(BvhBuildArgs a
     const int split = i + sp * d + min(d, 0);
     const int first = min(i, j), last = max(i, j);
     uint32_t w = (uint32_t)split;
-    if (first == split) {
-      w |= kLeftLeaf;
-      leaf_parent[split] = i;
-    } else {
-      parent[split] = i;
-    }
-    if (last == split + 1) {
-      w |= kRightLeaf;
-      leaf_parent[split + 1] = i;
-    } else {
-      parent[split + 1] = i;
-    }
+    if (first == split) w |= kLeftLeaf;
+    if (last == split + 1) w |= kRightLeaf;
     nodes[i].split = w;
     arrived[i] = 0;
   }
   __syncthreads();
 
-  // ---- boxes, bottom-up: every point climbs; the first thread to reach a node stops, the second merges the children
-  for (uint32_t pidx = tid; pidx < n; pidx += nthr) {
-    int node = leaf_parent[pidx];
-    while (node >= 0) {
-      __threadfence();  // publish this thread's box writes before announcing arrival
-      if (atomicAdd(&arrived[node], 1) == 0) break;
-      const uint32_t w = nodes[node].split;
+  // ---- boxes, bottom-up in passes: a node is merged from its children once both are ready.  Readiness is published
+  // one barrier after the box itself (state 2 = "merged in this pass"), so a reader never sees a flag before the box.
+  // The number of passes is the tree height (~log2 n for scattered points, at most 62).
+  int* ready = arrived;
+  for (;;) {
+    bool pending = false;
+    for (uint32_t i = tid; i + 1 < n; i += nthr) {
+      // flags and boxes written by other threads of this CTA are read with ld.cg (L2), never from a possibly
+      // stale L1 line
+      if (__ldcg(ready + i) != 0) continue;
+      const uint32_t w = nodes[i].split;  // written by this same thread above
       const uint32_t sp = w & kSplitMask;
+      const bool lready = (w & kLeftLeaf) || __ldcg(ready + sp) == 1;
+      const bool rready = (w & kRightLeaf) || __ldcg(ready + sp + 1) == 1;
+      if (!(lready && rready)) {
+        pending = true;
+        continue;
+      }
       float lo[3], hi[3];
 #pragma unroll
       for (int c = 0; c < 2; c++) {
@@ -261,11 +258,15 @@ __global__ void __launch_bounds__(kBuildThreads) bvh_build_kernel(BvhBuildArgs a
       }
 #pragma unroll
       for (int k = 0; k < 3; k++) {
-        nodes[node].lo[k] = lo[k];
-        nodes[node].hi[k] = hi[k];
+        nodes[i].lo[k] = lo[k];
+        nodes[i].hi[k] = hi[k];
       }
-      node = parent[node];
+      __stcg(ready + i, 2);
     }
+    __syncthreads();
+    for (uint32_t i = tid; i + 1 < n; i += nthr)
+      if (__ldcg(ready + i) == 2) __stcg(ready + i, 1);
+    if (!__syncthreads_or(pending)) break;
   }
 }
 
@@ -357,12 +358,18 @@ __device__ __forceinline__ void knn_bvh(const BvhHdr& h, const BvhNode* __restri
   float bound = __double2float_ru(d2_cut);  // a subtree is pruned when its lower bound > bound
 
   // pending subtrees: (node index, key range, lower bound); a subtree of <= kBvhLeaf points is scanned as a leaf
-  uint32_t st_node[kBvhStack], st_first[kBvhStack], st_last[kBvhStack];
+  // (the node index itself is not needed: a node's record is only read to test it, and that read also yields
+  // its split word, which is all the descent needs)
+  uint32_t st_split[kBvhStack], st_first[kBvhStack], st_last[kBvhStack];
   float st_lb[kBvhStack];
   int sp = 0;
-  uint32_t node = 0, first = 0, last = h.n - 1;
+  uint32_t first = 0, last = h.n - 1, cur_w = 0;
   bool have = true, done = false;
-  if (h.n > (uint32_t)kBvhLeaf && box_lower_bound(load_node(nodes), q) > bound) return;
+  if (h.n > (uint32_t)kBvhLeaf) {
+    const BvhNode root = load_node(nodes);
+    if (box_lower_bound(root, q) > bound) return;
+    cur_w = root.split;
+  }
 
   // All lanes advance their own traversal one node per step until each stands on a leaf it must scan (or is done);
   // then the warp scans the leaves together — the scan is ~10x the cost of a step, so it must run converged.
@@ -375,7 +382,7 @@ __device__ __forceinline__ void knn_bvh(const BvhHdr& h, const BvhNode* __restri
         } else {
           --sp;
           if (st_lb[sp] <= bound) {
-            node = st_node[sp];
+            cur_w = st_split[sp];
             first = st_first[sp];
             last = st_last[sp];
             have = true;
@@ -384,23 +391,25 @@ __device__ __forceinline__ void knn_bvh(const BvhHdr& h, const BvhNode* __restri
       } else if (last - first < (uint32_t)kBvhLeaf) {
         at_leaf = true;
       } else {
-        const uint32_t w = __ldg(&nodes[node].split);
+        const uint32_t w = cur_w;
         const uint32_t s = w & kSplitMask;
-        // a single-point child has no box of its own: bound 0 (it is scanned as a one-point leaf)
-        const float dl = (w & kLeftLeaf) ? 0.f : box_lower_bound(load_node(nodes + s), q);
-        const float dr = (w & kRightLeaf) ? 0.f : box_lower_bound(load_node(nodes + s + 1), q);
+        // children are adjacent records; a single-point child has no record of its own: bound 0 (it is scanned as
+        // a one-point leaf and its split word is never used)
+        const BvhNode cl = load_node(nodes + s), cr = load_node(nodes + s + 1);
+        const float dl = (w & kLeftLeaf) ? 0.f : box_lower_bound(cl, q);
+        const float dr = (w & kRightLeaf) ? 0.f : box_lower_bound(cr, q);
         const bool right_first = dr < dl;
         const float dn = right_first ? dr : dl, df = right_first ? dl : dr;
         const uint32_t l_first = first, l_last = s, r_first = s + 1, r_last = last;
         if (df <= bound) {  // far child stays pending
-          st_node[sp] = right_first ? s : s + 1;
+          st_split[sp] = right_first ? cl.split : cr.split;
           st_first[sp] = right_first ? l_first : r_first;
           st_last[sp] = right_first ? l_last : r_last;
           st_lb[sp] = df;
           sp++;
         }
         if (dn <= bound) {
-          node = right_first ? s + 1 : s;
+          cur_w = right_first ? cr.split : cl.split;
           first = right_first ? r_first : l_first;
           last = right_first ? r_last : l_last;
         } else {

@@ -3,6 +3,7 @@
 // kernels; every number in the results is produced by the CUDA kernels in extract.cu / register.cu.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -50,12 +51,13 @@ struct loamgpu_ctx {
   uint64_t launches = 0;
   uint32_t chunk_pairs = 256;
   int max_smem_optin = 0;
+  int morton_queries = 1;  // LOAMGPU_QUERY_ORDER=original switches the k-NN kernel to source-index order (A/B)
 
   DevBuf scan_in[2];                       // H2D staging of scans
   DevBuf ring_edge, ring_planar, ring_counts;
   DevBuf edge_idx, planar_idx, edge_pts, planar_pts, feat_counts;
   DevBuf ge_hdr, ge_nodes, ge_sorted, ge_keys, ge_aux, gp_hdr, gp_nodes, gp_sorted, gp_keys, gp_aux;
-  DevBuf state, rec_p, rec_a, rec_b, nearest;
+  DevBuf state, rec_p, rec_a, rec_b, nearest, nn_idx, nn_cnt;
   DevBuf misc, out_pose, out_term, out_iters, out_ne, out_np;
   DevBuf det_est, det_upd, det_assoc_n, det_lm_iters, det_lm_cost, init_pose;
 
@@ -265,17 +267,21 @@ int make_regp(loamgpu_ctx* ctx, const loamgpu_reg_params* rp, RegP* out) {
   return LOAMGPU_OK;
 }
 
-int reserve_register(loamgpu_ctx* ctx, uint32_t n_pairs, uint32_t capE, uint32_t capP, uint32_t detail_iters) {
-  CU(ctx->ge_hdr.reserve((size_t)n_pairs * sizeof(BvhHdr)));
-  CU(ctx->gp_hdr.reserve((size_t)n_pairs * sizeof(BvhHdr)));
-  CU(ctx->ge_nodes.reserve((size_t)n_pairs * capE * sizeof(BvhNode)));
-  CU(ctx->gp_nodes.reserve((size_t)n_pairs * capP * sizeof(BvhNode)));
-  CU(ctx->ge_aux.reserve((size_t)n_pairs * capE * 12));
-  CU(ctx->gp_aux.reserve((size_t)n_pairs * capP * 12));
-  CU(ctx->ge_sorted.reserve((size_t)n_pairs * capE * 32));
-  CU(ctx->gp_sorted.reserve((size_t)n_pairs * capP * 32));
-  CU(ctx->ge_keys.reserve((size_t)n_pairs * capE * 16));
-  CU(ctx->gp_keys.reserve((size_t)n_pairs * capP * 16));
+int reserve_register(loamgpu_ctx* ctx, uint32_t n_pairs, uint32_t capE, uint32_t capP, uint32_t detail_iters,
+                     uint32_t nn_stride) {
+  const size_t n_sets = (size_t)n_pairs + 1;  // every pair's target + the source of the last pair
+  CU(ctx->ge_hdr.reserve(n_sets * sizeof(BvhHdr)));
+  CU(ctx->gp_hdr.reserve(n_sets * sizeof(BvhHdr)));
+  CU(ctx->ge_nodes.reserve(n_sets * capE * sizeof(BvhNode)));
+  CU(ctx->gp_nodes.reserve(n_sets * capP * sizeof(BvhNode)));
+  CU(ctx->ge_aux.reserve(n_sets * capE * 4));
+  CU(ctx->gp_aux.reserve(n_sets * capP * 4));
+  CU(ctx->ge_sorted.reserve(n_sets * capE * 32));
+  CU(ctx->gp_sorted.reserve(n_sets * capP * 32));
+  CU(ctx->ge_keys.reserve(n_sets * capE * 16));
+  CU(ctx->gp_keys.reserve(n_sets * capP * 16));
+  CU(ctx->nn_idx.reserve((size_t)n_pairs * (capE + capP) * nn_stride * 4));
+  CU(ctx->nn_cnt.reserve((size_t)n_pairs * (capE + capP) * 4));
   CU(ctx->state.reserve((size_t)n_pairs * sizeof(PairState)));
   CU(ctx->rec_p.reserve((size_t)n_pairs * (capE + capP) * 32));
   CU(ctx->rec_a.reserve((size_t)n_pairs * (capE + capP) * 32));
@@ -307,12 +313,12 @@ int run_register(loamgpu_ctx* ctx, const RegP& rp, uint32_t n_pairs, uint64_t pa
   gb.pt_stride = capE;
   gb.kind = 0;
   gb.g = bvh_arrays(ctx, false, capE);
-  TIMED(LOAMGPU_K_GRID, launch_bvh_build(gb, n_pairs, ctx->stream));
+  TIMED(LOAMGPU_K_GRID, launch_bvh_build(gb, n_pairs + 1, ctx->stream));  // + the last pair's source set
   gb.pts = ctx->planar_pts.as<double4>();
   gb.pt_stride = capP;
   gb.kind = 1;
   gb.g = bvh_arrays(ctx, true, capP);
-  TIMED(LOAMGPU_K_GRID, launch_bvh_build(gb, n_pairs, ctx->stream));
+  TIMED(LOAMGPU_K_GRID, launch_bvh_build(gb, n_pairs + 1, ctx->stream));
   TIMED(LOAMGPU_K_MISC, launch_init_pairs(ctx->state.as<PairState>(), n_pairs, init_pose_dev, ctx->stream));
 
   AssocArgs aa;
@@ -332,6 +338,10 @@ int run_register(loamgpu_ctx* ctx, const RegP& rp, uint32_t n_pairs, uint64_t pa
   aa.rec_a = ctx->rec_a.as<double4>();
   aa.rec_b = ctx->rec_b.as<double4>();
   aa.nearest = detail ? ctx->nearest.as<int32_t>() : nullptr;
+  aa.nn_idx = ctx->nn_idx.as<uint32_t>();
+  aa.nn_cnt = ctx->nn_cnt.as<uint32_t>();
+  aa.nn_stride = (uint32_t)std::max(rp.ke, rp.kp);
+  aa.morton_queries = ctx->morton_queries;
   aa.rp = rp;
   LmArgs la;
   memset(&la, 0, sizeof la);
@@ -354,7 +364,8 @@ int run_register(loamgpu_ctx* ctx, const RegP& rp, uint32_t n_pairs, uint64_t pa
     la.d_lm_cost = ctx->det_lm_cost.as<double>();
   }
   for (int it = 0; it < rp.max_iterations; it++) {
-    TIMED(LOAMGPU_K_ASSOC, launch_assoc(aa, n_pairs, it, ctx->stream));
+    TIMED(LOAMGPU_K_ASSOC, launch_assoc_knn(aa, n_pairs, ctx->stream));
+    TIMED(LOAMGPU_K_FIT, launch_assoc_fit(aa, n_pairs, it, ctx->stream));
     la.outer_iter = it;
     TIMED(LOAMGPU_K_LM, launch_lm(la, n_pairs, ctx->stream));
   }
@@ -400,6 +411,7 @@ int loamgpu_create(int device, loamgpu_ctx** out) {
     cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming);
   }
   c->stream = c->own_stream;
+  if (const char* qo = getenv("LOAMGPU_QUERY_ORDER")) c->morton_queries = strcmp(qo, "original") != 0;
   *out = c;
   return LOAMGPU_OK;
 }
@@ -411,7 +423,7 @@ void loamgpu_destroy(loamgpu_ctx* c) {
   DevBuf* bufs[] = {&c->scan_in[0], &c->scan_in[1], &c->ring_edge, &c->ring_planar, &c->ring_counts, &c->edge_idx,
                     &c->planar_idx, &c->edge_pts, &c->planar_pts, &c->feat_counts, &c->ge_hdr, &c->ge_nodes,
                     &c->ge_sorted, &c->ge_keys, &c->ge_aux, &c->gp_hdr, &c->gp_nodes, &c->gp_sorted, &c->gp_keys, &c->gp_aux, &c->state,
-                    &c->rec_p, &c->rec_a, &c->rec_b, &c->nearest, &c->misc, &c->out_pose, &c->out_term,
+                    &c->rec_p, &c->rec_a, &c->rec_b, &c->nearest, &c->nn_idx, &c->nn_cnt, &c->misc, &c->out_pose, &c->out_term,
                     &c->out_iters, &c->out_ne, &c->out_np, &c->det_est, &c->det_upd, &c->det_assoc_n,
                     &c->det_lm_iters, &c->det_lm_cost, &c->init_pose};
   for (DevBuf* b : bufs) b->release();
@@ -608,7 +620,7 @@ int loamgpu_register(loamgpu_ctx* ctx, const double* src_edge, uint64_t n_se, co
   CU(ctx->edge_pts.reserve((size_t)2 * capE * 32));
   CU(ctx->planar_pts.reserve((size_t)2 * capP * 32));
   CU(ctx->feat_counts.reserve(16));
-  rc = reserve_register(ctx, 1, capE, capP, det_iters);
+  rc = reserve_register(ctx, 1, capE, capP, det_iters, (uint32_t)std::max(rp.ke, rp.kp));
   if (rc) return rc;
   CU(ctx->init_pose.reserve(7 * 8));
   CU(ctx->out_pose.reserve(7 * 8));
@@ -700,7 +712,7 @@ int loamgpu_knn(loamgpu_ctx* ctx, const double* targets, uint64_t n_t, const dou
   const uint32_t cap = (uint32_t)std::max<uint64_t>(n_t, 1);
   CU(ctx->planar_pts.reserve((size_t)cap * 32));
   CU(ctx->feat_counts.reserve(8));
-  int rc = reserve_register(ctx, 1, 1, cap, 0);
+  int rc = reserve_register(ctx, 1, 1, cap, 0, 1);
   if (rc) return rc;
   CU(ctx->misc.reserve((size_t)n_q * (24 + 4 * (size_t)k + 4)));
   std::vector<double> hp((size_t)cap * 4);
@@ -759,7 +771,7 @@ static int odometry_core(loamgpu_ctx* ctx, uint64_t n_scans, const loamgpu_lidar
   const uint32_t n_slots = chunk + 1;
   rc = reserve_extract(ctx, pl, chunk + 1, n_slots);
   if (rc) return rc;
-  rc = reserve_register(ctx, chunk, pl.capE_scan, pl.capP_scan, 0);
+  rc = reserve_register(ctx, chunk, pl.capE_scan, pl.capP_scan, 0, (uint32_t)std::max(rp.ke, rp.kp));
   if (rc) return rc;
   if (n_scans == 1) {  // no pair: just the feature counts
     const float* d = nullptr;

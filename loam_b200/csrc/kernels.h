@@ -63,7 +63,7 @@ struct BvhSetArrays {
   BvhNode* nodes;     // [n_sets][pt_cap]     internal nodes 0 .. n-2, root = 0
   double4* sorted;    // [n_sets][pt_cap]     (x,y,z, bits(original index)), Morton order
   uint2* keys;        // [n_sets][2][pt_cap]  radix-sort ping-pong scratch: (morton, original index)
-  int* aux;           // [n_sets][3][pt_cap]  build scratch: node parent, point parent, arrival counter
+  int* aux;           // [n_sets][pt_cap]     build scratch: per-node readiness
   uint32_t pt_cap;
 };
 
@@ -89,15 +89,20 @@ struct AssocArgs {
   uint64_t pair0;
   uint32_t n_slots;
   int src_offset;          // 1 for sequence odometry; explicit-pair calls use slots 1 (src) / 0 (tgt)
-  BvhSetArrays ge, gp;     // target NN structures, set index = pair
+  BvhSetArrays ge, gp;     // NN structures: set `pair` = target of the pair, set `pair + src_offset` = its source
   PairState* state;        // [pair]
   double4* rec_p;          // [pair][capE+capP]  transformed point, w = 0 invalid / 1 edge / 2 plane
   double4* rec_a;          // [pair][capE+capP]  edge: line point a ; plane: normal, w = d
   double4* rec_b;          // [pair][capE]       edge: line point b
+  uint32_t* nn_idx;        // [pair][capE+capP][nn_stride] neighbour indices of the current outer iteration
+  uint32_t* nn_cnt;        // [pair][capE+capP]            neighbours inside the radius
+  uint32_t nn_stride;      // max(num_edge_neighbors, num_plane_neighbors)
+  int morton_queries;      // 1: walk the source set in its Morton order (default), 0: original order
   int32_t* nearest;        // optional [outer_iter][pair][capE+capP] nearest target index or -1 (detail)
   RegP rp;
 };
-cudaError_t launch_assoc(const AssocArgs& a, uint32_t n_pairs, int outer_iter, cudaStream_t st);
+cudaError_t launch_assoc_knn(const AssocArgs& a, uint32_t n_pairs, cudaStream_t st);
+cudaError_t launch_assoc_fit(const AssocArgs& a, uint32_t n_pairs, int outer_iter, cudaStream_t st);
 
 struct LmArgs {
   PairState* state;

@@ -5,8 +5,9 @@
 //                           KD-tree build, registration-inl.h:20-23)
 //   K4  knn_bvh()           exact k-NN + strict radius filter (bvh.cuh; kdtree.cpp:10-28)
 //   K5  fit_line/fit_plane  per-query PCA line / column-pivoted-QR plane (geometry.cpp:42-73)
-//   K45 assoc_kernel        transform + K4 + K5 + guards for every source feature of every active pair
-//                           (associateEdges/associatePlanes, registration.cpp:23-103)
+//   K4  assoc_knn_kernel    transform + k-NN for every source feature of every active pair, queries in the
+//                           source set's Morton order (registration.cpp:34-37,75-78)
+//   K5  assoc_fit_kernel    line / plane fit + guards -> residual records (registration.cpp:39-57,80-98)
 //   K6/K7 lm_kernel         one CTA per pair: residuals + analytic SE(3) Jacobians + Huber corrector,
 //                           6x6 J^T J / J^T r / cost reduced warp-shuffle -> shared memory, and the
 //                           Levenberg-Marquardt controller (Ceres TrustRegionMinimizer semantics) entirely
@@ -70,7 +71,7 @@ __device__ __forceinline__ V3 principal_axis(double A[3][3]) {
 // geometry.cpp:42-59.  The condition number is never produced (the reference computes and discards it,
 // leaving DBL_MAX), so the min_line_condition_number guard can only fire for a threshold above DBL_MAX.
 template <int KMAX>
-__device__ __forceinline__ void fit_line(const double (&P)[KMAX][3], int K, V3& la, V3& lb) {
+__device__ __noinline__ void fit_line(const double (&P)[KMAX][3], int K, V3& la, V3& lb) {
   double c[3] = {0, 0, 0};
   for (int k = 0; k < K; k++) {
     c[0] += P[k][0];
@@ -96,8 +97,11 @@ __device__ __forceinline__ void fit_line(const double (&P)[KMAX][3], int K, V3& 
 // geometry.cpp:62-73 : column-pivoted Householder QR least squares of  points * abc = 1  (Eigen
 // ColPivHouseholderQR semantics incl. its rank threshold), then normal = abc/|abc|, d = 1/|abc| and the
 // SIGNED mean distance.
+// __noinline__ on purpose: inlined into assoc_fit_kernel, nvcc 12.9 / sm_100a produced a wrong signed mean distance
+// for near-collinear neighbour sets (normal and d were right, the final loop over P was not); as a real call the
+// results match the CPU oracle bit for bit (tests/test_gpu_odometry.py::test_sequence_matches_oracle pins this).
 template <int KMAX>
-__device__ __forceinline__ double fit_plane(const double (&P)[KMAX][3], int K, V3& nrm, double& dist) {
+__device__ __noinline__ double fit_plane(const double (&P)[KMAX][3], int K, V3& nrm, double& dist) {
   double A[KMAX][3], c[KMAX];
   int perm[3] = {0, 1, 2};
   for (int k = 0; k < K; k++) {
@@ -186,10 +190,56 @@ __device__ __forceinline__ double fit_plane(const double (&P)[KMAX][3], int K, V
   return sum / (double)K;
 }
 
-// ============================================================================ association (K45)
+// ============================================================================ association (K4 + K5)
 
+// K4: transform every source feature of every active pair by the current estimate (registration.cpp:34,75) and find
+// its k nearest target features.  Threads walk the source set in ITS OWN Morton order (the source scan's NN
+// structure holds a Morton-sorted copy), so the lanes of a warp carry neighbouring queries: they traverse the same
+// nodes (loads coalesce, caches hit) and need similar numbers of leaves.  Results land at the original feature index.
+template <int K>
+__global__ void __launch_bounds__(kAssocThreads) assoc_knn_kernel(AssocArgs a) {
+  const uint32_t pair = blockIdx.y;
+  const PairState* ps = a.state + pair;
+  if (ps->status != -1) return;
+  const uint32_t src_slot = (uint32_t)((a.pair0 + pair + a.src_offset) % a.n_slots);
+  const uint32_t nE = a.feat_counts[src_slot * 2], nP = a.feat_counts[src_slot * 2 + 1];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nE + nP) return;
+  const bool is_plane = i >= nE;
+  double est[7];
+#pragma unroll
+  for (int j = 0; j < 7; j++) est[j] = ps->est[j];
+  const BvhSetArrays& gs = is_plane ? a.gp : a.ge;
+  const uint32_t src_set = pair + (uint32_t)a.src_offset;
+  double4 sp;
+  if (a.morton_queries) {
+    sp = gs.sorted[(size_t)src_set * gs.pt_cap + (is_plane ? i - nE : i)];
+  } else {  // A/B switch: source features in their original order
+    sp = is_plane ? a.planar_pts[(size_t)src_slot * a.capP_scan + (i - nE)] : a.edge_pts[(size_t)src_slot * a.capE_scan + i];
+    sp.w = __longlong_as_double((long long)(is_plane ? i - nE : i));
+  }
+  const uint32_t li = (uint32_t)__double_as_longlong(sp.w);  // original index of this source feature
+  const V3 q = pose_act(est, V3{sp.x, sp.y, sp.z});
+  const BvhHdr g = gs.hdr[pair];
+  const int k = is_plane ? a.rp.kp : a.rp.ke;
+  const double md = is_plane ? a.rp.rp : a.rp.re;
+  TopK<K> tk;
+  knn_bvh<K>(g, gs.nodes + (size_t)pair * gs.pt_cap, gs.sorted + (size_t)pair * gs.pt_cap, q.x, q.y, q.z, k, md, tk);
+  const int m = radius_count(tk, k, md);
+  const size_t cap_src = (size_t)a.capE_scan + a.capP_scan;
+  const size_t rec = (size_t)pair * cap_src + (is_plane ? a.capE_scan + li : li);
+  a.rec_p[rec] = make_double4(q.x, q.y, q.z, 0.0);
+  a.nn_cnt[rec] = (uint32_t)m;
+  uint32_t* out = a.nn_idx + rec * (size_t)a.nn_stride;
+#pragma unroll
+  for (int j = 0; j < K; j++)
+    if (j < k) out[j] = tk.id[j];
+}
+
+// K5: line / plane fit + guards for every source feature (associateEdges/associatePlanes, registration.cpp:39-57,
+// 80-98), in source-index order.  Writes the residual records the LM kernel consumes.
 template <int KMAX>
-__global__ void __launch_bounds__(kAssocThreads) assoc_kernel(AssocArgs a, int outer_iter) {
+__global__ void __launch_bounds__(kAssocThreads) assoc_fit_kernel(AssocArgs a, int outer_iter) {
   const uint32_t pair = blockIdx.y;
   PairState* ps = a.state + pair;
   if (ps->status != -1) return;
@@ -202,25 +252,12 @@ __global__ void __launch_bounds__(kAssocThreads) assoc_kernel(AssocArgs a, int o
   const bool is_plane = active && i >= nE;
   bool ok = false;
   if (active) {
-    double est[7];
-#pragma unroll
-    for (int j = 0; j < 7; j++) est[j] = ps->est[j];
     const uint32_t li = is_plane ? i - nE : i;
     const size_t cap_src = (size_t)a.capE_scan + a.capP_scan;
     const size_t rec = (size_t)pair * cap_src + (is_plane ? a.capE_scan + li : li);
-    const double4 sp = is_plane ? a.planar_pts[(size_t)src_slot * a.capP_scan + li]
-                                : a.edge_pts[(size_t)src_slot * a.capE_scan + li];
-    const V3 q = pose_act(est, V3{sp.x, sp.y, sp.z});  // registration.cpp:34,75
-    const BvhSetArrays& gs = is_plane ? a.gp : a.ge;
-    const BvhHdr g = gs.hdr[pair];
-    const int k = is_plane ? a.rp.kp : a.rp.ke;
-    const double md = is_plane ? a.rp.rp : a.rp.re;
-    TopK<KMAX> tk;
-    knn_bvh<KMAX>(g, gs.nodes + (size_t)pair * gs.pt_cap, gs.sorted + (size_t)pair * gs.pt_cap, q.x, q.y, q.z, k,
-                  md, tk);
-    const int m = radius_count(tk, k, md);
+    const int m = (int)a.nn_cnt[rec];
+    const uint32_t* nn = a.nn_idx + rec * (size_t)a.nn_stride;
     const int need = is_plane ? a.rp.min_plane : a.rp.min_line;
-    double4 rp4 = make_double4(q.x, q.y, q.z, 0.0);
     if (m >= need && m > 0) {
       const double4* tp = is_plane ? a.planar_pts + (size_t)tgt_slot * a.capP_scan
                                    : a.edge_pts + (size_t)tgt_slot * a.capE_scan;
@@ -228,7 +265,7 @@ __global__ void __launch_bounds__(kAssocThreads) assoc_kernel(AssocArgs a, int o
 #pragma unroll
       for (int j = 0; j < KMAX; j++) {
         if (j < m) {
-          const double4 t = tp[tk.id[j]];
+          const double4 t = tp[nn[j]];
           N[j][0] = t.x;
           N[j][1] = t.y;
           N[j][2] = t.z;
@@ -240,7 +277,6 @@ __global__ void __launch_bounds__(kAssocThreads) assoc_kernel(AssocArgs a, int o
         // registration.cpp:49: condition_number is always DBL_MAX in the reference (geometry.cpp:55-56)
         if (!(1.7976931348623157e308 < a.rp.min_cond)) {
           ok = true;
-          rp4.w = 1.0;
           a.rec_a[rec] = make_double4(la.x, la.y, la.z, 0.0);
           a.rec_b[(size_t)pair * a.capE_scan + li] = make_double4(lb.x, lb.y, lb.z, 0.0);
         }
@@ -250,14 +286,13 @@ __global__ void __launch_bounds__(kAssocThreads) assoc_kernel(AssocArgs a, int o
         const double avg = fit_plane<KMAX>(N, m, nrm, dist);
         if (!(avg > a.rp.max_avg)) {  // registration.cpp:90
           ok = true;
-          rp4.w = 2.0;
           a.rec_a[rec] = make_double4(nrm.x, nrm.y, nrm.z, dist);
         }
       }
     }
-    a.rec_p[rec] = rp4;
+    if (ok) reinterpret_cast<double*>(a.rec_p + rec)[3] = is_plane ? 2.0 : 1.0;  // w: 0 invalid / 1 edge / 2 plane
     if (a.nearest) a.nearest[((size_t)outer_iter * gridDim.y + pair) * cap_src + (is_plane ? a.capE_scan + li : li)] =
-        ok ? (int32_t)tk.id[0] : -1;
+        ok ? (int32_t)nn[0] : -1;
   }
   const unsigned be = __ballot_sync(0xffffffffu, ok && !is_plane);
   const unsigned bp = __ballot_sync(0xffffffffu, ok && is_plane);
@@ -714,17 +749,31 @@ cudaError_t launch_bvh_build(const BvhBuildArgs& a, uint32_t n_sets, cudaStream_
   return cudaGetLastError();
 }
 
-cudaError_t launch_assoc(const AssocArgs& a, uint32_t n_pairs, int outer_iter, cudaStream_t st) {
+cudaError_t launch_assoc_knn(const AssocArgs& a, uint32_t n_pairs, cudaStream_t st) {
   if (n_pairs == 0) return cudaSuccess;
   const uint32_t cap = a.capE_scan + a.capP_scan;
   dim3 grid((cap + kAssocThreads - 1) / kAssocThreads, n_pairs);
   const int kmax = a.rp.ke > a.rp.kp ? a.rp.ke : a.rp.kp;
   if (kmax <= kKnnSmall)
-    assoc_kernel<kKnnSmall><<<grid, kAssocThreads, 0, st>>>(a, outer_iter);
+    assoc_knn_kernel<kKnnSmall><<<grid, kAssocThreads, 0, st>>>(a);
   else if (kmax <= kKnnRegMax)
-    assoc_kernel<kKnnRegMax><<<grid, kAssocThreads, 0, st>>>(a, outer_iter);
+    assoc_knn_kernel<kKnnRegMax><<<grid, kAssocThreads, 0, st>>>(a);
   else
-    assoc_kernel<kKnnMax><<<grid, kAssocThreads, 0, st>>>(a, outer_iter);
+    assoc_knn_kernel<kKnnMax><<<grid, kAssocThreads, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_assoc_fit(const AssocArgs& a, uint32_t n_pairs, int outer_iter, cudaStream_t st) {
+  if (n_pairs == 0) return cudaSuccess;
+  const uint32_t cap = a.capE_scan + a.capP_scan;
+  dim3 grid((cap + kAssocThreads - 1) / kAssocThreads, n_pairs);
+  const int kmax = a.rp.ke > a.rp.kp ? a.rp.ke : a.rp.kp;
+  if (kmax <= kKnnSmall)
+    assoc_fit_kernel<kKnnSmall><<<grid, kAssocThreads, 0, st>>>(a, outer_iter);
+  else if (kmax <= kKnnRegMax)
+    assoc_fit_kernel<kKnnRegMax><<<grid, kAssocThreads, 0, st>>>(a, outer_iter);
+  else
+    assoc_fit_kernel<kKnnMax><<<grid, kAssocThreads, 0, st>>>(a, outer_iter);
   return cudaGetLastError();
 }
 
