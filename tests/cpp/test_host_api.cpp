@@ -1,0 +1,239 @@
+// Host-side C++ API test (include/loam/*.h over the C-ABI).  The scenarios are the reference's own unit-test scenes
+// (tests/test_feature_extraction.cpp:27-299, tests/test_registration.cpp:8-199, tests/test_geometry.cpp) restated with
+// a self-contained checker (GoogleTest is not installed).
+//   test_host_api            run everything on cuda:0
+//   test_host_api --no-gpu   only what needs no device: value types, error paths, "no CPU fallback" behaviour
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "loam/loam.h"
+
+static int g_fail = 0, g_checks = 0;
+#define CHECK(cond)                                                        \
+  do {                                                                     \
+    g_checks++;                                                            \
+    if (!(cond)) {                                                         \
+      g_fail++;                                                            \
+      std::printf("FAIL %s:%d  %s\n", __FILE__, __LINE__, #cond);          \
+    }                                                                      \
+  } while (0)
+#define CHECK_NEAR(a, b, tol) CHECK(std::fabs((a) - (b)) <= (tol))
+
+struct PointF {  // PCL-style point: exercises the zero-copy float path
+  float x, y, z, intensity;
+};
+using V3 = Eigen::Vector3d;
+
+static void test_pose_algebra() {
+  const double h = std::sqrt(0.5);
+  const loam::Pose3d a(Eigen::Quaterniond(h, 0, 0, h), V3(1, 2, 3));  // 90 deg about z
+  const V3 p = a.act(V3(1, 0, 0));
+  CHECK_NEAR(p(0), 1.0, 1e-12);
+  CHECK_NEAR(p(1), 3.0, 1e-12);
+  CHECK_NEAR(p(2), 3.0, 1e-12);
+  const loam::Pose3d id = a.compose(a.inverse());
+  CHECK_NEAR(id.translation.norm(), 0.0, 1e-12);
+  CHECK_NEAR(id.rotation.angularDistance(Eigen::Quaterniond::Identity()), 0.0, 1e-12);
+  const Eigen::Matrix4d m = a.matrix();
+  CHECK_NEAR(m(0, 1), -1.0, 1e-12);
+  CHECK_NEAR(m(1, 0), 1.0, 1e-12);
+  CHECK_NEAR(m(2, 3), 3.0, 1e-12);
+  CHECK_NEAR(loam::geometry_internal::pointToLineDistance(V3(0, 2, 0), V3(-1, 0, 0), V3(1, 0, 0)), 2.0, 1e-12);
+  CHECK_NEAR(loam::geometry_internal::pointToPlaneDistance(V3(0, 0, -3), V3(0, 0, 1), 1.0), 4.0, 1e-12);
+}
+
+static void test_size_mismatch_message() {
+  std::vector<V3> scan(10, V3(1, 1, 1));
+  bool threw = false;
+  try {
+    loam::extractFeatures<loam::ParenAccessor>(scan, loam::LidarParams(2, 6, 0.1, 100.0));
+  } catch (const std::runtime_error& e) {
+    threw = std::string(e.what()).find("LOAM: provided lidar scan size ( 10)  does not match provided lidar parameters (2 x 6)") == 0;
+  }
+  CHECK(threw);
+}
+
+static void test_empty_nonstd_allocator() {  // compile-time + empty-cloud path (needs no device)
+  std::vector<V3, Eigen::aligned_allocator<V3>> scan;
+  const auto f = loam::extractFeatures<loam::ParenAccessor>(scan, loam::LidarParams(0, 0, 0.0, 1.0));
+  CHECK(f.edge_points.empty() && f.planar_points.empty());
+}
+
+static void test_no_device_is_loud() {
+  std::vector<V3> scan(11, V3(1, 1, 0));
+  bool threw = false;
+  try {
+    loam::computeCurvature<loam::ParenAccessor>(scan, loam::LidarParams(1, 11, 0.1, 100.0));
+  } catch (const std::runtime_error& e) {
+    threw = std::string(e.what()).find("cannot create a CUDA context") != std::string::npos;
+  }
+  CHECK(threw);
+}
+
+static void test_curvature_known_answers() {
+  loam::FeatureExtractionParams fp;
+  fp.neighbor_points = 5;
+  const loam::LidarParams lp(1, 11, 0.1, 100.0);
+  std::vector<V3> line, corner;
+  for (int i = -5; i <= 5; i++) {
+    line.emplace_back((double)i, 1.0, 0.0);
+    corner.emplace_back((double)i, std::fabs((double)i) + 1.0, 0.0);
+  }
+  const auto cl = loam::computeCurvature<loam::ParenAccessor>(line, lp, fp);
+  CHECK(cl.size() == 11 && cl[5].index == 5);
+  CHECK_NEAR(cl[0].curvature, -1.0, 1e-9);
+  CHECK_NEAR(cl[10].curvature, -1.0, 1e-9);
+  CHECK_NEAR(cl[5].curvature, 0.0, 1e-9);
+  const auto cc = loam::computeCurvature<loam::ParenAccessor>(corner, lp, fp);
+  CHECK_NEAR(cc[5].curvature, 900.0, 1e-9);
+}
+
+static void test_valid_mask_known_answers() {
+  loam::FeatureExtractionParams fp;
+  fp.neighbor_points = 5;
+  {  // ring edges
+    std::vector<V3> s;
+    for (int i = -5; i <= 5; i++) s.emplace_back((double)i, 1.0, 0.0);
+    const auto m = loam::computeValidPoints<loam::ParenAccessor>(s, loam::LidarParams(1, 11, 0.1, 100.0), fp);
+    for (int i = 0; i < 11; i++) CHECK(m[i] == (i == 5));
+  }
+  {  // occlusion: depth steps from 4 to 6 between columns 14 and 15 -> 15..19 hidden side invalid
+    std::vector<V3> s;
+    for (int i = 0; i < 30; i++) {
+      const double ang = -0.3 + 0.02 * i, r = i < 15 ? 4.0 : 6.0;
+      s.emplace_back(r * std::sin(ang), r * std::cos(ang), 0.0);
+    }
+    const auto m = loam::computeValidPoints<loam::ParenAccessor>(s, loam::LidarParams(1, 30, 0.1, 100.0), fp);
+    for (int i = 5; i <= 14; i++) CHECK(m[i]);
+    for (int i = 15; i <= 19; i++) CHECK(!m[i]);
+    for (int i = 20; i <= 24; i++) CHECK(m[i]);
+  }
+}
+
+// a small synthetic organised scan: box room seen from the origin
+template <typename P>
+static std::vector<P> room_scan(int rings, int cols) {
+  std::vector<P> s;
+  for (int r = 0; r < rings; r++) {
+    const double el = (-15.0 + 30.0 * r / (rings - 1)) * M_PI / 180.0;
+    for (int c = 0; c < cols; c++) {
+      const double az = 2 * M_PI * c / cols;
+      const double dx = std::cos(el) * std::cos(az), dy = std::cos(el) * std::sin(az), dz = std::sin(el);
+      double t = 1e9;
+      if (dx > 0) t = std::fmin(t, 7.0 / dx);
+      if (dx < 0) t = std::fmin(t, -9.0 / dx);
+      if (dy > 0) t = std::fmin(t, 5.0 / dy);
+      if (dy < 0) t = std::fmin(t, -6.0 / dy);
+      if (dz > 0) t = std::fmin(t, 3.0 / dz);
+      if (dz < 0) t = std::fmin(t, -1.5 / dz);
+      t += 0.004 * std::sin(12.9898 * r + 78.233 * c);  // deterministic roughness
+      P p{};
+      p.x = (decltype(p.x))(t * dx);
+      p.y = (decltype(p.y))(t * dy);
+      p.z = (decltype(p.z))(t * dz);
+      s.push_back(p);
+    }
+  }
+  return s;
+}
+struct PointD {
+  double x, y, z;
+};
+
+static void test_float_zero_copy_matches_double_path() {
+  const int R = 16, C = 512;
+  const auto sf = room_scan<PointF>(R, C);
+  std::vector<PointD> sd;
+  for (const PointF& p : sf) sd.push_back(PointD{p.x, p.y, p.z});  // the same values, widened
+  const loam::LidarParams lp(R, C, 0.5, 100.0);
+  const auto a = loam::gpu::extractFeatureIndices(sf, lp);
+  const auto b = loam::gpu::extractFeatureIndices(sd, lp);
+  CHECK(!a.first.empty() && !a.second.empty());
+  CHECK(a.first == b.first && a.second == b.second);
+  const auto f = loam::extractFeatures(sf, lp);
+  CHECK(f.edge_points.size() == a.first.size() && f.planar_points.size() == a.second.size());
+  CHECK(f.planar_points[0].x == sf[a.second[0]].x && f.planar_points[0].intensity == sf[a.second[0]].intensity);
+}
+
+// the reference's registration scene: three planes and two vertical edges on a 0.05 m lattice
+static loam::LoamFeatures<V3> simple_scene() {
+  loam::LoamFeatures<V3> f;
+  for (double y = 3; y < 6; y += 0.05)
+    for (double z = -1; z < 2; z += 0.05) f.planar_points.emplace_back(-3.0, y, z);
+  for (double x = -1; x < 2; x += 0.05)
+    for (double z = -1; z < 2; z += 0.05) f.planar_points.emplace_back(x, 5.0, z);
+  for (double x = 1; x < 3; x += 0.05)
+    for (double y = 1; y < 3; y += 0.05) f.planar_points.emplace_back(x, y, -1.0);
+  for (double z = -1; z < 3; z += 0.05) f.edge_points.emplace_back(-1.0, 4.0, z);
+  for (double z = -1; z < 3; z += 0.05) f.edge_points.emplace_back(3.0, 2.0, z);
+  return f;
+}
+static loam::LoamFeatures<V3> transformed(const loam::LoamFeatures<V3>& in, const loam::Pose3d& T) {
+  loam::LoamFeatures<V3> o;
+  for (const V3& p : in.edge_points) o.edge_points.push_back(T.act(p));
+  for (const V3& p : in.planar_points) o.planar_points.push_back(T.act(p));
+  return o;
+}
+
+static void test_registration_scenarios() {
+  const auto target = simple_scene();
+  CHECK(target.edge_points.size() == 162 && target.planar_points.size() == 8941);
+  const loam::Pose3d source_T_target(Eigen::Quaterniond(0.9993921140970299, 0.014692022378442412, 0.030140550562090015, 0.009544316157523478),
+                                     V3(0.01, 0.03, -0.01));
+  const auto source = transformed(target, source_T_target);
+  auto detail = std::make_shared<loam::RegistrationDetail>();
+  const loam::Pose3d est = loam::registerFeatures<loam::ParenAccessor>(source, target, loam::Pose3d::Identity(),
+                                                                      loam::RegistrationParams(), detail);
+  const loam::Pose3d err = source_T_target.compose(est);
+  CHECK(err.rotation.angularDistance(Eigen::Quaterniond::Identity()) < 1e-4);
+  CHECK(err.translation.norm() < 1e-4);
+  CHECK(detail->termination_type == loam::RegistrationDetail::CONVERGED);
+  CHECK(!detail->iteration_info.empty() && detail->iteration_info[0].plane_associations.size() > 8000);
+  CHECK(detail->iteration_info[0].edge_associations[0].first == 0);
+
+  // update is composed on the left (max_iterations = 1, non-identity start)
+  loam::RegistrationParams one;
+  one.max_iterations = 1;
+  const loam::Pose3d yaw(Eigen::Quaterniond(std::cos(0.05), 0, 0, std::sin(0.05)), V3(0, 0, 0));
+  const auto src2 = transformed(target, yaw);
+  const loam::Pose3d init(Eigen::Quaterniond(std::cos(-0.05), 0, 0, std::sin(-0.05)), V3(0.1, 0, 0));
+  const loam::Pose3d est2 = loam::registerFeatures<loam::ParenAccessor>(src2, target, init, one);
+  const loam::Pose3d err2 = yaw.compose(est2);
+  CHECK(err2.rotation.angularDistance(Eigen::Quaterniond::Identity()) < 1e-4);
+  CHECK(err2.translation.norm() < 1e-3);
+
+  // planar-only sets (empty edge clouds) registered onto themselves stay at identity
+  loam::LoamFeatures<V3, Eigen::aligned_allocator> planes;
+  planes.planar_points.assign(target.planar_points.begin(), target.planar_points.end());
+  const loam::Pose3d est3 = loam::registerFeatures<loam::ParenAccessor>(planes, planes, loam::Pose3d::Identity());
+  CHECK(est3.rotation.angularDistance(Eigen::Quaterniond::Identity()) < 1e-4 && est3.translation.norm() < 1e-3);
+
+  // too few associations: estimate unchanged, reported as such
+  loam::LoamFeatures<V3> tiny;
+  tiny.planar_points.assign(target.planar_points.begin(), target.planar_points.begin() + 20);
+  auto d2 = std::make_shared<loam::RegistrationDetail>();
+  const loam::Pose3d est4 = loam::registerFeatures<loam::ParenAccessor>(tiny, tiny, init, loam::RegistrationParams(), d2);
+  CHECK(d2->termination_type == loam::RegistrationDetail::INSUFFICIENT_ASSOCIATIONS && d2->iteration_info.empty());
+  CHECK_NEAR(est4.translation(0), 0.1, 0.0);
+}
+
+int main(int argc, char** argv) {
+  const bool no_gpu = argc > 1 && std::strcmp(argv[1], "--no-gpu") == 0;
+  test_pose_algebra();
+  test_size_mismatch_message();
+  test_empty_nonstd_allocator();
+  if (no_gpu) {
+    test_no_device_is_loud();
+  } else {
+    test_curvature_known_answers();
+    test_valid_mask_known_answers();
+    test_float_zero_copy_matches_double_path();
+    test_registration_scenarios();
+  }
+  std::printf("%s: %d checks, %d failed\n", no_gpu ? "host-only" : "gpu", g_checks, g_fail);
+  return g_fail ? 1 : 0;
+}
