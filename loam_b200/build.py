@@ -39,6 +39,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cmd = [nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
            "-fmad=false", "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"),
            "-I", os.path.join(HERE, "csrc"), "-o", LIB] + SRC
+    cmd[1:1] = os.environ.get("LOAMGPU_NVCC_FLAGS", "").split()
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

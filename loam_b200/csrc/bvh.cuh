@@ -347,7 +347,8 @@ constexpr int kBvhStack = 64;  // >= tree depth: 30 Morton bits + 32 position bi
 template <int K>
 __device__ __forceinline__ void knn_bvh(const BvhHdr& h, const BvhNode* __restrict__ nodes,
                                         const double4* __restrict__ sorted, double qx, double qy, double qz, int k,
-                                        double max_dist, TopK<K>& tk) {
+                                        double max_dist, TopK<K>& tk, double d2_hint) {
+  // d2_hint: a squared distance within which at least k points are known to lie (prunes only; inf = none)
   tk.init();
   if (h.n == 0) return;
   const double d2_cut = max_dist > 0 ? max_dist * max_dist * (1.0 + 1e-12) : CUDART_INF;
@@ -355,7 +356,7 @@ __device__ __forceinline__ void knn_bvh(const BvhHdr& h, const BvhNode* __restri
   q.lo[0] = __double2float_rd(qx); q.hi[0] = __double2float_ru(qx);
   q.lo[1] = __double2float_rd(qy); q.hi[1] = __double2float_ru(qy);
   q.lo[2] = __double2float_rd(qz); q.hi[2] = __double2float_ru(qz);
-  float bound = __double2float_ru(d2_cut);  // a subtree is pruned when its lower bound > bound
+  float bound = __double2float_ru(fmin(d2_cut, d2_hint));  // a subtree is pruned when its lower bound > bound
 
   // pending subtrees: (node index, key range, lower bound); a subtree of <= kBvhLeaf points is scanned as a leaf
   // (the node index itself is not needed: a node's record is only read to test it, and that read also yields
@@ -430,7 +431,7 @@ __device__ __forceinline__ void knn_bvh(const BvhHdr& h, const BvhNode* __restri
       id = ok ? id : 0xFFFFFFFFu;
       tk.insert(d2, id);
     }
-    bound = __double2float_ru(fmin(tk.kth(k), d2_cut));
+    bound = __double2float_ru(fmin(fmin(tk.kth(k), d2_cut), d2_hint));
     have = false;
   }
 }
@@ -453,7 +454,7 @@ __global__ void __launch_bounds__(128) knn_kernel(KnnArgs a) {
   const BvhHdr h = a.g.hdr[0];
   TopK<K> tk;
   knn_bvh<K>(h, a.g.nodes, a.g.sorted, a.queries[3 * i], a.queries[3 * i + 1], a.queries[3 * i + 2], a.k, a.max_dist,
-             tk);
+             tk, CUDART_INF);
   const int m = radius_count(tk, a.k, a.max_dist);
   a.count_out[i] = (uint32_t)m;
 #pragma unroll

@@ -364,7 +364,7 @@ int run_register(loamgpu_ctx* ctx, const RegP& rp, uint32_t n_pairs, uint64_t pa
     la.d_lm_cost = ctx->det_lm_cost.as<double>();
   }
   for (int it = 0; it < rp.max_iterations; it++) {
-    TIMED(LOAMGPU_K_ASSOC, launch_assoc_knn(aa, n_pairs, ctx->stream));
+    TIMED(LOAMGPU_K_ASSOC, launch_assoc_knn(aa, n_pairs, it, ctx->stream));
     TIMED(LOAMGPU_K_FIT, launch_assoc_fit(aa, n_pairs, it, ctx->stream));
     la.outer_iter = it;
     TIMED(LOAMGPU_K_LM, launch_lm(la, n_pairs, ctx->stream));

@@ -9,7 +9,14 @@ namespace loamgpu {
 
 constexpr int kExtractThreads = 256;
 constexpr int kAssocThreads = 128;
-constexpr int kLmThreads = 512;
+#ifndef LM_THREADS
+#define LM_THREADS 512
+#endif
+#ifndef LM_MINBLOCKS
+#define LM_MINBLOCKS 1
+#endif
+constexpr int kLmThreads = LM_THREADS;
+constexpr int kLmMinBlocks = LM_MINBLOCKS;
 constexpr int kBuildThreads = 1024;
 constexpr int kKnnSmall = 5;     // neighbour counts up to this use the 5-slot register top-k
 constexpr int kKnnRegMax = 8;    // ... up to this the 8-slot one
@@ -101,7 +108,7 @@ struct AssocArgs {
   int32_t* nearest;        // optional [outer_iter][pair][capE+capP] nearest target index or -1 (detail)
   RegP rp;
 };
-cudaError_t launch_assoc_knn(const AssocArgs& a, uint32_t n_pairs, cudaStream_t st);
+cudaError_t launch_assoc_knn(const AssocArgs& a, uint32_t n_pairs, int outer_iter, cudaStream_t st);
 cudaError_t launch_assoc_fit(const AssocArgs& a, uint32_t n_pairs, int outer_iter, cudaStream_t st);
 
 struct LmArgs {

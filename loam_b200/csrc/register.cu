@@ -62,10 +62,15 @@ __device__ __forceinline__ V3 principal_axis(double A[3][3]) {
       }
     }
   }
-  int big = 0;
-  if (A[1][1] > A[big][big]) big = 1;
-  if (A[2][2] > A[big][big]) big = 2;
-  return V3{V[0][big], V[1][big], V[2][big]};
+  // column of the largest eigenvalue, selected without run-time indexing (keeps A and V in registers)
+  double best = A[0][0];
+  V3 axis{V[0][0], V[1][0], V[2][0]};
+  if (A[1][1] > best) {
+    best = A[1][1];
+    axis = V3{V[0][1], V[1][1], V[2][1]};
+  }
+  if (A[2][2] > best) axis = V3{V[0][2], V[1][2], V[2][2]};
+  return axis;
 }
 
 // geometry.cpp:42-59.  The condition number is never produced (the reference computes and discards it,
@@ -190,6 +195,172 @@ __device__ __noinline__ double fit_plane(const double (&P)[KMAX][3], int K, V3& 
   return sum / (double)K;
 }
 
+// ---------------------------------------------------------------------------- register-resident fits (K <= 8)
+// Same arithmetic, in the same order, as fit_line / fit_plane above, but every loop is unrolled over the compile-time
+// capacity KMAX with row / rank predicates, so the neighbour matrix, the QR workspace and the permutation live in
+// registers (the generic versions index them dynamically, which puts ~280 B per thread in local memory).
+template <int KMAX>
+__device__ __forceinline__ void fit_line_reg(const double (&P)[KMAX][3], int K, V3& la, V3& lb) {
+  double c[3] = {0, 0, 0};
+#pragma unroll
+  for (int k = 0; k < KMAX; k++) {
+    if (k < K) {
+      c[0] += P[k][0];
+      c[1] += P[k][1];
+      c[2] += P[k][2];
+    }
+  }
+  c[0] /= (double)K;
+  c[1] /= (double)K;
+  c[2] /= (double)K;
+  double S[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+  for (int k = 0; k < KMAX; k++) {
+    if (k < K) {
+      const double v[3] = {P[k][0] - c[0], P[k][1] - c[1], P[k][2] - c[2]};
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) S[i][j] += v[i] * v[j];
+    }
+  }
+  const V3 dir = principal_axis(S);
+  la = V3{c[0] + 0.1 * dir.x, c[1] + 0.1 * dir.y, c[2] + 0.1 * dir.z};
+  lb = V3{c[0] - 0.1 * dir.x, c[1] - 0.1 * dir.y, c[2] - 0.1 * dir.z};
+}
+
+template <int KMAX>
+__device__ __forceinline__ double fit_plane_reg(const double (&P)[KMAX][3], int K, V3& nrm, double& dist) {
+  double A[KMAX][3], c[KMAX];
+  int perm[3] = {0, 1, 2};
+#pragma unroll
+  for (int k = 0; k < KMAX; k++) {
+    const bool in = k < K;
+    A[k][0] = in ? P[k][0] : 0.0;
+    A[k][1] = in ? P[k][1] : 0.0;
+    A[k][2] = in ? P[k][2] : 0.0;
+    c[k] = in ? 1.0 : 0.0;
+  }
+  const int size = K < 3 ? K : 3;
+  double maxnorm = 0.0;
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    double sq = 0;
+#pragma unroll
+    for (int k = 0; k < KMAX; k++)
+      if (k < K) sq += A[k][j] * A[k][j];
+    sq = sqrt(sq);
+    if (sq > maxnorm) maxnorm = sq;
+  }
+  const double th = maxnorm * 2.220446049250313e-16 / (double)K;
+  const double threshold_helper = th * th;
+  int nonzero = size;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    if (k < size) {
+      int big = k;
+      double bigsq = -1.0;
+#pragma unroll
+      for (int j = k; j < 3; j++) {
+        double sq = 0;
+#pragma unroll
+        for (int r = k; r < KMAX; r++)
+          if (r < K) sq += A[r][j] * A[r][j];
+        if (sq > bigsq) {
+          bigsq = sq;
+          big = j;
+        }
+      }
+      if (nonzero == size && bigsq < threshold_helper * (double)(K - k)) nonzero = k;
+#pragma unroll
+      for (int j = k + 1; j < 3; j++) {  // swap columns k and big (big is a run-time value: one static swap per case)
+        if (big == j) {
+#pragma unroll
+          for (int r = 0; r < KMAX; r++) {
+            const double t = A[r][k];
+            A[r][k] = A[r][j];
+            A[r][j] = t;
+          }
+          const int t = perm[k];
+          perm[k] = perm[j];
+          perm[j] = t;
+        }
+      }
+      double tail = 0;
+#pragma unroll
+      for (int r = k + 1; r < KMAX; r++)
+        if (r < K) tail += A[r][k] * A[r][k];
+      const double c0 = A[k][k];
+      double tau, beta;
+      if (tail <= 2.2250738585072014e-308) {
+        tau = 0;
+        beta = c0;
+#pragma unroll
+        for (int r = k + 1; r < KMAX; r++) A[r][k] = 0;
+      } else {
+        beta = sqrt(c0 * c0 + tail);
+        if (c0 >= 0) beta = -beta;
+#pragma unroll
+        for (int r = k + 1; r < KMAX; r++)
+          if (r < K) A[r][k] = A[r][k] / (c0 - beta);
+        tau = (beta - c0) / beta;
+      }
+      A[k][k] = beta;
+#pragma unroll
+      for (int j = k + 1; j < 3; j++) {
+        double w = A[k][j];
+#pragma unroll
+        for (int r = k + 1; r < KMAX; r++)
+          if (r < K) w += A[r][k] * A[r][j];
+        w *= tau;
+        A[k][j] -= w;
+#pragma unroll
+        for (int r = k + 1; r < KMAX; r++)
+          if (r < K) A[r][j] -= w * A[r][k];
+      }
+      {
+        double w = c[k];
+#pragma unroll
+        for (int r = k + 1; r < KMAX; r++)
+          if (r < K) w += A[r][k] * c[r];
+        w *= tau;
+        c[k] -= w;
+#pragma unroll
+        for (int r = k + 1; r < KMAX; r++)
+          if (r < K) c[r] -= w * A[r][k];
+      }
+    }
+  }
+  double y[3] = {0, 0, 0};
+#pragma unroll
+  for (int i = 2; i >= 0; i--) {
+    if (i < nonzero) {
+      double sacc = c[i];
+#pragma unroll
+      for (int j = i + 1; j < 3; j++)
+        if (j < nonzero) sacc -= A[i][j] * y[j];
+      y[i] = sacc / A[i][i];
+    }
+  }
+  double abc[3] = {0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    if (i < nonzero) {
+#pragma unroll
+      for (int t = 0; t < 3; t++)
+        if (perm[i] == t) abc[t] = y[i];
+    }
+  }
+  const double nn = sqrt(abc[0] * abc[0] + abc[1] * abc[1] + abc[2] * abc[2]);
+  nrm = V3{abc[0] / nn, abc[1] / nn, abc[2] / nn};
+  dist = 1.0 / nn;
+  double sum = 0;
+#pragma unroll
+  for (int k = 0; k < KMAX; k++)
+    if (k < K) sum += (P[k][0] * nrm.x + P[k][1] * nrm.y + P[k][2] * nrm.z) - dist;
+  return sum / (double)K;
+}
+
 // ============================================================================ association (K4 + K5)
 
 // K4: transform every source feature of every active pair by the current estimate (registration.cpp:34,75) and find
@@ -197,7 +368,7 @@ __device__ __noinline__ double fit_plane(const double (&P)[KMAX][3], int K, V3& 
 // structure holds a Morton-sorted copy), so the lanes of a warp carry neighbouring queries: they traverse the same
 // nodes (loads coalesce, caches hit) and need similar numbers of leaves.  Results land at the original feature index.
 template <int K>
-__global__ void __launch_bounds__(kAssocThreads) assoc_knn_kernel(AssocArgs a) {
+__global__ void __launch_bounds__(kAssocThreads) assoc_knn_kernel(AssocArgs a, int outer_iter) {
   const uint32_t pair = blockIdx.y;
   const PairState* ps = a.state + pair;
   if (ps->status != -1) return;
@@ -223,14 +394,32 @@ __global__ void __launch_bounds__(kAssocThreads) assoc_knn_kernel(AssocArgs a) {
   const BvhHdr g = gs.hdr[pair];
   const int k = is_plane ? a.rp.kp : a.rp.ke;
   const double md = is_plane ? a.rp.rp : a.rp.re;
-  TopK<K> tk;
-  knn_bvh<K>(g, gs.nodes + (size_t)pair * gs.pt_cap, gs.sorted + (size_t)pair * gs.pt_cap, q.x, q.y, q.z, k, md, tk);
-  const int m = radius_count(tk, k, md);
   const size_t cap_src = (size_t)a.capE_scan + a.capP_scan;
   const size_t rec = (size_t)pair * cap_src + (is_plane ? a.capE_scan + li : li);
+  uint32_t* out = a.nn_idx + rec * (size_t)a.nn_stride;
+  // From the second outer iteration on, the previous neighbours give a bound before the search starts: k target
+  // points lie within max_j |q - p_j|, so the k-th nearest distance cannot exceed it (the estimate moved by
+  // millimetres, the bound is nearly tight and most of the tree is pruned on the way down).
+  double d2_hint = CUDART_INF;
+  if (outer_iter > 0 && (int)a.nn_cnt[rec] == k) {
+    const double4* tp = is_plane ? a.planar_pts + (size_t)((a.pair0 + pair) % a.n_slots) * a.capP_scan
+                                 : a.edge_pts + (size_t)((a.pair0 + pair) % a.n_slots) * a.capE_scan;
+    double worst = 0.0;
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      if (j < k) {
+        const double4 t = tp[out[j]];
+        worst = fmax(worst, sqdist(q.x, q.y, q.z, t.x, t.y, t.z));
+      }
+    }
+    d2_hint = worst;
+  }
+  TopK<K> tk;
+  knn_bvh<K>(g, gs.nodes + (size_t)pair * gs.pt_cap, gs.sorted + (size_t)pair * gs.pt_cap, q.x, q.y, q.z, k, md, tk,
+             d2_hint);
+  const int m = radius_count(tk, k, md);
   a.rec_p[rec] = make_double4(q.x, q.y, q.z, 0.0);
   a.nn_cnt[rec] = (uint32_t)m;
-  uint32_t* out = a.nn_idx + rec * (size_t)a.nn_stride;
 #pragma unroll
   for (int j = 0; j < K; j++)
     if (j < k) out[j] = tk.id[j];
@@ -273,7 +462,10 @@ __global__ void __launch_bounds__(kAssocThreads) assoc_fit_kernel(AssocArgs a, i
       }
       if (!is_plane) {
         V3 la, lb;
-        fit_line<KMAX>(N, m, la, lb);
+        if (KMAX <= kKnnRegMax)
+          fit_line_reg<KMAX>(N, m, la, lb);
+        else
+          fit_line<KMAX>(N, m, la, lb);
         // registration.cpp:49: condition_number is always DBL_MAX in the reference (geometry.cpp:55-56)
         if (!(1.7976931348623157e308 < a.rp.min_cond)) {
           ok = true;
@@ -283,7 +475,7 @@ __global__ void __launch_bounds__(kAssocThreads) assoc_fit_kernel(AssocArgs a, i
       } else {
         V3 nrm;
         double dist;
-        const double avg = fit_plane<KMAX>(N, m, nrm, dist);
+        const double avg = KMAX <= kKnnRegMax ? fit_plane_reg<KMAX>(N, m, nrm, dist) : fit_plane<KMAX>(N, m, nrm, dist);
         if (!(avg > a.rp.max_avg)) {  // registration.cpp:90
           ok = true;
           a.rec_a[rec] = make_double4(nrm.x, nrm.y, nrm.z, dist);
@@ -400,7 +592,7 @@ __device__ __forceinline__ void accumulate_residual(const double4& rp, const dou
   for (int j = 0; j < 3; j++) {
     double acc = 0;
 #pragma unroll
-    for (int k = 0; k < 4; k++) acc += J4[k] * PJ[k][j];
+    for (int k = 0; k < 4; k++) acc = fma(J4[k], PJ[k][j], acc);
     J[j] = acc * sr1;
   }
   J[3] = g.x * sr1;
@@ -411,9 +603,11 @@ __device__ __forceinline__ void accumulate_residual(const double4& rp, const dou
   int t = 0;
 #pragma unroll
   for (int i = 0; i < 6; i++) {
-    e.g[i] += J[i] * rc;
+    // explicit fma: the library is built -fmad=false for the index-deciding arithmetic; these well-conditioned sums
+    // only have to agree with the CPU restatement to rounding
+    e.g[i] = fma(J[i], rc, e.g[i]);
 #pragma unroll
-    for (int j = i; j < 6; j++) e.H[t++] += J[i] * J[j];
+    for (int j = i; j < 6; j++, t++) e.H[t] = fma(J[i], J[j], e.H[t]);
   }
 }
 
@@ -538,7 +732,7 @@ __device__ __forceinline__ double norm7(const double* x) {
 
 // One CTA per pair.  Every thread runs the (tiny, uniform) controller redundantly on the reduced sums, so
 // no broadcast of the step is needed between evaluations.
-__global__ void __launch_bounds__(kLmThreads) lm_kernel(LmArgs a) {
+__global__ void __launch_bounds__(kLmThreads, kLmMinBlocks) lm_kernel(LmArgs a) {
   __shared__ double s_part[(kLmThreads / 32) * 28];
   __shared__ double s_tot[28];
   const uint32_t pair = blockIdx.x;
@@ -749,17 +943,17 @@ cudaError_t launch_bvh_build(const BvhBuildArgs& a, uint32_t n_sets, cudaStream_
   return cudaGetLastError();
 }
 
-cudaError_t launch_assoc_knn(const AssocArgs& a, uint32_t n_pairs, cudaStream_t st) {
+cudaError_t launch_assoc_knn(const AssocArgs& a, uint32_t n_pairs, int outer_iter, cudaStream_t st) {
   if (n_pairs == 0) return cudaSuccess;
   const uint32_t cap = a.capE_scan + a.capP_scan;
   dim3 grid((cap + kAssocThreads - 1) / kAssocThreads, n_pairs);
   const int kmax = a.rp.ke > a.rp.kp ? a.rp.ke : a.rp.kp;
   if (kmax <= kKnnSmall)
-    assoc_knn_kernel<kKnnSmall><<<grid, kAssocThreads, 0, st>>>(a);
+    assoc_knn_kernel<kKnnSmall><<<grid, kAssocThreads, 0, st>>>(a, outer_iter);
   else if (kmax <= kKnnRegMax)
-    assoc_knn_kernel<kKnnRegMax><<<grid, kAssocThreads, 0, st>>>(a);
+    assoc_knn_kernel<kKnnRegMax><<<grid, kAssocThreads, 0, st>>>(a, outer_iter);
   else
-    assoc_knn_kernel<kKnnMax><<<grid, kAssocThreads, 0, st>>>(a);
+    assoc_knn_kernel<kKnnMax><<<grid, kAssocThreads, 0, st>>>(a, outer_iter);
   return cudaGetLastError();
 }
 

@@ -130,6 +130,7 @@ static std::vector<P> room_scan(int rings, int cols) {
       if (dy < 0) t = std::fmin(t, -6.0 / dy);
       if (dz > 0) t = std::fmin(t, 3.0 / dz);
       if (dz < 0) t = std::fmin(t, -1.5 / dz);
+      if (std::fabs(az - 1.0) < 0.06 || std::fabs(az - 4.0) < 0.06) t = std::fmin(t, 2.0 / std::cos(el));  // two pillars
       t += 0.004 * std::sin(12.9898 * r + 78.233 * c);  // deterministic roughness
       P p{};
       p.x = (decltype(p.x))(t * dx);
