@@ -10,10 +10,10 @@ namespace loamgpu {
 constexpr int kExtractThreads = 256;
 constexpr int kAssocThreads = 128;
 #ifndef LM_THREADS
-#define LM_THREADS 512
+#define LM_THREADS 256
 #endif
 #ifndef LM_MINBLOCKS
-#define LM_MINBLOCKS 1
+#define LM_MINBLOCKS 2
 #endif
 constexpr int kLmThreads = LM_THREADS;
 constexpr int kLmMinBlocks = LM_MINBLOCKS;
