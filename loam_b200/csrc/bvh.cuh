@@ -56,7 +56,9 @@ constexpr int kRadixBins = 1 << kRadixBits;
 constexpr int kMortonBits = 30;
 
 __global__ void __launch_bounds__(kBuildThreads) bvh_build_kernel(BvhBuildArgs a) {
-  extern __shared__ uint32_t s_cnt[];  // [kRadixBins][kBuildThreads]
+  // dynamic shared memory: [0, kRadixBins*kBuildThreads) radix counters during the sort; afterwards, when the set
+  // fits (a.smem_tree), the sorted Morton codes (n words) and behind them one readiness byte per node
+  extern __shared__ uint32_t s_cnt[];
   __shared__ double s_red[32];
   __shared__ uint32_t s_scan[kBuildThreads / 32];
   __shared__ uint32_t s_wtot[kRadixBins * (kBuildThreads / 32)];
@@ -117,7 +119,13 @@ __global__ void __launch_bounds__(kBuildThreads) bvh_build_kernel(BvhBuildArgs a
   uint2* src = keyA;
   uint2* dst = keyB;
   const uint32_t lane = tid & 31, warp = tid >> 5;
-  for (int shift = 0; shift < kMortonBits; shift += kRadixBits) {
+  // Leaves stop at 8 points, so a set of n points needs only ~log2(n)/2 + 1 bits per axis to separate them (CPU
+  // simulation, DESIGN.md §5: 7 bits/axis give the same tree quality as 10 on a 14k-point set); fewer bits = fewer passes.
+  int bits_axis = 6;
+  while (bits_axis < 10 && (1u << (2 * (bits_axis - 1))) < n) bits_axis++;
+  const int key_shift = 3 * (10 - bits_axis);  // drop the finest levels of the 30-bit code
+  const int sort_bits = 3 * bits_axis;
+  for (int shift = key_shift; shift < key_shift + sort_bits; shift += kRadixBits) {
 #pragma unroll
     for (int b = 0; b < kRadixBins; b++) s_cnt[b * kBuildThreads + tid] = 0;
     for (uint32_t i = c0; i < c1; i++) s_cnt[((src[i].x >> shift) & (kRadixBins - 1)) * kBuildThreads + tid]++;
@@ -180,6 +188,17 @@ __global__ void __launch_bounds__(kBuildThreads) bvh_build_kernel(BvhBuildArgs a
 
   if (n < 2) return;  // a single point has no internal node; knn_bvh scans it directly
 
+  const bool in_smem = a.smem_tree != 0;
+  uint32_t* s_codes = s_cnt;
+  uint8_t* s_ready = reinterpret_cast<uint8_t*>(s_cnt + max((uint32_t)(kRadixBins * kBuildThreads), a.g.pt_cap));
+  if (in_smem) {
+    for (uint32_t i = tid; i < n; i += nthr) {
+      s_codes[i] = src[i].x >> key_shift;
+      s_ready[i] = 0;
+    }
+    __syncthreads();
+  }
+
   // ---- binary radix tree over the sorted (code, position) keys.  Internal node i covers the key range [first, last]
   // with i == first or i == last; its children are node/leaf `split` (range [first, split]) and `split + 1`
   // (range [split + 1, last]).
@@ -187,7 +206,7 @@ __global__ void __launch_bounds__(kBuildThreads) bvh_build_kernel(BvhBuildArgs a
   int* arrived = a.g.aux + (size_t)set * a.g.pt_cap;  // per internal node: 0 pending, 2 merged this pass, 1 ready
   auto delta = [&](int i, int j) -> int {  // common-prefix length of keys i and j, -1 outside the array
     if (j < 0 || j >= (int)n) return -1;
-    const uint32_t ci = key[i].x, cj = key[j].x;
+    const uint32_t ci = in_smem ? s_codes[i] : key[i].x >> key_shift, cj = in_smem ? s_codes[j] : key[j].x >> key_shift;
     return ci != cj ? __clz(ci ^ cj) : 32 + __clz((uint32_t)i ^ (uint32_t)j);
   };
   for (uint32_t t = tid; t + 1 < n; t += nthr) {
@@ -226,11 +245,11 @@ __global__ void __launch_bounds__(kBuildThreads) bvh_build_kernel(BvhBuildArgs a
     for (uint32_t i = tid; i + 1 < n; i += nthr) {
       // flags and boxes written by other threads of this CTA are read with ld.cg (L2), never from a possibly
       // stale L1 line
-      if (__ldcg(ready + i) != 0) continue;
+      if ((in_smem ? (int)s_ready[i] : __ldcg(ready + i)) != 0) continue;
       const uint32_t w = nodes[i].split;  // written by this same thread above
       const uint32_t sp = w & kSplitMask;
-      const bool lready = (w & kLeftLeaf) || __ldcg(ready + sp) == 1;
-      const bool rready = (w & kRightLeaf) || __ldcg(ready + sp + 1) == 1;
+      const bool lready = (w & kLeftLeaf) || (in_smem ? (int)s_ready[sp] : __ldcg(ready + sp)) == 1;
+      const bool rready = (w & kRightLeaf) || (in_smem ? (int)s_ready[sp + 1] : __ldcg(ready + sp + 1)) == 1;
       if (!(lready && rready)) {
         pending = true;
         continue;
@@ -261,11 +280,19 @@ __global__ void __launch_bounds__(kBuildThreads) bvh_build_kernel(BvhBuildArgs a
         nodes[i].lo[k] = lo[k];
         nodes[i].hi[k] = hi[k];
       }
-      __stcg(ready + i, 2);
+      if (in_smem)
+        s_ready[i] = 2;
+      else
+        __stcg(ready + i, 2);
     }
     __syncthreads();
-    for (uint32_t i = tid; i + 1 < n; i += nthr)
-      if (__ldcg(ready + i) == 2) __stcg(ready + i, 1);
+    for (uint32_t i = tid; i + 1 < n; i += nthr) {
+      if (in_smem) {
+        if (s_ready[i] == 2) s_ready[i] = 1;
+      } else if (__ldcg(ready + i) == 2) {
+        __stcg(ready + i, 1);
+      }
+    }
     if (!__syncthreads_or(pending)) break;
   }
 }

@@ -84,6 +84,7 @@ struct BvhBuildArgs {
   uint64_t slot0;
   uint32_t n_slots;
   BvhSetArrays g;
+  int smem_tree;           // set by launch_bvh_build: sorted codes + readiness flags fit in shared memory
 };
 cudaError_t launch_bvh_build(const BvhBuildArgs& a, uint32_t n_sets, cudaStream_t st);
 

@@ -15,6 +15,8 @@
 //
 // Tie-break (documented, deterministic): equal squared distances resolve by ascending target index
 // (nanoflann resolves them by tree-traversal order, i.e. unpinned in the reference).
+#include <algorithm>
+
 #include "bvh.cuh"
 #include "common.cuh"
 #include "kernels.h"
@@ -940,9 +942,17 @@ __global__ void finish_pairs_kernel(const PairState* st, uint32_t n, double* pos
 
 // ============================================================================ host launchers
 
-cudaError_t launch_bvh_build(const BvhBuildArgs& a, uint32_t n_sets, cudaStream_t st) {
+cudaError_t launch_bvh_build(const BvhBuildArgs& a_in, uint32_t n_sets, cudaStream_t st) {
   if (n_sets == 0) return cudaSuccess;
-  const size_t smem = (size_t)kRadixBins * kBuildThreads * sizeof(uint32_t);
+  BvhBuildArgs a = a_in;
+  const size_t sort_bytes = (size_t)kRadixBins * kBuildThreads * sizeof(uint32_t);
+  // radix counters, reused after the sort for the sorted codes; + one readiness byte per node
+  const size_t tree_bytes = std::max(sort_bytes, (size_t)a.g.pt_cap * 4) + a.g.pt_cap + 16;
+  int dev = 0, optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  a.smem_tree = tree_bytes + 4096 <= (size_t)optin;  // (the kernel also has ~2.4 KB of static shared memory)
+  const size_t smem = a.smem_tree ? tree_bytes : sort_bytes;
   cudaError_t err = cudaFuncSetAttribute(bvh_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
   bvh_build_kernel<<<n_sets, kBuildThreads, smem, st>>>(a);
