@@ -151,6 +151,8 @@ int plan_extract(loamgpu_ctx* ctx, int dtype, size_t stride, uint64_t n_points, 
   if (fe->neighbor_points == 0)
     return fail(ctx, LOAMGPU_ERR_INVALID,
                 "neighbor_points must be >= 1 (the reference indexes point idx-1 and throws std::out_of_range)");
+  if (fe->neighbor_points > 16 && fe->neighbor_points < lp->points_per_line)
+    return fail(ctx, LOAMGPU_ERR_UNSUPPORTED, "neighbor_points > 16 not supported");
   if (lp->points_per_line > 65535 || lp->scan_lines > 0xFFFFFFu || n_points > 0xFFFFFFFFull)
     return fail(ctx, LOAMGPU_ERR_UNSUPPORTED, "scan too large (points_per_line <= 65535, total points < 2^32)");
   const uint64_t P = lp->points_per_line;

@@ -64,9 +64,10 @@ struct Rec<double> {
   static constexpr int kElems = 3;
 };
 
-// the range buffer is reused for the walk state (P bytes, padded to 16) and the pick list (P uint16)
+// the range buffer is reused for the walk state (P bytes, padded to 16), the pick list (P uint16) and the
+// neighbour-priority bits (P uint32)
 __host__ __device__ inline uint32_t rng_doubles(uint32_t P) {
-  const uint32_t need = ((P + 15) & ~15u) + 2 * P;
+  const uint32_t need = ((P + 15) & ~15u) + 2 * ((P + 1) & ~1u) + 4 * P;
   return max(P, (need + 7) / 8);
 }
 
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(kExtractThreads) extract_ring_kernel(ExtractAr
   // previous ones, including suppression that spills across a sector boundary (features-inl.h:148-151).
   uint8_t* st = reinterpret_cast<uint8_t*>(rng);                  // walk state per column (rng is dead now)
   uint16_t* plist = reinterpret_cast<uint16_t*>(st + ((P + 15) & ~15u));  // columns picked in the current walk
+  uint32_t* hp = reinterpret_cast<uint32_t*>(plist + ((P + 1) & ~1u));    // higher-priority-neighbour bits per column
   __shared__ uint32_t s_m, s_base[2];
   if (tid == 0) s_base[0] = s_base[1] = 0;
   const uint32_t pps = P / S;
@@ -209,27 +211,34 @@ __global__ void __launch_bounds__(kExtractThreads) extract_ring_kernel(ExtractAr
     }
     if (tid == 0) s_m = 0;
     if (!__syncthreads_or(any)) continue;  // no candidate in this walk (uniform: every thread sees the same result)
+    // which of the 2*(N-1) neighbours are candidates of this walk with a higher priority: evaluated once, so the
+    // rounds below only read state bytes (bit 2(n-1) = column j-n, bit 2(n-1)+1 = column j+n)
+    for (uint32_t j = b + tid; j < e; j += nthr) {
+      if (st[j] != kOpen) continue;
+      uint32_t bits = 0;
+      for (uint32_t n = 1; n <= reach; n++) {
+        if (j >= b + n && st[j - n] != kNone && before(j - n, j)) bits |= 1u << (2 * (n - 1));
+        if (j + n < e && st[j + n] != kNone && before(j + n, j)) bits |= 2u << (2 * (n - 1));
+      }
+      hp[j] = bits;
+    }
+    // (hp[j] is only ever read by the thread that wrote it, and st[] is not modified before the first round)
     for (;;) {
       bool open_left = false;
       for (uint32_t j = b + tid; j < e; j += nthr) {
         if (st[j] != kOpen) continue;
+        uint32_t bits = hp[j];
         bool wait = false, drop = false;
-        for (uint32_t n = 1; n <= reach; n++) {
-          if (j >= b + n) {
-            const uint32_t t = j - n;
-            const uint8_t s = st[t];
-            if ((s == kOpen || s == kPicked) && before(t, j)) {
-              drop |= s == kPicked;
-              wait |= s == kOpen;
-            }
+        for (uint32_t n = 1; bits != 0; n++, bits >>= 2) {
+          if (bits & 1u) {
+            const uint8_t s = st[j - n];
+            drop |= s == kPicked;
+            wait |= s == kOpen;
           }
-          if (j + n < e) {
-            const uint32_t t = j + n;
-            const uint8_t s = st[t];
-            if ((s == kOpen || s == kPicked) && before(t, j)) {
-              drop |= s == kPicked;
-              wait |= s == kOpen;
-            }
+          if (bits & 2u) {
+            const uint8_t s = st[j + n];
+            drop |= s == kPicked;
+            wait |= s == kOpen;
           }
         }
         if (drop) {
@@ -243,15 +252,16 @@ __global__ void __launch_bounds__(kExtractThreads) extract_ring_kernel(ExtractAr
       }
       if (!__syncthreads_or(open_left)) break;
     }
-    // rank the picks by priority; accept the first cap + 1; only those invalidate their neighbours
+    // rank the picks by priority (one thread per pick, taken from the compact list); accept the first cap + 1;
+    // only those invalidate their neighbours
     const uint32_t m = s_m;
     const uint32_t base = s_base[planar ? 1 : 0];
-    for (uint32_t j = b + tid; j < e; j += nthr) {
-      if (st[j] != kPicked) continue;
+    for (uint32_t t = tid; t < m; t += nthr) {
+      const uint32_t j = plist[t];
       uint32_t rank = 0;
       for (uint32_t i = 0; i < m; i++) {
-        const uint32_t t = plist[i];
-        rank += (t != j && before(t, j)) ? 1u : 0u;
+        const uint32_t o = plist[i];
+        rank += (o != j && before(o, j)) ? 1u : 0u;
       }
       if (rank > cap) continue;
       (planar ? gp : ge)[base + rank] = ring * P + j;
