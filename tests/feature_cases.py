@@ -100,4 +100,7 @@ PARAM_SWEEP = [
     (6, 1, 30, 200, 20.0, 5.0, 1.0, 2.0),   # a single sector = the whole ring
     (3, 7, 2, 9, 10.0, 2.0, 0.5, 1.0),      # ragged sector remainder
     (1, 6, 10, 50, 1.0, 0.01, 0.5, 1.0),
+    (3, 6, 10, 50, 0.5, 1.0, 0.5, 1.0),     # thresholds overlap: a point can be an edge AND a planar candidate
+    (3, 200, 1, 2, 100.0, 1.0, 0.5, 1.0),   # 400 walks per ring
+    (3, 6, 3, 12, 100.0, 1.0, 0.5, 1.0),    # every walk hits its cap: exercises the truncate-and-reopen repair
 ]
