@@ -106,6 +106,8 @@ struct AssocArgs {
   uint32_t* nn_cnt;        // [pair][capE+capP]            neighbours inside the radius
   uint32_t nn_stride;      // max(num_edge_neighbors, num_plane_neighbors)
   int morton_queries;      // 1: walk the source set in its Morton order (default), 0: original order
+  uint32_t n_pairs;        // pairs of this launch
+  const uint32_t* active;  // [0] = number of pairs still iterating, [1..] their indices; null = all, in order
   int32_t* nearest;        // optional [outer_iter][pair][capE+capP] nearest target index or -1 (detail)
   RegP rp;
 };
@@ -123,6 +125,8 @@ struct LmArgs {
   uint32_t n_slots;
   int src_offset;
   int outer_iter;
+  uint32_t n_pairs;
+  const uint32_t* active;  // see AssocArgs
   RegP rp;
   // optional detail (single-pair API): per outer iteration rows
   double* d_iter_est;      // [cap][7]
@@ -132,6 +136,7 @@ struct LmArgs {
   double* d_lm_cost;       // [cap][2]
 };
 cudaError_t launch_lm(const LmArgs& a, uint32_t n_pairs, cudaStream_t st);
+cudaError_t launch_compact_active(const PairState* st, uint32_t n_pairs, uint32_t* active, cudaStream_t s);
 
 struct KnnArgs {
   const double* queries;  // [n][3]

@@ -375,9 +375,16 @@ __device__ __forceinline__ double fit_plane_reg(const double (&P)[KMAX][3], int 
 #ifndef KNN_MINBLOCKS
 #define KNN_MINBLOCKS 8
 #endif
+// Pairs still iterating: entry 0 of `active` is their count, the indices follow (null = all n_pairs, in order).
+// Rows of the grid stride over that list, so late outer iterations (few or no active pairs) can be launched with a
+// small grid instead of tens of thousands of CTAs that only discover they have nothing to do.
+__device__ __forceinline__ uint32_t active_count(const uint32_t* active, uint32_t n_pairs) {
+  return active ? active[0] : n_pairs;
+}
+__device__ __forceinline__ uint32_t active_pair(const uint32_t* active, uint32_t i) { return active ? active[1 + i] : i; }
+
 template <int K>
-__global__ void __launch_bounds__(kAssocThreads, KNN_MINBLOCKS) assoc_knn_kernel(AssocArgs a, int outer_iter) {
-  const uint32_t pair = blockIdx.y;
+__device__ __forceinline__ void assoc_knn_pair(const AssocArgs& a, int outer_iter, uint32_t pair) {
   const PairState* ps = a.state + pair;
   if (ps->status != -1) return;
   const uint32_t src_slot = (uint32_t)((a.pair0 + pair + a.src_offset) % a.n_slots);
@@ -433,11 +440,16 @@ __global__ void __launch_bounds__(kAssocThreads, KNN_MINBLOCKS) assoc_knn_kernel
     if (j < k) out[j] = tk.id[j];
 }
 
+template <int K>
+__global__ void __launch_bounds__(kAssocThreads, KNN_MINBLOCKS) assoc_knn_kernel(AssocArgs a, int outer_iter) {
+  const uint32_t n_act = active_count(a.active, a.n_pairs);
+  for (uint32_t i = blockIdx.y; i < n_act; i += gridDim.y) assoc_knn_pair<K>(a, outer_iter, active_pair(a.active, i));
+}
+
 // K5: line / plane fit + guards for every source feature (associateEdges/associatePlanes, registration.cpp:39-57,
 // 80-98), in source-index order.  Writes the residual records the LM kernel consumes.
 template <int KMAX>
-__global__ void __launch_bounds__(kAssocThreads) assoc_fit_kernel(AssocArgs a, int outer_iter) {
-  const uint32_t pair = blockIdx.y;
+__device__ __forceinline__ void assoc_fit_pair(const AssocArgs& a, int outer_iter, uint32_t pair) {
   PairState* ps = a.state + pair;
   if (ps->status != -1) return;
   const uint32_t tgt_slot = (uint32_t)((a.pair0 + pair) % a.n_slots);
@@ -491,7 +503,7 @@ __global__ void __launch_bounds__(kAssocThreads) assoc_fit_kernel(AssocArgs a, i
       }
     }
     if (ok) reinterpret_cast<double*>(a.rec_p + rec)[3] = is_plane ? 2.0 : 1.0;  // w: 0 invalid / 1 edge / 2 plane
-    if (a.nearest) a.nearest[((size_t)outer_iter * gridDim.y + pair) * cap_src + (is_plane ? a.capE_scan + li : li)] =
+    if (a.nearest) a.nearest[((size_t)outer_iter * a.n_pairs + pair) * cap_src + (is_plane ? a.capE_scan + li : li)] =
         ok ? (int32_t)nn[0] : -1;
   }
   const unsigned be = __ballot_sync(0xffffffffu, ok && !is_plane);
@@ -500,6 +512,12 @@ __global__ void __launch_bounds__(kAssocThreads) assoc_fit_kernel(AssocArgs a, i
     if (be) atomicAdd(&ps->n_edge_assoc, (uint32_t)__popc(be));
     if (bp) atomicAdd(&ps->n_plane_assoc, (uint32_t)__popc(bp));
   }
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(kAssocThreads) assoc_fit_kernel(AssocArgs a, int outer_iter) {
+  const uint32_t n_act = active_count(a.active, a.n_pairs);
+  for (uint32_t i = blockIdx.y; i < n_act; i += gridDim.y) assoc_fit_pair<KMAX>(a, outer_iter, active_pair(a.active, i));
 }
 
 // ============================================================================ LM solve + ICF update (K6/K7)
@@ -740,10 +758,7 @@ __device__ __forceinline__ double norm7(const double* x) {
 
 // One CTA per pair.  Every thread runs the (tiny, uniform) controller redundantly on the reduced sums, so
 // no broadcast of the step is needed between evaluations.
-__global__ void __launch_bounds__(kLmThreads, kLmMinBlocks) lm_kernel(LmArgs a) {
-  __shared__ double s_part[(kLmThreads / 32) * 28];
-  __shared__ double s_tot[28];
-  const uint32_t pair = blockIdx.x;
+__device__ void lm_pair(const LmArgs& a, uint32_t pair, double* s_part, double* s_tot) {
   PairState* ps = a.state + pair;
   if (ps->status != -1) return;
   const uint32_t src_slot = (uint32_t)((a.pair0 + pair + a.src_offset) % a.n_slots);
@@ -915,6 +930,42 @@ __global__ void __launch_bounds__(kLmThreads, kLmMinBlocks) lm_kernel(LmArgs a) 
   }
 }
 
+__global__ void __launch_bounds__(kLmThreads, kLmMinBlocks) lm_kernel(LmArgs a) {
+  __shared__ double s_part[(kLmThreads / 32) * 28];
+  __shared__ double s_tot[28];
+  const uint32_t n_act = active_count(a.active, a.n_pairs);
+  for (uint32_t i = blockIdx.x; i < n_act; i += gridDim.x) {
+    lm_pair(a, active_pair(a.active, i), s_part, s_tot);
+    __syncthreads();
+  }
+}
+
+// Rebuilds the list of pairs still iterating (ascending pair index) after an LM launch.
+__global__ void __launch_bounds__(1024) compact_active_kernel(const PairState* st, uint32_t n_pairs, uint32_t* active) {
+  __shared__ uint32_t s_warp[32];
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t per = (n_pairs + blockDim.x - 1) / blockDim.x;
+  const uint32_t b = min(tid * per, n_pairs), e = min(b + per, n_pairs);
+  uint32_t mine = 0;
+  for (uint32_t i = b; i < e; i++) mine += st[i].status == -1 ? 1u : 0u;
+  uint32_t inc = mine;
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if ((int)lane >= o) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  uint32_t off = 0, total = 0;
+  for (uint32_t w = 0; w < (blockDim.x >> 5); w++) {
+    if (w < warp) off += s_warp[w];
+    total += s_warp[w];
+  }
+  uint32_t pos = off + inc - mine;
+  for (uint32_t i = b; i < e; i++)
+    if (st[i].status == -1) active[1 + pos++] = i;
+  if (tid == 0) active[0] = total;
+}
+
 __global__ void init_pairs_kernel(PairState* st, uint32_t n, const double* init) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -959,10 +1010,16 @@ cudaError_t launch_bvh_build(const BvhBuildArgs& a_in, uint32_t n_sets, cudaStre
   return cudaGetLastError();
 }
 
+// Rows of pair-indexed grids: every pair in the first two outer iterations (nearly all are still active), a short
+// strided grid afterwards (typically nothing is left after 2-3 iterations).
+static uint32_t pair_rows(uint32_t n_pairs, int outer_iter, bool has_list, uint32_t late_rows) {
+  return (outer_iter < 2 || !has_list) ? n_pairs : std::min(n_pairs, late_rows);
+}
+
 cudaError_t launch_assoc_knn(const AssocArgs& a, uint32_t n_pairs, int outer_iter, cudaStream_t st) {
   if (n_pairs == 0) return cudaSuccess;
   const uint32_t cap = a.capE_scan + a.capP_scan;
-  dim3 grid((cap + kAssocThreads - 1) / kAssocThreads, n_pairs);
+  dim3 grid((cap + kAssocThreads - 1) / kAssocThreads, pair_rows(n_pairs, outer_iter, a.active != nullptr, 16));
   const int kmax = a.rp.ke > a.rp.kp ? a.rp.ke : a.rp.kp;
   if (kmax <= kKnnSmall)
     assoc_knn_kernel<kKnnSmall><<<grid, kAssocThreads, 0, st>>>(a, outer_iter);
@@ -976,7 +1033,7 @@ cudaError_t launch_assoc_knn(const AssocArgs& a, uint32_t n_pairs, int outer_ite
 cudaError_t launch_assoc_fit(const AssocArgs& a, uint32_t n_pairs, int outer_iter, cudaStream_t st) {
   if (n_pairs == 0) return cudaSuccess;
   const uint32_t cap = a.capE_scan + a.capP_scan;
-  dim3 grid((cap + kAssocThreads - 1) / kAssocThreads, n_pairs);
+  dim3 grid((cap + kAssocThreads - 1) / kAssocThreads, pair_rows(n_pairs, outer_iter, a.active != nullptr, 16));
   const int kmax = a.rp.ke > a.rp.kp ? a.rp.ke : a.rp.kp;
   if (kmax <= kKnnSmall)
     assoc_fit_kernel<kKnnSmall><<<grid, kAssocThreads, 0, st>>>(a, outer_iter);
@@ -989,7 +1046,13 @@ cudaError_t launch_assoc_fit(const AssocArgs& a, uint32_t n_pairs, int outer_ite
 
 cudaError_t launch_lm(const LmArgs& a, uint32_t n_pairs, cudaStream_t st) {
   if (n_pairs == 0) return cudaSuccess;
-  lm_kernel<<<n_pairs, kLmThreads, 0, st>>>(a);
+  lm_kernel<<<pair_rows(n_pairs, a.outer_iter, a.active != nullptr, 296), kLmThreads, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_compact_active(const PairState* s, uint32_t n_pairs, uint32_t* active, cudaStream_t st) {
+  if (n_pairs == 0) return cudaSuccess;
+  compact_active_kernel<<<1, 1024, 0, st>>>(s, n_pairs, active);
   return cudaGetLastError();
 }
 
