@@ -637,6 +637,13 @@ __device__ __forceinline__ void accumulate_residual(const double4& rp, const dou
   }
 }
 
+// read-only 32-byte record load (two LDG.128 through the non-coherent path; __ldg has no double4 overload)
+__device__ __forceinline__ double4 ldg_d4(const double4* p) {
+  const double2 lo = __ldg(reinterpret_cast<const double2*>(p));
+  const double2 hi = __ldg(reinterpret_cast<const double2*>(p) + 1);
+  return make_double4(lo.x, lo.y, hi.x, hi.y);
+}
+
 // Evaluate the whole problem of this pair at x; deterministic fixed-order reduction
 // (per-thread strided partial -> warp shuffle tree -> per-warp shared partials summed in warp order).
 __device__ void evaluate_problem(const double4* __restrict__ rec_p, const double4* __restrict__ rec_a,
@@ -654,14 +661,30 @@ __device__ void evaluate_problem(const double4* __restrict__ rec_p, const double
   for (int i = 0; i < 6; i++) e.g[i] = 0;
   e.cost = 0;
   const uint32_t total = nE + nP;
-  for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+  // software-pipelined: the records of the next residual are in flight while this one is evaluated (the records of
+  // the ~300 pairs resident on the GPU do not fit L2, so every evaluation streams them from HBM)
+  uint32_t i = threadIdx.x;
+  double4 rp = make_double4(0, 0, 0, 0), ra = rp, rb = rp;
+  if (i < total) {
     const uint32_t ri = i < nE ? i : capE + (i - nE);
-    const double4 rp = rec_p[ri];
-    if (rp.w == 0.0) continue;
-    const double4 ra = rec_a[ri];
-    double4 rb = make_double4(0, 0, 0, 0);
-    if (i < nE) rb = rec_b[i];
-    accumulate_residual(rp, ra, rb, x, PJ, e);
+    rp = ldg_d4(rec_p + ri);
+    ra = ldg_d4(rec_a + ri);
+    if (i < nE) rb = ldg_d4(rec_b + i);
+  }
+  while (i < total) {
+    const uint32_t ni = i + blockDim.x;
+    double4 np4 = make_double4(0, 0, 0, 0), na4 = np4, nb4 = np4;
+    if (ni < total) {
+      const uint32_t ri = ni < nE ? ni : capE + (ni - nE);
+      np4 = ldg_d4(rec_p + ri);
+      na4 = ldg_d4(rec_a + ri);
+      if (ni < nE) nb4 = ldg_d4(rec_b + ni);
+    }
+    if (rp.w != 0.0) accumulate_residual(rp, ra, rb, x, PJ, e);
+    rp = np4;
+    ra = na4;
+    rb = nb4;
+    i = ni;
   }
   double v[28];
 #pragma unroll
