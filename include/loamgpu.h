@@ -152,6 +152,33 @@ int loamgpu_register(loamgpu_ctx* ctx, const double* src_edge, uint64_t n_src_ed
 int loamgpu_knn(loamgpu_ctx* ctx, const double* targets, uint64_t n_targets, const double* queries,
                 uint64_t n_queries, uint32_t k, double max_dist, uint32_t* idx_out, uint32_t* count_out);
 
+/* ------------------------------------------- device-resident local map (scan-to-map) */
+/* The reference's README.md:63 leaves "maintain a local map of points" to the caller, who then
+ * passes the accumulated map as the `target` of registerFeatures (registration.h:128-131) and
+ * pays a KD-tree build over the whole map on every call (registration-inl.h:20-23).  A
+ * loamgpu_map keeps the target's feature points and their NN structures on the device between
+ * calls.  Point indices (loamgpu_detail associations) refer to the map's current point order:
+ * insertion order, after eviction.  One map belongs to the device of the context that made it.
+ *
+ *   loamgpu_map_create      map from n_edge x 3 / n_planar x 3 doubles (either may be empty)
+ *   loamgpu_map_update      append features (transformed into the map frame by `pose`, i.e.
+ *                           Pose3d::act, when pose != NULL), then keep only the newest max_edge /
+ *                           max_planar points (0 = unbounded) and rebuild the NN structures
+ *   loamgpu_register_to_map registerFeatures(source, <map>, init, params, detail): identical
+ *                           results to loamgpu_register with the map's points as the target
+ * loamgpu_register itself switches to the same multi-CTA NN build for large targets. */
+typedef struct loamgpu_map loamgpu_map;
+int loamgpu_map_create(loamgpu_ctx* ctx, const double* edge, uint64_t n_edge, const double* planar,
+                       uint64_t n_planar, loamgpu_map** out);
+void loamgpu_map_destroy(loamgpu_ctx* ctx, loamgpu_map* map);
+int loamgpu_map_size(const loamgpu_map* map, uint64_t* n_edge, uint64_t* n_planar);
+int loamgpu_map_update(loamgpu_ctx* ctx, loamgpu_map* map, const double* edge, uint64_t n_edge,
+                       const double* planar, uint64_t n_planar, const double pose[7], uint64_t max_edge,
+                       uint64_t max_planar);
+int loamgpu_register_to_map(loamgpu_ctx* ctx, const loamgpu_map* map, const double* src_edge, uint64_t n_src_edge,
+                            const double* src_planar, uint64_t n_src_planar, const double init_pose[7],
+                            const loamgpu_reg_params* params, double out_pose[7], loamgpu_detail* detail);
+
 /* ------------------------------------------------------- sequence odometry (batched) */
 /* extract + scan-to-scan register over a sequence of organised float4 scans
  * ({x,y,z,unused} floats, n_scans * scan_lines*points_per_line records): every scan is

@@ -24,7 +24,8 @@ SYMBOLS = [
     "loamgpu_create", "loamgpu_destroy", "loamgpu_last_error", "loamgpu_set_stream", "loamgpu_default_fe_params",
     "loamgpu_default_reg_params", "loamgpu_launch_count", "loamgpu_extract", "loamgpu_curvature",
     "loamgpu_valid_mask", "loamgpu_register", "loamgpu_knn", "loamgpu_odometry_host", "loamgpu_odometry_device",
-    "loamgpu_set_chunk_pairs", "loamgpu_set_profiling", "loamgpu_kernel_times",
+    "loamgpu_set_chunk_pairs", "loamgpu_set_profiling", "loamgpu_kernel_times", "loamgpu_map_create",
+    "loamgpu_map_destroy", "loamgpu_map_size", "loamgpu_map_update", "loamgpu_register_to_map",
 ]
 KERNEL_CLASSES = ["extract", "pack", "nn_build", "knn", "lm", "misc", "fit"]
 
@@ -88,6 +89,12 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     lib.loamgpu_valid_mask.argtypes = [vp, vp, C.c_int, C.c_size_t, u64, vp, vp, vp]
     lib.loamgpu_register.argtypes = [vp, vp, u64, vp, u64, vp, u64, vp, u64, vp, vp, vp, vp]
     lib.loamgpu_knn.argtypes = [vp, vp, u64, vp, u64, u32, f64, vp, vp]
+    lib.loamgpu_map_create.argtypes = [vp, vp, u64, vp, u64, C.POINTER(C.c_void_p)]
+    lib.loamgpu_map_destroy.argtypes = [vp, vp]
+    lib.loamgpu_map_destroy.restype = None
+    lib.loamgpu_map_size.argtypes = [vp, vp, vp]
+    lib.loamgpu_map_update.argtypes = [vp, vp, vp, u64, vp, u64, vp, u64, u64]
+    lib.loamgpu_register_to_map.argtypes = [vp, vp, vp, u64, vp, u64, vp, vp, vp, vp]
     lib.loamgpu_odometry_host.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.loamgpu_odometry_device.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, vp, vp, vp]
     _lib = lib
@@ -192,37 +199,57 @@ class Context:
         return out.astype(bool)
 
     # ---------------------------------------------------------------- registration
-    def register(self, src_edge, src_planar, tgt_edge, tgt_planar, init_pose, rp: CRegParams, want_detail=False):
-        se, sp, te, tp = (_xyz64(x) for x in (src_edge, src_planar, tgt_edge, tgt_planar))
-        init = np.ascontiguousarray(init_pose, dtype=np.float64)
-        out = np.empty(7, dtype=np.float64)
-        det = None
-        bufs = None
-        if want_detail:
-            cap = max(int(rp.max_iterations), 1)
-            bufs = dict(
-                iter_est=np.zeros((cap, 7)), iter_update=np.zeros((cap, 7)),
-                n_edge_assoc=np.zeros(cap, dtype=np.uint32), n_plane_assoc=np.zeros(cap, dtype=np.uint32),
-                edge_assoc=np.zeros((cap, max(len(se), 1), 2), dtype=np.uint32),
-                plane_assoc=np.zeros((cap, max(len(sp), 1), 2), dtype=np.uint32),
-                lm_iters=np.zeros(cap, dtype=np.uint32), lm_cost=np.zeros((cap, 2)))
-            det = CDetail(cap, max(len(se), 1), max(len(sp), 1), 0, 1,
-                          bufs["iter_est"].ctypes.data_as(PD), bufs["iter_update"].ctypes.data_as(PD),
-                          bufs["n_edge_assoc"].ctypes.data_as(PU32), bufs["n_plane_assoc"].ctypes.data_as(PU32),
-                          bufs["edge_assoc"].ctypes.data_as(PU32), bufs["plane_assoc"].ctypes.data_as(PU32),
-                          bufs["lm_iters"].ctypes.data_as(PU32), bufs["lm_cost"].ctypes.data_as(PD))
-        self._check(self.lib.loamgpu_register(self.h, _ptr(se), len(se), _ptr(sp), len(sp), _ptr(te), len(te),
-                                              _ptr(tp), len(tp), _ptr(init), C.addressof(rp), _ptr(out),
-                                              C.addressof(det) if det is not None else None))
-        if not want_detail:
-            return out
+    @staticmethod
+    def _detail_buffers(rp, n_se, n_sp):
+        cap = max(int(rp.max_iterations), 1)
+        bufs = dict(
+            iter_est=np.zeros((cap, 7)), iter_update=np.zeros((cap, 7)),
+            n_edge_assoc=np.zeros(cap, dtype=np.uint32), n_plane_assoc=np.zeros(cap, dtype=np.uint32),
+            edge_assoc=np.zeros((cap, max(n_se, 1), 2), dtype=np.uint32),
+            plane_assoc=np.zeros((cap, max(n_sp, 1), 2), dtype=np.uint32),
+            lm_iters=np.zeros(cap, dtype=np.uint32), lm_cost=np.zeros((cap, 2)))
+        det = CDetail(cap, max(n_se, 1), max(n_sp, 1), 0, 1,
+                      bufs["iter_est"].ctypes.data_as(PD), bufs["iter_update"].ctypes.data_as(PD),
+                      bufs["n_edge_assoc"].ctypes.data_as(PU32), bufs["n_plane_assoc"].ctypes.data_as(PU32),
+                      bufs["edge_assoc"].ctypes.data_as(PU32), bufs["plane_assoc"].ctypes.data_as(PU32),
+                      bufs["lm_iters"].ctypes.data_as(PU32), bufs["lm_cost"].ctypes.data_as(PD))
+        return det, bufs
+
+    @staticmethod
+    def _detail_info(det, bufs):
         n = det.n_iters
-        info = dict(n_iters=n, termination=det.termination, iter_est=bufs["iter_est"][:n].copy(),
+        return dict(n_iters=n, termination=det.termination, iter_est=bufs["iter_est"][:n].copy(),
                     iter_update=bufs["iter_update"][:n].copy(), lm_iters=bufs["lm_iters"][:n].copy(),
                     lm_cost=bufs["lm_cost"][:n].copy(),
                     edge_assoc=[bufs["edge_assoc"][i, :bufs["n_edge_assoc"][i]].copy() for i in range(n)],
                     plane_assoc=[bufs["plane_assoc"][i, :bufs["n_plane_assoc"][i]].copy() for i in range(n)])
-        return out, info
+
+    def register(self, src_edge, src_planar, tgt_edge, tgt_planar, init_pose, rp: CRegParams, want_detail=False):
+        se, sp, te, tp = (_xyz64(x) for x in (src_edge, src_planar, tgt_edge, tgt_planar))
+        init = np.ascontiguousarray(init_pose, dtype=np.float64)
+        out = np.empty(7, dtype=np.float64)
+        det, bufs = self._detail_buffers(rp, len(se), len(sp)) if want_detail else (None, None)
+        self._check(self.lib.loamgpu_register(self.h, _ptr(se), len(se), _ptr(sp), len(sp), _ptr(te), len(te),
+                                              _ptr(tp), len(tp), _ptr(init), C.addressof(rp), _ptr(out),
+                                              C.addressof(det) if det is not None else None))
+        return (out, self._detail_info(det, bufs)) if want_detail else out
+
+    # ---------------------------------------------------------------- device-resident local map
+    def map_create(self, edge, planar) -> "DeviceMap":
+        e, p = _xyz64(edge), _xyz64(planar)
+        h = C.c_void_p()
+        self._check(self.lib.loamgpu_map_create(self.h, _ptr(e), len(e), _ptr(p), len(p), C.byref(h)))
+        return DeviceMap(self, h)
+
+    def register_to_map(self, dmap: "DeviceMap", src_edge, src_planar, init_pose, rp: CRegParams, want_detail=False):
+        se, sp = _xyz64(src_edge), _xyz64(src_planar)
+        init = np.ascontiguousarray(init_pose, dtype=np.float64)
+        out = np.empty(7, dtype=np.float64)
+        det, bufs = self._detail_buffers(rp, len(se), len(sp)) if want_detail else (None, None)
+        self._check(self.lib.loamgpu_register_to_map(self.h, dmap.h, _ptr(se), len(se), _ptr(sp), len(sp), _ptr(init),
+                                                     C.addressof(rp), _ptr(out),
+                                                     C.addressof(det) if det is not None else None))
+        return (out, self._detail_info(det, bufs)) if want_detail else out
 
     def knn(self, targets, queries, k: int, max_dist: float):
         t, q = _xyz64(targets), _xyz64(queries)
@@ -257,6 +284,36 @@ class Context:
         self._check(self.lib.loamgpu_odometry_device(self.h, scans_ptr, n_scans, C.addressof(lp), C.addressof(fe),
                                                      C.addressof(rp), poses_ptr, term_ptr, iters_ptr, ne_ptr,
                                                      np_ptr))
+
+
+class DeviceMap:
+    """Handle of a loamgpu_map: registration target kept on the device (points + NN structures)."""
+
+    def __init__(self, ctx: Context, h):
+        self.ctx, self.h = ctx, h
+
+    def size(self):
+        ne, npl = u64(0), u64(0)
+        self.ctx._check(self.ctx.lib.loamgpu_map_size(self.h, C.byref(ne), C.byref(npl)))
+        return int(ne.value), int(npl.value)
+
+    def update(self, edge, planar, pose=None, max_edge: int = 0, max_planar: int = 0):
+        """Append features (moved into the map frame by `pose` if given), keep the newest max_* points, rebuild."""
+        e, p = _xyz64(edge), _xyz64(planar)
+        ps = None if pose is None else np.ascontiguousarray(pose, dtype=np.float64)
+        self.ctx._check(self.ctx.lib.loamgpu_map_update(self.ctx.h, self.h, _ptr(e), len(e), _ptr(p), len(p), _ptr(ps),
+                                                        max_edge, max_planar))
+
+    def close(self):
+        if self.h and self.ctx.h:
+            self.ctx.lib.loamgpu_map_destroy(self.ctx.h, self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def default_fe_params() -> CFeParams:

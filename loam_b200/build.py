@@ -12,8 +12,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SRC = [os.path.join(HERE, "csrc", f) for f in ("extract.cu", "register.cu", "capi.cu")]
-DEPS = SRC + [os.path.join(HERE, "csrc", f) for f in ("common.cuh", "kernels.h")] + [
+SRC = [os.path.join(HERE, "csrc", f) for f in ("extract.cu", "register.cu", "bvh_big.cu", "capi.cu")]
+DEPS = SRC + [os.path.join(HERE, "csrc", f) for f in ("common.cuh", "kernels.h", "bvh.cuh")] + [
     os.path.join(ROOT, "include", "loamgpu.h")]
 LIB = os.path.join(HERE, "lib", "libloamgpu.so")
 

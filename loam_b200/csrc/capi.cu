@@ -52,13 +52,14 @@ struct loamgpu_ctx {
   uint32_t chunk_pairs = 256;
   int max_smem_optin = 0;
   int morton_queries = 1;  // LOAMGPU_QUERY_ORDER=original switches the k-NN kernel to source-index order (A/B)
+  uint64_t big_target_min = 60000;  // targets at least this large get the multi-CTA NN build ($LOAMGPU_BIG_TARGET_MIN)
 
   DevBuf scan_in[2];                       // H2D staging of scans
   DevBuf ring_edge, ring_planar, ring_counts;
   DevBuf edge_idx, planar_idx, edge_pts, planar_pts, feat_counts;
   DevBuf ge_hdr, ge_nodes, ge_sorted, ge_keys, ge_aux, gp_hdr, gp_nodes, gp_sorted, gp_keys, gp_aux;
   DevBuf state, rec_p, rec_a, rec_b, nearest, nn_idx, nn_cnt, active;
-  DevBuf misc, out_pose, out_term, out_iters, out_ne, out_np;
+  DevBuf big_scratch, misc, out_pose, out_term, out_iters, out_ne, out_np;
   DevBuf det_est, det_upd, det_assoc_n, det_lm_iters, det_lm_cost, init_pose;
 
   // optional per-kernel-class timing (CUDA events on the launching stream)
@@ -71,6 +72,15 @@ struct loamgpu_ctx {
   std::vector<cudaEvent_t> prof_pool;   // free events
   double prof_ms[LOAMGPU_K_COUNT] = {};
   uint64_t prof_n[LOAMGPU_K_COUNT] = {};
+};
+
+// Device-resident registration target ("local map"): feature points in insertion order + their NN structures.
+struct loamgpu_map {
+  int device = 0;
+  uint64_t n[2] = {0, 0};                    // edge / planar points
+  DevBuf pts[2];                             // double4 (x,y,z,0), insertion order
+  DevBuf hdr[2], nodes[2], sorted[2], keys[2], scratch;
+  bool built = false;
 };
 
 namespace {
@@ -304,9 +314,42 @@ BvhSetArrays bvh_arrays(loamgpu_ctx* ctx, bool planar, uint32_t cap) {
   return g;
 }
 
+BvhSetArrays map_arrays(const loamgpu_map* m, int kind) {
+  BvhSetArrays g;
+  g.hdr = m->hdr[kind].as<BvhHdr>();
+  g.nodes = m->nodes[kind].as<BvhNode>();
+  g.sorted = m->sorted[kind].as<double4>();
+  g.keys = m->keys[kind].as<uint2>();
+  g.aux = nullptr;
+  g.pt_cap = (uint32_t)std::max<uint64_t>(m->n[kind], 1);
+  return g;
+}
+
+// (Re)build both NN structures of a map with the multi-CTA build.
+int build_map(loamgpu_ctx* ctx, loamgpu_map* m) {
+  const uint32_t nmax = (uint32_t)std::max<uint64_t>(std::max(m->n[0], m->n[1]), 1);
+  CU(m->scratch.reserve(bvh_big_scratch_bytes(nmax)));
+  for (int kind = 0; kind < 2; kind++) {
+    const size_t cap = (size_t)std::max<uint64_t>(m->n[kind], 1);
+    CU(m->hdr[kind].reserve(sizeof(BvhHdr)));
+    CU(m->nodes[kind].reserve(cap * sizeof(BvhNode)));
+    CU(m->sorted[kind].reserve(cap * 32));
+    CU(m->keys[kind].reserve(cap * 16));
+    ProfScope ps(ctx, LOAMGPU_K_GRID);
+    ctx->launches--;  // the launcher counts its own kernels
+    CU(launch_bvh_build_big(m->pts[kind].as<double4>(), (uint32_t)m->n[kind], map_arrays(m, kind), m->scratch.p,
+                            ctx->stream, &ctx->launches));
+  }
+  m->built = true;
+  return LOAMGPU_OK;
+}
+
 // Register n_pairs pairs whose features sit in slots: tgt = (pair0+p) % n_slots, src = (pair0+p+src_offset) % n_slots.
+// With `map` every pair registers onto the map instead (src_offset must be 0: set p / slot p = source of pair p).
 int run_register(loamgpu_ctx* ctx, const RegP& rp, uint32_t n_pairs, uint64_t pair0, uint32_t n_slots, int src_offset,
-                 uint32_t capE, uint32_t capP, const double* init_pose_dev, bool detail) {
+                 uint32_t capE, uint32_t capP, const double* init_pose_dev, bool detail,
+                 const loamgpu_map* map = nullptr) {
+  const uint32_t n_sets = n_pairs + (map ? 0u : 1u);  // without a map: + the last pair's source set
   BvhBuildArgs gb;
   memset(&gb, 0, sizeof gb);
   gb.counts = ctx->feat_counts.as<uint32_t>();
@@ -316,12 +359,12 @@ int run_register(loamgpu_ctx* ctx, const RegP& rp, uint32_t n_pairs, uint64_t pa
   gb.pt_stride = capE;
   gb.kind = 0;
   gb.g = bvh_arrays(ctx, false, capE);
-  TIMED(LOAMGPU_K_GRID, launch_bvh_build(gb, n_pairs + 1, ctx->stream));  // + the last pair's source set
+  TIMED(LOAMGPU_K_GRID, launch_bvh_build(gb, n_sets, ctx->stream));
   gb.pts = ctx->planar_pts.as<double4>();
   gb.pt_stride = capP;
   gb.kind = 1;
   gb.g = bvh_arrays(ctx, true, capP);
-  TIMED(LOAMGPU_K_GRID, launch_bvh_build(gb, n_pairs + 1, ctx->stream));
+  TIMED(LOAMGPU_K_GRID, launch_bvh_build(gb, n_sets, ctx->stream));
   TIMED(LOAMGPU_K_MISC, launch_init_pairs(ctx->state.as<PairState>(), n_pairs, init_pose_dev, ctx->stream));
 
   AssocArgs aa;
@@ -345,6 +388,13 @@ int run_register(loamgpu_ctx* ctx, const RegP& rp, uint32_t n_pairs, uint64_t pa
   aa.nn_cnt = ctx->nn_cnt.as<uint32_t>();
   aa.nn_stride = (uint32_t)std::max(rp.ke, rp.kp);
   aa.morton_queries = ctx->morton_queries;
+  if (map) {
+    aa.ext_target = 1;
+    aa.te = map_arrays(map, 0);
+    aa.tp = map_arrays(map, 1);
+    aa.te_pts = map->pts[0].as<double4>();
+    aa.tp_pts = map->pts[1].as<double4>();
+  }
   aa.rp = rp;
   LmArgs la;
   memset(&la, 0, sizeof la);
@@ -419,6 +469,7 @@ int loamgpu_create(int device, loamgpu_ctx** out) {
   }
   c->stream = c->own_stream;
   if (const char* qo = getenv("LOAMGPU_QUERY_ORDER")) c->morton_queries = strcmp(qo, "original") != 0;
+  if (const char* bt = getenv("LOAMGPU_BIG_TARGET_MIN")) c->big_target_min = strtoull(bt, nullptr, 10);
   *out = c;
   return LOAMGPU_OK;
 }
@@ -432,7 +483,7 @@ void loamgpu_destroy(loamgpu_ctx* c) {
                     &c->ge_sorted, &c->ge_keys, &c->ge_aux, &c->gp_hdr, &c->gp_nodes, &c->gp_sorted, &c->gp_keys, &c->gp_aux, &c->state,
                     &c->rec_p, &c->rec_a, &c->rec_b, &c->nearest, &c->nn_idx, &c->nn_cnt, &c->active, &c->misc, &c->out_pose, &c->out_term,
                     &c->out_iters, &c->out_ne, &c->out_np, &c->det_est, &c->det_upd, &c->det_assoc_n,
-                    &c->det_lm_iters, &c->det_lm_cost, &c->init_pose};
+                    &c->det_lm_iters, &c->det_lm_cost, &c->init_pose, &c->big_scratch};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < 2; i++) {
     if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
@@ -605,27 +656,23 @@ static void widen(const double* src, uint64_t n, std::vector<double>& dst, size_
   }
 }
 
-int loamgpu_register(loamgpu_ctx* ctx, const double* src_edge, uint64_t n_se, const double* src_planar, uint64_t n_sp,
-                     const double* tgt_edge, uint64_t n_te, const double* tgt_planar, uint64_t n_tp,
-                     const double init_pose[7], const loamgpu_reg_params* params, double out_pose[7],
-                     loamgpu_detail* detail) {
-  if (!ctx) return LOAMGPU_ERR_INVALID;
-  if (!init_pose || !out_pose) return fail(ctx, LOAMGPU_ERR_INVALID, "null pose pointer");
-  if ((n_se && !src_edge) || (n_sp && !src_planar) || (n_te && !tgt_edge) || (n_tp && !tgt_planar))
-    return fail(ctx, LOAMGPU_ERR_INVALID, "null feature buffer");
-  if (std::max(std::max(n_se, n_sp), std::max(n_te, n_tp)) > 0x7FFFFFFFull)
-    return fail(ctx, LOAMGPU_ERR_UNSUPPORTED, "feature set too large");
-  CU(cudaSetDevice(ctx->device));
+// Shared body of loamgpu_register / loamgpu_register_to_map.  With `map` the target arguments are ignored.
+static int register_core(loamgpu_ctx* ctx, const double* src_edge, uint64_t n_se, const double* src_planar, uint64_t n_sp,
+                         const double* tgt_edge, uint64_t n_te, const double* tgt_planar, uint64_t n_tp,
+                         const loamgpu_map* map, const double init_pose[7], const loamgpu_reg_params* params,
+                         double out_pose[7], loamgpu_detail* detail) {
   RegP rp;
   int rc = make_regp(ctx, params, &rp);
   if (rc) return rc;
+  if (map) n_te = n_tp = 0;
   const uint32_t capE = (uint32_t)std::max<uint64_t>(std::max(n_se, n_te), 1);
   const uint32_t capP = (uint32_t)std::max<uint64_t>(std::max(n_sp, n_tp), 1);
   const bool want_detail = detail != nullptr;
   const uint32_t det_iters = want_detail ? (uint32_t)std::max(rp.max_iterations, 1) : 0;
-  // slots: 0 = target, 1 = source
-  CU(ctx->edge_pts.reserve((size_t)2 * capE * 32));
-  CU(ctx->planar_pts.reserve((size_t)2 * capP * 32));
+  // slots: 0 = target, 1 = source   (with a map: 0 = source)
+  const uint32_t n_slots = map ? 1 : 2;
+  CU(ctx->edge_pts.reserve((size_t)n_slots * capE * 32));
+  CU(ctx->planar_pts.reserve((size_t)n_slots * capP * 32));
   CU(ctx->feat_counts.reserve(16));
   rc = reserve_register(ctx, 1, capE, capP, det_iters, (uint32_t)std::max(rp.ke, rp.kp));
   if (rc) return rc;
@@ -641,17 +688,20 @@ int loamgpu_register(loamgpu_ctx* ctx, const double* src_edge, uint64_t n_se, co
     CU(ctx->det_lm_cost.reserve((size_t)det_iters * 16));
     CU(cudaMemsetAsync(ctx->det_assoc_n.p, 0, (size_t)det_iters * 8, ctx->stream));
   }
-  std::vector<double> he((size_t)2 * capE * 4), hp((size_t)2 * capP * 4);
-  widen(tgt_edge, n_te, he, 0);
-  widen(src_edge, n_se, he, capE);
-  widen(tgt_planar, n_tp, hp, 0);
-  widen(src_planar, n_sp, hp, capP);
-  const uint32_t counts[4] = {(uint32_t)n_te, (uint32_t)n_tp, (uint32_t)n_se, (uint32_t)n_sp};
+  std::vector<double> he((size_t)n_slots * capE * 4), hp((size_t)n_slots * capP * 4);
+  if (!map) {
+    widen(tgt_edge, n_te, he, 0);
+    widen(tgt_planar, n_tp, hp, 0);
+  }
+  widen(src_edge, n_se, he, map ? 0 : capE);
+  widen(src_planar, n_sp, hp, map ? 0 : capP);
+  const uint32_t counts[4] = {(uint32_t)(map ? n_se : n_te), (uint32_t)(map ? n_sp : n_tp), (uint32_t)n_se,
+                              (uint32_t)n_sp};
   CU(cudaMemcpyAsync(ctx->edge_pts.p, he.data(), he.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->planar_pts.p, hp.data(), hp.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->feat_counts.p, counts, 16, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->init_pose.p, init_pose, 56, cudaMemcpyHostToDevice, ctx->stream));
-  rc = run_register(ctx, rp, 1, 0, 2, 1, capE, capP, ctx->init_pose.as<double>(), want_detail);
+  rc = run_register(ctx, rp, 1, 0, n_slots, map ? 0 : 1, capE, capP, ctx->init_pose.as<double>(), want_detail, map);
   if (rc) return rc;
   TIMED(LOAMGPU_K_MISC, launch_finish_pairs(ctx->state.as<PairState>(), 1, ctx->out_pose.as<double>(),
                                             ctx->out_term.as<int32_t>(), ctx->out_iters.as<uint32_t>(), ctx->stream));
@@ -707,6 +757,155 @@ int loamgpu_register(loamgpu_ctx* ctx, const double* src_edge, uint64_t n_se, co
   return LOAMGPU_OK;
 }
 
+// Upload n x 3 doubles as double4 records behind `at` existing records of a map's point array.
+static int map_upload(loamgpu_ctx* ctx, loamgpu_map* m, int kind, const double* pts, uint64_t n, uint64_t at) {
+  if (n == 0) return LOAMGPU_OK;
+  std::vector<double> h((size_t)n * 4);
+  widen(pts, n, h, 0);
+  CU(cudaMemcpyAsync(m->pts[kind].as<double4>() + at, h.data(), h.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));  // `h` is pageable and dies here
+  return LOAMGPU_OK;
+}
+
+// Grow a map's point array to `want` records, keeping the first `keep` (cudaMalloc'd buffers do not realloc).
+static int map_grow(loamgpu_ctx* ctx, loamgpu_map* m, int kind, uint64_t keep, uint64_t want) {
+  if (want * 32 <= m->pts[kind].cap) return LOAMGPU_OK;
+  DevBuf nb;
+  CU(nb.reserve((size_t)(want + want / 2) * 32));
+  if (keep) CU(cudaMemcpyAsync(nb.p, m->pts[kind].p, (size_t)keep * 32, cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  m->pts[kind].release();
+  m->pts[kind] = nb;
+  return LOAMGPU_OK;
+}
+
+int loamgpu_register(loamgpu_ctx* ctx, const double* src_edge, uint64_t n_se, const double* src_planar, uint64_t n_sp,
+                     const double* tgt_edge, uint64_t n_te, const double* tgt_planar, uint64_t n_tp,
+                     const double init_pose[7], const loamgpu_reg_params* params, double out_pose[7],
+                     loamgpu_detail* detail) {
+  if (!ctx) return LOAMGPU_ERR_INVALID;
+  if (!init_pose || !out_pose) return fail(ctx, LOAMGPU_ERR_INVALID, "null pose pointer");
+  if ((n_se && !src_edge) || (n_sp && !src_planar) || (n_te && !tgt_edge) || (n_tp && !tgt_planar))
+    return fail(ctx, LOAMGPU_ERR_INVALID, "null feature buffer");
+  if (std::max(std::max(n_se, n_sp), std::max(n_te, n_tp)) > 0x3FFFFFFFull)
+    return fail(ctx, LOAMGPU_ERR_UNSUPPORTED, "feature set too large");
+  CU(cudaSetDevice(ctx->device));
+  if (std::max(n_te, n_tp) >= ctx->big_target_min) {
+    // large target (scan-to-map): multi-CTA NN build over a temporary device-resident map
+    loamgpu_map* m = nullptr;
+    int rc = loamgpu_map_create(ctx, tgt_edge, n_te, tgt_planar, n_tp, &m);
+    if (rc) return rc;
+    rc = register_core(ctx, src_edge, n_se, src_planar, n_sp, nullptr, 0, nullptr, 0, m, init_pose, params, out_pose,
+                       detail);
+    loamgpu_map_destroy(ctx, m);
+    return rc;
+  }
+  return register_core(ctx, src_edge, n_se, src_planar, n_sp, tgt_edge, n_te, tgt_planar, n_tp, nullptr, init_pose, params,
+                       out_pose, detail);
+}
+
+// ------------------------------------------------------------------------------------ device-resident local map
+
+int loamgpu_map_create(loamgpu_ctx* ctx, const double* edge, uint64_t n_edge, const double* planar, uint64_t n_planar,
+                       loamgpu_map** out) {
+  if (!ctx || !out) return LOAMGPU_ERR_INVALID;
+  *out = nullptr;
+  if ((n_edge && !edge) || (n_planar && !planar)) return fail(ctx, LOAMGPU_ERR_INVALID, "null feature buffer");
+  if (std::max(n_edge, n_planar) > 0x3FFFFFFFull) return fail(ctx, LOAMGPU_ERR_UNSUPPORTED, "feature set too large");
+  CU(cudaSetDevice(ctx->device));
+  loamgpu_map* m = new loamgpu_map();
+  m->device = ctx->device;
+  int rc = map_grow(ctx, m, 0, 0, std::max<uint64_t>(n_edge, 1));
+  if (!rc) rc = map_grow(ctx, m, 1, 0, std::max<uint64_t>(n_planar, 1));
+  if (!rc) rc = map_upload(ctx, m, 0, edge, n_edge, 0);
+  if (!rc) rc = map_upload(ctx, m, 1, planar, n_planar, 0);
+  if (!rc) {
+    m->n[0] = n_edge;
+    m->n[1] = n_planar;
+    rc = build_map(ctx, m);
+  }
+  if (rc) {
+    loamgpu_map_destroy(ctx, m);
+    return rc;
+  }
+  *out = m;
+  return LOAMGPU_OK;
+}
+
+void loamgpu_map_destroy(loamgpu_ctx* ctx, loamgpu_map* m) {
+  if (!m) return;
+  if (ctx) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  for (int k = 0; k < 2; k++) {
+    m->pts[k].release();
+    m->hdr[k].release();
+    m->nodes[k].release();
+    m->sorted[k].release();
+    m->keys[k].release();
+  }
+  m->scratch.release();
+  delete m;
+}
+
+int loamgpu_map_size(const loamgpu_map* m, uint64_t* n_edge, uint64_t* n_planar) {
+  if (!m) return LOAMGPU_ERR_INVALID;
+  if (n_edge) *n_edge = m->n[0];
+  if (n_planar) *n_planar = m->n[1];
+  return LOAMGPU_OK;
+}
+
+int loamgpu_map_update(loamgpu_ctx* ctx, loamgpu_map* m, const double* edge, uint64_t n_edge, const double* planar,
+                       uint64_t n_planar, const double pose[7], uint64_t max_edge, uint64_t max_planar) {
+  if (!ctx || !m) return LOAMGPU_ERR_INVALID;
+  if ((n_edge && !edge) || (n_planar && !planar)) return fail(ctx, LOAMGPU_ERR_INVALID, "null feature buffer");
+  if (m->device != ctx->device) return fail(ctx, LOAMGPU_ERR_INVALID, "map belongs to another device");
+  CU(cudaSetDevice(ctx->device));
+  const double* add[2] = {edge, planar};
+  const uint64_t n_add[2] = {n_edge, n_planar}, cap[2] = {max_edge, max_planar};
+  if (pose) {
+    CU(ctx->init_pose.reserve(56));
+    CU(cudaMemcpyAsync(ctx->init_pose.p, pose, 56, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  for (int k = 0; k < 2; k++) {
+    const uint64_t total = m->n[k] + n_add[k];
+    if (total > 0x3FFFFFFFull) return fail(ctx, LOAMGPU_ERR_UNSUPPORTED, "feature set too large");
+    int rc = map_grow(ctx, m, k, m->n[k], std::max<uint64_t>(total, 1));
+    if (!rc) rc = map_upload(ctx, m, k, add[k], n_add[k], m->n[k]);
+    if (rc) return rc;
+    if (pose && n_add[k])
+      TIMED(LOAMGPU_K_MISC, launch_transform_points(m->pts[k].as<double4>() + m->n[k], (uint32_t)n_add[k],
+                                                    ctx->init_pose.as<double>(), ctx->stream));
+    uint64_t n_new = total;
+    if (cap[k] && total > cap[k]) {  // sliding window: the oldest points leave
+      const uint64_t drop = total - cap[k];
+      n_new = cap[k];
+      // overlapping move toward the front: stage through the sort scratch of this kind
+      CU(m->sorted[k].reserve((size_t)n_new * 32));
+      CU(cudaMemcpyAsync(m->sorted[k].p, m->pts[k].as<double4>() + drop, (size_t)n_new * 32, cudaMemcpyDeviceToDevice,
+                         ctx->stream));
+      CU(cudaMemcpyAsync(m->pts[k].p, m->sorted[k].p, (size_t)n_new * 32, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    m->n[k] = n_new;
+  }
+  return build_map(ctx, m);
+}
+
+int loamgpu_register_to_map(loamgpu_ctx* ctx, const loamgpu_map* map, const double* src_edge, uint64_t n_se,
+                            const double* src_planar, uint64_t n_sp, const double init_pose[7],
+                            const loamgpu_reg_params* params, double out_pose[7], loamgpu_detail* detail) {
+  if (!ctx || !map) return LOAMGPU_ERR_INVALID;
+  if (!init_pose || !out_pose) return fail(ctx, LOAMGPU_ERR_INVALID, "null pose pointer");
+  if ((n_se && !src_edge) || (n_sp && !src_planar)) return fail(ctx, LOAMGPU_ERR_INVALID, "null feature buffer");
+  if (std::max(n_se, n_sp) > 0x3FFFFFFFull) return fail(ctx, LOAMGPU_ERR_UNSUPPORTED, "feature set too large");
+  if (map->device != ctx->device) return fail(ctx, LOAMGPU_ERR_INVALID, "map belongs to another device");
+  if (!map->built) return fail(ctx, LOAMGPU_ERR_INVALID, "map has no NN structure");
+  CU(cudaSetDevice(ctx->device));
+  return register_core(ctx, src_edge, n_se, src_planar, n_sp, nullptr, 0, nullptr, 0, map, init_pose, params, out_pose,
+                       detail);
+}
+
 int loamgpu_knn(loamgpu_ctx* ctx, const double* targets, uint64_t n_t, const double* queries, uint64_t n_q, uint32_t k,
                 double max_dist, uint32_t* idx_out, uint32_t* count_out) {
   if (!ctx) return LOAMGPU_ERR_INVALID;
@@ -736,7 +935,14 @@ int loamgpu_knn(loamgpu_ctx* ctx, const double* targets, uint64_t n_t, const dou
   gb.pt_stride = cap;
   gb.kind = 1;
   gb.g = bvh_arrays(ctx, true, cap);
-  TIMED(LOAMGPU_K_GRID, launch_bvh_build(gb, 1, ctx->stream));
+  if (n_t >= ctx->big_target_min) {
+    CU(ctx->big_scratch.reserve(bvh_big_scratch_bytes((uint32_t)n_t)));
+    ProfScope ps(ctx, LOAMGPU_K_GRID);
+    ctx->launches--;  // the launcher counts its own kernels
+    CU(launch_bvh_build_big(gb.pts, (uint32_t)n_t, gb.g, ctx->big_scratch.p, ctx->stream, &ctx->launches));
+  } else {
+    TIMED(LOAMGPU_K_GRID, launch_bvh_build(gb, 1, ctx->stream));
+  }
   double* dq = ctx->misc.as<double>();
   uint32_t* didx = reinterpret_cast<uint32_t*>(dq + 3 * n_q);
   uint32_t* dcnt = didx + (size_t)n_q * k;

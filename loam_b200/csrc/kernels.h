@@ -88,6 +88,12 @@ struct BvhBuildArgs {
 };
 cudaError_t launch_bvh_build(const BvhBuildArgs& a, uint32_t n_sets, cudaStream_t st);
 
+// Multi-CTA build of ONE large set (bvh_big.cu): same layout as launch_bvh_build produces for set 0 of `g`
+// (g.hdr, g.nodes, g.sorted; g.keys is the sort scratch).  `scratch` holds bvh_big_scratch_bytes(n) bytes.
+size_t bvh_big_scratch_bytes(uint32_t n);
+cudaError_t launch_bvh_build_big(const double4* pts, uint32_t n, const BvhSetArrays& g, void* scratch, cudaStream_t st,
+                                 uint64_t* launches);
+
 struct AssocArgs {
   // source / target feature slots of pair p: src = (pair0 + p + 1) % n_slots, tgt = (pair0 + p) % n_slots
   const double4* edge_pts;
@@ -109,6 +115,12 @@ struct AssocArgs {
   uint32_t n_pairs;        // pairs of this launch
   const uint32_t* active;  // [0] = number of pairs still iterating, [1..] their indices; null = all, in order
   int32_t* nearest;        // optional [outer_iter][pair][capE+capP] nearest target index or -1 (detail)
+  // external target (device-resident local map): when ext_target != 0 every pair registers onto set 0 of te / tp,
+  // whose points in original order are te_pts / tp_pts; ge / gp then hold only the source sets (set = pair)
+  int ext_target;
+  BvhSetArrays te, tp;
+  const double4* te_pts;
+  const double4* tp_pts;
   RegP rp;
 };
 cudaError_t launch_assoc_knn(const AssocArgs& a, uint32_t n_pairs, int outer_iter, cudaStream_t st);
@@ -149,6 +161,8 @@ struct KnnArgs {
 };
 cudaError_t launch_knn(const KnnArgs& a, cudaStream_t st);
 
+// p <- pose * p for n double4 points in place (map insertion: scan frame -> map frame, Pose3d::act, geometry.cpp:21)
+cudaError_t launch_transform_points(double4* pts, uint32_t n, const double* pose_dev, cudaStream_t s);
 cudaError_t launch_init_pairs(PairState* st, uint32_t n_pairs, const double* init_pose_or_null, cudaStream_t s);
 // Copy per-pair results to flat output arrays (device pointers; any may be null) and finalise MAX_ITER.
 cudaError_t launch_finish_pairs(const PairState* st, uint32_t n_pairs, double* poses, int32_t* term, uint32_t* iters,

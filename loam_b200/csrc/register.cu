@@ -406,7 +406,9 @@ __device__ __forceinline__ void assoc_knn_pair(const AssocArgs& a, int outer_ite
   }
   const uint32_t li = (uint32_t)__double_as_longlong(sp.w);  // original index of this source feature
   const V3 q = pose_act(est, V3{sp.x, sp.y, sp.z});
-  const BvhHdr g = gs.hdr[pair];
+  const BvhSetArrays& gt = a.ext_target ? (is_plane ? a.tp : a.te) : gs;  // the target's structure
+  const uint32_t tset = a.ext_target ? 0u : pair;
+  const BvhHdr g = gt.hdr[tset];
   const int k = is_plane ? a.rp.kp : a.rp.ke;
   const double md = is_plane ? a.rp.rp : a.rp.re;
   const size_t cap_src = (size_t)a.capE_scan + a.capP_scan;
@@ -417,8 +419,9 @@ __device__ __forceinline__ void assoc_knn_pair(const AssocArgs& a, int outer_ite
   // millimetres, the bound is nearly tight and most of the tree is pruned on the way down).
   double d2_hint = CUDART_INF;
   if (outer_iter > 0 && (int)a.nn_cnt[rec] == k) {
-    const double4* tp = is_plane ? a.planar_pts + (size_t)((a.pair0 + pair) % a.n_slots) * a.capP_scan
-                                 : a.edge_pts + (size_t)((a.pair0 + pair) % a.n_slots) * a.capE_scan;
+    const double4* tp = a.ext_target ? (is_plane ? a.tp_pts : a.te_pts)
+                        : is_plane   ? a.planar_pts + (size_t)((a.pair0 + pair) % a.n_slots) * a.capP_scan
+                                     : a.edge_pts + (size_t)((a.pair0 + pair) % a.n_slots) * a.capE_scan;
     double worst = 0.0;
 #pragma unroll
     for (int j = 0; j < K; j++) {
@@ -430,7 +433,7 @@ __device__ __forceinline__ void assoc_knn_pair(const AssocArgs& a, int outer_ite
     d2_hint = worst;
   }
   TopK<K> tk;
-  knn_bvh<K>(g, gs.nodes + (size_t)pair * gs.pt_cap, gs.sorted + (size_t)pair * gs.pt_cap, q.x, q.y, q.z, k, md, tk,
+  knn_bvh<K>(g, gt.nodes + (size_t)tset * gt.pt_cap, gt.sorted + (size_t)tset * gt.pt_cap, q.x, q.y, q.z, k, md, tk,
              d2_hint);
   const int m = radius_count(tk, k, md);
   a.rec_p[rec] = make_double4(q.x, q.y, q.z, 0.0);
@@ -468,8 +471,9 @@ __device__ __forceinline__ void assoc_fit_pair(const AssocArgs& a, int outer_ite
     const uint32_t* nn = a.nn_idx + rec * (size_t)a.nn_stride;
     const int need = is_plane ? a.rp.min_plane : a.rp.min_line;
     if (m >= need && m > 0) {
-      const double4* tp = is_plane ? a.planar_pts + (size_t)tgt_slot * a.capP_scan
-                                   : a.edge_pts + (size_t)tgt_slot * a.capE_scan;
+      const double4* tp = a.ext_target ? (is_plane ? a.tp_pts : a.te_pts)
+                          : is_plane   ? a.planar_pts + (size_t)tgt_slot * a.capP_scan
+                                       : a.edge_pts + (size_t)tgt_slot * a.capE_scan;
       double N[KMAX][3];
 #pragma unroll
       for (int j = 0; j < KMAX; j++) {
@@ -1002,6 +1006,17 @@ __global__ void init_pairs_kernel(PairState* st, uint32_t n, const double* init)
   st[i] = s;
 }
 
+__global__ void transform_points_kernel(double4* pts, uint32_t n, const double* pose) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double ps[7];
+#pragma unroll
+  for (int j = 0; j < 7; j++) ps[j] = pose[j];
+  const double4 p = pts[i];
+  const V3 q = pose_act(ps, V3{p.x, p.y, p.z});
+  pts[i] = make_double4(q.x, q.y, q.z, 0.0);
+}
+
 __global__ void finish_pairs_kernel(const PairState* st, uint32_t n, double* poses, int32_t* term, uint32_t* iters) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -1088,6 +1103,12 @@ cudaError_t launch_knn(const KnnArgs& a, cudaStream_t st) {
     knn_kernel<kKnnRegMax><<<blocks, 128, 0, st>>>(a);
   else
     knn_kernel<kKnnMax><<<blocks, 128, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_transform_points(double4* pts, uint32_t n, const double* pose_dev, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  transform_points_kernel<<<(n + 255) / 256, 256, 0, st>>>(pts, n, pose_dev);
   return cudaGetLastError();
 }
 
