@@ -63,6 +63,38 @@ __device__ __forceinline__ void quat_mul(const double* a, const double* b, doubl
   o[3] = w;
 }
 
+// ------------------------------------------------------------------ TMA bulk copy + mbarrier (sm_90+/sm_100a PTX)
+// One elected thread arms the barrier with the byte count and issues cp.async.bulk (SASS: UBLKCP); the data lands
+// in shared memory through the async proxy and every waiting thread sees it once the barrier phase completes.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
 // ------------------------------------------------------------------ NN structure: LBVH (binary radix tree)
 // Points are sorted by 30-bit Morton code; a binary radix tree over the sorted (code, position) keys has n - 1
 // internal nodes, root = node 0.  Node i covers a key range [first, last] (derived top-down during traversal) and

@@ -553,143 +553,235 @@ __device__ __forceinline__ void manifold_plus(const double* x, const double* del
   out[6] = x[6] + delta[5];
 }
 
-// One residual: value, tangent Jacobian row (6), Huber corrector; accumulates into e.
-__device__ __forceinline__ void accumulate_residual(const double4& rp, const double4& ra, const double4& rb,
-                                                    const double* x, const double (&PJ)[4][3], Eval& e) {
-  const V3 p{rp.x, rp.y, rp.z};
-  const V3 u{x[0], x[1], x[2]};
-  const double w = x[3];
-  V3 uv = cross(u, p);
-  uv.x += uv.x;
-  uv.y += uv.y;
-  uv.z += uv.z;
-  const V3 uuv = cross(u, uv);
-  const V3 pt{p.x + w * uv.x + uuv.x + x[4], p.y + w * uv.y + uuv.y + x[5], p.z + w * uv.z + uuv.z + x[6]};
-  double r;
-  V3 g;
-  if (rp.w == 1.0) {  // point-to-line, geometry-inl.h:21-27
-    const V3 a{ra.x, ra.y, ra.z}, b{rb.x, rb.y, rb.z};
-    const V3 d1{pt.x - a.x, pt.y - a.y, pt.z - a.z}, d2{pt.x - b.x, pt.y - b.y, pt.z - b.z};
-    const V3 ab{a.x - b.x, a.y - b.y, a.z - b.z};
-    const V3 c = cross(d1, d2);
-    const double num = norm(c), den = norm(ab);
-    r = num / den;
-    if (num > 0) {
-      const V3 ch{c.x / num, c.y / num, c.z / num};
-      g = cross(ab, ch);
-      g.x /= den;
-      g.y /= den;
-      g.z /= den;
-    } else {
-      g = V3{0, 0, 0};
-    }
-  } else {  // point-to-plane, geometry-inl.h:30-33
-    const double s = ra.x * pt.x + ra.y * pt.y + ra.z * pt.z - ra.w;
-    r = fabs(s);
-    const double sg = copysign(1.0, s);
-    g = V3{sg * ra.x, sg * ra.y, sg * ra.z};
+// Per-evaluation linear maps.  For a fixed iterate x = (u, w, t) the transformed point and its tangent Jacobian are
+// linear in the source point p (Eigen's un-normalised rotation v + w 2(u x v) + u x 2(u x v), registration-inl.h:94):
+//     pt          = M p + t                  M   = (1 - 2|u|^2) I + 2 u u^T + 2 w [u]x
+//     d pt / d d_j = B_j p                    B_j = 2w [c_j]x + 2 (u c_j^T + c_j u^T) - 4 (u.c_j) I + 2 PJ[3][j] [u]x
+// with c_j = (PJ[0][j], PJ[1][j], PJ[2][j]) and PJ the 4x3 plus-Jacobian of the (w-first) QuaternionManifold applied to
+// Eigen's (x,y,z,w) memory.  Building the 39 numbers once per evaluation replaces ~130 fp64
+// instructions per residual (three pairs of cross products and the 4x3 chain) by 36 FMAs; the kernel was fp64-pipe
+// bound (61 % busy, profiles/r1_kernels_full_v9.md).  Layout in shared memory: M[9] t[3] B0[9] B1[9] B2[9].
+constexpr int kLinDoubles = 40;
+
+__device__ __forceinline__ void build_linear_maps(const double* x, double* s_lin) {
+  const int j = threadIdx.x;
+  if (j > 3) return;
+  const double u0 = x[0], u1 = x[1], u2 = x[2], w = x[3];
+  if (j == 3) {
+    const double uu = u0 * u0 + u1 * u1 + u2 * u2;
+    const double dg = 1.0 - 2.0 * uu;
+    s_lin[0] = dg + 2.0 * u0 * u0;      s_lin[1] = 2.0 * u0 * u1 - 2.0 * w * u2;  s_lin[2] = 2.0 * u0 * u2 + 2.0 * w * u1;
+    s_lin[3] = 2.0 * u1 * u0 + 2.0 * w * u2;  s_lin[4] = dg + 2.0 * u1 * u1;      s_lin[5] = 2.0 * u1 * u2 - 2.0 * w * u0;
+    s_lin[6] = 2.0 * u2 * u0 - 2.0 * w * u1;  s_lin[7] = 2.0 * u2 * u1 + 2.0 * w * u0;  s_lin[8] = dg + 2.0 * u2 * u2;
+    s_lin[9] = x[4];
+    s_lin[10] = x[5];
+    s_lin[11] = x[6];
+    return;
   }
-  // ambient Jacobian wrt (qx qy qz qw): d pt/d u_i = w*2(e_i x p) + e_i x uv + u x 2(e_i x p) ; d pt/d w = uv
-  double J4[4];
-  {
-    const V3 e0{1, 0, 0}, e1{0, 1, 0}, e2{0, 0, 1};
-    const V3 es[3] = {e0, e1, e2};
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-      V3 Ai = cross(es[i], p);
-      Ai.x += Ai.x;
-      Ai.y += Ai.y;
-      Ai.z += Ai.z;
-      const V3 t1 = cross(es[i], uv), t2 = cross(u, Ai);
-      J4[i] = g.x * (w * Ai.x + t1.x + t2.x) + g.y * (w * Ai.y + t1.y + t2.y) + g.z * (w * Ai.z + t1.z + t2.z);
-    }
-    J4[3] = g.x * uv.x + g.y * uv.y + g.z * uv.z;
-  }
-  // Huber(1.0) + corrector (rho'' <= 0 branch): scale residual and Jacobian row by sqrt(rho')
-  const double s2 = r * r;
-  double rho0, sr1;
-  if (s2 > 1.0) {
-    const double rr = sqrt(s2);
-    const double rho1 = fmax(2.2250738585072014e-308, 1.0 / rr);
-    rho0 = 2.0 * rr - 1.0;
-    sr1 = sqrt(rho1);
+  // plus-Jacobian column j: rows = memory slots (x,y,z,w)
+  double c0, c1, c2, c3;
+  if (j == 0) {
+    c0 = -x[1]; c1 = x[0]; c2 = -x[3]; c3 = x[2];
+  } else if (j == 1) {
+    c0 = -x[2]; c1 = x[3]; c2 = x[0]; c3 = -x[1];
   } else {
-    rho0 = s2;
-    sr1 = 1.0;
+    c0 = -x[3]; c1 = -x[2]; c2 = x[1]; c3 = x[0];
   }
-  double J[6];
+  const double uc = u0 * c0 + u1 * c1 + u2 * c2;
+  const double dg = -4.0 * uc;
+  double* B = s_lin + 12 + 9 * j;
+  // 2w [c]x + 2 c3 [u]x  =  [2w c + 2 c3 u]x
+  const double k0 = 2.0 * (w * c0 + c3 * u0), k1 = 2.0 * (w * c1 + c3 * u1), k2 = 2.0 * (w * c2 + c3 * u2);
+  B[0] = dg + 4.0 * u0 * c0;              B[1] = 2.0 * (u0 * c1 + c0 * u1) - k2;  B[2] = 2.0 * (u0 * c2 + c0 * u2) + k1;
+  B[3] = 2.0 * (u1 * c0 + c1 * u0) + k2;  B[4] = dg + 4.0 * u1 * c1;              B[5] = 2.0 * (u1 * c2 + c1 * u2) - k0;
+  B[6] = 2.0 * (u2 * c0 + c2 * u0) - k1;  B[7] = 2.0 * (u2 * c1 + c2 * u1) + k0;  B[8] = dg + 4.0 * u2 * c2;
+}
+
+#ifndef LM_RPT
+#define LM_RPT 2
+#endif
+constexpr int kLmRpt = LM_RPT;                // residuals per thread per tile: independent dependency chains (ILP)
+constexpr int kLmTile = kLmRpt * kLmThreads;  // records per tile
+
+// R residuals of one class at once, straight-line code so the R dependency chains interleave (the kernel runs at
+// 16 warps/SM; with one residual per thread it stalled on fixed-latency fp64 dependencies and shared-memory loads).
+// valid[r] == false contributes exactly nothing (selects, never arithmetic on possibly uninitialised records).
+template <int R, bool kEdge>
+__device__ __forceinline__ void accumulate_residuals(const double4 (&rp)[R], const double4 (&ra)[R],
+                                                     const double4 (&rb)[R], const bool (&valid)[R],
+                                                     const double* __restrict__ s_lin, Eval& e) {
+  double r[R], gx[R], gy[R], gz[R];
+#pragma unroll
+  for (int q = 0; q < R; q++) {
+    const double px = rp[q].x, py = rp[q].y, pz = rp[q].z;
+    const double ptx = fma(s_lin[0], px, fma(s_lin[1], py, fma(s_lin[2], pz, s_lin[9])));
+    const double pty = fma(s_lin[3], px, fma(s_lin[4], py, fma(s_lin[5], pz, s_lin[10])));
+    const double ptz = fma(s_lin[6], px, fma(s_lin[7], py, fma(s_lin[8], pz, s_lin[11])));
+    if (kEdge) {  // point-to-line, geometry-inl.h:21-27 :  |(pt-a) x (pt-b)| / |a-b|
+      const double d1x = ptx - ra[q].x, d1y = pty - ra[q].y, d1z = ptz - ra[q].z;
+      const double d2x = ptx - rb[q].x, d2y = pty - rb[q].y, d2z = ptz - rb[q].z;
+      const double abx = ra[q].x - rb[q].x, aby = ra[q].y - rb[q].y, abz = ra[q].z - rb[q].z;
+      const double cx = fma(d1y, d2z, -(d1z * d2y)), cy = fma(d1z, d2x, -(d1x * d2z)), cz = fma(d1x, d2y, -(d1y * d2x));
+      const double num = sqrt(fma(cx, cx, fma(cy, cy, cz * cz)));
+      const double inv_den = 1.0 / sqrt(fma(abx, abx, fma(aby, aby, abz * abz)));
+      // d r / d pt = (ab x c/|c|) / |ab| ; a point exactly on the line has no gradient (ceres::Jet norm at 0)
+      const double sc = num > 0 ? inv_den / num : 0.0;
+      r[q] = valid[q] ? num * inv_den : 0.0;
+      gx[q] = valid[q] ? fma(aby, cz, -(abz * cy)) * sc : 0.0;
+      gy[q] = valid[q] ? fma(abz, cx, -(abx * cz)) * sc : 0.0;
+      gz[q] = valid[q] ? fma(abx, cy, -(aby * cx)) * sc : 0.0;
+    } else {  // point-to-plane, geometry-inl.h:30-33 :  |n . pt - d| , Jet abs: derivative sign = sign of the value
+      const double sd = fma(ra[q].x, ptx, fma(ra[q].y, pty, ra[q].z * ptz)) - ra[q].w;
+      const double sg = copysign(1.0, sd);
+      r[q] = valid[q] ? fabs(sd) : 0.0;
+      gx[q] = valid[q] ? sg * ra[q].x : 0.0;
+      gy[q] = valid[q] ? sg * ra[q].y : 0.0;
+      gz[q] = valid[q] ? sg * ra[q].z : 0.0;
+    }
+  }
+  // Huber(1.0) + corrector (rho'' <= 0 branch): residual and Jacobian row scaled by sqrt(rho'); rare (r > 1 m)
+  double rho0[R], rc[R];
+  bool any_big = false;
+#pragma unroll
+  for (int q = 0; q < R; q++) {
+    rho0[q] = r[q] * r[q];
+    rc[q] = r[q];
+    any_big |= rho0[q] > 1.0;
+  }
+  if (any_big) {
+#pragma unroll
+    for (int q = 0; q < R; q++) {
+      if (rho0[q] > 1.0) {
+        const double rr = sqrt(rho0[q]);
+        const double sr1 = sqrt(fmax(2.2250738585072014e-308, 1.0 / rr));
+        rho0[q] = 2.0 * rr - 1.0;
+        rc[q] *= sr1;
+        gx[q] *= sr1;
+        gy[q] *= sr1;
+        gz[q] *= sr1;
+      }
+    }
+  }
+  // rotation part of the tangent Jacobian: each B_j is read from shared memory once and applied to the R points
+  double J[R][3];
 #pragma unroll
   for (int j = 0; j < 3; j++) {
-    double acc = 0;
+    const double* B = s_lin + 12 + 9 * j;
+    const double b0 = B[0], b1 = B[1], b2 = B[2], b3 = B[3], b4 = B[4], b5 = B[5], b6 = B[6], b7 = B[7], b8 = B[8];
 #pragma unroll
-    for (int k = 0; k < 4; k++) acc = fma(J4[k], PJ[k][j], acc);
-    J[j] = acc * sr1;
+    for (int q = 0; q < R; q++) {
+      const double px = rp[q].x, py = rp[q].y, pz = rp[q].z;
+      const double vx = fma(b0, px, fma(b1, py, b2 * pz));
+      const double vy = fma(b3, px, fma(b4, py, b5 * pz));
+      const double vz = fma(b6, px, fma(b7, py, b8 * pz));
+      J[q][j] = fma(gx[q], vx, fma(gy[q], vy, gz[q] * vz));
+    }
   }
-  J[3] = g.x * sr1;
-  J[4] = g.y * sr1;
-  J[5] = g.z * sr1;
-  const double rc = r * sr1;
-  e.cost += 0.5 * rho0;
-  int t = 0;
 #pragma unroll
-  for (int i = 0; i < 6; i++) {
-    // explicit fma: the library is built -fmad=false for the index-deciding arithmetic; these well-conditioned sums
-    // only have to agree with the CPU restatement to rounding
-    e.g[i] = fma(J[i], rc, e.g[i]);
+  for (int q = 0; q < R; q++) {
+    const double Jr[6] = {J[q][0], J[q][1], J[q][2], gx[q], gy[q], gz[q]};
+    e.cost = fma(0.5, rho0[q], e.cost);
+    int t = 0;
 #pragma unroll
-    for (int j = i; j < 6; j++, t++) e.H[t] = fma(J[i], J[j], e.H[t]);
+    for (int i = 0; i < 6; i++) {
+      // explicit fma: the library is built -fmad=false for the index-deciding arithmetic; these well-conditioned sums
+      // only have to agree with the CPU restatement to rounding
+      e.g[i] = fma(Jr[i], rc[q], e.g[i]);
+#pragma unroll
+      for (int j = i; j < 6; j++, t++) e.H[t] = fma(Jr[i], Jr[j], e.H[t]);
+    }
   }
 }
 
-// read-only 32-byte record load (two LDG.128 through the non-coherent path; __ldg has no double4 overload)
-__device__ __forceinline__ double4 ldg_d4(const double4* p) {
-  const double2 lo = __ldg(reinterpret_cast<const double2*>(p));
-  const double2 hi = __ldg(reinterpret_cast<const double2*>(p) + 1);
-  return make_double4(lo.x, lo.y, hi.x, hi.y);
+// Residual records of one pair are streamed HBM -> shared memory by TMA bulk copies, kLmStages tiles of kLmTile
+// records ahead of the arithmetic, so the bytes in flight do not depend on registers.  Edge residuals (records
+// [0, nE): p, a, b) and plane residuals (records [capE, capE + nP): p, a) are tiled separately: a tile holds one class.
+struct LmStage {
+  double4 p[kLmTile];  // transformed source point, w = kind (0 = no residual for this source feature)
+  double4 a[kLmTile];  // line point a / plane normal + d
+  double4 b[kLmTile];  // line point b (edge tiles only)
+};
+#ifndef LM_STAGES
+#define LM_STAGES 2
+#endif
+constexpr int kLmStages = LM_STAGES;
+
+struct LmPipe {
+  LmStage* stages;   // [kLmStages]
+  uint64_t* full;    // [kLmStages] mbarriers, armed by the producer thread with the tile's byte count
+  uint32_t tile_no;  // tiles consumed so far by this CTA (same value in every thread): stage = tile_no % kLmStages
+};
+
+// thread 0: arm the stage's barrier and issue the bulk copies of tile `tile` (edge tiles first, then plane tiles)
+__device__ __forceinline__ void lm_issue_tile(const double4* __restrict__ rec_p, const double4* __restrict__ rec_a,
+                                              const double4* __restrict__ rec_b, uint32_t nE, uint32_t nP, uint32_t capE,
+                                              uint32_t tilesE, uint32_t tile, LmStage* st, uint64_t* bar) {
+  if (tile < tilesE) {
+    const uint32_t lo = tile * kLmTile, n = min((uint32_t)kLmTile, nE - lo);
+    mbar_expect_tx(bar, n * 96u);
+    bulk_g2s(st->p, rec_p + lo, n * 32u, bar);
+    bulk_g2s(st->a, rec_a + lo, n * 32u, bar);
+    bulk_g2s(st->b, rec_b + lo, n * 32u, bar);
+  } else {
+    const uint32_t lo = (tile - tilesE) * kLmTile, n = min((uint32_t)kLmTile, nP - lo);
+    mbar_expect_tx(bar, n * 64u);
+    bulk_g2s(st->p, rec_p + capE + lo, n * 32u, bar);
+    bulk_g2s(st->a, rec_a + capE + lo, n * 32u, bar);
+  }
 }
 
 // Evaluate the whole problem of this pair at x; deterministic fixed-order reduction
 // (per-thread strided partial -> warp shuffle tree -> per-warp shared partials summed in warp order).
 __device__ void evaluate_problem(const double4* __restrict__ rec_p, const double4* __restrict__ rec_a,
                                  const double4* __restrict__ rec_b, uint32_t nE, uint32_t nP, uint32_t capE,
-                                 const double* x, double* s_part /*[nwarps][28]*/, double* s_tot /*[28]*/, Eval& out) {
-  double PJ[4][3];
-  PJ[0][0] = -x[1]; PJ[0][1] = -x[2]; PJ[0][2] = -x[3];
-  PJ[1][0] = x[0];  PJ[1][1] = x[3];  PJ[1][2] = -x[2];
-  PJ[2][0] = -x[3]; PJ[2][1] = x[0];  PJ[2][2] = x[1];
-  PJ[3][0] = x[2];  PJ[3][1] = -x[1]; PJ[3][2] = x[0];
+                                 const double* x, double* s_part /*[nwarps][28]*/, double* s_tot /*[28]*/,
+                                 double* s_lin /*[kLinDoubles]*/, LmPipe& pipe, Eval& out) {
+  const uint32_t tilesE = (nE + kLmTile - 1) / kLmTile, tilesP = (nP + kLmTile - 1) / kLmTile;
+  const uint32_t tiles = tilesE + tilesP;
+  const uint32_t g0 = pipe.tile_no;
+  if (threadIdx.x == 0) {  // every stage is free here: the previous evaluation consumed all the tiles it issued
+    for (uint32_t k = 0; k < min(tiles, (uint32_t)kLmStages); k++)
+      lm_issue_tile(rec_p, rec_a, rec_b, nE, nP, capE, tilesE, k, pipe.stages + (g0 + k) % kLmStages,
+                    pipe.full + (g0 + k) % kLmStages);
+  }
+  __syncthreads();  // the previous evaluation's readers of s_lin / s_tot are done
+  build_linear_maps(x, s_lin);
+  __syncthreads();
   Eval e;
 #pragma unroll
   for (int i = 0; i < 21; i++) e.H[i] = 0;
 #pragma unroll
   for (int i = 0; i < 6; i++) e.g[i] = 0;
   e.cost = 0;
-  const uint32_t total = nE + nP;
-  // software-pipelined: the records of the next residual are in flight while this one is evaluated (the records of
-  // the ~300 pairs resident on the GPU do not fit L2, so every evaluation streams them from HBM)
-  uint32_t i = threadIdx.x;
-  double4 rp = make_double4(0, 0, 0, 0), ra = rp, rb = rp;
-  if (i < total) {
-    const uint32_t ri = i < nE ? i : capE + (i - nE);
-    rp = ldg_d4(rec_p + ri);
-    ra = ldg_d4(rec_a + ri);
-    if (i < nE) rb = ldg_d4(rec_b + i);
-  }
-  while (i < total) {
-    const uint32_t ni = i + blockDim.x;
-    double4 np4 = make_double4(0, 0, 0, 0), na4 = np4, nb4 = np4;
-    if (ni < total) {
-      const uint32_t ri = ni < nE ? ni : capE + (ni - nE);
-      np4 = ldg_d4(rec_p + ri);
-      na4 = ldg_d4(rec_a + ri);
-      if (ni < nE) nb4 = ldg_d4(rec_b + ni);
+  for (uint32_t k = 0; k < tiles; k++) {
+    const uint32_t g = g0 + k, sidx = g % kLmStages;
+    LmStage* st = pipe.stages + sidx;
+    const bool edge = k < tilesE;
+    const uint32_t n_tile = edge ? min((uint32_t)kLmTile, nE - k * kLmTile) : min((uint32_t)kLmTile, nP - (k - tilesE) * kLmTile);
+    mbar_wait(pipe.full + sidx, (g / kLmStages) & 1u);
+    double4 rp[kLmRpt], ra[kLmRpt], rb[kLmRpt];
+    bool valid[kLmRpt];
+#pragma unroll
+    for (int q = 0; q < kLmRpt; q++) {
+      const uint32_t slot = q * kLmThreads + threadIdx.x;
+      const bool in = slot < n_tile;
+      rp[q] = in ? st->p[slot] : make_double4(0, 0, 0, 0);
+      valid[q] = rp[q].w != 0.0;
+      ra[q] = st->a[slot];  // (beyond n_tile: stale shared memory, masked by valid)
+      rb[q] = ra[q];
     }
-    if (rp.w != 0.0) accumulate_residual(rp, ra, rb, x, PJ, e);
-    rp = np4;
-    ra = na4;
-    rb = nb4;
-    i = ni;
+    if (edge) {  // CTA-uniform
+#pragma unroll
+      for (int q = 0; q < kLmRpt; q++) rb[q] = st->b[q * kLmThreads + threadIdx.x];
+      accumulate_residuals<kLmRpt, true>(rp, ra, rb, valid, s_lin, e);
+    } else {
+      accumulate_residuals<kLmRpt, false>(rp, ra, rb, valid, s_lin, e);
+    }
+    __syncthreads();  // everyone has read the stage before it is refilled
+    if (threadIdx.x == 0 && k + kLmStages < tiles)
+      lm_issue_tile(rec_p, rec_a, rec_b, nE, nP, capE, tilesE, k + kLmStages, st, pipe.full + sidx);
   }
+  pipe.tile_no = g0 + tiles;
   double v[28];
 #pragma unroll
   for (int i = 0; i < 21; i++) v[i] = e.H[i];
@@ -703,7 +795,6 @@ __device__ void evaluate_problem(const double4* __restrict__ rec_p, const double
     v[i] = t;
   }
   const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  __syncthreads();  // protect s_part / s_tot from the previous evaluation's readers
   if ((threadIdx.x & 31) == 0) {
 #pragma unroll
     for (int i = 0; i < 28; i++) s_part[warp * 28 + i] = v[i];
@@ -785,7 +876,7 @@ __device__ __forceinline__ double norm7(const double* x) {
 
 // One CTA per pair.  Every thread runs the (tiny, uniform) controller redundantly on the reduced sums, so
 // no broadcast of the step is needed between evaluations.
-__device__ void lm_pair(const LmArgs& a, uint32_t pair, double* s_part, double* s_tot) {
+__device__ void lm_pair(const LmArgs& a, uint32_t pair, double* s_part, double* s_tot, double* s_lin, LmPipe& pipe) {
   PairState* ps = a.state + pair;
   if (ps->status != -1) return;
   const uint32_t src_slot = (uint32_t)((a.pair0 + pair + a.src_offset) % a.n_slots);
@@ -820,7 +911,7 @@ __device__ void lm_pair(const LmArgs& a, uint32_t pair, double* s_part, double* 
   uint32_t lm_iterations = 0;
   double cost0 = 0, x_cost = 0;
   if (n_ea + n_pa > 0) {
-    evaluate_problem(rec_p, rec_a, rec_b, nE, nP, a.capE_scan, x, s_part, s_tot, ev);
+    evaluate_problem(rec_p, rec_a, rec_b, nE, nP, a.capE_scan, x, s_part, s_tot, s_lin, pipe, ev);
     x_cost = ev.cost;
     cost0 = x_cost;
 #pragma unroll
@@ -888,7 +979,7 @@ __device__ void lm_pair(const LmArgs& a, uint32_t pair, double* s_part, double* 
       for (int j = 0; j < 6; j++) delta[j] = step[j] * scale[j];
       manifold_plus(x, delta, cand);
       Eval ec;
-      evaluate_problem(rec_p, rec_a, rec_b, nE, nP, a.capE_scan, cand, s_part, s_tot, ec);
+      evaluate_problem(rec_p, rec_a, rec_b, nE, nP, a.capE_scan, cand, s_part, s_tot, s_lin, pipe, ec);
       const double cand_cost = ec.cost;
       if (armed) {
         double dn = 0;
@@ -958,11 +1049,21 @@ __device__ void lm_pair(const LmArgs& a, uint32_t pair, double* s_part, double* 
 }
 
 __global__ void __launch_bounds__(kLmThreads, kLmMinBlocks) lm_kernel(LmArgs a) {
+  extern __shared__ __align__(128) unsigned char lm_smem[];  // kLmStages x LmStage
   __shared__ double s_part[(kLmThreads / 32) * 28];
   __shared__ double s_tot[28];
+  __shared__ __align__(16) double s_lin[kLinDoubles];
+  __shared__ __align__(8) uint64_t s_full[kLmStages];
+  LmPipe pipe;
+  pipe.stages = reinterpret_cast<LmStage*>(lm_smem);
+  pipe.full = s_full;
+  pipe.tile_no = 0;
+  if (threadIdx.x == 0)
+    for (int i = 0; i < kLmStages; i++) mbar_init(s_full + i, 1);
+  __syncthreads();
   const uint32_t n_act = active_count(a.active, a.n_pairs);
   for (uint32_t i = blockIdx.x; i < n_act; i += gridDim.x) {
-    lm_pair(a, active_pair(a.active, i), s_part, s_tot);
+    lm_pair(a, active_pair(a.active, i), s_part, s_tot, s_lin, pipe);
     __syncthreads();
   }
 }
@@ -1084,7 +1185,10 @@ cudaError_t launch_assoc_fit(const AssocArgs& a, uint32_t n_pairs, int outer_ite
 
 cudaError_t launch_lm(const LmArgs& a, uint32_t n_pairs, cudaStream_t st) {
   if (n_pairs == 0) return cudaSuccess;
-  lm_kernel<<<pair_rows(n_pairs, a.outer_iter, a.active != nullptr, 296), kLmThreads, 0, st>>>(a);
+  const size_t smem = (size_t)kLmStages * sizeof(LmStage);
+  cudaError_t err = cudaFuncSetAttribute(lm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  lm_kernel<<<pair_rows(n_pairs, a.outer_iter, a.active != nullptr, 296), kLmThreads, smem, st>>>(a);
   return cudaGetLastError();
 }
 
