@@ -37,9 +37,16 @@ __device__ double block_reduce_minmax(double v, bool is_max, double* s_red) {
   __syncthreads();
   if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
   __syncthreads();
-  double r = s_red[0];
-  for (int w = 1; w < (int)(blockDim.x >> 5); w++) r = is_max ? fmax(r, s_red[w]) : fmin(r, s_red[w]);
-  return r;
+  if (threadIdx.x < 32) {  // warp 0 folds the per-warp partials, everyone reads the result
+    double r = threadIdx.x < (blockDim.x >> 5) ? s_red[threadIdx.x] : (is_max ? -CUDART_INF : CUDART_INF);
+    for (int o = 16; o > 0; o >>= 1) {
+      const double t = __shfl_xor_sync(0xffffffffu, r, o);
+      r = is_max ? fmax(r, t) : fmin(r, t);
+    }
+    if (threadIdx.x == 0) s_red[32] = r;
+  }
+  __syncthreads();
+  return s_red[32];
 }
 
 __device__ __forceinline__ uint32_t spread10(uint32_t v) {  // 10 bits -> every third bit
@@ -59,7 +66,7 @@ __global__ void __launch_bounds__(kBuildThreads) bvh_build_kernel(BvhBuildArgs a
   // dynamic shared memory: [0, kRadixBins*kBuildThreads) radix counters during the sort; afterwards, when the set
   // fits (a.smem_tree), the sorted Morton codes (n words) and behind them one readiness byte per node
   extern __shared__ uint32_t s_cnt[];
-  __shared__ double s_red[32];
+  __shared__ double s_red[33];
   __shared__ uint32_t s_scan[kBuildThreads / 32];
   __shared__ uint32_t s_wtot[kRadixBins * (kBuildThreads / 32)];
 
@@ -236,64 +243,78 @@ __global__ void __launch_bounds__(kBuildThreads) bvh_build_kernel(BvhBuildArgs a
   }
   __syncthreads();
 
-  // ---- boxes, bottom-up in passes: a node is merged from its children once both are ready.  Readiness is published
-  // one barrier after the box itself (state 2 = "merged in this pass"), so a reader never sees a flag before the box.
+  // ---- boxes, bottom-up in passes: a node is merged from its children once both were merged in an EARLIER pass
+  // (ready[] holds the 1-based pass in which a node was merged, 0 = not yet), so one barrier per pass separates a
+  // box from its readers.  A thread tracks its own pending nodes in a register bit mask and only revisits those.
   // The number of passes is the tree height (~log2 n for scattered points, at most 62).
   int* ready = arrived;
-  for (;;) {
-    bool pending = false;
-    for (uint32_t i = tid; i + 1 < n; i += nthr) {
-      // flags and boxes written by other threads of this CTA are read with ld.cg (L2), never from a possibly
-      // stale L1 line
-      if ((in_smem ? (int)s_ready[i] : __ldcg(ready + i)) != 0) continue;
-      const uint32_t w = nodes[i].split;  // written by this same thread above
-      const uint32_t sp = w & kSplitMask;
-      const bool lready = (w & kLeftLeaf) || (in_smem ? (int)s_ready[sp] : __ldcg(ready + sp)) == 1;
-      const bool rready = (w & kRightLeaf) || (in_smem ? (int)s_ready[sp + 1] : __ldcg(ready + sp + 1)) == 1;
-      if (!(lready && rready)) {
-        pending = true;
-        continue;
-      }
-      float lo[3], hi[3];
+  auto merged_pass = [&](uint32_t i) -> uint32_t { return in_smem ? (uint32_t)s_ready[i] : (uint32_t)__ldcg(ready + i); };
+  auto try_merge = [&](uint32_t i, uint32_t pass) -> bool {  // true: node i got its box in this pass
+    const uint32_t w = nodes[i].split;  // written by this same thread above
+    const uint32_t sp = w & kSplitMask;
+    // flags and boxes written by other threads of this CTA are read with ld.cg (L2), never from a possibly stale L1 line
+    if (!(w & kLeftLeaf)) {
+      const uint32_t m = merged_pass(sp);
+      if (m == 0 || m >= pass) return false;
+    }
+    if (!(w & kRightLeaf)) {
+      const uint32_t m = merged_pass(sp + 1);
+      if (m == 0 || m >= pass) return false;
+    }
+    float lo[3], hi[3];
 #pragma unroll
-      for (int c = 0; c < 2; c++) {
-        float clo[3], chi[3];
-        if (w & (c == 0 ? kLeftLeaf : kRightLeaf)) {
-          const double4 pt = sorted[sp + c];
-          clo[0] = __double2float_rd(pt.x); chi[0] = __double2float_ru(pt.x);
-          clo[1] = __double2float_rd(pt.y); chi[1] = __double2float_ru(pt.y);
-          clo[2] = __double2float_rd(pt.z); chi[2] = __double2float_ru(pt.z);
-        } else {
-          const float4* f = reinterpret_cast<const float4*>(nodes + sp + c);
-          const float4 va = __ldcg(f), vb = __ldcg(f + 1);
-          clo[0] = va.x; clo[1] = va.y; clo[2] = va.z;
-          chi[0] = vb.x; chi[1] = vb.y; chi[2] = vb.z;
-        }
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          lo[k] = c == 0 ? clo[k] : fminf(lo[k], clo[k]);
-          hi[k] = c == 0 ? chi[k] : fmaxf(hi[k], chi[k]);
-        }
+    for (int c = 0; c < 2; c++) {
+      float clo[3], chi[3];
+      if (w & (c == 0 ? kLeftLeaf : kRightLeaf)) {
+        const double4 pt = sorted[sp + c];
+        clo[0] = __double2float_rd(pt.x); chi[0] = __double2float_ru(pt.x);
+        clo[1] = __double2float_rd(pt.y); chi[1] = __double2float_ru(pt.y);
+        clo[2] = __double2float_rd(pt.z); chi[2] = __double2float_ru(pt.z);
+      } else {
+        const float4* f = reinterpret_cast<const float4*>(nodes + sp + c);
+        const float4 va = __ldcg(f), vb = __ldcg(f + 1);
+        clo[0] = va.x; clo[1] = va.y; clo[2] = va.z;
+        chi[0] = vb.x; chi[1] = vb.y; chi[2] = vb.z;
       }
 #pragma unroll
       for (int k = 0; k < 3; k++) {
-        nodes[i].lo[k] = lo[k];
-        nodes[i].hi[k] = hi[k];
-      }
-      if (in_smem)
-        s_ready[i] = 2;
-      else
-        __stcg(ready + i, 2);
-    }
-    __syncthreads();
-    for (uint32_t i = tid; i + 1 < n; i += nthr) {
-      if (in_smem) {
-        if (s_ready[i] == 2) s_ready[i] = 1;
-      } else if (__ldcg(ready + i) == 2) {
-        __stcg(ready + i, 1);
+        lo[k] = c == 0 ? clo[k] : fminf(lo[k], clo[k]);
+        hi[k] = c == 0 ? chi[k] : fmaxf(hi[k], chi[k]);
       }
     }
-    if (!__syncthreads_or(pending)) break;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      nodes[i].lo[k] = lo[k];
+      nodes[i].hi[k] = hi[k];
+    }
+    if (in_smem)
+      s_ready[i] = (uint8_t)pass;
+    else
+      __stcg(ready + i, (int)pass);
+    return true;
+  };
+  const uint32_t n_int = n - 1;
+  const uint32_t mine = tid < n_int ? (n_int - tid + nthr - 1) / nthr : 0u;  // nodes tid, tid + nthr, ...
+  if (mine <= 64) {
+    unsigned long long pend = mine == 64 ? ~0ull : ((1ull << mine) - 1ull);
+    for (uint32_t pass = 1;; pass++) {
+      unsigned long long m = pend;
+      while (m) {
+        const int k = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        if (try_merge(tid + (uint32_t)k * nthr, pass)) pend &= ~(1ull << k);
+      }
+      if (!__syncthreads_or(pend != 0)) break;
+    }
+  } else {  // very large sets in one CTA (the multi-CTA build normally takes those): rescan
+    for (uint32_t pass = 1;; pass++) {
+      bool pending = false;
+      for (uint32_t i = tid; i < n_int; i += nthr) {
+        if (merged_pass(i) != 0) continue;
+        if (!try_merge(i, pass)) pending = true;
+      }
+      if (!__syncthreads_or(pending)) break;
+    }
   }
 }
 
@@ -343,6 +364,13 @@ struct QueryF {  // the query rounded down / up to float, for conservative box t
   float lo[3], hi[3];
 };
 
+// max(a, b, 0) in one instruction (3-input FMNMX3 of sm_100)
+__device__ __forceinline__ float fmax3_nonneg(float a, float b) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(0.f));
+  return r;
+}
+
 // Lower bound (never above the true value) of the squared distance from the query to any point inside the box.
 __device__ __forceinline__ float box_lower_bound(const BvhNode& b, const QueryF& q) {
   float s = 0.f;
@@ -350,8 +378,8 @@ __device__ __forceinline__ float box_lower_bound(const BvhNode& b, const QueryF&
   for (int d = 0; d < 3; d++) {
     const float below = __fsub_rd(b.lo[d], q.hi[d]);  // > 0 when the query is below the box
     const float above = __fsub_rd(q.lo[d], b.hi[d]);  // > 0 when the query is above the box
-    const float g = fmaxf(fmaxf(below, above), 0.f);
-    s = __fadd_rd(s, __fmul_rd(g, g));
+    const float g = fmax3_nonneg(below, above);
+    s = __fmaf_rd(g, g, s);  // one rounding, downward: still never above the exact g*g + s
   }
   return s;  // empty boxes (lo = +inf, hi = -inf) give +inf
 }

@@ -7,7 +7,10 @@
 
 namespace loamgpu {
 
-constexpr int kExtractThreads = 256;
+#ifndef EXTRACT_THREADS
+#define EXTRACT_THREADS 256
+#endif
+constexpr int kExtractThreads = EXTRACT_THREADS;
 constexpr int kAssocThreads = 128;
 #ifndef LM_THREADS
 #define LM_THREADS 256

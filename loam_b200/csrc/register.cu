@@ -518,8 +518,11 @@ __device__ __forceinline__ void assoc_fit_pair(const AssocArgs& a, int outer_ite
   }
 }
 
+#ifndef FIT_MINBLOCKS
+#define FIT_MINBLOCKS 6
+#endif
 template <int KMAX>
-__global__ void __launch_bounds__(kAssocThreads) assoc_fit_kernel(AssocArgs a, int outer_iter) {
+__global__ void __launch_bounds__(kAssocThreads, FIT_MINBLOCKS) assoc_fit_kernel(AssocArgs a, int outer_iter) {
   const uint32_t n_act = active_count(a.active, a.n_pairs);
   for (uint32_t i = blockIdx.y; i < n_act; i += gridDim.y) assoc_fit_pair<KMAX>(a, outer_iter, active_pair(a.active, i));
 }
