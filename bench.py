@@ -116,6 +116,26 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.sm)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank's host threads to the CPUs closest to its GPU (NVML's ideal CPU affinity) BEFORE the pinned
+    staging buffers are allocated, so they are first-touched on that NUMA node: with 8 ranks streaming 1 MiB per
+    scan each, buffers on the wrong socket make the host side the bottleneck of `e2e`.  Returns the CPU count."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def physical_gpu_index(local_rank):
     vis = os.environ.get("CUDA_VISIBLE_DEVICES")
     if vis:
@@ -246,6 +266,7 @@ def ours(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    numa_cpus = bind_to_gpu_numa_node(physical_gpu_index(local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -372,7 +393,9 @@ def ours(a):
             "config": {"workload": workload_name(a), "rings": R, "cols": P, "scans_per_step_per_gpu": a.scans,
                        "params": "default FeatureExtractionParams / RegistrationParams, identity init",
                        "l2": f"inputs larger than L2 ({n * n_points * 16 / 2**20:.0f} MiB of scans per step per GPU)",
-                       "sharding": "contiguous sequence segments per rank, no data-path collective"},
+                       "sharding": "contiguous sequence segments per rank, no data-path collective",
+                       "host_affinity": (f"each rank bound to its GPU's NUMA-local CPUs ({numa_cpus})" if numa_cpus
+                                         else "unbound")},
             "e2e": {"value": total_scans / (e2e_ms / 1e3), "unit": UNIT,
                     "h2d_bytes_per_step": int(world * n * n_points * 16),
                     "d2h_bytes_per_step": int(world * ((n - 1) * (56 + 4 + 4) + n * 8)),

@@ -101,7 +101,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // splits it into [first, split] / [split + 1, last]; its children are nodes `split` and `split + 1` — adjacent
 // records — unless the child range is a single point (flag bits).  Boxes are float32 rounded outward, so box tests
 // run on the fp32 pipe and still give a true lower bound on the fp64 point distances.
-constexpr int kBvhLeaf = 8;  // subtrees of at most this many points are scanned, not descended
+#ifndef BVH_LEAF
+#define BVH_LEAF 8
+#endif
+constexpr int kBvhLeaf = BVH_LEAF;  // subtrees of at most this many points are scanned, not descended
 constexpr uint32_t kLeftLeaf = 0x80000000u, kRightLeaf = 0x40000000u, kSplitMask = 0x3FFFFFFFu;
 struct BvhHdr {
   uint32_t n;  // points
