@@ -73,7 +73,7 @@ def peaks():
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler(threading.Thread):
-    """Samples SM clock + clock event reasons of one GPU every 100 ms while the timed region runs."""
+    """Samples SM clock + clock event reasons of one GPU every 20 ms while the timed region runs."""
 
     REASONS = {0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
                0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
@@ -107,7 +107,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self.stop_flag.wait(0.1)
+            self.stop_flag.wait(0.02)
 
     def summary(self):
         if not self.sm:

@@ -86,6 +86,50 @@ std::vector<double> widen(const std::vector<PointType, Alloc<PointType>>& pts) {
 }
 }  // namespace gpu
 
+namespace gpu {
+/// Host buffers behind a loamgpu_detail and their conversion into RegistrationDetail (registration.h:79-109).
+struct DetailBuffers {
+  uint32_t cap, ne, np;
+  std::vector<double> iter_est, iter_upd;
+  std::vector<uint32_t> n_ea, n_pa, ea, pa;
+  loamgpu_detail d;
+  DetailBuffers(const RegistrationParams& params, size_t n_src_edge, size_t n_src_planar)
+      : cap(static_cast<uint32_t>(params.max_iterations ? params.max_iterations : 1)),
+        ne(static_cast<uint32_t>(n_src_edge ? n_src_edge : 1)),
+        np(static_cast<uint32_t>(n_src_planar ? n_src_planar : 1)),
+        iter_est(7 * cap), iter_upd(7 * cap), n_ea(cap), n_pa(cap), ea(static_cast<size_t>(cap) * ne * 2),
+        pa(static_cast<size_t>(cap) * np * 2) {
+    std::memset(&d, 0, sizeof d);
+    d.max_iters_cap = cap;
+    d.n_src_edge = ne;
+    d.n_src_planar = np;
+    d.iter_est = iter_est.data();
+    d.iter_update = iter_upd.data();
+    d.n_edge_assoc = n_ea.data();
+    d.n_plane_assoc = n_pa.data();
+    d.edge_assoc = ea.data();
+    d.plane_assoc = pa.data();
+  }
+  /// appends one IterationInfo per recorded iteration and overwrites termination_type (registration-inl.h:60,76)
+  void appendTo(RegistrationDetail& detail) const {
+    for (uint32_t it = 0; it < d.n_iters && it < cap; it++) {
+      std::vector<std::pair<size_t, size_t>> edges(n_ea[it]), planes(n_pa[it]);
+      for (uint32_t k = 0; k < n_ea[it]; k++) {
+        const uint32_t* r = ea.data() + (static_cast<size_t>(it) * ne + k) * 2;
+        edges[k] = {r[0], r[1]};
+      }
+      for (uint32_t k = 0; k < n_pa[it]; k++) {
+        const uint32_t* r = pa.data() + (static_cast<size_t>(it) * np + k) * 2;
+        planes[k] = {r[0], r[1]};
+      }
+      detail.iteration_info.emplace_back(poseFrom7(iter_est.data() + 7 * it), edges, planes,
+                                         poseFrom7(iter_upd.data() + 7 * it));
+    }
+    detail.termination_type = static_cast<RegistrationDetail::TerminationType>(d.termination);
+  }
+};
+}  // namespace gpu
+
 template <template <typename> class Accessor = FieldAccessor, typename PointType, template <typename> class Alloc>
 Pose3d registerFeatures(const LoamFeatures<PointType, Alloc>& source, const LoamFeatures<PointType, Alloc>& target,
                         const Pose3d& target_T_source_init, const RegistrationParams& params = RegistrationParams(),
@@ -96,44 +140,15 @@ Pose3d registerFeatures(const LoamFeatures<PointType, Alloc>& source, const Loam
   const loamgpu_reg_params rp = gpu::toC(params);
   double init[7], out[7];
   gpu::poseTo7(target_T_source_init, init);
-
   if (!detail) {
     gpu::check(ctx, loamgpu_register(ctx, se.data(), se.size() / 3, sp.data(), sp.size() / 3, te.data(), te.size() / 3,
                                      tp.data(), tp.size() / 3, init, &rp, out, nullptr));
     return gpu::poseFrom7(out);
   }
-
-  const uint32_t cap = static_cast<uint32_t>(params.max_iterations ? params.max_iterations : 1);
-  const uint32_t ne = static_cast<uint32_t>(se.size() / 3 ? se.size() / 3 : 1), np = static_cast<uint32_t>(sp.size() / 3 ? sp.size() / 3 : 1);
-  std::vector<double> iter_est(7 * cap), iter_upd(7 * cap);
-  std::vector<uint32_t> n_ea(cap), n_pa(cap), ea(static_cast<size_t>(cap) * ne * 2), pa(static_cast<size_t>(cap) * np * 2);
-  loamgpu_detail d;
-  std::memset(&d, 0, sizeof d);
-  d.max_iters_cap = cap;
-  d.n_src_edge = ne;
-  d.n_src_planar = np;
-  d.iter_est = iter_est.data();
-  d.iter_update = iter_upd.data();
-  d.n_edge_assoc = n_ea.data();
-  d.n_plane_assoc = n_pa.data();
-  d.edge_assoc = ea.data();
-  d.plane_assoc = pa.data();
+  gpu::DetailBuffers buf(params, se.size() / 3, sp.size() / 3);
   gpu::check(ctx, loamgpu_register(ctx, se.data(), se.size() / 3, sp.data(), sp.size() / 3, te.data(), te.size() / 3,
-                                   tp.data(), tp.size() / 3, init, &rp, out, &d));
-  for (uint32_t it = 0; it < d.n_iters && it < cap; it++) {
-    std::vector<std::pair<size_t, size_t>> edges(n_ea[it]), planes(n_pa[it]);
-    for (uint32_t k = 0; k < n_ea[it]; k++) {
-      const uint32_t* r = ea.data() + (static_cast<size_t>(it) * ne + k) * 2;
-      edges[k] = {r[0], r[1]};
-    }
-    for (uint32_t k = 0; k < n_pa[it]; k++) {
-      const uint32_t* r = pa.data() + (static_cast<size_t>(it) * np + k) * 2;
-      planes[k] = {r[0], r[1]};
-    }
-    detail->iteration_info.emplace_back(gpu::poseFrom7(iter_est.data() + 7 * it), edges, planes,
-                                        gpu::poseFrom7(iter_upd.data() + 7 * it));
-  }
-  detail->termination_type = static_cast<RegistrationDetail::TerminationType>(d.termination);
+                                   tp.data(), tp.size() / 3, init, &rp, out, &buf.d));
+  buf.appendTo(*detail);
   return gpu::poseFrom7(out);
 }
 

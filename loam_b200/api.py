@@ -277,24 +277,58 @@ def computeValidPoints(input_scan, lidar_params: LidarParams, params=None, devic
         raise _map_error(e) from None
 
 
-def registerFeatures(source: LoamFeatures, target: LoamFeatures, target_T_source_init: Pose3d, params=None,
-                     detail: RegistrationDetail | None = None, device: int = 0) -> Pose3d:
-    """loam::registerFeatures (registration.h:128-131)."""
-    params = params or RegistrationParams()
-    ctx = get_context(device)
-    args = (_as_cloud(source.edge_points), _as_cloud(source.planar_points), _as_cloud(target.edge_points),
-            _as_cloud(target.planar_points), target_T_source_init._to7(), params._to_c())
-    try:
-        if detail is None:
-            return Pose3d._from7(ctx.register(*args))
-        pose, info = ctx.register(*args, want_detail=True)
-    except _capi.LoamGpuError as e:
-        raise _map_error(e) from None
+def _fill_detail(detail, info):
     for i in range(info["n_iters"]):
         detail.iteration_info.append(RegistrationIterationInfo(
             Pose3d._from7(info["iter_est"][i]), [tuple(map(int, r)) for r in info["edge_assoc"][i]],
             [tuple(map(int, r)) for r in info["plane_assoc"][i]], Pose3d._from7(info["iter_update"][i])))
     detail.termination_type = RegistrationTerminationType(info["termination"])
+
+
+class LocalMap:
+    """Device-resident registration target (extension, mirrors include/loam/local_map.h): the reference leaves
+    "maintain a local map of points" to its caller (README.md:63), who passes the accumulated map as `target` and pays
+    a KD-tree build over all of it per call.  A LocalMap keeps the points and their NN structures on the GPU."""
+
+    def __init__(self, features: LoamFeatures | None = None, device: int = 0):
+        features = features or LoamFeatures()
+        self._device = device
+        try:
+            self._map = get_context(device).map_create(_as_cloud(features.edge_points), _as_cloud(features.planar_points))
+        except _capi.LoamGpuError as e:
+            raise _map_error(e) from None
+
+    def insert(self, features: LoamFeatures, map_T_features: Pose3d | None = None, max_edge: int = 0, max_planar: int = 0):
+        """Append features (moved into the map frame by map_T_features), keep the newest max_* points, rebuild."""
+        try:
+            self._map.update(_as_cloud(features.edge_points), _as_cloud(features.planar_points),
+                             None if map_T_features is None else map_T_features._to7(), max_edge, max_planar)
+        except _capi.LoamGpuError as e:
+            raise _map_error(e) from None
+
+    def size(self):
+        return self._map.size()
+
+
+def registerFeatures(source: LoamFeatures, target, target_T_source_init: Pose3d, params=None,
+                     detail: RegistrationDetail | None = None, device: int = 0) -> Pose3d:
+    """loam::registerFeatures (registration.h:128-131); `target` may also be a LocalMap."""
+    params = params or RegistrationParams()
+    src = (_as_cloud(source.edge_points), _as_cloud(source.planar_points))
+    try:
+        if isinstance(target, LocalMap):
+            ctx = get_context(target._device)
+            call = lambda **kw: ctx.register_to_map(target._map, *src, target_T_source_init._to7(), params._to_c(), **kw)
+        else:
+            ctx = get_context(device)
+            call = lambda **kw: ctx.register(*src, _as_cloud(target.edge_points), _as_cloud(target.planar_points),
+                                             target_T_source_init._to7(), params._to_c(), **kw)
+        if detail is None:
+            return Pose3d._from7(call())
+        pose, info = call(want_detail=True)
+    except _capi.LoamGpuError as e:
+        raise _map_error(e) from None
+    _fill_detail(detail, info)
     return Pose3d._from7(pose)
 
 

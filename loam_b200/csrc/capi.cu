@@ -341,6 +341,8 @@ int build_map(loamgpu_ctx* ctx, loamgpu_map* m) {
                             ctx->stream, &ctx->launches));
   }
   m->built = true;
+  // a map may be used next through another context (stream) of the same device: finish the build before returning
+  CU(cudaStreamSynchronize(ctx->stream));
   return LOAMGPU_OK;
 }
 

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "loam/loam.h"
+#include "loam/local_map.h"
 
 static int g_fail = 0, g_checks = 0;
 #define CHECK(cond)                                                        \
@@ -222,6 +223,39 @@ static void test_registration_scenarios() {
   CHECK_NEAR(est4.translation(0), 0.1, 0.0);
 }
 
+static void test_local_map_matches_plain_registration() {
+  const auto target = simple_scene();
+  const loam::Pose3d source_T_target(Eigen::Quaterniond(0.9993921140970299, 0.014692022378442412, 0.030140550562090015, 0.009544316157523478),
+                                     V3(-0.1, 0.1, 0.0));
+  const auto source = transformed(target, source_T_target);
+  auto d_plain = std::make_shared<loam::RegistrationDetail>(), d_map = std::make_shared<loam::RegistrationDetail>();
+  const loam::Pose3d plain = loam::registerFeatures<loam::ParenAccessor>(source, target, loam::Pose3d::Identity(),
+                                                                        loam::RegistrationParams(), d_plain);
+  loam::LocalMap map;  // grown in two inserts: first half, then the rest (identity pose: points arrive unchanged)
+  CHECK(map.numEdgePoints() == 0 && map.numPlanarPoints() == 0);
+  auto first = target, rest = target;
+  first.edge_points.resize(80);
+  first.planar_points.resize(4000);
+  rest.edge_points.erase(rest.edge_points.begin(), rest.edge_points.begin() + 80);
+  rest.planar_points.erase(rest.planar_points.begin(), rest.planar_points.begin() + 4000);
+  map.insert<loam::ParenAccessor>(first, loam::Pose3d::Identity());
+  map.insert<loam::ParenAccessor>(rest, loam::Pose3d::Identity());
+  CHECK(map.numEdgePoints() == target.edge_points.size() && map.numPlanarPoints() == target.planar_points.size());
+  const loam::Pose3d via_map = loam::registerFeatures<loam::ParenAccessor>(source, map, loam::Pose3d::Identity(),
+                                                                          loam::RegistrationParams(), d_map);
+  CHECK(via_map.translation(0) == plain.translation(0) && via_map.translation(1) == plain.translation(1) &&
+        via_map.translation(2) == plain.translation(2));
+  CHECK(via_map.rotation.w() == plain.rotation.w() && via_map.rotation.x() == plain.rotation.x());
+  CHECK(d_map->termination_type == d_plain->termination_type);
+  CHECK(d_map->iteration_info.size() == d_plain->iteration_info.size());
+  CHECK(!d_map->iteration_info.empty() &&
+        d_map->iteration_info[0].plane_associations == d_plain->iteration_info[0].plane_associations &&
+        d_map->iteration_info[0].edge_associations == d_plain->iteration_info[0].edge_associations);
+  loam::LocalMap moved(std::move(map));  // ownership moves, the handle stays valid
+  const loam::Pose3d again = loam::registerFeatures<loam::ParenAccessor>(source, moved, loam::Pose3d::Identity());
+  CHECK(again.translation(0) == plain.translation(0));
+}
+
 int main(int argc, char** argv) {
   const bool no_gpu = argc > 1 && std::strcmp(argv[1], "--no-gpu") == 0;
   test_pose_algebra();
@@ -234,6 +268,7 @@ int main(int argc, char** argv) {
     test_valid_mask_known_answers();
     test_float_zero_copy_matches_double_path();
     test_registration_scenarios();
+    test_local_map_matches_plain_registration();
   }
   std::printf("%s: %d checks, %d failed\n", no_gpu ? "host-only" : "gpu", g_checks, g_fail);
   return g_fail ? 1 : 0;

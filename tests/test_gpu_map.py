@@ -189,3 +189,19 @@ def test_scan_to_local_map_matches_oracle(ctx, oracle):
     # and the answer is the motion: within a few mm / 1e-3 rad of the ground truth
     gt = synth.relative_pose(0, n_map)
     assert H.angular_distance(got[0][:4], gt[:4]) < 2e-3 and np.abs(got[0][4:] - gt[4:]).max() < 2e-2
+
+
+def test_python_module_local_map(ctx, scene):
+    import loam_b200 as loam
+    ed, pl = scene
+    sTt = H.REG_SCENARIOS[0][1]
+    src = loam.LoamFeatures(H.transform(ed, sTt), H.transform(pl, sTt))
+    lmap = loam.LocalMap(loam.LoamFeatures(ed[:50], pl[:5000]))
+    lmap.insert(loam.LoamFeatures(ed[50:], pl[5000:]), loam.Pose3d.Identity())
+    assert lmap.size() == (len(ed), len(pl))
+    d_map, d_plain = loam.RegistrationDetail(), loam.RegistrationDetail()
+    via_map = loam.registerFeatures(src, lmap, loam.Pose3d(), loam.RegistrationParams(), d_map)
+    plain = loam.registerFeatures(src, loam.LoamFeatures(ed, pl), loam.Pose3d(), loam.RegistrationParams(), d_plain)
+    assert np.array_equal(via_map._to7(), plain._to7())
+    assert d_map.termination_type == d_plain.termination_type == loam.CONVERGED
+    assert d_map.iteration_info[0].plane_associations == d_plain.iteration_info[0].plane_associations
