@@ -16,6 +16,7 @@
 // Tie-break (documented, deterministic): equal squared distances resolve by ascending target index
 // (nanoflann resolves them by tree-traversal order, i.e. unpinned in the reference).
 #include <algorithm>
+#include <cstdio>
 
 #include "bvh.cuh"
 #include "common.cuh"
@@ -737,8 +738,8 @@ __device__ __forceinline__ void lm_issue_tile(const double4* __restrict__ rec_p,
 // (per-thread strided partial -> warp shuffle tree -> per-warp shared partials summed in warp order).
 __device__ void evaluate_problem(const double4* __restrict__ rec_p, const double4* __restrict__ rec_a,
                                  const double4* __restrict__ rec_b, uint32_t nE, uint32_t nP, uint32_t capE,
-                                 const double* x, double* s_part /*[nwarps][28]*/, double* s_tot /*[28]*/,
-                                 double* s_lin /*[kLinDoubles]*/, LmPipe& pipe, Eval& out) {
+                                 const double* x, double* s_part /*[nwarps][28]*/, double* s_tot /*[28]: H[21] g[6] cost*/,
+                                 double* s_lin /*[kLinDoubles]*/, LmPipe& pipe) {
   const uint32_t tilesE = (nE + kLmTile - 1) / kLmTile, tilesP = (nP + kLmTile - 1) / kLmTile;
   const uint32_t tiles = tilesE + tilesP;
   const uint32_t g0 = pipe.tile_no;
@@ -809,11 +810,6 @@ __device__ void evaluate_problem(const double4* __restrict__ rec_p, const double
     s_tot[threadIdx.x] = t;
   }
   __syncthreads();
-#pragma unroll
-  for (int i = 0; i < 21; i++) out.H[i] = s_tot[i];
-#pragma unroll
-  for (int i = 0; i < 6; i++) out.g[i] = s_tot[21 + i];
-  out.cost = s_tot[27];
 }
 
 __device__ __forceinline__ int hidx(int i, int j) {  // upper-triangle index, i <= j
@@ -821,21 +817,25 @@ __device__ __forceinline__ int hidx(int i, int j) {  // upper-triangle index, i 
 }
 
 // Solve (A) y = b for symmetric positive definite 6x6 by Cholesky; returns false if not SPD / not finite.
+// One reciprocal per pivot (the serial chain of 27 fp64 divisions + 6 square roots was a visible part of the
+// ~16 us every CTA spent per LM iteration outside the residual evaluations).
 __device__ __forceinline__ bool chol6_solve(const double (&A)[6][6], const double (&b)[6], double (&y)[6]) {
-  double L[6][6];
+  double L[6][6], inv[6];
 #pragma unroll
-  for (int i = 0; i < 6; i++) {
+  for (int j = 0; j < 6; j++) {
+    double s = A[j][j];
 #pragma unroll
-    for (int j = 0; j <= i; j++) {
-      double s = A[i][j];
+    for (int k = 0; k < j; k++) s -= L[j][k] * L[j][k];
+    if (!(s > 0.0)) return false;
+    const double d = sqrt(s);
+    inv[j] = 1.0 / d;
+    L[j][j] = d;
 #pragma unroll
-      for (int k = 0; k < j; k++) s -= L[i][k] * L[j][k];
-      if (i == j) {
-        if (!(s > 0.0)) return false;
-        L[i][i] = sqrt(s);
-      } else {
-        L[i][j] = s / L[j][j];
-      }
+    for (int i = j + 1; i < 6; i++) {
+      double t = A[i][j];
+#pragma unroll
+      for (int k = 0; k < j; k++) t -= L[i][k] * L[j][k];
+      L[i][j] = t * inv[j];
     }
   }
   double z[6];
@@ -844,14 +844,14 @@ __device__ __forceinline__ bool chol6_solve(const double (&A)[6][6], const doubl
     double s = b[i];
 #pragma unroll
     for (int k = 0; k < i; k++) s -= L[i][k] * z[k];
-    z[i] = s / L[i][i];
+    z[i] = s * inv[i];
   }
 #pragma unroll
   for (int i = 5; i >= 0; i--) {
     double s = z[i];
 #pragma unroll
     for (int k = i + 1; k < 6; k++) s -= L[k][i] * y[k];
-    y[i] = s / L[i][i];
+    y[i] = s * inv[i];
   }
   bool fin = true;
 #pragma unroll
@@ -879,7 +879,8 @@ __device__ __forceinline__ double norm7(const double* x) {
 
 // One CTA per pair.  Every thread runs the (tiny, uniform) controller redundantly on the reduced sums, so
 // no broadcast of the step is needed between evaluations.
-__device__ void lm_pair(const LmArgs& a, uint32_t pair, double* s_part, double* s_tot, double* s_lin, LmPipe& pipe) {
+__device__ void lm_pair(const LmArgs& a, uint32_t pair, double* s_part, double* s_sum /*[2][28]*/, double* s_lin,
+                        LmPipe& pipe) {
   PairState* ps = a.state + pair;
   if (ps->status != -1) return;
   const uint32_t src_slot = (uint32_t)((a.pair0 + pair + a.src_offset) % a.n_slots);
@@ -909,17 +910,27 @@ __device__ void lm_pair(const LmArgs& a, uint32_t pair, double* s_part, double* 
 
   double x[7] = {0, 0, 0, 1, 0, 0, 0};
   double x_norm = norm7(x);
-  Eval ev;
+  // reduced sums (H[21], g[6], cost) of the accepted point and of the candidate live in two shared-memory buffers
+  // that swap roles when a step is accepted: nothing of that size is copied or kept in per-thread local memory
+  const double* cur = s_sum;
+  double* other = s_sum + 28;
   double scale[6], diag[6];
   uint32_t lm_iterations = 0;
   double cost0 = 0, x_cost = 0;
   if (n_ea + n_pa > 0) {
-    evaluate_problem(rec_p, rec_a, rec_b, nE, nP, a.capE_scan, x, s_part, s_tot, s_lin, pipe, ev);
-    x_cost = ev.cost;
+#ifdef LM_TIMING
+    long long t_eval = 0, t_all0 = clock64();
+    { const long long c0 = clock64();
+#endif
+    evaluate_problem(rec_p, rec_a, rec_b, nE, nP, a.capE_scan, x, s_part, s_sum, s_lin, pipe);
+#ifdef LM_TIMING
+    t_eval += clock64() - c0; }
+#endif
+    x_cost = cur[27];
     cost0 = x_cost;
 #pragma unroll
-    for (int j = 0; j < 6; j++) scale[j] = 1.0 / (1.0 + sqrt(ev.H[hidx(j, j)]));
-    double gmax = grad_max_norm(x, ev.g);
+    for (int j = 0; j < 6; j++) scale[j] = 1.0 / (1.0 + sqrt(cur[hidx(j, j)]));
+    double gmax = grad_max_norm(x, cur + 21);
     bool step_successful = true, armed = false;
     int iteration = 0;
     for (;;) {
@@ -931,10 +942,10 @@ __device__ void lm_pair(const LmArgs& a, uint32_t pair, double* s_part, double* 
       double Hs[6][6], gs[6];
 #pragma unroll
       for (int i = 0; i < 6; i++) {
-        gs[i] = ev.g[i] * scale[i];
+        gs[i] = cur[21 + i] * scale[i];
 #pragma unroll
         for (int j = i; j < 6; j++) {
-          const double v = ev.H[hidx(i, j)] * scale[i] * scale[j];
+          const double v = cur[hidx(i, j)] * scale[i] * scale[j];
           Hs[i][j] = v;
           Hs[j][i] = v;
         }
@@ -981,9 +992,14 @@ __device__ void lm_pair(const LmArgs& a, uint32_t pair, double* s_part, double* 
 #pragma unroll
       for (int j = 0; j < 6; j++) delta[j] = step[j] * scale[j];
       manifold_plus(x, delta, cand);
-      Eval ec;
-      evaluate_problem(rec_p, rec_a, rec_b, nE, nP, a.capE_scan, cand, s_part, s_tot, s_lin, pipe, ec);
-      const double cand_cost = ec.cost;
+#ifdef LM_TIMING
+      const long long c1 = clock64();
+#endif
+      evaluate_problem(rec_p, rec_a, rec_b, nE, nP, a.capE_scan, cand, s_part, other, s_lin, pipe);
+#ifdef LM_TIMING
+      t_eval += clock64() - c1;
+#endif
+      const double cand_cost = other[27];
       if (armed) {
         double dn = 0;
 #pragma unroll
@@ -996,9 +1012,13 @@ __device__ void lm_pair(const LmArgs& a, uint32_t pair, double* s_part, double* 
 #pragma unroll
         for (int i = 0; i < 7; i++) x[i] = cand[i];
         x_norm = norm7(x);
-        ev = ec;
+        {
+          double* t = const_cast<double*>(cur);
+          cur = other;
+          other = t;
+        }
         x_cost = cand_cost;
-        gmax = grad_max_norm(x, ev.g);
+        gmax = grad_max_norm(x, cur + 21);
         step_successful = true;
         const double q = 2.0 * rel - 1.0;
         radius = radius / fmax(1.0 / 3.0, 1.0 - q * q * q);
@@ -1014,6 +1034,11 @@ __device__ void lm_pair(const LmArgs& a, uint32_t pair, double* s_part, double* 
       }
     }
     lm_iterations = (uint32_t)iteration;
+#ifdef LM_TIMING
+    if (threadIdx.x == 0 && (pair % 64) == 0)
+      printf("LMT pair %u outer %d: total %lld cycles, in evaluations %lld, lm iterations %d, residuals %u\n", pair,
+             a.outer_iter, clock64() - t_all0, t_eval, iteration, nE + nP);
+#endif
   }
 
   // ---- ICF update (registration-inl.h:59-73)
@@ -1054,7 +1079,7 @@ __device__ void lm_pair(const LmArgs& a, uint32_t pair, double* s_part, double* 
 __global__ void __launch_bounds__(kLmThreads, kLmMinBlocks) lm_kernel(LmArgs a) {
   extern __shared__ __align__(128) unsigned char lm_smem[];  // kLmStages x LmStage
   __shared__ double s_part[(kLmThreads / 32) * 28];
-  __shared__ double s_tot[28];
+  __shared__ double s_sum[2 * 28];
   __shared__ __align__(16) double s_lin[kLinDoubles];
   __shared__ __align__(8) uint64_t s_full[kLmStages];
   LmPipe pipe;
@@ -1066,7 +1091,7 @@ __global__ void __launch_bounds__(kLmThreads, kLmMinBlocks) lm_kernel(LmArgs a) 
   __syncthreads();
   const uint32_t n_act = active_count(a.active, a.n_pairs);
   for (uint32_t i = blockIdx.x; i < n_act; i += gridDim.x) {
-    lm_pair(a, active_pair(a.active, i), s_part, s_tot, s_lin, pipe);
+    lm_pair(a, active_pair(a.active, i), s_part, s_sum, s_lin, pipe);
     __syncthreads();
   }
 }
