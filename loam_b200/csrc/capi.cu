@@ -52,6 +52,7 @@ struct loamgpu_ctx {
   uint32_t chunk_pairs = 256;
   int max_smem_optin = 0;
   int morton_queries = 1;  // LOAMGPU_QUERY_ORDER=original switches the k-NN kernel to source-index order (A/B)
+  uint32_t lm_cluster = 0;          // 0 = automatic (see run_register)
   uint64_t big_target_min = 60000;  // targets at least this large get the multi-CTA NN build ($LOAMGPU_BIG_TARGET_MIN)
 
   DevBuf scan_in[2];                       // H2D staging of scans
@@ -350,7 +351,7 @@ int build_map(loamgpu_ctx* ctx, loamgpu_map* m) {
 // With `map` every pair registers onto the map instead (src_offset must be 0: set p / slot p = source of pair p).
 int run_register(loamgpu_ctx* ctx, const RegP& rp, uint32_t n_pairs, uint64_t pair0, uint32_t n_slots, int src_offset,
                  uint32_t capE, uint32_t capP, const double* init_pose_dev, bool detail,
-                 const loamgpu_map* map = nullptr) {
+                 const loamgpu_map* map = nullptr, bool single_call = false) {
   const uint32_t n_sets = n_pairs + (map ? 0u : 1u);  // without a map: + the last pair's source set
   BvhBuildArgs gb;
   memset(&gb, 0, sizeof gb);
@@ -411,6 +412,11 @@ int run_register(loamgpu_ctx* ctx, const RegP& rp, uint32_t n_pairs, uint64_t pa
   la.n_slots = n_slots;
   la.src_offset = src_offset;
   la.rp = rp;
+  // CTAs per pair in the LM kernel.  Sequence odometry keeps 1 whatever the chunk size (sums are then formed in the
+  // same order for every chunking: results do not depend on it; measured: clusters of 2 / 4 are slower on full
+  // chunks, 1.04 / 1.34 vs 0.82 ms); explicit single registrations spread the pair over a cluster of 8 CTAs, which
+  // cuts the latency of the one call the reference API is made of ($LOAMGPU_LM_CLUSTER overrides both).
+  la.cluster = ctx->lm_cluster ? ctx->lm_cluster : (single_call ? 8u : 1u);
   if (detail) {
     la.d_iter_est = ctx->det_est.as<double>();
     la.d_iter_update = ctx->det_upd.as<double>();
@@ -420,13 +426,22 @@ int run_register(loamgpu_ctx* ctx, const RegP& rp, uint32_t n_pairs, uint64_t pa
   }
   aa.n_pairs = la.n_pairs = n_pairs;
   for (int it = 0; it < rp.max_iterations; it++) {
-    aa.active = la.active = it == 0 ? nullptr : ctx->active.as<uint32_t>();
+    aa.active = la.active = (it == 0 || single_call) ? nullptr : ctx->active.as<uint32_t>();
     TIMED(LOAMGPU_K_ASSOC, launch_assoc_knn(aa, n_pairs, it, ctx->stream));
     TIMED(LOAMGPU_K_FIT, launch_assoc_fit(aa, n_pairs, it, ctx->stream));
     la.outer_iter = it;
     TIMED(LOAMGPU_K_LM, launch_lm(la, n_pairs, ctx->stream));
-    if (it + 1 < rp.max_iterations)
-      TIMED(LOAMGPU_K_MISC, launch_compact_active(aa.state, n_pairs, ctx->active.as<uint32_t>(), ctx->stream));
+    if (it + 1 >= rp.max_iterations) break;
+    if (single_call) {
+      // one pair: ask the device whether it is still iterating instead of launching up to max_iterations x 3 kernels
+      // that would find nothing to do (the wait costs less than the idle launches; batches keep launching ahead)
+      int32_t status = -1;
+      CU(cudaMemcpyAsync(&status, &ctx->state.as<PairState>()->status, sizeof status, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+      if (status != -1) break;
+      continue;
+    }
+    TIMED(LOAMGPU_K_MISC, launch_compact_active(aa.state, n_pairs, ctx->active.as<uint32_t>(), ctx->stream));
   }
   return LOAMGPU_OK;
 }
@@ -471,6 +486,10 @@ int loamgpu_create(int device, loamgpu_ctx** out) {
   }
   c->stream = c->own_stream;
   if (const char* qo = getenv("LOAMGPU_QUERY_ORDER")) c->morton_queries = strcmp(qo, "original") != 0;
+  if (const char* v = getenv("LOAMGPU_LM_CLUSTER")) {
+    const unsigned long cs = strtoul(v, nullptr, 10);
+    c->lm_cluster = (cs == 1 || cs == 2 || cs == 4 || cs == 8) ? (uint32_t)cs : 0u;
+  }
   if (const char* bt = getenv("LOAMGPU_BIG_TARGET_MIN")) c->big_target_min = strtoull(bt, nullptr, 10);
   *out = c;
   return LOAMGPU_OK;
@@ -703,7 +722,8 @@ static int register_core(loamgpu_ctx* ctx, const double* src_edge, uint64_t n_se
   CU(cudaMemcpyAsync(ctx->planar_pts.p, hp.data(), hp.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->feat_counts.p, counts, 16, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->init_pose.p, init_pose, 56, cudaMemcpyHostToDevice, ctx->stream));
-  rc = run_register(ctx, rp, 1, 0, n_slots, map ? 0 : 1, capE, capP, ctx->init_pose.as<double>(), want_detail, map);
+  rc = run_register(ctx, rp, 1, 0, n_slots, map ? 0 : 1, capE, capP, ctx->init_pose.as<double>(), want_detail, map,
+                    /*single_call=*/true);
   if (rc) return rc;
   TIMED(LOAMGPU_K_MISC, launch_finish_pairs(ctx->state.as<PairState>(), 1, ctx->out_pose.as<double>(),
                                             ctx->out_term.as<int32_t>(), ctx->out_iters.as<uint32_t>(), ctx->stream));

@@ -142,6 +142,7 @@ struct LmArgs {
   int outer_iter;
   uint32_t n_pairs;
   const uint32_t* active;  // see AssocArgs
+  uint32_t cluster;        // CTAs (thread-block cluster size, 1..8) sharing one pair
   RegP rp;
   // optional detail (single-pair API): per outer iteration rows
   double* d_iter_est;      // [cap][7]

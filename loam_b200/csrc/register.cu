@@ -15,12 +15,17 @@
 //
 // Tie-break (documented, deterministic): equal squared distances resolve by ascending target index
 // (nanoflann resolves them by tree-traversal order, i.e. unpinned in the reference).
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cstdio>
+#include <cstring>
 
 #include "bvh.cuh"
 #include "common.cuh"
 #include "kernels.h"
+
+namespace cg = cooperative_groups;
 
 namespace loamgpu {
 
@@ -714,6 +719,11 @@ struct LmPipe {
   LmStage* stages;   // [kLmStages]
   uint64_t* full;    // [kLmStages] mbarriers, armed by the producer thread with the tile's byte count
   uint32_t tile_no;  // tiles consumed so far by this CTA (same value in every thread): stage = tile_no % kLmStages
+  // A pair may be shared by the CTAs of a thread-block cluster: CTA `rank` of `size` takes the tiles rank, rank + size,
+  // ...; partial sums are exchanged through distributed shared memory (size 1 = plain one-CTA-per-pair operation).
+  uint32_t rank, size;
+  double* partial;   // [2][28] this CTA's partial sums, double-buffered by evaluation parity
+  uint32_t eval_no;  // evaluations done by this cluster (same value in every thread of every CTA)
 };
 
 // thread 0: arm the stage's barrier and issue the bulk copies of tile `tile` (edge tiles first, then plane tiles)
@@ -736,19 +746,22 @@ __device__ __forceinline__ void lm_issue_tile(const double4* __restrict__ rec_p,
 
 // Evaluate the whole problem of this pair at x; deterministic fixed-order reduction
 // (per-thread strided partial -> warp shuffle tree -> per-warp shared partials summed in warp order).
+template <bool kClustered>
 __device__ void evaluate_problem(const double4* __restrict__ rec_p, const double4* __restrict__ rec_a,
                                  const double4* __restrict__ rec_b, uint32_t nE, uint32_t nP, uint32_t capE,
                                  const double* x, double* s_part /*[nwarps][28]*/, double* s_tot /*[28]: H[21] g[6] cost*/,
                                  double* s_lin /*[kLinDoubles]*/, LmPipe& pipe) {
   const uint32_t tilesE = (nE + kLmTile - 1) / kLmTile, tilesP = (nP + kLmTile - 1) / kLmTile;
-  const uint32_t tiles = tilesE + tilesP;
+  const uint32_t tiles_all = tilesE + tilesP;
+  // this CTA's tiles: global tile rank + j * size, j = 0 .. tiles - 1
+  const uint32_t tiles = tiles_all > pipe.rank ? (tiles_all - pipe.rank + pipe.size - 1) / pipe.size : 0u;
   const uint32_t g0 = pipe.tile_no;
   if (threadIdx.x == 0) {  // every stage is free here: the previous evaluation consumed all the tiles it issued
-    for (uint32_t k = 0; k < min(tiles, (uint32_t)kLmStages); k++)
-      lm_issue_tile(rec_p, rec_a, rec_b, nE, nP, capE, tilesE, k, pipe.stages + (g0 + k) % kLmStages,
-                    pipe.full + (g0 + k) % kLmStages);
+    for (uint32_t j = 0; j < min(tiles, (uint32_t)kLmStages); j++)
+      lm_issue_tile(rec_p, rec_a, rec_b, nE, nP, capE, tilesE, pipe.rank + j * pipe.size,
+                    pipe.stages + (g0 + j) % kLmStages, pipe.full + (g0 + j) % kLmStages);
   }
-  __syncthreads();  // the previous evaluation's readers of s_lin / s_tot are done
+  __syncthreads();  // the previous evaluation's readers of s_lin are done
   build_linear_maps(x, s_lin);
   __syncthreads();
   Eval e;
@@ -757,8 +770,9 @@ __device__ void evaluate_problem(const double4* __restrict__ rec_p, const double
 #pragma unroll
   for (int i = 0; i < 6; i++) e.g[i] = 0;
   e.cost = 0;
-  for (uint32_t k = 0; k < tiles; k++) {
-    const uint32_t g = g0 + k, sidx = g % kLmStages;
+  for (uint32_t j = 0; j < tiles; j++) {
+    const uint32_t k = pipe.rank + j * pipe.size;  // global tile
+    const uint32_t g = g0 + j, sidx = g % kLmStages;
     LmStage* st = pipe.stages + sidx;
     const bool edge = k < tilesE;
     const uint32_t n_tile = edge ? min((uint32_t)kLmTile, nE - k * kLmTile) : min((uint32_t)kLmTile, nP - (k - tilesE) * kLmTile);
@@ -782,8 +796,9 @@ __device__ void evaluate_problem(const double4* __restrict__ rec_p, const double
       accumulate_residuals<kLmRpt, false>(rp, ra, rb, valid, s_lin, e);
     }
     __syncthreads();  // everyone has read the stage before it is refilled
-    if (threadIdx.x == 0 && k + kLmStages < tiles)
-      lm_issue_tile(rec_p, rec_a, rec_b, nE, nP, capE, tilesE, k + kLmStages, st, pipe.full + sidx);
+    if (threadIdx.x == 0 && j + kLmStages < tiles)
+      lm_issue_tile(rec_p, rec_a, rec_b, nE, nP, capE, tilesE, pipe.rank + (j + kLmStages) * pipe.size, st,
+                    pipe.full + sidx);
   }
   pipe.tile_no = g0 + tiles;
   double v[28];
@@ -804,11 +819,32 @@ __device__ void evaluate_problem(const double4* __restrict__ rec_p, const double
     for (int i = 0; i < 28; i++) s_part[warp * 28 + i] = v[i];
   }
   __syncthreads();
-  if (threadIdx.x < 28) {
-    double t = 0;
-    for (int wv = 0; wv < nw; wv++) t += s_part[wv * 28 + threadIdx.x];
-    s_tot[threadIdx.x] = t;
+  if (!kClustered) {
+    if (threadIdx.x < 28) {
+      double t = 0;
+      for (int wv = 0; wv < nw; wv++) t += s_part[wv * 28 + threadIdx.x];
+      s_tot[threadIdx.x] = t;
+    }
+  } else {
+    // this CTA's partial -> its own buffer of this evaluation's parity; after the cluster barrier every CTA adds the
+    // partials of all ranks in rank order, so all CTAs of the cluster hold bit-identical totals and run the
+    // controller in lock step.  The buffer of parity p is rewritten two evaluations later, i.e. after another
+    // cluster barrier that every reader of this evaluation has passed.
+    double* mine = pipe.partial + 28 * (pipe.eval_no & 1u);
+    if (threadIdx.x < 28) {
+      double t = 0;
+      for (int wv = 0; wv < nw; wv++) t += s_part[wv * 28 + threadIdx.x];
+      mine[threadIdx.x] = t;
+    }
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();
+    if (threadIdx.x < 28) {
+      double t = 0;
+      for (uint32_t r = 0; r < pipe.size; r++) t += cluster.map_shared_rank(mine, r)[threadIdx.x];
+      s_tot[threadIdx.x] = t;
+    }
   }
+  pipe.eval_no++;
   __syncthreads();
 }
 
@@ -879,6 +915,7 @@ __device__ __forceinline__ double norm7(const double* x) {
 
 // One CTA per pair.  Every thread runs the (tiny, uniform) controller redundantly on the reduced sums, so
 // no broadcast of the step is needed between evaluations.
+template <bool kClustered>
 __device__ void lm_pair(const LmArgs& a, uint32_t pair, double* s_part, double* s_sum /*[2][28]*/, double* s_lin,
                         LmPipe& pipe) {
   PairState* ps = a.state + pair;
@@ -886,13 +923,18 @@ __device__ void lm_pair(const LmArgs& a, uint32_t pair, double* s_part, double* 
   const uint32_t src_slot = (uint32_t)((a.pair0 + pair + a.src_offset) % a.n_slots);
   const uint32_t nE = a.feat_counts[src_slot * 2], nP = a.feat_counts[src_slot * 2 + 1];
   const uint32_t n_ea = ps->n_edge_assoc, n_pa = ps->n_plane_assoc;
-  __syncthreads();  // everyone has read the counters before thread 0 resets them
-  if (threadIdx.x == 0) {
+  // everyone (every CTA of the cluster) has read the counters before thread 0 of rank 0 resets them
+  if (!kClustered)
+    __syncthreads();
+  else
+    cg::this_cluster().sync();
+  const bool writer = threadIdx.x == 0 && pipe.rank == 0;
+  if (writer) {
     ps->n_edge_assoc = 0;
     ps->n_plane_assoc = 0;
   }
   if ((uint64_t)n_ea + n_pa < a.rp.min_assoc) {  // registration-inl.h:45-48
-    if (threadIdx.x == 0) ps->status = 2;
+    if (writer) ps->status = 2;
     return;
   }
   const size_t cap_src = (size_t)a.capE_scan + a.capP_scan;
@@ -922,7 +964,7 @@ __device__ void lm_pair(const LmArgs& a, uint32_t pair, double* s_part, double* 
     long long t_eval = 0, t_all0 = clock64();
     { const long long c0 = clock64();
 #endif
-    evaluate_problem(rec_p, rec_a, rec_b, nE, nP, a.capE_scan, x, s_part, s_sum, s_lin, pipe);
+    evaluate_problem<kClustered>(rec_p, rec_a, rec_b, nE, nP, a.capE_scan, x, s_part, s_sum, s_lin, pipe);
 #ifdef LM_TIMING
     t_eval += clock64() - c0; }
 #endif
@@ -995,7 +1037,7 @@ __device__ void lm_pair(const LmArgs& a, uint32_t pair, double* s_part, double* 
 #ifdef LM_TIMING
       const long long c1 = clock64();
 #endif
-      evaluate_problem(rec_p, rec_a, rec_b, nE, nP, a.capE_scan, cand, s_part, other, s_lin, pipe);
+      evaluate_problem<kClustered>(rec_p, rec_a, rec_b, nE, nP, a.capE_scan, cand, s_part, other, s_lin, pipe);
 #ifdef LM_TIMING
       t_eval += clock64() - c1;
 #endif
@@ -1042,7 +1084,7 @@ __device__ void lm_pair(const LmArgs& a, uint32_t pair, double* s_part, double* 
   }
 
   // ---- ICF update (registration-inl.h:59-73)
-  if (threadIdx.x == 0) {
+  if (writer) {
     double est[7], nxt[7];
 #pragma unroll
     for (int j = 0; j < 7; j++) est[j] = ps->est[j];
@@ -1076,24 +1118,39 @@ __device__ void lm_pair(const LmArgs& a, uint32_t pair, double* s_part, double* 
   }
 }
 
+// kClustered = false: one CTA per pair (sequence odometry).  kClustered = true: launched with a cluster dimension, the
+// CTAs of a cluster share one pair (single registrations).
+template <bool kClustered>
 __global__ void __launch_bounds__(kLmThreads, kLmMinBlocks) lm_kernel(LmArgs a) {
   extern __shared__ __align__(128) unsigned char lm_smem[];  // kLmStages x LmStage
   __shared__ double s_part[(kLmThreads / 32) * 28];
   __shared__ double s_sum[2 * 28];
+  __shared__ double s_partial[kClustered ? 2 * 28 : 1];
   __shared__ __align__(16) double s_lin[kLinDoubles];
   __shared__ __align__(8) uint64_t s_full[kLmStages];
   LmPipe pipe;
   pipe.stages = reinterpret_cast<LmStage*>(lm_smem);
   pipe.full = s_full;
   pipe.tile_no = 0;
+  pipe.rank = 0;
+  pipe.size = 1;
+  if (kClustered) {
+    cg::cluster_group cluster = cg::this_cluster();
+    pipe.rank = cluster.block_rank();
+    pipe.size = cluster.num_blocks();
+  }
+  pipe.partial = s_partial;
+  pipe.eval_no = 0;
   if (threadIdx.x == 0)
     for (int i = 0; i < kLmStages; i++) mbar_init(s_full + i, 1);
   __syncthreads();
   const uint32_t n_act = active_count(a.active, a.n_pairs);
-  for (uint32_t i = blockIdx.x; i < n_act; i += gridDim.x) {
-    lm_pair(a, active_pair(a.active, i), s_part, s_sum, s_lin, pipe);
+  const uint32_t cluster_id = blockIdx.x / pipe.size, n_clusters = gridDim.x / pipe.size;
+  for (uint32_t i = cluster_id; i < n_act; i += n_clusters) {
+    lm_pair<kClustered>(a, active_pair(a.active, i), s_part, s_sum, s_lin, pipe);
     __syncthreads();
   }
+  if (kClustered) cg::this_cluster().sync();  // nobody leaves while a peer may still read its partial sums
 }
 
 // Rebuilds the list of pairs still iterating (ascending pair index) after an LM launch.
@@ -1214,10 +1271,30 @@ cudaError_t launch_assoc_fit(const AssocArgs& a, uint32_t n_pairs, int outer_ite
 cudaError_t launch_lm(const LmArgs& a, uint32_t n_pairs, cudaStream_t st) {
   if (n_pairs == 0) return cudaSuccess;
   const size_t smem = (size_t)kLmStages * sizeof(LmStage);
-  cudaError_t err = cudaFuncSetAttribute(lm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const uint32_t rows = pair_rows(n_pairs, a.outer_iter, a.active != nullptr, 296);
+  const uint32_t csize = a.cluster > 1 ? a.cluster : 1u;
+  if (csize == 1) {
+    cudaError_t err = cudaFuncSetAttribute(lm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    lm_kernel<false><<<rows, kLmThreads, smem, st>>>(a);
+    return cudaGetLastError();
+  }
+  cudaError_t err = cudaFuncSetAttribute(lm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
-  lm_kernel<<<pair_rows(n_pairs, a.outer_iter, a.active != nullptr, 296), kLmThreads, smem, st>>>(a);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(rows * csize);
+  cfg.blockDim = dim3(kLmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, lm_kernel<true>, a);
 }
 
 cudaError_t launch_compact_active(const PairState* s, uint32_t n_pairs, uint32_t* active, cudaStream_t st) {
