@@ -376,11 +376,12 @@ def ours(a):
         dom = max(ktimes, key=lambda k: ktimes[k][0])
         dom_ms, dom_n = ktimes[dom]
         achieved = (ab[dom] * a.steps / 1e9) / (dom_ms / 1e3) if dom_ms > 0 else 0.0
-        traffic = None
+        traffic, limiter = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
+        if os.path.exists(tp):  # per-launch DRAM bytes and the limiter named by the committed `ncu --set full` capture
             try:
-                traffic = json.load(open(tp)).get(dom)
+                tj = json.load(open(tp))
+                traffic, limiter = tj.get(dom), tj.get("_limiter", {}).get(dom)
             except Exception:
                 traffic = None
         total_scans = a.scans * world * a.steps  # halo scans (extracted by two ranks) are counted once
@@ -406,7 +407,8 @@ def ours(a):
                          "algorithmic_bytes_per_launch": ab[dom] * a.steps / max(dom_n, 1),
                          "avg_launch_ms": dom_ms / max(dom_n, 1), "launches": dom_n,
                          "whole_path_GBps": (whole / 1e9) / (dev_ms / 1e3),
-                         "whole_path_frac": (whole / 1e9) / (dev_ms / 1e3) / peak},
+                         "whole_path_frac": (whole / 1e9) / (dev_ms / 1e3) / peak,
+                         "limiter": limiter},
             "kernel_ms_per_step": {k: v[0] / a.steps for k, v in ktimes.items()},
             "kernel_share": {k: (v[0] / kernel_ms_total if kernel_ms_total else 0.0) for k, v in ktimes.items()},
             "results": {"mean_edge": float(ne.mean()), "mean_planar": float(npl.mean()),
