@@ -152,6 +152,29 @@ int loamgpu_register(loamgpu_ctx* ctx, const double* src_edge, uint64_t n_src_ed
 int loamgpu_knn(loamgpu_ctx* ctx, const double* targets, uint64_t n_targets, const double* queries,
                 uint64_t n_queries, uint32_t k, double max_dist, uint32_t* idx_out, uint32_t* count_out);
 
+/* ---------------------------------------------------- explicit batches (host buffers) */
+/* loamgpu_extract for n_scans organised scans of the same geometry stored back to back
+ * (n_scans * n_points_per_scan records; n_points_per_scan must equal scan_lines*points_per_line,
+ * checked like validateLidarScan, common.h:104-113).  Row s of edge_idx / planar_idx (row pitch
+ * edge_cap / planar_cap, each at least scan_lines*number_sectors*(max_*_feats_per_sector+1))
+ * receives the indices of scan s relative to that scan; n_edge[s] / n_planar[s] their counts. */
+int loamgpu_extract_batch(loamgpu_ctx* ctx, const void* pts, int dtype, size_t stride_bytes, uint64_t n_scans,
+                          uint64_t n_points_per_scan, const loamgpu_lidar_params* lidar,
+                          const loamgpu_fe_params* fe, uint32_t* edge_idx,
+                          uint64_t edge_cap, uint32_t* n_edge, uint32_t* planar_idx, uint64_t planar_cap,
+                          uint32_t* n_planar);
+/* loamgpu_register for n_pairs independent (source, target) pairs in one call (loop-closure
+ * candidates, scan-to-keyframe sets ...).  The four feature clouds are concatenated in pair
+ * order (n x 3 doubles each); n_*[p] are the per-pair point counts.  init_poses: [n_pairs][7]
+ * or NULL (identity).  Outputs per pair: pose [7], termination, outer iterations (the last two
+ * may be NULL).  Same results as n_pairs loamgpu_register calls up to the rounding of the
+ * 6x6 normal-equation sums (a pair is reduced by one CTA here, by a cluster of 8 there). */
+int loamgpu_register_pairs(loamgpu_ctx* ctx, uint64_t n_pairs, const double* src_edge, const uint64_t* n_src_edge,
+                           const double* src_planar, const uint64_t* n_src_planar, const double* tgt_edge,
+                           const uint64_t* n_tgt_edge, const double* tgt_planar, const uint64_t* n_tgt_planar,
+                           const double* init_poses, const loamgpu_reg_params* params, double* out_poses,
+                           int32_t* termination, uint32_t* iterations);
+
 /* ------------------------------------------- device-resident local map (scan-to-map) */
 /* The reference's README.md:63 leaves "maintain a local map of points" to the caller, who then
  * passes the accumulated map as the `target` of registerFeatures (registration.h:128-131) and

@@ -26,6 +26,7 @@ SYMBOLS = [
     "loamgpu_valid_mask", "loamgpu_register", "loamgpu_knn", "loamgpu_odometry_host", "loamgpu_odometry_device",
     "loamgpu_set_chunk_pairs", "loamgpu_set_profiling", "loamgpu_kernel_times", "loamgpu_map_create",
     "loamgpu_map_destroy", "loamgpu_map_size", "loamgpu_map_update", "loamgpu_register_to_map",
+    "loamgpu_extract_batch", "loamgpu_register_pairs",
 ]
 KERNEL_CLASSES = ["extract", "pack", "nn_build", "knn", "lm", "misc", "fit"]
 
@@ -89,6 +90,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     lib.loamgpu_valid_mask.argtypes = [vp, vp, C.c_int, C.c_size_t, u64, vp, vp, vp]
     lib.loamgpu_register.argtypes = [vp, vp, u64, vp, u64, vp, u64, vp, u64, vp, vp, vp, vp]
     lib.loamgpu_knn.argtypes = [vp, vp, u64, vp, u64, u32, f64, vp, vp]
+    lib.loamgpu_extract_batch.argtypes = [vp, vp, C.c_int, C.c_size_t, u64, u64, vp, vp, vp, u64, vp, vp, u64, vp]
+    lib.loamgpu_register_pairs.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.loamgpu_map_create.argtypes = [vp, vp, u64, vp, u64, C.POINTER(C.c_void_p)]
     lib.loamgpu_map_destroy.argtypes = [vp, vp]
     lib.loamgpu_map_destroy.restype = None
@@ -233,6 +236,43 @@ class Context:
                                               _ptr(tp), len(tp), _ptr(init), C.addressof(rp), _ptr(out),
                                               C.addressof(det) if det is not None else None))
         return (out, self._detail_info(det, bufs)) if want_detail else out
+
+    # ---------------------------------------------------------------- explicit batches
+    def extract_batch(self, scans, lp: CLidarParams, fe: CFeParams):
+        """scans: [n_scans, R*P, >=3] float32/float64.  Returns a list of (edge_idx, planar_idx) per scan."""
+        a = np.asarray(scans)
+        if a.ndim != 3:
+            raise ValueError("scans must be [n_scans, points, >=3]")
+        n_scans, n_per = a.shape[0], a.shape[1]
+        a = np.ascontiguousarray(a if a.dtype == np.float32 else a.astype(np.float64))
+        dt = F32 if a.dtype == np.float32 else F64
+        stride = a.strides[1] if n_per else (16 if dt == F32 else 24)
+        cap_e = max(1, int(lp.scan_lines * fe.number_sectors * (fe.max_edge_feats_per_sector + 1)))
+        cap_p = max(1, int(lp.scan_lines * fe.number_sectors * (fe.max_planar_feats_per_sector + 1)))
+        cap_e, cap_p = min(cap_e, max(n_per, 1)), min(cap_p, max(n_per, 1))
+        e = np.zeros((n_scans, cap_e), dtype=np.uint32)
+        p = np.zeros((n_scans, cap_p), dtype=np.uint32)
+        ne = np.zeros(n_scans, dtype=np.uint32)
+        npl = np.zeros(n_scans, dtype=np.uint32)
+        self._check(self.lib.loamgpu_extract_batch(self.h, _ptr(a), dt, stride, n_scans, n_per, C.addressof(lp), C.addressof(fe),
+                                                   _ptr(e), cap_e, _ptr(ne), _ptr(p), cap_p, _ptr(npl)))
+        return [(e[i, :ne[i]].copy(), p[i, :npl[i]].copy()) for i in range(n_scans)]
+
+    def register_pairs(self, pairs, init_poses, rp: CRegParams):
+        """pairs: sequence of (src_edge, src_planar, tgt_edge, tgt_planar); init_poses: [n,7] or None.
+        Returns poses[n,7], termination[n], iterations[n]."""
+        n = len(pairs)
+        cols = [[_xyz64(pr[k]) for pr in pairs] for k in range(4)]
+        cat = [np.ascontiguousarray(np.concatenate(c)) if n else np.zeros((0, 3)) for c in cols]
+        cnt = [np.array([len(x) for x in c], dtype=np.uint64) for c in cols]
+        init = None if init_poses is None else np.ascontiguousarray(init_poses, dtype=np.float64).reshape(n, 7)
+        poses = np.zeros((n, 7))
+        term = np.zeros(n, dtype=np.int32)
+        its = np.zeros(n, dtype=np.uint32)
+        self._check(self.lib.loamgpu_register_pairs(self.h, n, _ptr(cat[0]), _ptr(cnt[0]), _ptr(cat[1]), _ptr(cnt[1]),
+                                                    _ptr(cat[2]), _ptr(cnt[2]), _ptr(cat[3]), _ptr(cnt[3]), _ptr(init),
+                                                    C.addressof(rp), _ptr(poses), _ptr(term), _ptr(its)))
+        return poses, term, its
 
     # ---------------------------------------------------------------- device-resident local map
     def map_create(self, edge, planar) -> "DeviceMap":

@@ -281,8 +281,9 @@ int make_regp(loamgpu_ctx* ctx, const loamgpu_reg_params* rp, RegP* out) {
 }
 
 int reserve_register(loamgpu_ctx* ctx, uint32_t n_pairs, uint32_t capE, uint32_t capP, uint32_t detail_iters,
-                     uint32_t nn_stride) {
-  const size_t n_sets = (size_t)n_pairs + 1;  // every pair's target + the source of the last pair
+                     uint32_t nn_stride, uint32_t n_sets_or_0 = 0) {
+  // sequence: every pair's target + the source of the last pair; explicit pairs: a target and a source set per pair
+  const size_t n_sets = n_sets_or_0 ? n_sets_or_0 : (size_t)n_pairs + 1;
   CU(ctx->ge_hdr.reserve(n_sets * sizeof(BvhHdr)));
   CU(ctx->gp_hdr.reserve(n_sets * sizeof(BvhHdr)));
   CU(ctx->ge_nodes.reserve(n_sets * capE * sizeof(BvhNode)));
@@ -351,8 +352,10 @@ int build_map(loamgpu_ctx* ctx, loamgpu_map* m) {
 // With `map` every pair registers onto the map instead (src_offset must be 0: set p / slot p = source of pair p).
 int run_register(loamgpu_ctx* ctx, const RegP& rp, uint32_t n_pairs, uint64_t pair0, uint32_t n_slots, int src_offset,
                  uint32_t capE, uint32_t capP, const double* init_pose_dev, bool detail,
-                 const loamgpu_map* map = nullptr, bool single_call = false) {
-  const uint32_t n_sets = n_pairs + (map ? 0u : 1u);  // without a map: + the last pair's source set
+                 const loamgpu_map* map = nullptr, bool single_call = false, uint32_t n_sets_or_0 = 0,
+                 uint32_t init_stride = 0) {
+  // sets to build = feature slots pair0 .. pair0 + n_sets - 1 (without a map: + the last pair's source set)
+  const uint32_t n_sets = n_sets_or_0 ? n_sets_or_0 : n_pairs + (map ? 0u : 1u);
   BvhBuildArgs gb;
   memset(&gb, 0, sizeof gb);
   gb.counts = ctx->feat_counts.as<uint32_t>();
@@ -368,7 +371,7 @@ int run_register(loamgpu_ctx* ctx, const RegP& rp, uint32_t n_pairs, uint64_t pa
   gb.kind = 1;
   gb.g = bvh_arrays(ctx, true, capP);
   TIMED(LOAMGPU_K_GRID, launch_bvh_build(gb, n_sets, ctx->stream));
-  TIMED(LOAMGPU_K_MISC, launch_init_pairs(ctx->state.as<PairState>(), n_pairs, init_pose_dev, ctx->stream));
+  TIMED(LOAMGPU_K_MISC, launch_init_pairs(ctx->state.as<PairState>(), n_pairs, init_pose_dev, init_stride, ctx->stream));
 
   AssocArgs aa;
   memset(&aa, 0, sizeof aa);
@@ -824,6 +827,133 @@ int loamgpu_register(loamgpu_ctx* ctx, const double* src_edge, uint64_t n_se, co
   }
   return register_core(ctx, src_edge, n_se, src_planar, n_sp, tgt_edge, n_te, tgt_planar, n_tp, nullptr, init_pose, params,
                        out_pose, detail);
+}
+
+// ------------------------------------------------------------------------------------ explicit batches
+
+int loamgpu_extract_batch(loamgpu_ctx* ctx, const void* pts, int dtype, size_t stride, uint64_t n_scans,
+                          uint64_t n_points_per_scan, const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe,
+                          uint32_t* edge_idx,
+                          uint64_t edge_cap, uint32_t* n_edge, uint32_t* planar_idx, uint64_t planar_cap,
+                          uint32_t* n_planar) {
+  if (!ctx) return LOAMGPU_ERR_INVALID;
+  if (!lp || !fe) return fail(ctx, LOAMGPU_ERR_INVALID, "null parameter struct");
+  if (n_scans == 0) return LOAMGPU_OK;
+  if (!n_edge || !n_planar) return fail(ctx, LOAMGPU_ERR_INVALID, "null count pointer");
+  CU(cudaSetDevice(ctx->device));
+  const uint64_t n_per = n_points_per_scan;
+  ExtractPlan pl;
+  int rc = plan_extract(ctx, dtype, stride, n_per, lp, fe, &pl);  // validateLidarScan: size must be lines x points
+  if (rc) return rc;
+  if (n_per == 0) {
+    for (uint64_t s = 0; s < n_scans; s++) n_edge[s] = n_planar[s] = 0;
+    return LOAMGPU_OK;
+  }
+  if (!pts) return fail(ctx, LOAMGPU_ERR_INVALID, "null point buffer");
+  if (pl.capE_scan > edge_cap || pl.capP_scan > planar_cap || !edge_idx || !planar_idx)
+    return fail(ctx, LOAMGPU_ERR_INVALID,
+                "output index buffers too small: rows of scan_lines*number_sectors*(max_*_feats_per_sector+1) needed");
+  const size_t scan_bytes = (size_t)n_per * stride;
+  const uint32_t chunk = (uint32_t)std::min<uint64_t>(n_scans, std::max<uint32_t>(ctx->chunk_pairs, 1));
+  CU(ctx->scan_in[0].reserve((size_t)chunk * scan_bytes));
+  rc = reserve_extract(ctx, pl, chunk, chunk);
+  if (rc) return rc;
+  std::vector<uint32_t> counts((size_t)chunk * 2);
+  for (uint64_t s0 = 0; s0 < n_scans; s0 += chunk) {
+    const uint32_t ns = (uint32_t)std::min<uint64_t>(chunk, n_scans - s0);
+    CU(cudaMemcpyAsync(ctx->scan_in[0].p, (const unsigned char*)pts + s0 * scan_bytes, (size_t)ns * scan_bytes,
+                       cudaMemcpyHostToDevice, ctx->stream));
+    rc = run_extract(ctx, pl, ctx->scan_in[0].p, dtype, stride, lp, fe, ns, 0, chunk, nullptr, nullptr);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(counts.data(), ctx->feat_counts.p, (size_t)ns * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    // index rows: device row pitch = per-scan capacity, host row pitch = the caller's capacities
+    CU(cudaMemcpy2DAsync(edge_idx + s0 * edge_cap, edge_cap * 4, ctx->edge_idx.p, (size_t)pl.capE_scan * 4,
+                         (size_t)pl.capE_scan * 4, ns, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpy2DAsync(planar_idx + s0 * planar_cap, planar_cap * 4, ctx->planar_idx.p, (size_t)pl.capP_scan * 4,
+                         (size_t)pl.capP_scan * 4, ns, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t i = 0; i < ns; i++) {
+      n_edge[s0 + i] = counts[2 * i];
+      n_planar[s0 + i] = counts[2 * i + 1];
+    }
+  }
+  return LOAMGPU_OK;
+}
+
+int loamgpu_register_pairs(loamgpu_ctx* ctx, uint64_t n_pairs, const double* src_edge, const uint64_t* n_src_edge,
+                           const double* src_planar, const uint64_t* n_src_planar, const double* tgt_edge,
+                           const uint64_t* n_tgt_edge, const double* tgt_planar, const uint64_t* n_tgt_planar,
+                           const double* init_poses, const loamgpu_reg_params* params, double* out_poses,
+                           int32_t* termination, uint32_t* iterations) {
+  if (!ctx) return LOAMGPU_ERR_INVALID;
+  if (n_pairs == 0) return LOAMGPU_OK;
+  if (!n_src_edge || !n_src_planar || !n_tgt_edge || !n_tgt_planar || !out_poses)
+    return fail(ctx, LOAMGPU_ERR_INVALID, "null count / output pointer");
+  CU(cudaSetDevice(ctx->device));
+  RegP rp;
+  int rc = make_regp(ctx, params, &rp);
+  if (rc) return rc;
+  const uint64_t* cnt[4] = {n_tgt_edge, n_tgt_planar, n_src_edge, n_src_planar};
+  const double* data[4] = {tgt_edge, tgt_planar, src_edge, src_planar};
+  uint64_t maxE = 1, maxP = 1, total[4] = {0, 0, 0, 0};
+  for (uint64_t p = 0; p < n_pairs; p++) {
+    maxE = std::max(maxE, std::max(n_tgt_edge[p], n_src_edge[p]));
+    maxP = std::max(maxP, std::max(n_tgt_planar[p], n_src_planar[p]));
+    for (int a = 0; a < 4; a++) total[a] += cnt[a][p];
+  }
+  for (int a = 0; a < 4; a++)
+    if (total[a] && !data[a]) return fail(ctx, LOAMGPU_ERR_INVALID, "null feature buffer");
+  if (std::max(maxE, maxP) >= ctx->big_target_min)
+    return fail(ctx, LOAMGPU_ERR_UNSUPPORTED, "feature sets this large go through loamgpu_register / loamgpu_map_*");
+  const uint32_t capE = (uint32_t)maxE, capP = (uint32_t)maxP;
+  // pairs per chunk: bounded by the configured chunk size and by ~2 GB of feature slots
+  const uint64_t per_pair_bytes = 2 * ((uint64_t)capE + capP) * 32;
+  const uint32_t chunk = (uint32_t)std::max<uint64_t>(
+      1, std::min<uint64_t>(std::min<uint64_t>(n_pairs, ctx->chunk_pairs), (2ull << 30) / per_pair_bytes));
+  const uint32_t n_slots = 2 * chunk;  // slots [0, chunk) = targets, [chunk, 2 chunk) = sources
+  CU(ctx->edge_pts.reserve((size_t)n_slots * capE * 32));
+  CU(ctx->planar_pts.reserve((size_t)n_slots * capP * 32));
+  CU(ctx->feat_counts.reserve((size_t)n_slots * 8));
+  rc = reserve_register(ctx, chunk, capE, capP, 0, (uint32_t)std::max(rp.ke, rp.kp), n_slots);
+  if (rc) return rc;
+  CU(ctx->init_pose.reserve((size_t)chunk * 56));
+  CU(ctx->out_pose.reserve((size_t)chunk * 56));
+  CU(ctx->out_term.reserve((size_t)chunk * 4));
+  CU(ctx->out_iters.reserve((size_t)chunk * 4));
+  std::vector<double> he((size_t)n_slots * capE * 4), hp((size_t)n_slots * capP * 4);
+  std::vector<uint32_t> hc((size_t)n_slots * 2);
+  uint64_t off[4] = {0, 0, 0, 0};  // running point offsets into the four concatenated clouds
+  for (uint64_t p0 = 0; p0 < n_pairs; p0 += chunk) {
+    const uint32_t np = (uint32_t)std::min<uint64_t>(chunk, n_pairs - p0);
+    for (uint32_t i = 0; i < np; i++) {
+      const uint64_t p = p0 + i;
+      widen(tgt_edge ? tgt_edge + 3 * off[0] : nullptr, n_tgt_edge[p], he, (size_t)i * capE);
+      widen(tgt_planar ? tgt_planar + 3 * off[1] : nullptr, n_tgt_planar[p], hp, (size_t)i * capP);
+      widen(src_edge ? src_edge + 3 * off[2] : nullptr, n_src_edge[p], he, (size_t)(chunk + i) * capE);
+      widen(src_planar ? src_planar + 3 * off[3] : nullptr, n_src_planar[p], hp, (size_t)(chunk + i) * capP);
+      hc[2 * i] = (uint32_t)n_tgt_edge[p];
+      hc[2 * i + 1] = (uint32_t)n_tgt_planar[p];
+      hc[2 * (chunk + i)] = (uint32_t)n_src_edge[p];
+      hc[2 * (chunk + i) + 1] = (uint32_t)n_src_planar[p];
+      for (int a = 0; a < 4; a++) off[a] += cnt[a][p];
+    }
+    for (uint32_t i = np; i < chunk; i++) hc[2 * i] = hc[2 * i + 1] = hc[2 * (chunk + i)] = hc[2 * (chunk + i) + 1] = 0;
+    CU(cudaMemcpyAsync(ctx->edge_pts.p, he.data(), he.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->planar_pts.p, hp.data(), hp.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->feat_counts.p, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (init_poses)
+      CU(cudaMemcpyAsync(ctx->init_pose.p, init_poses + 7 * p0, (size_t)np * 56, cudaMemcpyHostToDevice, ctx->stream));
+    rc = run_register(ctx, rp, np, 0, n_slots, (int)chunk, capE, capP, init_poses ? ctx->init_pose.as<double>() : nullptr,
+                      false, nullptr, false, n_slots, 7);
+    if (rc) return rc;
+    TIMED(LOAMGPU_K_MISC, launch_finish_pairs(ctx->state.as<PairState>(), np, ctx->out_pose.as<double>(),
+                                              ctx->out_term.as<int32_t>(), ctx->out_iters.as<uint32_t>(), ctx->stream));
+    CU(cudaMemcpyAsync(out_poses + 7 * p0, ctx->out_pose.p, (size_t)np * 56, cudaMemcpyDeviceToHost, ctx->stream));
+    if (termination) CU(cudaMemcpyAsync(termination + p0, ctx->out_term.p, (size_t)np * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (iterations) CU(cudaMemcpyAsync(iterations + p0, ctx->out_iters.p, (size_t)np * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));  // the host staging vectors are reused by the next chunk
+  }
+  return LOAMGPU_OK;
 }
 
 // ------------------------------------------------------------------------------------ device-resident local map

@@ -167,7 +167,9 @@ cudaError_t launch_knn(const KnnArgs& a, cudaStream_t st);
 
 // p <- pose * p for n double4 points in place (map insertion: scan frame -> map frame, Pose3d::act, geometry.cpp:21)
 cudaError_t launch_transform_points(double4* pts, uint32_t n, const double* pose_dev, cudaStream_t s);
-cudaError_t launch_init_pairs(PairState* st, uint32_t n_pairs, const double* init_pose_or_null, cudaStream_t s);
+// init poses: null = identity for every pair; init_stride 0 = the same pose for every pair, 7 = one pose per pair
+cudaError_t launch_init_pairs(PairState* st, uint32_t n_pairs, const double* init_pose_or_null, uint32_t init_stride,
+                              cudaStream_t s);
 // Copy per-pair results to flat output arrays (device pointers; any may be null) and finalise MAX_ITER.
 cudaError_t launch_finish_pairs(const PairState* st, uint32_t n_pairs, double* poses, int32_t* term, uint32_t* iters,
                                 cudaStream_t s);

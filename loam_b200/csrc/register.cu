@@ -1179,12 +1179,12 @@ __global__ void __launch_bounds__(1024) compact_active_kernel(const PairState* s
   if (tid == 0) active[0] = total;
 }
 
-__global__ void init_pairs_kernel(PairState* st, uint32_t n, const double* init) {
+__global__ void init_pairs_kernel(PairState* st, uint32_t n, const double* init, uint32_t init_stride) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   PairState s;
   const double ident[7] = {0, 0, 0, 1, 0, 0, 0};
-  for (int j = 0; j < 7; j++) s.est[j] = init ? init[j] : ident[j];
+  for (int j = 0; j < 7; j++) s.est[j] = init ? init[(size_t)i * init_stride + j] : ident[j];
   s.status = -1;
   s.iters = 0;
   s.n_edge_assoc = 0;
@@ -1321,9 +1321,10 @@ cudaError_t launch_transform_points(double4* pts, uint32_t n, const double* pose
   return cudaGetLastError();
 }
 
-cudaError_t launch_init_pairs(PairState* s, uint32_t n_pairs, const double* init_pose_or_null, cudaStream_t st) {
+cudaError_t launch_init_pairs(PairState* s, uint32_t n_pairs, const double* init_pose_or_null, uint32_t init_stride,
+                              cudaStream_t st) {
   if (n_pairs == 0) return cudaSuccess;
-  init_pairs_kernel<<<(n_pairs + 127) / 128, 128, 0, st>>>(s, n_pairs, init_pose_or_null);
+  init_pairs_kernel<<<(n_pairs + 127) / 128, 128, 0, st>>>(s, n_pairs, init_pose_or_null, init_stride);
   return cudaGetLastError();
 }
 
