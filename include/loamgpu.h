@@ -214,6 +214,16 @@ int loamgpu_register_to_map(loamgpu_ctx* ctx, const loamgpu_map* map, const doub
 int loamgpu_odometry_host(loamgpu_ctx* ctx, const float* scans, uint64_t n_scans, const loamgpu_lidar_params* lidar,
                           const loamgpu_fe_params* fe, const loamgpu_reg_params* reg, double* poses,
                           int32_t* termination, uint32_t* iterations, uint32_t* n_edge, uint32_t* n_planar);
+/* _host without the final wait: copies and kernels are only enqueued (input and output buffers
+ * must stay valid, and should be page-locked, until loamgpu_synchronize returns).  Consecutive
+ * calls pipeline: the host-to-device copies of a call overlap the kernels of the previous one,
+ * which is how a long recording is streamed through in pieces. */
+int loamgpu_odometry_host_async(loamgpu_ctx* ctx, const float* scans, uint64_t n_scans,
+                                const loamgpu_lidar_params* lidar, const loamgpu_fe_params* fe,
+                                const loamgpu_reg_params* reg, double* poses, int32_t* termination,
+                                uint32_t* iterations, uint32_t* n_edge, uint32_t* n_planar);
+/* wait for everything this context has enqueued */
+int loamgpu_synchronize(loamgpu_ctx* ctx);
 int loamgpu_odometry_device(loamgpu_ctx* ctx, const float* scans_dev, uint64_t n_scans,
                             const loamgpu_lidar_params* lidar, const loamgpu_fe_params* fe,
                             const loamgpu_reg_params* reg, double* poses_dev, int32_t* termination_dev,

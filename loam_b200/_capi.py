@@ -26,7 +26,7 @@ SYMBOLS = [
     "loamgpu_valid_mask", "loamgpu_register", "loamgpu_knn", "loamgpu_odometry_host", "loamgpu_odometry_device",
     "loamgpu_set_chunk_pairs", "loamgpu_set_profiling", "loamgpu_kernel_times", "loamgpu_map_create",
     "loamgpu_map_destroy", "loamgpu_map_size", "loamgpu_map_update", "loamgpu_register_to_map",
-    "loamgpu_extract_batch", "loamgpu_register_pairs",
+    "loamgpu_extract_batch", "loamgpu_register_pairs", "loamgpu_odometry_host_async", "loamgpu_synchronize",
 ]
 KERNEL_CLASSES = ["extract", "pack", "nn_build", "knn", "lm", "misc", "fit"]
 
@@ -99,6 +99,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     lib.loamgpu_map_update.argtypes = [vp, vp, vp, u64, vp, u64, vp, u64, u64]
     lib.loamgpu_register_to_map.argtypes = [vp, vp, vp, u64, vp, u64, vp, vp, vp, vp]
     lib.loamgpu_odometry_host.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.loamgpu_odometry_host_async.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.loamgpu_synchronize.argtypes = [vp]
     lib.loamgpu_odometry_device.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, vp, vp, vp]
     _lib = lib
     return lib
@@ -317,6 +319,16 @@ class Context:
                           np_ptr):
         self._check(self.lib.loamgpu_odometry_host(self.h, scans_ptr, n_scans, C.addressof(lp), C.addressof(fe),
                                                    C.addressof(rp), poses_ptr, term_ptr, iters_ptr, ne_ptr, np_ptr))
+
+    def odometry_host_async_ptr(self, scans_ptr: int, n_scans: int, lp, fe, rp, poses_ptr, term_ptr, iters_ptr, ne_ptr,
+                                np_ptr):
+        """Enqueue only (page-locked host buffers, valid until synchronize()); consecutive calls pipeline."""
+        self._check(self.lib.loamgpu_odometry_host_async(self.h, scans_ptr, n_scans, C.addressof(lp), C.addressof(fe),
+                                                         C.addressof(rp), poses_ptr, term_ptr, iters_ptr, ne_ptr,
+                                                         np_ptr))
+
+    def synchronize(self):
+        self._check(self.lib.loamgpu_synchronize(self.h))
 
     def odometry_device_ptr(self, scans_ptr: int, n_scans: int, lp, fe, rp, poses_ptr, term_ptr, iters_ptr, ne_ptr,
                             np_ptr):

@@ -2,6 +2,7 @@
 // device buffers, streams, chunked sequence pipeline.  Host code only packs buffers and launches
 // kernels; every number in the results is produced by the CUDA kernels in extract.cu / register.cu.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -53,6 +54,7 @@ struct loamgpu_ctx {
   int max_smem_optin = 0;
   int morton_queries = 1;  // LOAMGPU_QUERY_ORDER=original switches the k-NN kernel to source-index order (A/B)
   uint32_t lm_cluster = 0;          // 0 = automatic (see run_register)
+  bool staging_unguarded = true;    // scan_in[] was last used outside the event-guarded odometry_host pipeline
   uint64_t big_target_min = 60000;  // targets at least this large get the multi-CTA NN build ($LOAMGPU_BIG_TARGET_MIN)
 
   DevBuf scan_in[2];                       // H2D staging of scans
@@ -612,6 +614,7 @@ int loamgpu_extract(loamgpu_ctx* ctx, const void* pts, int dtype, size_t stride,
   if (!pts) return fail(ctx, LOAMGPU_ERR_INVALID, "null point buffer");
   const size_t bytes = (size_t)n_points * stride;
   CU(ctx->scan_in[0].reserve(bytes));
+  ctx->staging_unguarded = true;
   rc = reserve_extract(ctx, pl, 1, 1);
   if (rc) return rc;
   CU(cudaMemcpyAsync(ctx->scan_in[0].p, pts, bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -643,6 +646,7 @@ static int curvature_or_mask(loamgpu_ctx* ctx, const void* pts, int dtype, size_
   if (!pts || (!curv && !mask)) return fail(ctx, LOAMGPU_ERR_INVALID, "null buffer");
   const size_t bytes = (size_t)n_points * stride;
   CU(ctx->scan_in[0].reserve(bytes));
+  ctx->staging_unguarded = true;
   CU(ctx->misc.reserve((size_t)n_points * 9));
   CU(cudaMemcpyAsync(ctx->scan_in[0].p, pts, bytes, cudaMemcpyHostToDevice, ctx->stream));
   ExtractArgs a;
@@ -856,6 +860,7 @@ int loamgpu_extract_batch(loamgpu_ctx* ctx, const void* pts, int dtype, size_t s
   const size_t scan_bytes = (size_t)n_per * stride;
   const uint32_t chunk = (uint32_t)std::min<uint64_t>(n_scans, std::max<uint32_t>(ctx->chunk_pairs, 1));
   CU(ctx->scan_in[0].reserve((size_t)chunk * scan_bytes));
+  ctx->staging_unguarded = true;
   rc = reserve_extract(ctx, pl, chunk, chunk);
   if (rc) return rc;
   std::vector<uint32_t> counts((size_t)chunk * 2);
@@ -1152,11 +1157,11 @@ static int odometry_core(loamgpu_ctx* ctx, uint64_t n_scans, const loamgpu_lidar
   // the first chunk is the only one that cannot hide behind kernels.  Copying a scan takes ~0.6x the time of
   // processing it (55 GB/s measured), so longer ramps expose more than they save; 128 -> 256 measured best
   // ($LOAMGPU_LEAD / $LOAMGPU_RAMP override).  The device variant uses full chunks throughout.
-  const uint32_t ramp = []() { const char* e = getenv("LOAMGPU_RAMP"); return e ? (uint32_t)atoi(e) : 2u; }();
+  const double ramp = []() { const char* e = getenv("LOAMGPU_RAMP"); return e ? std::max(1.0, atof(e)) : 2.0; }();
   uint32_t np = 0, want = lead;
   for (uint64_t p0 = 0; p0 < n_pairs; p0 += np, buf ^= 1) {
     np = (uint32_t)std::min<uint64_t>(want, n_pairs - p0);
-    want = std::min<uint32_t>(chunk, want * ramp);
+    want = std::min<uint32_t>(chunk, (uint32_t)std::ceil(want * ramp));
     // scans needed: p0 .. p0+np ; scan p0 is already in its slot except for the first chunk
     const uint64_t s0 = p0 == 0 ? 0 : p0 + 1;
     const uint32_t ns = (uint32_t)(p0 + np + 1 - s0);
@@ -1193,9 +1198,26 @@ int loamgpu_odometry_device(loamgpu_ctx* ctx, const float* scans_dev, uint64_t n
   return odometry_core(ctx, n_scans, lp, fe, reg, poses_dev, term_dev, iters_dev, ne_dev, np_dev, 1, fetch);
 }
 
+int loamgpu_synchronize(loamgpu_ctx* ctx) {
+  if (!ctx) return LOAMGPU_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->copy_stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return LOAMGPU_OK;
+}
+
 int loamgpu_odometry_host(loamgpu_ctx* ctx, const float* scans, uint64_t n_scans, const loamgpu_lidar_params* lp,
                           const loamgpu_fe_params* fe, const loamgpu_reg_params* reg, double* poses, int32_t* termination,
                           uint32_t* iterations, uint32_t* n_edge, uint32_t* n_planar) {
+  const int rc = loamgpu_odometry_host_async(ctx, scans, n_scans, lp, fe, reg, poses, termination, iterations, n_edge,
+                                             n_planar);
+  if (rc) return rc;
+  return loamgpu_synchronize(ctx);
+}
+
+int loamgpu_odometry_host_async(loamgpu_ctx* ctx, const float* scans, uint64_t n_scans, const loamgpu_lidar_params* lp,
+                                const loamgpu_fe_params* fe, const loamgpu_reg_params* reg, double* poses,
+                                int32_t* termination, uint32_t* iterations, uint32_t* n_edge, uint32_t* n_planar) {
   if (!ctx) return LOAMGPU_ERR_INVALID;
   if (!lp || !fe || !reg) return fail(ctx, LOAMGPU_ERR_INVALID, "null parameter struct");
   if (n_scans == 0) return LOAMGPU_OK;
@@ -1211,9 +1233,14 @@ int loamgpu_odometry_host(loamgpu_ctx* ctx, const float* scans, uint64_t n_scans
   CU(ctx->out_iters.reserve(std::max<uint64_t>(n_pairs, 1) * 4));
   CU(ctx->out_ne.reserve(n_scans * 4));
   CU(ctx->out_np.reserve(n_scans * 4));
-  // make sure earlier work on the compute stream no longer reads the staging buffers
-  CU(cudaEventRecord(ctx->ev_consumed[0], ctx->stream));
-  CU(cudaEventRecord(ctx->ev_consumed[1], ctx->stream));
+  // Staging buffers are guarded by per-buffer events recorded right after the extract that consumed them, so the first
+  // copies of this call may overlap the registration kernels of a previous, still running call.  Other entry points
+  // use the staging memory on the compute stream without those events: after one of them, wait for all of it.
+  if (ctx->staging_unguarded) {
+    CU(cudaEventRecord(ctx->ev_consumed[0], ctx->stream));
+    CU(cudaEventRecord(ctx->ev_consumed[1], ctx->stream));
+    ctx->staging_unguarded = false;
+  }
   auto fetch = [&](uint64_t s0, uint32_t ns, int buf, const float** out) {
     // copy stream: wait until the previous user of this staging buffer is done, copy, signal the compute stream
     cudaError_t e = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[buf], 0);
@@ -1236,7 +1263,6 @@ int loamgpu_odometry_host(loamgpu_ctx* ctx, const float* scans, uint64_t n_scans
     CU(cudaMemcpyAsync(iterations, ctx->out_iters.p, n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
   if (n_edge) CU(cudaMemcpyAsync(n_edge, ctx->out_ne.p, n_scans * 4, cudaMemcpyDeviceToHost, ctx->stream));
   if (n_planar) CU(cudaMemcpyAsync(n_planar, ctx->out_np.p, n_scans * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
   return LOAMGPU_OK;
 }
 

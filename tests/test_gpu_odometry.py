@@ -90,3 +90,36 @@ def test_single_scan_and_launch_counter(ctx):
     poses, term, its, ne, npl = ctx.odometry_host(synth.make_scan(R, P, k=0)[None], lp, fe, rp)
     assert poses.shape == (0, 7) and ne[0] > 0 and npl[0] > 0
     assert ctx.launch_count == before + 2  # extract + pack
+
+
+def test_async_host_calls_pipeline_without_changing_results(ctx):
+    """loamgpu_odometry_host_async: three different sequences enqueued back to back (page-locked buffers, staging
+    memory shared between the calls, copies of call k+1 overlapping the kernels of call k), one wait at the end;
+    then an unrelated entry point that uses the same staging memory.  Everything equals the synchronous calls."""
+    import torch
+    R, P, n = 64, 1024, 7
+    lp, fe, rp = (H.to_capi(x) for x in (LidarParams(R, P, 1.0, 120.0), FeParams.default(), RegParams.default()))
+    seqs = [np.stack([synth.make_scan(R, P, k=100 * j + k) for k in range(n)]) for j in range(3)]
+    ref = [ctx.odometry_host(s, lp, fe, rp) for s in seqs]
+    ctx.set_chunk_pairs(2)  # several chunks per call: both staging buffers are in use when the next call starts
+    try:
+        h_scans = [torch.from_numpy(s).pin_memory() for s in seqs]
+        outs = [(torch.zeros((n - 1, 7), dtype=torch.float64).pin_memory(), torch.zeros(n - 1, dtype=torch.int32).pin_memory(),
+                 torch.zeros(n - 1, dtype=torch.int32).pin_memory(), torch.zeros(n, dtype=torch.int32).pin_memory(),
+                 torch.zeros(n, dtype=torch.int32).pin_memory()) for _ in seqs]
+        for rep in range(2):
+            for hs, o in zip(h_scans, outs):
+                ctx.odometry_host_async_ptr(hs.data_ptr(), n, lp, fe, rp, *(t.data_ptr() for t in o))
+            ctx.synchronize()
+            for r, o in zip(ref, outs):
+                assert np.array_equal(r[0], o[0].numpy()) and np.array_equal(r[1], o[1].numpy())
+                assert np.array_equal(r[2], o[2].numpy().astype(np.uint32))
+                assert np.array_equal(r[3], o[3].numpy().astype(np.uint32)) and np.array_equal(r[4], o[4].numpy().astype(np.uint32))
+        # an async call still in flight, then single-scan extraction through the same staging memory
+        ctx.odometry_host_async_ptr(h_scans[1].data_ptr(), n, lp, fe, rp, *(t.data_ptr() for t in outs[0]))
+        e, p = ctx.extract(seqs[2][0], lp, fe)
+        ctx.synchronize()
+        assert len(e) == ref[2][3][0] and len(p) == ref[2][4][0]
+        assert np.array_equal(ref[1][0], outs[0][0].numpy())
+    finally:
+        ctx.set_chunk_pairs(256)
