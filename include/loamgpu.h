@@ -228,7 +228,9 @@ int loamgpu_odometry_device(loamgpu_ctx* ctx, const float* scans_dev, uint64_t n
                             const loamgpu_lidar_params* lidar, const loamgpu_fe_params* fe,
                             const loamgpu_reg_params* reg, double* poses_dev, int32_t* termination_dev,
                             uint32_t* iterations_dev, uint32_t* n_edge_dev, uint32_t* n_planar_dev);
-/* pairs processed per internal chunk by the odometry calls (default 256) */
+/* pairs processed per internal chunk by the sequence / batch calls; 0 (default) = automatic: 1024 for
+ * device-resident calls, 512 for asynchronous and 256 for synchronous host calls and explicit batches,
+ * bounded by a share of the free device memory */
 int loamgpu_set_chunk_pairs(loamgpu_ctx* ctx, uint32_t pairs);
 
 #ifdef __cplusplus

@@ -50,10 +50,11 @@ struct loamgpu_ctx {
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
   std::string err;
   uint64_t launches = 0;
-  uint32_t chunk_pairs = 256;
+  uint32_t chunk_pairs = 0;  // pairs per internal chunk of the sequence calls; 0 = automatic (pick_chunk)
   int max_smem_optin = 0;
   int morton_queries = 1;  // LOAMGPU_QUERY_ORDER=original switches the k-NN kernel to source-index order (A/B)
   uint32_t lm_cluster = 0;          // 0 = automatic (see run_register)
+  uint64_t mem_budget = 0;          // bytes the automatic chunk size may plan with (a third of the memory free at creation, <= 24 GB)
   bool staging_unguarded = true;    // scan_in[] was last used outside the event-guarded odometry_host pipeline
   uint64_t big_target_min = 60000;  // targets at least this large get the multi-CTA NN build ($LOAMGPU_BIG_TARGET_MIN)
 
@@ -490,6 +491,10 @@ int loamgpu_create(int device, loamgpu_ctx** out) {
     cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming);
   }
   c->stream = c->own_stream;
+  {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) c->mem_budget = std::min<uint64_t>(free_b / 3, 24ull << 30);
+  }
   if (const char* qo = getenv("LOAMGPU_QUERY_ORDER")) c->morton_queries = strcmp(qo, "original") != 0;
   if (const char* v = getenv("LOAMGPU_LM_CLUSTER")) {
     const unsigned long cs = strtoul(v, nullptr, 10);
@@ -591,8 +596,8 @@ int loamgpu_kernel_times(loamgpu_ctx* ctx, double* ms, uint64_t* launches) {
 }
 
 int loamgpu_set_chunk_pairs(loamgpu_ctx* c, uint32_t pairs) {
-  if (!c || pairs == 0) return LOAMGPU_ERR_INVALID;
-  c->chunk_pairs = pairs;
+  if (!c) return LOAMGPU_ERR_INVALID;
+  c->chunk_pairs = pairs;  // 0 = automatic
   return LOAMGPU_OK;
 }
 
@@ -858,7 +863,7 @@ int loamgpu_extract_batch(loamgpu_ctx* ctx, const void* pts, int dtype, size_t s
     return fail(ctx, LOAMGPU_ERR_INVALID,
                 "output index buffers too small: rows of scan_lines*number_sectors*(max_*_feats_per_sector+1) needed");
   const size_t scan_bytes = (size_t)n_per * stride;
-  const uint32_t chunk = (uint32_t)std::min<uint64_t>(n_scans, std::max<uint32_t>(ctx->chunk_pairs, 1));
+  const uint32_t chunk = (uint32_t)std::min<uint64_t>(n_scans, ctx->chunk_pairs ? ctx->chunk_pairs : 256u);
   CU(ctx->scan_in[0].reserve((size_t)chunk * scan_bytes));
   ctx->staging_unguarded = true;
   rc = reserve_extract(ctx, pl, chunk, chunk);
@@ -914,7 +919,7 @@ int loamgpu_register_pairs(loamgpu_ctx* ctx, uint64_t n_pairs, const double* src
   // pairs per chunk: bounded by the configured chunk size and by ~2 GB of feature slots
   const uint64_t per_pair_bytes = 2 * ((uint64_t)capE + capP) * 32;
   const uint32_t chunk = (uint32_t)std::max<uint64_t>(
-      1, std::min<uint64_t>(std::min<uint64_t>(n_pairs, ctx->chunk_pairs), (2ull << 30) / per_pair_bytes));
+      1, std::min<uint64_t>(std::min<uint64_t>(n_pairs, ctx->chunk_pairs ? ctx->chunk_pairs : 256u), (2ull << 30) / per_pair_bytes));
   const uint32_t n_slots = 2 * chunk;  // slots [0, chunk) = targets, [chunk, 2 chunk) = sources
   CU(ctx->edge_pts.reserve((size_t)n_slots * capE * 32));
   CU(ctx->planar_pts.reserve((size_t)n_slots * capP * 32));
@@ -1125,10 +1130,45 @@ int loamgpu_knn(loamgpu_ctx* ctx, const double* targets, uint64_t n_t, const dou
 
 // Core of both odometry entry points.  `fetch(c0, n, buf)` must make scans [c0, c0+n) available on the device and
 // return their device pointer (the _device variant just offsets; the _host variant copies on the copy stream).
+// Pairs per chunk of a sequence call.  Measured on 64x1024 (DESIGN.md "Host pipeline"): device-resident scans and
+// asynchronous host calls gain from large chunks (the one-CTA-per-pair grids fill whole waves, fewer idle tail
+// launches: 35.8k scans/s at 256 pairs, 38.0k at 592, 39.8k at 1023), a synchronous host call is fastest with 256
+// (its first copy is exposed and grows with the chunk).  Bounded by a share of the free device memory.
+enum OdometryMode { kResident = 0, kHostSync = 1, kHostAsync = 2 };
+
+static uint32_t pick_chunk(loamgpu_ctx* ctx, OdometryMode mode, uint64_t n_scans, uint64_t n_per, uint32_t capE,
+                           uint32_t capP, uint32_t nn_stride) {
+  const uint64_t n_pairs_max = std::max<uint64_t>(n_scans, 2) - 1;
+  if (ctx->chunk_pairs) return (uint32_t)std::min<uint64_t>(ctx->chunk_pairs, n_pairs_max);
+  // host-async: at least two chunks per typical call, so the copy of a chunk runs under the extract AND the
+  // registration of the previous one (a single 1023-pair chunk per call measured 32.1k scans/s, 512 + 511: 35.7k)
+  uint64_t want = mode == kHostSync ? 256 : mode == kHostAsync ? 512 : 1024;
+  const uint64_t cap = (uint64_t)capE + capP;
+  // per pair: k-NN lists, residual records, two NN structures (nodes, sorted copy, sort keys, flags), feature slots
+  // (indices + widened points), ring pick lists, and for host calls two staging copies of the scan
+  const uint64_t per_pair = cap * ((uint64_t)nn_stride * 4 + 4 + 96 + 84 + 36 + 4) + (mode == kResident ? 0 : 2 * n_per * 16);
+  if (ctx->mem_budget && per_pair)  // (queried once at context creation: cudaMemGetInfo per call is far too slow)
+    want = std::min<uint64_t>(want, std::max<uint64_t>(32, ctx->mem_budget / per_pair));
+  return (uint32_t)std::min<uint64_t>(want, n_pairs_max);
+}
+
+static int chunk_for(loamgpu_ctx* ctx, OdometryMode mode, uint64_t n_scans, const loamgpu_lidar_params* lp,
+                     const loamgpu_fe_params* fe, const loamgpu_reg_params* reg, uint32_t* chunk) {
+  ExtractPlan pl;
+  RegP rp;
+  const uint64_t n_per = lp->scan_lines * lp->points_per_line;
+  int rc = plan_extract(ctx, LOAMGPU_F32, 16, n_per, lp, fe, &pl);
+  if (rc) return rc;
+  rc = make_regp(ctx, reg, &rp);
+  if (rc) return rc;
+  *chunk = pick_chunk(ctx, mode, n_scans, n_per, pl.capE_scan, pl.capP_scan, (uint32_t)std::max(rp.ke, rp.kp));
+  return LOAMGPU_OK;
+}
+
 template <typename Fetch>
 static int odometry_core(loamgpu_ctx* ctx, uint64_t n_scans, const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe,
                          const loamgpu_reg_params* reg, double* poses_dev, int32_t* term_dev, uint32_t* iters_dev,
-                         uint32_t* ne_dev, uint32_t* np_dev, uint32_t lead_div, Fetch fetch) {
+                         uint32_t* ne_dev, uint32_t* np_dev, OdometryMode mode, uint32_t chunk, Fetch fetch) {
   ExtractPlan pl;
   const uint64_t n_per = lp->scan_lines * lp->points_per_line;
   int rc = plan_extract(ctx, LOAMGPU_F32, 16, n_per, lp, fe, &pl);
@@ -1137,9 +1177,9 @@ static int odometry_core(loamgpu_ctx* ctx, uint64_t n_scans, const loamgpu_lidar
   RegP rp;
   rc = make_regp(ctx, reg, &rp);
   if (rc) return rc;
-  const uint32_t chunk = (uint32_t)std::min<uint64_t>(ctx->chunk_pairs, std::max<uint64_t>(n_scans, 2) - 1);
   const uint32_t lead0 = []() { const char* e = getenv("LOAMGPU_LEAD"); return e ? (uint32_t)atoi(e) : 128u; }();
-  const uint32_t lead = lead_div <= 1 ? chunk : std::max<uint32_t>(1, std::min<uint32_t>(chunk, lead0));
+  // only a synchronous host call starts with a shorter chunk (see below)
+  const uint32_t lead = mode != kHostSync ? chunk : std::max<uint32_t>(1, std::min<uint32_t>(chunk, lead0));
   const uint32_t n_slots = chunk + 1;
   rc = reserve_extract(ctx, pl, chunk + 1, n_slots);
   if (rc) return rc;
@@ -1153,10 +1193,11 @@ static int odometry_core(loamgpu_ctx* ctx, uint64_t n_scans, const loamgpu_lidar
   }
   const uint64_t n_pairs = n_scans - 1;
   int buf = 0;
-  // The host variant starts with a shorter chunk (`lead` pairs, then x`ramp` up to the full size): the H2D copy of
-  // the first chunk is the only one that cannot hide behind kernels.  Copying a scan takes ~0.6x the time of
+  // A synchronous host call starts with a shorter chunk (`lead` pairs, then x`ramp` up to the full size): the H2D copy
+  // of the first chunk is the only one that cannot hide behind kernels.  Copying a scan takes ~0.6x the time of
   // processing it (55 GB/s measured), so longer ramps expose more than they save; 128 -> 256 measured best
-  // ($LOAMGPU_LEAD / $LOAMGPU_RAMP override).  The device variant uses full chunks throughout.
+  // ($LOAMGPU_LEAD / $LOAMGPU_RAMP override).  Device-resident and asynchronous host calls use full chunks
+  // throughout (an asynchronous call's first copy hides behind the previous call's kernels).
   const double ramp = []() { const char* e = getenv("LOAMGPU_RAMP"); return e ? std::max(1.0, atof(e)) : 2.0; }();
   uint32_t np = 0, want = lead;
   for (uint64_t p0 = 0; p0 < n_pairs; p0 += np, buf ^= 1) {
@@ -1195,7 +1236,10 @@ int loamgpu_odometry_device(loamgpu_ctx* ctx, const float* scans_dev, uint64_t n
     *out = scans_dev + s0 * n_per * 4;
     return (int)LOAMGPU_OK;
   };
-  return odometry_core(ctx, n_scans, lp, fe, reg, poses_dev, term_dev, iters_dev, ne_dev, np_dev, 1, fetch);
+  uint32_t chunk = 0;
+  const int rc = chunk_for(ctx, kResident, n_scans, lp, fe, reg, &chunk);
+  if (rc) return rc;
+  return odometry_core(ctx, n_scans, lp, fe, reg, poses_dev, term_dev, iters_dev, ne_dev, np_dev, kResident, chunk, fetch);
 }
 
 int loamgpu_synchronize(loamgpu_ctx* ctx) {
@@ -1206,11 +1250,20 @@ int loamgpu_synchronize(loamgpu_ctx* ctx) {
   return LOAMGPU_OK;
 }
 
+}  // extern "C"
+
+static int odometry_host_impl(loamgpu_ctx* ctx, OdometryMode mode, const float* scans, uint64_t n_scans,
+                              const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe, const loamgpu_reg_params* reg,
+                              double* poses, int32_t* termination, uint32_t* iterations, uint32_t* n_edge,
+                              uint32_t* n_planar);
+
+extern "C" {
+
 int loamgpu_odometry_host(loamgpu_ctx* ctx, const float* scans, uint64_t n_scans, const loamgpu_lidar_params* lp,
                           const loamgpu_fe_params* fe, const loamgpu_reg_params* reg, double* poses, int32_t* termination,
                           uint32_t* iterations, uint32_t* n_edge, uint32_t* n_planar) {
-  const int rc = loamgpu_odometry_host_async(ctx, scans, n_scans, lp, fe, reg, poses, termination, iterations, n_edge,
-                                             n_planar);
+  const int rc = odometry_host_impl(ctx, kHostSync, scans, n_scans, lp, fe, reg, poses, termination, iterations, n_edge,
+                                    n_planar);
   if (rc) return rc;
   return loamgpu_synchronize(ctx);
 }
@@ -1218,6 +1271,16 @@ int loamgpu_odometry_host(loamgpu_ctx* ctx, const float* scans, uint64_t n_scans
 int loamgpu_odometry_host_async(loamgpu_ctx* ctx, const float* scans, uint64_t n_scans, const loamgpu_lidar_params* lp,
                                 const loamgpu_fe_params* fe, const loamgpu_reg_params* reg, double* poses,
                                 int32_t* termination, uint32_t* iterations, uint32_t* n_edge, uint32_t* n_planar) {
+  return odometry_host_impl(ctx, kHostAsync, scans, n_scans, lp, fe, reg, poses, termination, iterations, n_edge,
+                            n_planar);
+}
+
+}  // extern "C"
+
+static int odometry_host_impl(loamgpu_ctx* ctx, OdometryMode mode, const float* scans, uint64_t n_scans,
+                              const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe, const loamgpu_reg_params* reg,
+                              double* poses, int32_t* termination, uint32_t* iterations, uint32_t* n_edge,
+                              uint32_t* n_planar) {
   if (!ctx) return LOAMGPU_ERR_INVALID;
   if (!lp || !fe || !reg) return fail(ctx, LOAMGPU_ERR_INVALID, "null parameter struct");
   if (n_scans == 0) return LOAMGPU_OK;
@@ -1226,7 +1289,11 @@ int loamgpu_odometry_host_async(loamgpu_ctx* ctx, const float* scans, uint64_t n
   const uint64_t n_per = lp->scan_lines * lp->points_per_line;
   const size_t scan_bytes = (size_t)n_per * 16;
   const uint64_t n_pairs = n_scans - 1;
-  const uint32_t chunk = (uint32_t)std::min<uint64_t>(ctx->chunk_pairs, std::max<uint64_t>(n_scans, 2) - 1);
+  uint32_t chunk = 0;
+  {
+    const int rc = chunk_for(ctx, mode, n_scans, lp, fe, reg, &chunk);
+    if (rc) return rc;
+  }
   for (int b = 0; b < 2; b++) CU(ctx->scan_in[b].reserve((size_t)(chunk + 1) * scan_bytes));
   CU(ctx->out_pose.reserve(std::max<uint64_t>(n_pairs, 1) * 56));
   CU(ctx->out_term.reserve(std::max<uint64_t>(n_pairs, 1) * 4));
@@ -1254,7 +1321,8 @@ int loamgpu_odometry_host_async(loamgpu_ctx* ctx, const float* scans, uint64_t n
     return (int)LOAMGPU_OK;
   };
   int rc = odometry_core(ctx, n_scans, lp, fe, reg, ctx->out_pose.as<double>(), ctx->out_term.as<int32_t>(),
-                         ctx->out_iters.as<uint32_t>(), ctx->out_ne.as<uint32_t>(), ctx->out_np.as<uint32_t>(), 8, fetch);
+                         ctx->out_iters.as<uint32_t>(), ctx->out_ne.as<uint32_t>(), ctx->out_np.as<uint32_t>(), mode, chunk,
+                         fetch);
   if (rc) return rc;
   if (poses && n_pairs) CU(cudaMemcpyAsync(poses, ctx->out_pose.p, n_pairs * 56, cudaMemcpyDeviceToHost, ctx->stream));
   if (termination && n_pairs)
@@ -1265,5 +1333,3 @@ int loamgpu_odometry_host_async(loamgpu_ctx* ctx, const float* scans, uint64_t n
   if (n_planar) CU(cudaMemcpyAsync(n_planar, ctx->out_np.p, n_scans * 4, cudaMemcpyDeviceToHost, ctx->stream));
   return LOAMGPU_OK;
 }
-
-}  // extern "C"

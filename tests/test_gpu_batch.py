@@ -36,7 +36,7 @@ def test_extract_batch_chunks_layouts_and_errors(ctx):
         chunked = ctx.extract_batch(scans, lp, fe)
         f64 = ctx.extract_batch(scans[:, :, :3].astype(np.float64), lp, fe)  # f64x3 layout, same values
     finally:
-        ctx.set_chunk_pairs(256)
+        ctx.set_chunk_pairs(0)  # back to automatic
     for a, b, c in zip(ref, chunked, f64):
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
         assert np.array_equal(a[0], c[0]) and np.array_equal(a[1], c[1])
@@ -78,7 +78,7 @@ def test_register_pairs_equals_single_calls(ctx, oracle):
         poses2, term2, its2 = ctx.register_pairs(pairs, np.array(inits), rp)
         poses3, _, _ = ctx.register_pairs(pairs[:4], None, rp)
     finally:
-        ctx.set_chunk_pairs(256)
+        ctx.set_chunk_pairs(0)  # back to automatic
     assert np.array_equal(poses, poses2) and np.array_equal(term, term2) and np.array_equal(its, its2)
     assert np.array_equal(poses3, poses[:4])
     # and against the CPU oracle

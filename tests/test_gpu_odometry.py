@@ -61,7 +61,7 @@ def test_chunking_and_residency_do_not_change_results(ctx):
                             d_ne.data_ptr(), d_np.data_ptr())
     torch.cuda.synchronize()
     ctx.set_stream(None)
-    ctx.set_chunk_pairs(256)
+    ctx.set_chunk_pairs(0)  # back to automatic
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
     assert np.array_equal(a[0], d_pose.cpu().numpy())
@@ -122,4 +122,4 @@ def test_async_host_calls_pipeline_without_changing_results(ctx):
         assert len(e) == ref[2][3][0] and len(p) == ref[2][4][0]
         assert np.array_equal(ref[1][0], outs[0][0].numpy())
     finally:
-        ctx.set_chunk_pairs(256)
+        ctx.set_chunk_pairs(0)  # back to automatic
