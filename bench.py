@@ -398,7 +398,10 @@ def ours(a):
         if os.path.exists(tp):  # per-launch DRAM bytes and the limiter named by the committed `ncu --set full` capture
             try:
                 tj = json.load(open(tp))
-                traffic, limiter = tj.get(dom), tj.get("_limiter", {}).get(dom)
+                limiter = tj.get("_limiter", {}).get(dom)
+                units = n if tj.get("unit", {}).get(dom) == "scan" else n - 1
+                per_unit = tj.get("per_unit", {}).get(dom)
+                traffic = per_unit * units * a.steps / max(dom_n, 1) if per_unit else None
             except Exception:
                 traffic = None
         total_scans = a.scans * world * a.steps  # halo scans (extracted by two ranks) are counted once

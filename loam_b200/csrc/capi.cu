@@ -1168,7 +1168,8 @@ static int chunk_for(loamgpu_ctx* ctx, OdometryMode mode, uint64_t n_scans, cons
 template <typename Fetch>
 static int odometry_core(loamgpu_ctx* ctx, uint64_t n_scans, const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe,
                          const loamgpu_reg_params* reg, double* poses_dev, int32_t* term_dev, uint32_t* iters_dev,
-                         uint32_t* ne_dev, uint32_t* np_dev, OdometryMode mode, uint32_t chunk, Fetch fetch) {
+                         uint32_t* ne_dev, uint32_t* np_dev, OdometryMode mode, uint32_t chunk, bool short_lead,
+                         Fetch fetch) {
   ExtractPlan pl;
   const uint64_t n_per = lp->scan_lines * lp->points_per_line;
   int rc = plan_extract(ctx, LOAMGPU_F32, 16, n_per, lp, fe, &pl);
@@ -1178,8 +1179,9 @@ static int odometry_core(loamgpu_ctx* ctx, uint64_t n_scans, const loamgpu_lidar
   rc = make_regp(ctx, reg, &rp);
   if (rc) return rc;
   const uint32_t lead0 = []() { const char* e = getenv("LOAMGPU_LEAD"); return e ? (uint32_t)atoi(e) : 128u; }();
-  // only a synchronous host call starts with a shorter chunk (see below)
-  const uint32_t lead = mode != kHostSync ? chunk : std::max<uint32_t>(1, std::min<uint32_t>(chunk, lead0));
+  // a host call whose first copy has nothing to hide behind starts with a shorter chunk (see below)
+  (void)mode;
+  const uint32_t lead = !short_lead ? chunk : std::max<uint32_t>(1, std::min<uint32_t>(chunk, lead0));
   const uint32_t n_slots = chunk + 1;
   rc = reserve_extract(ctx, pl, chunk + 1, n_slots);
   if (rc) return rc;
@@ -1239,7 +1241,8 @@ int loamgpu_odometry_device(loamgpu_ctx* ctx, const float* scans_dev, uint64_t n
   uint32_t chunk = 0;
   const int rc = chunk_for(ctx, kResident, n_scans, lp, fe, reg, &chunk);
   if (rc) return rc;
-  return odometry_core(ctx, n_scans, lp, fe, reg, poses_dev, term_dev, iters_dev, ne_dev, np_dev, kResident, chunk, fetch);
+  return odometry_core(ctx, n_scans, lp, fe, reg, poses_dev, term_dev, iters_dev, ne_dev, np_dev, kResident, chunk,
+                       /*short_lead=*/false, fetch);
 }
 
 int loamgpu_synchronize(loamgpu_ctx* ctx) {
@@ -1294,6 +1297,9 @@ static int odometry_host_impl(loamgpu_ctx* ctx, OdometryMode mode, const float* 
     const int rc = chunk_for(ctx, mode, n_scans, lp, fe, reg, &chunk);
     if (rc) return rc;
   }
+  // The first copy of a call is exposed unless kernels of a previous asynchronous call are still running: a
+  // synchronous call, and an asynchronous call that finds the compute stream idle, start with a short lead chunk.
+  const bool short_lead = mode == kHostSync || cudaStreamQuery(ctx->stream) == cudaSuccess;
   for (int b = 0; b < 2; b++) CU(ctx->scan_in[b].reserve((size_t)(chunk + 1) * scan_bytes));
   CU(ctx->out_pose.reserve(std::max<uint64_t>(n_pairs, 1) * 56));
   CU(ctx->out_term.reserve(std::max<uint64_t>(n_pairs, 1) * 4));
@@ -1322,7 +1328,7 @@ static int odometry_host_impl(loamgpu_ctx* ctx, OdometryMode mode, const float* 
   };
   int rc = odometry_core(ctx, n_scans, lp, fe, reg, ctx->out_pose.as<double>(), ctx->out_term.as<int32_t>(),
                          ctx->out_iters.as<uint32_t>(), ctx->out_ne.as<uint32_t>(), ctx->out_np.as<uint32_t>(), mode, chunk,
-                         fetch);
+                         short_lead, fetch);
   if (rc) return rc;
   if (poses && n_pairs) CU(cudaMemcpyAsync(poses, ctx->out_pose.p, n_pairs * 56, cudaMemcpyDeviceToHost, ctx->stream));
   if (termination && n_pairs)
