@@ -11,8 +11,11 @@ data-path collective (torch.distributed is used for the barrier and the max-over
 
   value : whole-job scans/sec with the scans already resident in HBM (loamgpu_odometry_device),
           device time from CUDA events on the launching stream, max over ranks.
-  e2e   : the same through the host-buffer C-ABI call (loamgpu_odometry_host): pinned host scans in,
-          poses/terminations/iteration counts/feature counts out to host, copies inside the timed region.
+  e2e   : the same through the host-buffer C-ABI call: pinned host scans in, poses/terminations/iteration counts/
+          feature counts out to pinned host memory, every copy inside the timed region.  `e2e.value` = K asynchronous
+          calls (loamgpu_odometry_host_async: how a recording is streamed through in pieces; the copies of a call run
+          under the kernels of the previous one) and one wait after the last; `e2e.value_each_call_waited` = the
+          synchronous call (loamgpu_odometry_host) K times.
   roofline     : the dominant kernel class (by CUDA-event time inside the timed region): algorithmic bytes
                   / its summed launch time, against MEASURED_PEAKS.json's HBM copy bandwidth.
   cpu_baseline : the reference feature code (oracle/_ref, real reference sources) + the restated registration
