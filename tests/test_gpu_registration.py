@@ -156,3 +156,43 @@ def test_python_module_mirror(ctx, scene):
     # left composition of each recorded update reproduces the next recorded estimate (registration-inl.h:65)
     nxt = info.estimate_update.compose(info.target_T_source_init)
     np.testing.assert_allclose(nxt._to7(), detail.iteration_info[1].target_T_source_init._to7(), atol=1e-15)
+
+
+def test_two_contexts_on_two_host_threads_agree(scene):
+    """The reference is stateless and re-entrant (callers may invoke it from many threads); here that
+    means one loamgpu context per thread.  Two threads, each with its own context and stream, register different
+    problems concurrently; every result equals the single-threaded one bit for bit."""
+    import threading
+    ed, pl = scene
+    rp = _capi.default_reg_params()
+    problems = [(H.transform(ed, c[1]), H.transform(pl, c[1]), ed, pl) for c in H.REG_SCENARIOS[:4]]
+    solo = _capi.Context(0)
+    expect = [solo.register(*p, IDENT, rp) for p in problems]
+    solo.close()
+    results, errors = {}, []
+
+    def worker(tid):
+        try:
+            c = _capi.Context(0)
+            for rep in range(3):
+                for i, p in enumerate(problems):
+                    j = (i + tid) % len(problems)
+                    results[(tid, rep, j)] = c.register(*problems[j], IDENT, rp)
+                    e, pidx = c.extract(synth.make_scan(16, 512, k=tid), _capi.CLidarParams(16, 512, 1.0, 120.0),
+                                        _capi.default_fe_params())
+                    results[(tid, rep, "n_feat")] = (len(e), len(pidx))
+            c.close()
+        except Exception as ex:  # pragma: no cover
+            errors.append(ex)
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for (tid, rep, j), v in results.items():
+        if j == "n_feat":
+            assert v == results[(tid, 0, "n_feat")]
+        else:
+            assert np.array_equal(v, expect[j]), (tid, rep, j)
