@@ -381,6 +381,10 @@ __device__ __forceinline__ double fit_plane_reg(const double (&P)[KMAX][3], int 
 #ifndef KNN_MINBLOCKS
 #define KNN_MINBLOCKS 8
 #endif
+#ifndef KNN_THREADS
+#define KNN_THREADS 128
+#endif
+constexpr int kKnnThreads = KNN_THREADS;
 // Pairs still iterating: entry 0 of `active` is their count, the indices follow (null = all n_pairs, in order).
 // Rows of the grid stride over that list, so late outer iterations (few or no active pairs) can be launched with a
 // small grid instead of tens of thousands of CTAs that only discover they have nothing to do.
@@ -450,7 +454,7 @@ __device__ __forceinline__ void assoc_knn_pair(const AssocArgs& a, int outer_ite
 }
 
 template <int K>
-__global__ void __launch_bounds__(kAssocThreads, KNN_MINBLOCKS) assoc_knn_kernel(AssocArgs a, int outer_iter) {
+__global__ void __launch_bounds__(kKnnThreads, KNN_MINBLOCKS) assoc_knn_kernel(AssocArgs a, int outer_iter) {
   const uint32_t n_act = active_count(a.active, a.n_pairs);
   for (uint32_t i = blockIdx.y; i < n_act; i += gridDim.y) assoc_knn_pair<K>(a, outer_iter, active_pair(a.active, i));
 }
@@ -1243,14 +1247,14 @@ static uint32_t pair_rows(uint32_t n_pairs, int outer_iter, bool has_list, uint3
 cudaError_t launch_assoc_knn(const AssocArgs& a, uint32_t n_pairs, int outer_iter, cudaStream_t st) {
   if (n_pairs == 0) return cudaSuccess;
   const uint32_t cap = a.capE_scan + a.capP_scan;
-  dim3 grid((cap + kAssocThreads - 1) / kAssocThreads, pair_rows(n_pairs, outer_iter, a.active != nullptr, 16));
+  dim3 grid((cap + kKnnThreads - 1) / kKnnThreads, pair_rows(n_pairs, outer_iter, a.active != nullptr, 16));
   const int kmax = a.rp.ke > a.rp.kp ? a.rp.ke : a.rp.kp;
   if (kmax <= kKnnSmall)
-    assoc_knn_kernel<kKnnSmall><<<grid, kAssocThreads, 0, st>>>(a, outer_iter);
+    assoc_knn_kernel<kKnnSmall><<<grid, kKnnThreads, 0, st>>>(a, outer_iter);
   else if (kmax <= kKnnRegMax)
-    assoc_knn_kernel<kKnnRegMax><<<grid, kAssocThreads, 0, st>>>(a, outer_iter);
+    assoc_knn_kernel<kKnnRegMax><<<grid, kKnnThreads, 0, st>>>(a, outer_iter);
   else
-    assoc_knn_kernel<kKnnMax><<<grid, kAssocThreads, 0, st>>>(a, outer_iter);
+    assoc_knn_kernel<kKnnMax><<<grid, kKnnThreads, 0, st>>>(a, outer_iter);
   return cudaGetLastError();
 }
 
