@@ -49,3 +49,28 @@ def test_algorithmic_bytes_model():
     assert ab["nn_build"] == 32 * F[:-1].sum()
     assert ab["knn"] == (it * F[1:]).sum() * (16 + 16 * 5 + 8)
     assert ab["lm"] == (it * F[1:]).sum() * 48 and ab["misc"] == 0
+
+
+import pytest
+
+
+@pytest.mark.gpu
+def test_our_arm_line_has_the_contract_keys():
+    lines = run_bench(["--steps", "2", "--warmup", "1", "--scans", "12", "--rings", "16", "--cols", "512",
+                       "--cpu-seconds", "0.5"])
+    d = json.loads(lines[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+        assert k in d, k
+    assert "impl" not in d and d["n_gpus"] == 1 and d["steps"] == 2 and d["scaling"] == "weak" and d["value"] > 0
+    assert d["gpu_launches"] > 0
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 12 * 16 * 512 * 16 and e["d2h_bytes_per_step"] > 0
+    assert e["value_each_call_waited"] > 0 and "asynchronous" in e["mode"]
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["peak"] > 0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert r["kernel"] in d["kernel_ms_per_step"] and r["launches"] > 0
+    cb = d["cpu_baseline"]
+    assert cb["cores"] == 1 and cb["kind"] == "port" and cb["value"] > 0 and "pairs" in cb["sample"]
+    assert abs(sum(d["kernel_share"].values()) - 1.0) < 1e-9
+    assert "workload" in d["config"] and "l2" in d["config"]
