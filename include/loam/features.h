@@ -8,6 +8,7 @@
 
 #include "loam/common.h"
 #include "loam/detail/gpu.h"
+#include "loam/geometry.h"
 
 namespace loam {
 
@@ -84,6 +85,39 @@ LoamFeatures<PointType, Alloc> extractFeatures(const std::vector<PointType, Allo
   out.planar_points.reserve(idx.second.size());
   for (uint32_t i : idx.first) out.edge_points.push_back(input_scan[i]);
   for (uint32_t i : idx.second) out.planar_points.push_back(input_scan[i]);
+  return out;
+}
+
+/// EXTENSION (no counterpart in the reference, which leaves de-warping to its caller — README.md:63): extractFeatures
+/// of a motion-compensated scan, the compensation fused into the kernel's ring staging (loamgpu_extract_dewarped).
+/// Column c of every ring is moved into the frame of the sweep start by interp(Identity, start_T_end, c / P).  The
+/// moved points are not PointType-representable in general, so the features come back widened (the type
+/// featuresToEigen produces, features.h:188-198) and go to registerFeatures as they are.
+template <template <typename> class Accessor = FieldAccessor, typename PointType, template <typename> class Alloc>
+LoamFeatures<Eigen::Vector3d> extractFeaturesDewarped(const std::vector<PointType, Alloc<PointType>>& input_scan,
+                                                      const LidarParams& lidar_params, const Pose3d& start_T_end,
+                                                      const FeatureExtractionParams& params = FeatureExtractionParams()) {
+  validateLidarScan(input_scan, lidar_params);
+  LoamFeatures<Eigen::Vector3d> out;
+  if (input_scan.empty()) return out;
+  loamgpu_ctx* ctx = gpu::ThreadContext::get();
+  const gpu::CloudView view = gpu::makeCloudView<Accessor>(input_scan);
+  const loamgpu_lidar_params lp = gpu::toC(lidar_params);
+  const loamgpu_fe_params fp = gpu::toC(params);
+  const double motion[7] = {start_T_end.rotation.x(),    start_T_end.rotation.y(),    start_T_end.rotation.z(),
+                            start_T_end.rotation.w(),    start_T_end.translation(0), start_T_end.translation(1),
+                            start_T_end.translation(2)};
+  std::vector<uint32_t> e(input_scan.size()), p(input_scan.size());
+  std::vector<double> moved(3 * input_scan.size());
+  uint64_t ne = 0, np = 0;
+  gpu::check(ctx, loamgpu_extract_dewarped(ctx, view.data, view.dtype, view.stride, input_scan.size(), &lp, &fp, motion,
+                                           e.data(), e.size(), &ne, p.data(), p.size(), &np, moved.data()));
+  out.edge_points.reserve(ne);
+  out.planar_points.reserve(np);
+  for (uint64_t i = 0; i < ne; i++)
+    out.edge_points.emplace_back(moved[3 * e[i]], moved[3 * e[i] + 1], moved[3 * e[i] + 2]);
+  for (uint64_t i = 0; i < np; i++)
+    out.planar_points.emplace_back(moved[3 * p[i]], moved[3 * p[i] + 1], moved[3 * p[i] + 2]);
   return out;
 }
 

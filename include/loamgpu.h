@@ -138,6 +138,22 @@ int loamgpu_curvature(loamgpu_ctx* ctx, const void* pts, int dtype, size_t strid
 int loamgpu_valid_mask(loamgpu_ctx* ctx, const void* pts, int dtype, size_t stride_bytes, uint64_t n_points,
                        const loamgpu_lidar_params* lidar, const loamgpu_fe_params* fe, uint8_t* mask);
 
+/* EXTENSION — SURVEY §8f-3, the step the reference leaves to its caller immediately before this
+ * path ("de-warp", README.md:63): loamgpu_extract of a motion-compensated scan, with the
+ * compensation fused into the ring staging (no separate pass over the scan).  Column c of every
+ * ring was measured at fraction s = c / points_per_line of the sweep; each point is moved into the
+ * frame of the sweep start by T(s) = interp(Identity, start_T_end, s) (rotation: normalised linear
+ * interpolation of the quaternion on Identity's hemisphere, translation: linear) before ranges,
+ * curvature, mask and selection look at it.  start_T_end is a pose [qx qy qz qw tx ty tz].
+ * dewarped_xyz (nullable, n_points x 3 doubles) receives the moved points — the feature points to
+ * hand to loamgpu_register are dewarped_xyz[idx], not pts[idx].  The move uses IEEE + - * / sqrt
+ * only, in a fixed order, so its results are bit-reproducible on a CPU; the
+ * indices equal the reference's extraction run on the moved points. */
+int loamgpu_extract_dewarped(loamgpu_ctx* ctx, const void* pts, int dtype, size_t stride_bytes, uint64_t n_points,
+                             const loamgpu_lidar_params* lidar, const loamgpu_fe_params* fe,
+                             const double start_T_end[7], uint32_t* edge_idx, uint64_t edge_cap, uint64_t* n_edge,
+                             uint32_t* planar_idx, uint64_t planar_cap, uint64_t* n_planar, double* dewarped_xyz);
+
 /* ---------------------------------------------------- registration (host buffers) */
 /* replaces loam::registerFeatures, registration.h:128-131 / registration-inl.h:11-78.
  * Feature clouds are n x 3 contiguous doubles (the reference widens with featuresToEigen,

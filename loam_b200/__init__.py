@@ -7,7 +7,7 @@ include/loamgpu.h.  There is no CPU path in this package.
 from .api import (FeatureExtractionParams, LidarParams, LoamFeatures, Pose3d, Quaterniond, RegistrationDetail,
                   RegistrationIterationInfo, RegistrationParams, RegistrationTerminationType, computeCurvature,
                   computeValidPoints, extractFeatures, extractFeatureIndices, registerFeatures, odometry,
-                  get_context, LocalMap)
+                  get_context, LocalMap, extractFeaturesDewarped)
 
 CONVERGED = RegistrationTerminationType.CONVERGED
 MAX_ITER = RegistrationTerminationType.MAX_ITER
@@ -17,5 +17,6 @@ __all__ = [
     "LidarParams", "FeatureExtractionParams", "RegistrationParams", "Pose3d", "Quaterniond", "LoamFeatures",
     "RegistrationDetail", "RegistrationIterationInfo", "RegistrationTerminationType", "extractFeatures",
     "computeCurvature", "computeValidPoints", "registerFeatures", "extractFeatureIndices", "odometry",
+    "extractFeaturesDewarped",
     "get_context", "LocalMap", "CONVERGED", "MAX_ITER", "INSUFFICIENT_ASSOCIATIONS",
 ]

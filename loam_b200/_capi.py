@@ -27,6 +27,7 @@ SYMBOLS = [
     "loamgpu_set_chunk_pairs", "loamgpu_set_profiling", "loamgpu_kernel_times", "loamgpu_map_create",
     "loamgpu_map_destroy", "loamgpu_map_size", "loamgpu_map_update", "loamgpu_register_to_map",
     "loamgpu_extract_batch", "loamgpu_register_pairs", "loamgpu_odometry_host_async", "loamgpu_synchronize",
+    "loamgpu_extract_dewarped",
 ]
 KERNEL_CLASSES = ["extract", "pack", "nn_build", "knn", "lm", "misc", "fit"]
 
@@ -86,6 +87,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     lib.loamgpu_kernel_times.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     vp = C.c_void_p
     lib.loamgpu_extract.argtypes = [vp, vp, C.c_int, C.c_size_t, u64, vp, vp, vp, u64, vp, vp, u64, vp]
+    lib.loamgpu_extract_dewarped.argtypes = [vp, vp, C.c_int, C.c_size_t, u64, vp, vp, vp, vp, u64, vp, vp, u64, vp, vp]
     lib.loamgpu_curvature.argtypes = [vp, vp, C.c_int, C.c_size_t, u64, vp, vp, vp]
     lib.loamgpu_valid_mask.argtypes = [vp, vp, C.c_int, C.c_size_t, u64, vp, vp, vp]
     lib.loamgpu_register.argtypes = [vp, vp, u64, vp, u64, vp, u64, vp, u64, vp, vp, vp, vp]
@@ -188,6 +190,20 @@ class Context:
         self._check(self.lib.loamgpu_extract(self.h, _ptr(a), dt, stride, n, C.addressof(lp), C.addressof(fe),
                                              _ptr(e), len(e), C.addressof(ne), _ptr(p), len(p), C.addressof(npl)))
         return e[:ne.value].copy(), p[:npl.value].copy()
+
+    def extract_dewarped(self, points, lp: CLidarParams, fe: CFeParams, start_T_end, want_points: bool = True):
+        """loamgpu_extract_dewarped: (edge_idx, planar_idx, de-warped n x 3 float64 points or None)."""
+        a, dt, stride = _cloud(points)
+        n = len(a)
+        m = np.ascontiguousarray(start_T_end, dtype=np.float64).reshape(7)
+        e = np.empty(max(n, 1), dtype=np.uint32)
+        p = np.empty(max(n, 1), dtype=np.uint32)
+        moved = np.empty((n, 3), dtype=np.float64) if want_points else None
+        ne, npl = u64(0), u64(0)
+        self._check(self.lib.loamgpu_extract_dewarped(
+            self.h, _ptr(a), dt, stride, n, C.addressof(lp), C.addressof(fe), _ptr(m), _ptr(e), len(e),
+            C.addressof(ne), _ptr(p), len(p), C.addressof(npl), _ptr(moved) if want_points and n else None))
+        return e[:ne.value].copy(), p[:npl.value].copy(), moved
 
     def curvature(self, points, lp, fe):
         a, dt, stride = _cloud(points)

@@ -253,6 +253,21 @@ def extractFeatures(input_scan, lidar_params: LidarParams, params=None, device: 
     return LoamFeatures(cloud[e].copy(), cloud[p].copy())
 
 
+def extractFeaturesDewarped(input_scan, lidar_params: LidarParams, start_T_end: Pose3d, params=None,
+                            device: int = 0) -> LoamFeatures:
+    """Extension (mirrors loam::extractFeaturesDewarped, include/loam/features.h): the de-warp the reference leaves to
+    its caller (README.md:63) fused into extractFeatures.  Column c of each ring is moved into the frame of the sweep
+    start by interp(Identity, start_T_end, c / points_per_line); the returned feature points are the moved points
+    (float64), ready for registerFeatures."""
+    params = params or FeatureExtractionParams()
+    cloud = _as_cloud(input_scan)
+    try:
+        e, p, moved = get_context(device).extract_dewarped(cloud, lidar_params._c, params._to_c(), start_T_end._to7())
+    except _capi.LoamGpuError as err:
+        raise _map_error(err) from None
+    return LoamFeatures(moved[e], moved[p])
+
+
 def computeCurvature(input_scan, lidar_params: LidarParams, params=None, device: int = 0):
     """loam::computeCurvature (features.h:119-122): structured array with fields index, curvature."""
     params = params or FeatureExtractionParams()

@@ -228,9 +228,16 @@ int reserve_extract(loamgpu_ctx* ctx, const ExtractPlan& pl, uint32_t n_scans, u
 // Extract `n_scans` device-resident scans into feature slots (scan0 + i) % n_slots.
 int run_extract(loamgpu_ctx* ctx, const ExtractPlan& pl, const void* dev_pts, int dtype, size_t stride,
                 const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe, uint32_t n_scans, uint64_t scan0,
-                uint32_t n_slots, uint32_t* n_edge_out, uint32_t* n_planar_out) {
+                uint32_t n_slots, uint32_t* n_edge_out, uint32_t* n_planar_out, const double* motion = nullptr,
+                double* dewarp_out = nullptr) {
   ExtractArgs a;
   fill_extract_args(a, pl, dev_pts, dtype, stride, lp, fe);
+  if (motion) {  // de-warp fused into the staging loop (strided loads; the bulk copy cannot transform)
+    a.dewarp = 1;
+    a.use_bulk = 0;
+    memcpy(a.motion, motion, sizeof a.motion);
+    a.dewarp_out = dewarp_out;
+  }
   a.ring_edge = ctx->ring_edge.as<uint32_t>();
   a.ring_planar = ctx->ring_planar.as<uint32_t>();
   a.ring_counts = ctx->ring_counts.as<uint32_t>();
@@ -603,10 +610,10 @@ int loamgpu_set_chunk_pairs(loamgpu_ctx* c, uint32_t pairs) {
 
 // ------------------------------------------------------------------------------------------ extraction
 
-int loamgpu_extract(loamgpu_ctx* ctx, const void* pts, int dtype, size_t stride, uint64_t n_points,
-                    const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe, uint32_t* edge_idx,
-                    uint64_t edge_cap, uint64_t* n_edge, uint32_t* planar_idx, uint64_t planar_cap,
-                    uint64_t* n_planar) {
+static int extract_one(loamgpu_ctx* ctx, const void* pts, int dtype, size_t stride, uint64_t n_points,
+                       const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe, const double* motion,
+                       uint32_t* edge_idx, uint64_t edge_cap, uint64_t* n_edge, uint32_t* planar_idx,
+                       uint64_t planar_cap, uint64_t* n_planar, double* dewarped_xyz) {
   if (!ctx) return LOAMGPU_ERR_INVALID;
   if (!n_edge || !n_planar) return fail(ctx, LOAMGPU_ERR_INVALID, "null count pointer");
   CU(cudaSetDevice(ctx->device));
@@ -617,14 +624,28 @@ int loamgpu_extract(loamgpu_ctx* ctx, const void* pts, int dtype, size_t stride,
   *n_planar = 0;
   if (n_points == 0) return LOAMGPU_OK;
   if (!pts) return fail(ctx, LOAMGPU_ERR_INVALID, "null point buffer");
+  if (motion) {
+    for (int i = 0; i < 7; i++)
+      if (!std::isfinite(motion[i])) return fail(ctx, LOAMGPU_ERR_INVALID, "start_T_end is not finite");
+    // the de-warped ring is staged as doubles whatever the input type
+    if (extract_smem_bytes(LOAMGPU_F64, pl.P, pl.S) > (size_t)ctx->max_smem_optin)
+      return fail(ctx, LOAMGPU_ERR_UNSUPPORTED, "points_per_line too large for one CTA's shared memory");
+  }
   const size_t bytes = (size_t)n_points * stride;
   CU(ctx->scan_in[0].reserve(bytes));
   ctx->staging_unguarded = true;
   rc = reserve_extract(ctx, pl, 1, 1);
   if (rc) return rc;
+  double* d_dewarped = nullptr;
+  if (motion && dewarped_xyz) {
+    CU(ctx->misc.reserve((size_t)n_points * 24));
+    d_dewarped = ctx->misc.as<double>();
+  }
   CU(cudaMemcpyAsync(ctx->scan_in[0].p, pts, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  rc = run_extract(ctx, pl, ctx->scan_in[0].p, dtype, stride, lp, fe, 1, 0, 1, nullptr, nullptr);
+  rc = run_extract(ctx, pl, ctx->scan_in[0].p, dtype, stride, lp, fe, 1, 0, 1, nullptr, nullptr, motion, d_dewarped);
   if (rc) return rc;
+  if (d_dewarped)
+    CU(cudaMemcpyAsync(dewarped_xyz, d_dewarped, (size_t)n_points * 24, cudaMemcpyDeviceToHost, ctx->stream));
   uint32_t counts[2];
   CU(cudaMemcpyAsync(counts, ctx->feat_counts.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
@@ -637,6 +658,24 @@ int loamgpu_extract(loamgpu_ctx* ctx, const void* pts, int dtype, size_t stride,
   *n_edge = counts[0];
   *n_planar = counts[1];
   return LOAMGPU_OK;
+}
+
+int loamgpu_extract(loamgpu_ctx* ctx, const void* pts, int dtype, size_t stride, uint64_t n_points,
+                    const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe, uint32_t* edge_idx,
+                    uint64_t edge_cap, uint64_t* n_edge, uint32_t* planar_idx, uint64_t planar_cap,
+                    uint64_t* n_planar) {
+  return extract_one(ctx, pts, dtype, stride, n_points, lp, fe, nullptr, edge_idx, edge_cap, n_edge, planar_idx,
+                     planar_cap, n_planar, nullptr);
+}
+
+int loamgpu_extract_dewarped(loamgpu_ctx* ctx, const void* pts, int dtype, size_t stride, uint64_t n_points,
+                             const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe, const double* start_T_end,
+                             uint32_t* edge_idx, uint64_t edge_cap, uint64_t* n_edge, uint32_t* planar_idx,
+                             uint64_t planar_cap, uint64_t* n_planar, double* dewarped_xyz) {
+  if (!ctx) return LOAMGPU_ERR_INVALID;
+  if (!start_T_end) return fail(ctx, LOAMGPU_ERR_INVALID, "null start_T_end");
+  return extract_one(ctx, pts, dtype, stride, n_points, lp, fe, start_T_end, edge_idx, edge_cap, n_edge, planar_idx,
+                     planar_cap, n_planar, dewarped_xyz);
 }
 
 static int curvature_or_mask(loamgpu_ctx* ctx, const void* pts, int dtype, size_t stride, uint64_t n_points,

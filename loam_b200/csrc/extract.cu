@@ -42,7 +42,10 @@ __host__ __device__ inline uint32_t rng_doubles(uint32_t P) {
   return max(P, (need + 7) / 8);
 }
 
-template <typename T>
+// T = scalar type of the staged ring (what the arithmetic widens from), TIn = scalar type of the caller's records.
+// They differ only for de-warping float input: the moved points are not float-representable, so the ring is staged
+// as doubles.
+template <typename T, typename TIn = T>
 __global__ void __launch_bounds__(kExtractThreads) extract_ring_kernel(ExtractArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t P = a.P, N = a.N, S = a.S;
@@ -70,11 +73,46 @@ __global__ void __launch_bounds__(kExtractThreads) extract_ring_kernel(ExtractAr
     }
     mbar_wait(bar, 0);
   } else {
+    double mq[4] = {a.motion[0], a.motion[1], a.motion[2], a.motion[3]};
+    if (mq[3] < 0.0) {  // hemisphere of Identity
+      mq[0] = -mq[0];
+      mq[1] = -mq[1];
+      mq[2] = -mq[2];
+      mq[3] = -mq[3];
+    }
     for (uint32_t j = tid; j < P; j += nthr) {
-      const T* src = reinterpret_cast<const T*>(ring_src + (size_t)j * a.stride);
-      stage[j * Rec<T>::kElems + 0] = src[0];
-      stage[j * Rec<T>::kElems + 1] = src[1];
-      stage[j * Rec<T>::kElems + 2] = src[2];
+      const TIn* src = reinterpret_cast<const TIn*>(ring_src + (size_t)j * a.stride);
+      T x = (T)src[0], y = (T)src[1], z = (T)src[2];
+      if (a.dewarp) {  // (only instantiated with T = double) operation order fixed, DESIGN.md §5c: the tests replay it on the CPU
+        const double s = (double)j / (double)P;
+        double pose[7];
+        pose[0] = dmul(s, mq[0]);
+        pose[1] = dmul(s, mq[1]);
+        pose[2] = dmul(s, mq[2]);
+        pose[3] = dadd(dsub(1.0, s), dmul(s, mq[3]));
+        const double nn = __dsqrt_rn(dadd(dadd(dadd(dmul(pose[0], pose[0]), dmul(pose[1], pose[1])), dmul(pose[2], pose[2])),
+                                          dmul(pose[3], pose[3])));
+        pose[0] = __ddiv_rn(pose[0], nn);
+        pose[1] = __ddiv_rn(pose[1], nn);
+        pose[2] = __ddiv_rn(pose[2], nn);
+        pose[3] = __ddiv_rn(pose[3], nn);
+        pose[4] = dmul(s, a.motion[4]);
+        pose[5] = dmul(s, a.motion[5]);
+        pose[6] = dmul(s, a.motion[6]);
+        const V3 m = pose_act(pose, V3{(double)x, (double)y, (double)z});
+        x = (T)m.x;
+        y = (T)m.y;
+        z = (T)m.z;
+        if (a.dewarp_out) {
+          double* o = a.dewarp_out + ((size_t)scan * a.R * P + (size_t)ring * P + j) * 3;
+          o[0] = m.x;
+          o[1] = m.y;
+          o[2] = m.z;
+        }
+      }
+      stage[j * Rec<T>::kElems + 0] = x;
+      stage[j * Rec<T>::kElems + 1] = y;
+      stage[j * Rec<T>::kElems + 2] = z;
     }
     __syncthreads();
   }
@@ -311,9 +349,21 @@ size_t extract_smem_bytes(int dtype, uint32_t P, uint32_t S) {
 }
 
 cudaError_t launch_extract(const ExtractArgs& a, uint32_t n_scans, cudaStream_t st) {
-  const size_t smem = extract_smem_bytes(a.dtype, a.P, a.S);
+  const size_t smem = extract_smem_bytes(a.dewarp ? (int)LOAMGPU_F64 : a.dtype, a.P, a.S);
   dim3 grid(a.R, n_scans);
   cudaError_t err;
+  if (a.dewarp) {  // double staging whatever the input type; strided loads (use_bulk is off)
+    if (a.dtype == LOAMGPU_F32) {
+      err = cudaFuncSetAttribute(extract_ring_kernel<double, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (err != cudaSuccess) return err;
+      extract_ring_kernel<double, float><<<grid, kExtractThreads, smem, st>>>(a);
+    } else {
+      err = cudaFuncSetAttribute(extract_ring_kernel<double, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (err != cudaSuccess) return err;
+      extract_ring_kernel<double, double><<<grid, kExtractThreads, smem, st>>>(a);
+    }
+    return cudaGetLastError();
+  }
   if (a.dtype == LOAMGPU_F32) {
     err = cudaFuncSetAttribute(extract_ring_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;

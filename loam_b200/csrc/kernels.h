@@ -40,6 +40,11 @@ struct ExtractArgs {
   uint32_t* ring_counts;        // [scan][R][2]
   double* curv_out;             // optional [scan][R*P]  (computeCurvature)
   uint8_t* mask_out;            // optional [scan][R*P]  (computeValidPoints)
+  // de-warp fused into the ring staging (extension): every point is moved into the frame of the sweep start by
+  // interp(Identity, motion, column / P) before anything else looks at it
+  int dewarp;
+  double motion[7];             // start_T_end: qx qy qz qw tx ty tz
+  double* dewarp_out;           // optional [scan][R*P][3] de-warped points
 };
 
 struct PackArgs {

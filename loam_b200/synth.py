@@ -99,6 +99,78 @@ def make_scan(rings: int, cols: int, k: int = 0, sigma: float = 0.01, seed: int 
     return out
 
 
+def sweep_poses(cols: int, start_T_end):
+    """Per-column sensor pose relative to the sweep start, the model loamgpu_extract_dewarped inverts: column c is
+    measured at s = c / cols, rotation = normalised linear interpolation of the quaternion, translation linear.
+    Returns [cols, 7] (qx,qy,qz,qw,tx,ty,tz)."""
+    m = np.asarray(start_T_end, dtype=np.float64)
+    q = m[:4] if m[3] >= 0 else -m[:4]
+    s = (np.arange(cols, dtype=np.float64) / cols)[:, None]
+    qs = s * q[None, :]
+    qs[:, 3] = (1.0 - s[:, 0]) + s[:, 0] * q[3]
+    qs /= np.linalg.norm(qs, axis=1, keepdims=True)
+    return np.concatenate([qs, s * m[None, 4:7]], axis=1)
+
+
+def make_warped_scan(rings: int, cols: int, k: int, start_T_end, sigma: float = 0.0, seed: int | None = None,
+                     start_pose=None):
+    """Scan k as a sensor that keeps moving during the sweep would record it (yaw + planar motions only): column c is
+    cast from world_T_sensor(k) ∘ sweep_poses[c] and stored in that column's own instantaneous frame.  float32
+    [rings*cols, 4].  De-warping it with start_T_end gives the scene as seen from the pose at the sweep start."""
+    m = np.asarray(start_T_end, dtype=np.float64)
+    assert m[0] == 0.0 and m[1] == 0.0 and m[6] == 0.0, "generator handles yaw + planar motion only"
+    x0, y0, yaw0 = start_pose if start_pose is not None else (trajectory(k)[0], trajectory(k)[1], trajectory(k)[3])
+    sp = sweep_poses(cols, m)
+    yaw = yaw0 + 2.0 * np.arctan2(sp[:, 2], sp[:, 3])  # [cols]
+    c0, s0 = math.cos(yaw0), math.sin(yaw0)
+    px = x0 + c0 * sp[:, 4] - s0 * sp[:, 5]
+    py = y0 + s0 * sp[:, 4] + c0 * sp[:, 5]
+    fov = fov_for_rings(rings)
+    el = np.deg2rad(np.linspace(-fov / 2, fov / 2, rings))[:, None]
+    az = (2 * np.pi * np.arange(cols) / cols)[None, :]
+    ds = np.stack([np.cos(el) * np.cos(az), np.cos(el) * np.sin(az), np.sin(el) * np.ones_like(az)], axis=-1)
+    cy, sy = np.cos(yaw)[None, :], np.sin(yaw)[None, :]
+    dw = np.stack([cy * ds[..., 0] - sy * ds[..., 1], sy * ds[..., 0] + cy * ds[..., 1], ds[..., 2]], axis=-1)
+    pos = (px[None, :], py[None, :], np.zeros((1, cols)))
+    t = np.full(dw.shape[:2], np.inf)
+    lo = (ROOM[0], ROOM[2], ROOM[4])
+    hi = (ROOM[1], ROOM[3], ROOM[5])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for a in range(3):
+            d = dw[..., a]
+            ta = np.where(d > 0, (hi[a] - pos[a]) / d, np.where(d < 0, (lo[a] - pos[a]) / d, np.inf))
+            t = np.minimum(t, ta)
+        dxy2 = dw[..., 0] ** 2 + dw[..., 1] ** 2
+        for j in range(N_CYL):
+            ang = 2 * np.pi * j / N_CYL + 0.1
+            ox, oy = pos[0] - CYL_RING * math.cos(ang), pos[1] - CYL_RING * math.sin(ang)
+            b = ox * dw[..., 0] + oy * dw[..., 1]
+            c = ox * ox + oy * oy - CYL_RADIUS**2
+            disc = b * b - dxy2 * c
+            tc = (-b - np.sqrt(np.maximum(disc, 0))) / dxy2
+            ok = (disc > 0) & (tc > 0)
+            t = np.where(ok, np.minimum(t, tc), t)
+    if sigma > 0:
+        rng = np.random.RandomState(1000 + k if seed is None else seed)
+        t = t + rng.normal(0.0, sigma, size=t.shape)
+    out = np.zeros((rings * cols, 4), dtype=np.float32)
+    out[:, :3] = (ds * t[..., None]).astype(np.float32).reshape(-1, 3)
+    return out
+
+
+def distance_to_scene(world_pts):
+    """Distance of world-frame points to the nearest scene surface (room faces, cylinders) — what a correctly
+    de-warped noise-free scan drives to ~0."""
+    p = np.asarray(world_pts, dtype=np.float64)
+    d = np.minimum.reduce([np.abs(p[:, 0] - ROOM[0]), np.abs(p[:, 0] - ROOM[1]), np.abs(p[:, 1] - ROOM[2]),
+                           np.abs(p[:, 1] - ROOM[3]), np.abs(p[:, 2] - ROOM[4]), np.abs(p[:, 2] - ROOM[5])])
+    for j in range(N_CYL):
+        ang = 2 * np.pi * j / N_CYL + 0.1
+        r = np.hypot(p[:, 0] - CYL_RING * math.cos(ang), p[:, 1] - CYL_RING * math.sin(ang))
+        d = np.minimum(d, np.abs(r - CYL_RADIUS))
+    return d
+
+
 def make_scans_torch(rings: int, cols: int, k0: int, count: int, device, sigma: float = 0.01, chunk: int = 64):
     """Bulk generation on `device` with torch: float32 [count, rings*cols, 4].
 

@@ -211,6 +211,39 @@ void orc_pose_act(const double* pose, const double* pt, double* out) {
   out[2] = r[2] + pose[6];
 }
 
+/* De-warp (motion compensation) of an organised scan — an EXTENSION: the reference leaves it to its caller
+ * (README.md:63), so this restatement is the definition the CUDA path is checked against, not a pinned behaviour.
+ * Column c of every ring is measured at fraction s = c / P of the sweep; the sensor pose at that instant, relative
+ * to the start of the sweep, is interp(Identity, start_T_end, s) with the rotation interpolated by normalised
+ * linear interpolation of the quaternion (hemisphere of Identity) and the translation linearly.  out = T(s) * p,
+ * i.e. every point expressed in the frame of the sweep start.  Only IEEE +,-,*,/ and sqrt: bit-reproducible. */
+void orc_dewarp(const double* xyz, uint64_t n, uint64_t points_per_line, const double* start_T_end, double* out) {
+  double q[4] = {start_T_end[0], start_T_end[1], start_T_end[2], start_T_end[3]};
+  if (q[3] < 0.0) {
+    q[0] = -q[0];
+    q[1] = -q[1];
+    q[2] = -q[2];
+    q[3] = -q[3];
+  }
+  for (uint64_t i = 0; i < n; i++) {
+    const double s = (double)(i % points_per_line) / (double)points_per_line;
+    double pose[7];
+    pose[0] = s * q[0];
+    pose[1] = s * q[1];
+    pose[2] = s * q[2];
+    pose[3] = (1.0 - s) + s * q[3];
+    const double nn = sqrt(((pose[0] * pose[0] + pose[1] * pose[1]) + pose[2] * pose[2]) + pose[3] * pose[3]);
+    pose[0] = pose[0] / nn;
+    pose[1] = pose[1] / nn;
+    pose[2] = pose[2] / nn;
+    pose[3] = pose[3] / nn;
+    pose[4] = s * start_T_end[4];
+    pose[5] = s * start_T_end[5];
+    pose[6] = s * start_T_end[6];
+    orc_pose_act(pose, xyz + 3 * i, out + 3 * i);
+  }
+}
+
 /* geometry.cpp:16-18 */
 void orc_pose_compose(const double* p1, const double* p2, double* out) {
   double q[4], r[3];

@@ -113,6 +113,8 @@ double orc_point_to_plane(const double* p, const double* n, double d);
 void orc_pose_compose(const double* p1, const double* p2, double* out);
 void orc_pose_inverse(const double* p, double* out);
 void orc_pose_act(const double* pose, const double* pt, double* out);
+/* de-warp of an organised scan into the frame of the sweep start (extension, see loam_oracle.c) */
+void orc_dewarp(const double* xyz, uint64_t n, uint64_t points_per_line, const double* start_T_end, double* out);
 double orc_quat_angular_distance(const double* q1, const double* q2);
 
 /* registration-inl.h:11-78 + registration.cpp:23-103 + restated Ceres 2.2.0 LM.

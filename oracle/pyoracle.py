@@ -194,6 +194,13 @@ class Oracle:
         self.lib.orc_pose_act(pose.ctypes, pt.ctypes, o.ctypes)
         return o
 
+    def dewarp(self, xyz, points_per_line, start_T_end):
+        xyz = _as_xyz(xyz)
+        m = np.ascontiguousarray(start_T_end, dtype=np.float64)
+        out = np.empty_like(xyz)
+        self.lib.orc_dewarp(xyz.ctypes, u64(len(xyz)), u64(points_per_line), m.ctypes, out.ctypes)
+        return out
+
     def angular_distance(self, q1, q2):
         q1, q2 = (np.ascontiguousarray(v, dtype=np.float64) for v in (q1, q2))
         return self.lib.orc_quat_angular_distance(q1.ctypes, q2.ctypes)

@@ -161,6 +161,42 @@ static void test_float_zero_copy_matches_double_path() {
   CHECK(f.planar_points[0].x == sf[a.second[0]].x && f.planar_points[0].intensity == sf[a.second[0]].intensity);
 }
 
+// extension: de-warp fused into the extraction (include/loam/features.h, loamgpu_extract_dewarped)
+static void test_dewarped_extraction() {
+  const int R = 16, C = 512;
+  const auto sf = room_scan<PointF>(R, C);
+  const loam::LidarParams lp(R, C, 0.5, 100.0);
+  // identity motion: the same picks as the plain call, points widened
+  const auto idx = loam::gpu::extractFeatureIndices(sf, lp);
+  const auto f0 = loam::extractFeaturesDewarped(sf, lp, loam::Pose3d::Identity());
+  CHECK(f0.edge_points.size() == idx.first.size() && f0.planar_points.size() == idx.second.size());
+  CHECK(f0.planar_points[0](0) == (double)sf[idx.second[0]].x && f0.planar_points[0](2) == (double)sf[idx.second[0]].z);
+  // pure translation t: column c moves by (c / C) t, so every feature point is input + s t for its own column
+  const loam::Pose3d T(Eigen::Quaterniond::Identity(), V3(0.4, -0.2, 0.1));
+  const auto f1 = loam::extractFeaturesDewarped(sf, lp, T);
+  CHECK(!f1.edge_points.empty() && !f1.planar_points.empty());
+  int matched = 0;
+  for (const V3& q : f1.planar_points) {
+    for (int c = 0; c < C && matched >= 0; c++) {
+      const double s = (double)c / C;
+      bool hit = false;
+      for (int r = 0; r < R && !hit; r++) {
+        const PointF& p = sf[(size_t)r * C + c];
+        hit = std::fabs(q(0) - (p.x + s * 0.4)) < 1e-12 && std::fabs(q(1) - (p.y - s * 0.2)) < 1e-12 &&
+              std::fabs(q(2) - (p.z + s * 0.1)) < 1e-12;
+      }
+      if (hit) {
+        matched++;
+        break;
+      }
+    }
+  }
+  CHECK(matched == (int)f1.planar_points.size());
+  // the widened features feed registerFeatures directly
+  const loam::Pose3d est = loam::registerFeatures<loam::ParenAccessor>(f1, f1, loam::Pose3d::Identity());
+  CHECK_NEAR(est.translation.norm(), 0.0, 1e-6);
+}
+
 // the reference's registration scene: three planes and two vertical edges on a 0.05 m lattice
 static loam::LoamFeatures<V3> simple_scene() {
   loam::LoamFeatures<V3> f;
@@ -267,6 +303,7 @@ int main(int argc, char** argv) {
     test_curvature_known_answers();
     test_valid_mask_known_answers();
     test_float_zero_copy_matches_double_path();
+    test_dewarped_extraction();
     test_registration_scenarios();
     test_local_map_matches_plain_registration();
   }
