@@ -360,6 +360,55 @@ struct TopK {
   }
 };
 
+#ifndef KNN_FASTINS
+#define KNN_FASTINS 0
+#endif
+// The K + 1 best candidates ordered by distance ALONE (equal distances keep their arrival order).  The insertion
+// network needs one fp64 compare per slot instead of the three instructions of the (distance, index) comparison, and
+// the spare slot tells afterwards whether the index tie-break could have mattered: the first k results — which
+// candidates they are and their order — are independent of it unless two of the first k + 1 distances are equal
+// (a candidate that ties the k-th distance is never pruned, see knn_bvh, so it reaches slot k or earlier).
+// ambiguous() is then true and the caller repeats the query with the exact TopK.  On scan data that is one query in
+// millions; on the tie-heavy test sets it is the path under test.
+template <int K>
+struct TopKFast {
+  double d[K + 1];
+  uint32_t id[K + 1];
+
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int i = 0; i <= K; i++) {
+      d[i] = CUDART_INF;
+      id[i] = 0xFFFFFFFFu;
+    }
+  }
+  __device__ __forceinline__ void insert(double dn, uint32_t in) {
+    bool c[K + 1];
+#pragma unroll
+    for (int i = 0; i <= K; i++) c[i] = dn < d[i];
+#pragma unroll
+    for (int i = K; i > 0; --i) {
+      d[i] = c[i] ? (c[i - 1] ? d[i - 1] : dn) : d[i];
+      id[i] = c[i] ? (c[i - 1] ? id[i - 1] : in) : id[i];
+    }
+    d[0] = c[0] ? dn : d[0];
+    id[0] = c[0] ? in : id[0];
+  }
+  __device__ __forceinline__ double kth(int k) const {
+    double v = d[K - 1];
+#pragma unroll
+    for (int i = 0; i < K - 1; i++)
+      if (i == k - 1) v = d[i];
+    return v;
+  }
+  __device__ __forceinline__ bool ambiguous(int k) const {
+    bool amb = false;
+#pragma unroll
+    for (int i = 0; i < K; i++) amb |= i < k && d[i] == d[i + 1] && d[i] < CUDART_INF;
+    return amb;
+  }
+};
+
 struct QueryF {  // the query rounded down / up to float, for conservative box tests
   float lo[3], hi[3];
 };
@@ -386,6 +435,9 @@ __device__ __forceinline__ float box_lower_bound(const BvhNode& b, const QueryF&
 
 #ifndef KNN_LD256
 #define KNN_LD256 1
+#endif
+#ifndef KNN_STACK4
+#define KNN_STACK4 0
 #endif
 // 32-byte records (node, point) are fetched with ONE 256-bit load (sm_100: ld.global.nc.v8.b32 / .v4.f64, SASS
 // LDG.E.256) instead of two 128-bit ones: half the load instructions of the traversal.  Both record arrays are
@@ -424,25 +476,31 @@ __device__ __forceinline__ double4 load_point(const double4* __restrict__ p) {
 // best (or the radius cut), so candidates that tie the k-th distance are still seen and resolved by index.
 constexpr int kBvhStack = 64;  // >= tree depth: 30 Morton bits + 32 position bits for duplicate codes
 
-template <int K>
+template <int K, typename TK>
 __device__ __forceinline__ void knn_bvh(const BvhHdr& h, const BvhNode* __restrict__ nodes,
                                         const double4* __restrict__ sorted, double qx, double qy, double qz, int k,
-                                        double max_dist, TopK<K>& tk, double d2_hint) {
+                                        double max_dist, TK& tk, double d2_hint) {
   // d2_hint: a squared distance within which at least k points are known to lie (prunes only; inf = none)
   tk.init();
   if (h.n == 0) return;
-  const double d2_cut = max_dist > 0 ? max_dist * max_dist * (1.0 + 1e-12) : CUDART_INF;
+  // one cap for both the radius cut and the caller's hint: a candidate beyond the hint lies strictly beyond the k-th
+  // nearest (k points are known within it), so it can be dropped like one beyond the radius
+  const double d2_cut = fmin(max_dist > 0 ? max_dist * max_dist * (1.0 + 1e-12) : CUDART_INF, d2_hint);
   QueryF q;
   q.lo[0] = __double2float_rd(qx); q.hi[0] = __double2float_ru(qx);
   q.lo[1] = __double2float_rd(qy); q.hi[1] = __double2float_ru(qy);
   q.lo[2] = __double2float_rd(qz); q.hi[2] = __double2float_ru(qz);
-  float bound = __double2float_ru(fmin(d2_cut, d2_hint));  // a subtree is pruned when its lower bound > bound
+  float bound = __double2float_ru(d2_cut);  // a subtree is pruned when its lower bound > bound
 
   // pending subtrees: (node index, key range, lower bound); a subtree of <= kBvhLeaf points is scanned as a leaf
   // (the node index itself is not needed: a node's record is only read to test it, and that read also yields
   // its split word, which is all the descent needs)
+#if KNN_STACK4
+  uint4 st[kBvhStack];  // (split word, first, last, lower bound): one 128-bit local store / load per push / pop
+#else
   uint32_t st_split[kBvhStack], st_first[kBvhStack], st_last[kBvhStack];
   float st_lb[kBvhStack];
+#endif
   int sp = 0;
   uint32_t first = 0, last = h.n - 1, cur_w = 0;
   bool have = true, done = false;
@@ -462,12 +520,22 @@ __device__ __forceinline__ void knn_bvh(const BvhHdr& h, const BvhNode* __restri
           done = true;
         } else {
           --sp;
+#if KNN_STACK4
+          const uint4 e = st[sp];
+          if (__uint_as_float(e.w) <= bound) {
+            cur_w = e.x;
+            first = e.y;
+            last = e.z;
+            have = true;
+          }
+#else
           if (st_lb[sp] <= bound) {
             cur_w = st_split[sp];
             first = st_first[sp];
             last = st_last[sp];
             have = true;
           }
+#endif
         }
       } else if (last - first < (uint32_t)kBvhLeaf) {
         at_leaf = true;
@@ -483,10 +551,15 @@ __device__ __forceinline__ void knn_bvh(const BvhHdr& h, const BvhNode* __restri
         const float dn = right_first ? dr : dl, df = right_first ? dl : dr;
         const uint32_t l_first = first, l_last = s, r_first = s + 1, r_last = last;
         if (df <= bound) {  // far child stays pending
+#if KNN_STACK4
+          st[sp] = make_uint4(right_first ? cl.split : cr.split, right_first ? l_first : r_first,
+                              right_first ? l_last : r_last, __float_as_uint(df));
+#else
           st_split[sp] = right_first ? cl.split : cr.split;
           st_first[sp] = right_first ? l_first : r_first;
           st_last[sp] = right_first ? l_last : r_last;
           st_lb[sp] = df;
+#endif
           sp++;
         }
         if (dn <= bound) {
@@ -511,14 +584,14 @@ __device__ __forceinline__ void knn_bvh(const BvhHdr& h, const BvhNode* __restri
       id = ok ? id : 0xFFFFFFFFu;
       tk.insert(d2, id);
     }
-    bound = __double2float_ru(fmin(fmin(tk.kth(k), d2_cut), d2_hint));
+    bound = __double2float_ru(fmin(tk.kth(k), d2_cut));
     have = false;
   }
 }
 
 // kdtree.cpp:24-26 : keep neighbours with max_dist <= 0 || sqrt(d2) < max_dist (strict). Sorted => prefix.
-template <int K>
-__device__ __forceinline__ int radius_count(const TopK<K>& tk, int k, double max_dist) {
+template <int K, typename TK>
+__device__ __forceinline__ int radius_count(const TK& tk, int k, double max_dist) {
   int m = 0;
 #pragma unroll
   for (int i = 0; i < K; i++) {
@@ -527,15 +600,53 @@ __device__ __forceinline__ int radius_count(const TopK<K>& tk, int k, double max
   return m;
 }
 
+// The exact repeat of an ambiguous query (inlined: as a __noinline__ call ptxas 12.9 crashes on it under --fmad false).
+template <int K>
+__device__ __forceinline__ void knn_bvh_exact(uint32_t n, const BvhNode* nodes, const double4* sorted, double qx, double qy,
+                                           double qz, int k, double max_dist, double d2_hint, double* d_out,
+                                           uint32_t* id_out) {
+  BvhHdr h;
+  h.n = n;
+  TopK<K> t;
+  knn_bvh<K>(h, nodes, sorted, qx, qy, qz, k, max_dist, t, d2_hint);
+#pragma unroll
+  for (int i = 0; i < K; i++) {
+    d_out[i] = t.d[i];
+    id_out[i] = t.id[i];
+  }
+}
+
+// k nearest by (squared distance, index) — what every caller uses.
+template <int K>
+__device__ __forceinline__ void knn_query(const BvhHdr& h, const BvhNode* __restrict__ nodes,
+                                          const double4* __restrict__ sorted, double qx, double qy, double qz, int k,
+                                          double max_dist, TopK<K>& tk, double d2_hint) {
+  if constexpr (KNN_FASTINS && K <= 8) {
+    TopKFast<K> tf;
+    knn_bvh<K>(h, nodes, sorted, qx, qy, qz, k, max_dist, tf, d2_hint);
+    if (tf.ambiguous(k)) {
+      knn_bvh_exact<K>(h.n, nodes, sorted, qx, qy, qz, k, max_dist, d2_hint, tk.d, tk.id);
+    } else {
+#pragma unroll
+      for (int i = 0; i < K; i++) {
+        tk.d[i] = tf.d[i];
+        tk.id[i] = tf.id[i];
+      }
+    }
+  } else {  // wide result sets (k up to 32, not a hot path): the exact comparison directly
+    knn_bvh<K>(h, nodes, sorted, qx, qy, qz, k, max_dist, tk, d2_hint);
+  }
+}
+
 template <int K>
 __global__ void __launch_bounds__(128) knn_kernel(KnnArgs a) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n_queries) return;
   const BvhHdr h = a.g.hdr[0];
   TopK<K> tk;
-  knn_bvh<K>(h, a.g.nodes, a.g.sorted, a.queries[3 * i], a.queries[3 * i + 1], a.queries[3 * i + 2], a.k, a.max_dist,
-             tk, CUDART_INF);
-  const int m = radius_count(tk, a.k, a.max_dist);
+  knn_query<K>(h, a.g.nodes, a.g.sorted, a.queries[3 * i], a.queries[3 * i + 1], a.queries[3 * i + 2], a.k,
+               a.max_dist, tk, CUDART_INF);
+  const int m = radius_count<K>(tk, a.k, a.max_dist);
   a.count_out[i] = (uint32_t)m;
 #pragma unroll
   for (int j = 0; j < K; j++)
