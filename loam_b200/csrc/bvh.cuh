@@ -360,55 +360,6 @@ struct TopK {
   }
 };
 
-#ifndef KNN_FASTINS
-#define KNN_FASTINS 0
-#endif
-// The K + 1 best candidates ordered by distance ALONE (equal distances keep their arrival order).  The insertion
-// network needs one fp64 compare per slot instead of the three instructions of the (distance, index) comparison, and
-// the spare slot tells afterwards whether the index tie-break could have mattered: the first k results — which
-// candidates they are and their order — are independent of it unless two of the first k + 1 distances are equal
-// (a candidate that ties the k-th distance is never pruned, see knn_bvh, so it reaches slot k or earlier).
-// ambiguous() is then true and the caller repeats the query with the exact TopK.  On scan data that is one query in
-// millions; on the tie-heavy test sets it is the path under test.
-template <int K>
-struct TopKFast {
-  double d[K + 1];
-  uint32_t id[K + 1];
-
-  __device__ __forceinline__ void init() {
-#pragma unroll
-    for (int i = 0; i <= K; i++) {
-      d[i] = CUDART_INF;
-      id[i] = 0xFFFFFFFFu;
-    }
-  }
-  __device__ __forceinline__ void insert(double dn, uint32_t in) {
-    bool c[K + 1];
-#pragma unroll
-    for (int i = 0; i <= K; i++) c[i] = dn < d[i];
-#pragma unroll
-    for (int i = K; i > 0; --i) {
-      d[i] = c[i] ? (c[i - 1] ? d[i - 1] : dn) : d[i];
-      id[i] = c[i] ? (c[i - 1] ? id[i - 1] : in) : id[i];
-    }
-    d[0] = c[0] ? dn : d[0];
-    id[0] = c[0] ? in : id[0];
-  }
-  __device__ __forceinline__ double kth(int k) const {
-    double v = d[K - 1];
-#pragma unroll
-    for (int i = 0; i < K - 1; i++)
-      if (i == k - 1) v = d[i];
-    return v;
-  }
-  __device__ __forceinline__ bool ambiguous(int k) const {
-    bool amb = false;
-#pragma unroll
-    for (int i = 0; i < K; i++) amb |= i < k && d[i] == d[i + 1] && d[i] < CUDART_INF;
-    return amb;
-  }
-};
-
 struct QueryF {  // the query rounded down / up to float, for conservative box tests
   float lo[3], hi[3];
 };
@@ -437,7 +388,7 @@ __device__ __forceinline__ float box_lower_bound(const BvhNode& b, const QueryF&
 #define KNN_LD256 1
 #endif
 #ifndef KNN_STACK4
-#define KNN_STACK4 0
+#define KNN_STACK4 1
 #endif
 // 32-byte records (node, point) are fetched with ONE 256-bit load (sm_100: ld.global.nc.v8.b32 / .v4.f64, SASS
 // LDG.E.256) instead of two 128-bit ones: half the load instructions of the traversal.  Both record arrays are
@@ -476,10 +427,10 @@ __device__ __forceinline__ double4 load_point(const double4* __restrict__ p) {
 // best (or the radius cut), so candidates that tie the k-th distance are still seen and resolved by index.
 constexpr int kBvhStack = 64;  // >= tree depth: 30 Morton bits + 32 position bits for duplicate codes
 
-template <int K, typename TK>
+template <int K>
 __device__ __forceinline__ void knn_bvh(const BvhHdr& h, const BvhNode* __restrict__ nodes,
                                         const double4* __restrict__ sorted, double qx, double qy, double qz, int k,
-                                        double max_dist, TK& tk, double d2_hint) {
+                                        double max_dist, TopK<K>& tk, double d2_hint) {
   // d2_hint: a squared distance within which at least k points are known to lie (prunes only; inf = none)
   tk.init();
   if (h.n == 0) return;
@@ -590,8 +541,8 @@ __device__ __forceinline__ void knn_bvh(const BvhHdr& h, const BvhNode* __restri
 }
 
 // kdtree.cpp:24-26 : keep neighbours with max_dist <= 0 || sqrt(d2) < max_dist (strict). Sorted => prefix.
-template <int K, typename TK>
-__device__ __forceinline__ int radius_count(const TK& tk, int k, double max_dist) {
+template <int K>
+__device__ __forceinline__ int radius_count(const TopK<K>& tk, int k, double max_dist) {
   int m = 0;
 #pragma unroll
   for (int i = 0; i < K; i++) {
@@ -600,53 +551,15 @@ __device__ __forceinline__ int radius_count(const TK& tk, int k, double max_dist
   return m;
 }
 
-// The exact repeat of an ambiguous query (inlined: as a __noinline__ call ptxas 12.9 crashes on it under --fmad false).
-template <int K>
-__device__ __forceinline__ void knn_bvh_exact(uint32_t n, const BvhNode* nodes, const double4* sorted, double qx, double qy,
-                                           double qz, int k, double max_dist, double d2_hint, double* d_out,
-                                           uint32_t* id_out) {
-  BvhHdr h;
-  h.n = n;
-  TopK<K> t;
-  knn_bvh<K>(h, nodes, sorted, qx, qy, qz, k, max_dist, t, d2_hint);
-#pragma unroll
-  for (int i = 0; i < K; i++) {
-    d_out[i] = t.d[i];
-    id_out[i] = t.id[i];
-  }
-}
-
-// k nearest by (squared distance, index) — what every caller uses.
-template <int K>
-__device__ __forceinline__ void knn_query(const BvhHdr& h, const BvhNode* __restrict__ nodes,
-                                          const double4* __restrict__ sorted, double qx, double qy, double qz, int k,
-                                          double max_dist, TopK<K>& tk, double d2_hint) {
-  if constexpr (KNN_FASTINS && K <= 8) {
-    TopKFast<K> tf;
-    knn_bvh<K>(h, nodes, sorted, qx, qy, qz, k, max_dist, tf, d2_hint);
-    if (tf.ambiguous(k)) {
-      knn_bvh_exact<K>(h.n, nodes, sorted, qx, qy, qz, k, max_dist, d2_hint, tk.d, tk.id);
-    } else {
-#pragma unroll
-      for (int i = 0; i < K; i++) {
-        tk.d[i] = tf.d[i];
-        tk.id[i] = tf.id[i];
-      }
-    }
-  } else {  // wide result sets (k up to 32, not a hot path): the exact comparison directly
-    knn_bvh<K>(h, nodes, sorted, qx, qy, qz, k, max_dist, tk, d2_hint);
-  }
-}
-
 template <int K>
 __global__ void __launch_bounds__(128) knn_kernel(KnnArgs a) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n_queries) return;
   const BvhHdr h = a.g.hdr[0];
   TopK<K> tk;
-  knn_query<K>(h, a.g.nodes, a.g.sorted, a.queries[3 * i], a.queries[3 * i + 1], a.queries[3 * i + 2], a.k,
-               a.max_dist, tk, CUDART_INF);
-  const int m = radius_count<K>(tk, a.k, a.max_dist);
+  knn_bvh<K>(h, a.g.nodes, a.g.sorted, a.queries[3 * i], a.queries[3 * i + 1], a.queries[3 * i + 2], a.k,
+             a.max_dist, tk, CUDART_INF);
+  const int m = radius_count(tk, a.k, a.max_dist);
   a.count_out[i] = (uint32_t)m;
 #pragma unroll
   for (int j = 0; j < K; j++)

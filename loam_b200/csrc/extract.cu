@@ -45,7 +45,7 @@ __host__ __device__ inline uint32_t rng_doubles(uint32_t P) {
 // T = scalar type of the staged ring (what the arithmetic widens from), TIn = scalar type of the caller's records.
 // They differ only for de-warping float input: the moved points are not float-representable, so the ring is staged
 // as doubles.
-template <typename T, typename TIn = T>
+template <typename T, typename TIn = T, bool kDewarp = false>
 __global__ void __launch_bounds__(kExtractThreads) extract_ring_kernel(ExtractArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t P = a.P, N = a.N, S = a.S;
@@ -73,17 +73,23 @@ __global__ void __launch_bounds__(kExtractThreads) extract_ring_kernel(ExtractAr
     }
     mbar_wait(bar, 0);
   } else {
-    double mq[4] = {a.motion[0], a.motion[1], a.motion[2], a.motion[3]};
-    if (mq[3] < 0.0) {  // hemisphere of Identity
-      mq[0] = -mq[0];
-      mq[1] = -mq[1];
-      mq[2] = -mq[2];
-      mq[3] = -mq[3];
+    double mq[4] = {0.0, 0.0, 0.0, 1.0};
+    if constexpr (kDewarp) {
+      mq[0] = a.motion[0];
+      mq[1] = a.motion[1];
+      mq[2] = a.motion[2];
+      mq[3] = a.motion[3];
+      if (mq[3] < 0.0) {  // hemisphere of Identity
+        mq[0] = -mq[0];
+        mq[1] = -mq[1];
+        mq[2] = -mq[2];
+        mq[3] = -mq[3];
+      }
     }
     for (uint32_t j = tid; j < P; j += nthr) {
       const TIn* src = reinterpret_cast<const TIn*>(ring_src + (size_t)j * a.stride);
       T x = (T)src[0], y = (T)src[1], z = (T)src[2];
-      if (a.dewarp) {  // (only instantiated with T = double) operation order fixed, DESIGN.md §5c: the tests replay it on the CPU
+      if constexpr (kDewarp) {  // operation order fixed, DESIGN.md §5c: the tests replay it on the CPU
         const double s = (double)j / (double)P;
         double pose[7];
         pose[0] = dmul(s, mq[0]);
@@ -354,13 +360,13 @@ cudaError_t launch_extract(const ExtractArgs& a, uint32_t n_scans, cudaStream_t 
   cudaError_t err;
   if (a.dewarp) {  // double staging whatever the input type; strided loads (use_bulk is off)
     if (a.dtype == LOAMGPU_F32) {
-      err = cudaFuncSetAttribute(extract_ring_kernel<double, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      err = cudaFuncSetAttribute(extract_ring_kernel<double, float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (err != cudaSuccess) return err;
-      extract_ring_kernel<double, float><<<grid, kExtractThreads, smem, st>>>(a);
+      extract_ring_kernel<double, float, true><<<grid, kExtractThreads, smem, st>>>(a);
     } else {
-      err = cudaFuncSetAttribute(extract_ring_kernel<double, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      err = cudaFuncSetAttribute(extract_ring_kernel<double, double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (err != cudaSuccess) return err;
-      extract_ring_kernel<double, double><<<grid, kExtractThreads, smem, st>>>(a);
+      extract_ring_kernel<double, double, true><<<grid, kExtractThreads, smem, st>>>(a);
     }
     return cudaGetLastError();
   }

@@ -443,9 +443,9 @@ __device__ __forceinline__ void assoc_knn_pair(const AssocArgs& a, int outer_ite
     d2_hint = worst;
   }
   TopK<K> tk;
-  knn_query<K>(g, gt.nodes + (size_t)tset * gt.pt_cap, gt.sorted + (size_t)tset * gt.pt_cap, q.x, q.y, q.z, k, md, tk,
-               d2_hint);
-  const int m = radius_count<K>(tk, k, md);
+  knn_bvh<K>(g, gt.nodes + (size_t)tset * gt.pt_cap, gt.sorted + (size_t)tset * gt.pt_cap, q.x, q.y, q.z, k, md, tk,
+             d2_hint);
+  const int m = radius_count(tk, k, md);
   a.rec_p[rec] = make_double4(q.x, q.y, q.z, 0.0);
   a.nn_cnt[rec] = (uint32_t)m;
 #pragma unroll

@@ -192,9 +192,16 @@ static void test_dewarped_extraction() {
     }
   }
   CHECK(matched == (int)f1.planar_points.size());
-  // the widened features feed registerFeatures directly
-  const loam::Pose3d est = loam::registerFeatures<loam::ParenAccessor>(f1, f1, loam::Pose3d::Identity());
-  CHECK_NEAR(est.translation.norm(), 0.0, 1e-6);
+  // the widened features feed registerFeatures directly: the same features displaced by a known pose come back
+  // (plumbing check with a loose bound; parity of the registration itself is tested elsewhere)
+  const loam::Pose3d T0(Eigen::Quaterniond::Identity(), V3(0.05, -0.03, 0.02));
+  loam::LoamFeatures<V3> src;
+  for (const V3& q : f1.edge_points) src.edge_points.push_back(T0.inverse().act(q));
+  for (const V3& q : f1.planar_points) src.planar_points.push_back(T0.inverse().act(q));
+  const loam::Pose3d est = loam::registerFeatures<loam::ParenAccessor>(src, f1, loam::Pose3d::Identity());
+  CHECK_NEAR(est.translation(0), 0.05, 1e-2);
+  CHECK_NEAR(est.translation(1), -0.03, 1e-2);
+  CHECK_NEAR(est.translation(2), 0.02, 1e-2);
 }
 
 // the reference's registration scene: three planes and two vertical edges on a 0.05 m lattice
