@@ -62,7 +62,7 @@ constexpr int kRadixBits = 4;
 constexpr int kRadixBins = 1 << kRadixBits;
 constexpr int kMortonBits = 30;
 
-__global__ void __launch_bounds__(kBuildThreads) bvh_build_kernel(BvhBuildArgs a) {
+__global__ void __launch_bounds__(kBuildThreads, BUILD_MINBLOCKS) bvh_build_kernel(BvhBuildArgs a) {
   // dynamic shared memory: [0, kRadixBins*kBuildThreads) radix counters during the sort; afterwards, when the set
   // fits (a.smem_tree), the sorted Morton codes (n words) and behind them one readiness byte per node
   extern __shared__ uint32_t s_cnt[];

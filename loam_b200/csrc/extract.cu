@@ -18,6 +18,10 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#ifndef EXTRACT_WARP_SWEEPS
+#define EXTRACT_WARP_SWEEPS 1
+#endif
+
 namespace loamgpu {
 
 namespace {
@@ -238,32 +242,48 @@ __global__ void __launch_bounds__(kExtractThreads) extract_ring_kernel(ExtractAr
       hp[j] = bits;
     }
     // (hp[j] is only ever read by the thread that wrote it, and st[] is not modified before the first round)
+    // A warp owns runs of 32 consecutive columns, and a candidate only waits on columns within +-(N-1): most
+    // dependency chains never leave the warp.  Those are resolved in warp-local sweeps (one __syncwarp each) and only
+    // chains that cross a warp's span cost a CTA barrier.  Any interleaving gives the same result: a state byte
+    // changes once (open -> picked / dropped) and a stale "open" seen across warps only delays a decision.
     for (;;) {
-      bool open_left = false;
-      for (uint32_t j = b + tid; j < e; j += nthr) {
-        if (st[j] != kOpen) continue;
-        uint32_t bits = hp[j];
-        bool wait = false, drop = false;
-        for (uint32_t n = 1; bits != 0; n++, bits >>= 2) {
-          if (bits & 1u) {
-            const uint8_t s = st[j - n];
-            drop |= s == kPicked;
-            wait |= s == kOpen;
+      bool open_left;
+      for (;;) {
+        open_left = false;
+        bool progress = false;
+        for (uint32_t j = b + tid; j < e; j += nthr) {
+          if (st[j] != kOpen) continue;
+          uint32_t bits = hp[j];
+          bool wait = false, drop = false;
+          for (uint32_t n = 1; bits != 0; n++, bits >>= 2) {
+            if (bits & 1u) {
+              const uint8_t s = st[j - n];
+              drop |= s == kPicked;
+              wait |= s == kOpen;
+            }
+            if (bits & 2u) {
+              const uint8_t s = st[j + n];
+              drop |= s == kPicked;
+              wait |= s == kOpen;
+            }
           }
-          if (bits & 2u) {
-            const uint8_t s = st[j + n];
-            drop |= s == kPicked;
-            wait |= s == kOpen;
+          if (drop) {
+            st[j] = kDropped;
+            progress = true;
+          } else if (!wait) {
+            st[j] = kPicked;
+            plist[atomicAdd(&s_m, 1u)] = (uint16_t)j;
+            progress = true;
+          } else {
+            open_left = true;
           }
         }
-        if (drop) {
-          st[j] = kDropped;
-        } else if (!wait) {
-          st[j] = kPicked;
-          plist[atomicAdd(&s_m, 1u)] = (uint16_t)j;
-        } else {
-          open_left = true;
-        }
+#if EXTRACT_WARP_SWEEPS
+        __syncwarp();
+        if (!(__any_sync(0xffffffffu, progress) && __any_sync(0xffffffffu, open_left))) break;
+#else
+        break;
+#endif
       }
       if (!__syncthreads_or(open_left)) break;
     }

@@ -20,7 +20,13 @@ constexpr int kAssocThreads = 128;
 #endif
 constexpr int kLmThreads = LM_THREADS;
 constexpr int kLmMinBlocks = LM_MINBLOCKS;
-constexpr int kBuildThreads = 1024;
+#ifndef BUILD_THREADS
+#define BUILD_THREADS 1024
+#endif
+#ifndef BUILD_MINBLOCKS
+#define BUILD_MINBLOCKS 1
+#endif
+constexpr int kBuildThreads = BUILD_THREADS;  // one CTA per feature set (single-CTA NN build)
 constexpr int kKnnSmall = 5;     // neighbour counts up to this use the 5-slot register top-k
 constexpr int kKnnRegMax = 8;    // ... up to this the 8-slot one
 constexpr int kKnnMax = 32;      // hard limit on num_*_neighbors
