@@ -244,6 +244,22 @@ int loamgpu_odometry_device(loamgpu_ctx* ctx, const float* scans_dev, uint64_t n
                             const loamgpu_lidar_params* lidar, const loamgpu_fe_params* fe,
                             const loamgpu_reg_params* reg, double* poses_dev, int32_t* termination_dev,
                             uint32_t* iterations_dev, uint32_t* n_edge_dev, uint32_t* n_planar_dev);
+/* EXTENSION: the sequence calls on sweeps that still need de-warping.  start_T_end is
+ * [n_scans][7] (qx qy qz qw tx ty tz): the sensor motion during sweep s, e.g. the previous pair's
+ * estimate under a constant-velocity model, or an IMU / wheel-odometry prediction.  Every scan is
+ * de-warped inside the extraction kernel exactly as loamgpu_extract_dewarped does it; the feature
+ * points that reach registration are the moved points.  Same outputs as the plain calls.  (All-identity
+ * motions give bit-identical results to loamgpu_odometry_host / _device.) */
+int loamgpu_odometry_host_dewarped(loamgpu_ctx* ctx, const float* scans, uint64_t n_scans, const double* start_T_end,
+                                   const loamgpu_lidar_params* lidar, const loamgpu_fe_params* fe,
+                                   const loamgpu_reg_params* reg, double* poses, int32_t* termination,
+                                   uint32_t* iterations, uint32_t* n_edge, uint32_t* n_planar);
+int loamgpu_odometry_device_dewarped(loamgpu_ctx* ctx, const float* scans_dev, uint64_t n_scans,
+                                     const double* start_T_end_dev, const loamgpu_lidar_params* lidar,
+                                     const loamgpu_fe_params* fe, const loamgpu_reg_params* reg, double* poses_dev,
+                                     int32_t* termination_dev, uint32_t* iterations_dev, uint32_t* n_edge_dev,
+                                     uint32_t* n_planar_dev);
+
 /* pairs processed per internal chunk by the sequence / batch calls; 0 (default) = automatic: 1024 for
  * device-resident calls, 512 for asynchronous and 256 for synchronous host calls and explicit batches,
  * bounded by a share of the free device memory */

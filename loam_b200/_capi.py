@@ -27,7 +27,7 @@ SYMBOLS = [
     "loamgpu_set_chunk_pairs", "loamgpu_set_profiling", "loamgpu_kernel_times", "loamgpu_map_create",
     "loamgpu_map_destroy", "loamgpu_map_size", "loamgpu_map_update", "loamgpu_register_to_map",
     "loamgpu_extract_batch", "loamgpu_register_pairs", "loamgpu_odometry_host_async", "loamgpu_synchronize",
-    "loamgpu_extract_dewarped",
+    "loamgpu_extract_dewarped", "loamgpu_odometry_host_dewarped", "loamgpu_odometry_device_dewarped",
 ]
 KERNEL_CLASSES = ["extract", "pack", "nn_build", "knn", "lm", "misc", "fit"]
 
@@ -104,6 +104,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     lib.loamgpu_odometry_host_async.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.loamgpu_synchronize.argtypes = [vp]
     lib.loamgpu_odometry_device.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.loamgpu_odometry_host_dewarped.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.loamgpu_odometry_device_dewarped.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     _lib = lib
     return lib
 
@@ -317,8 +319,10 @@ class Context:
         return idx, cnt
 
     # ---------------------------------------------------------------- sequence odometry
-    def odometry_host(self, scans: np.ndarray, lp, fe, rp):
-        """scans: float32 [n_scans, R*P, 4] host array.  Returns poses[n-1,7], termination, iterations, n_edge, n_planar."""
+    def odometry_host(self, scans: np.ndarray, lp, fe, rp, sweep_motions=None):
+        """scans: float32 [n_scans, R*P, 4] host array.  Returns poses[n-1,7], termination, iterations, n_edge, n_planar.
+        sweep_motions: optional [n_scans, 7] start_T_end per sweep — the scans are de-warped inside the extraction
+        kernel (loamgpu_odometry_host_dewarped)."""
         s = np.ascontiguousarray(scans, dtype=np.float32)
         n = s.shape[0]
         poses = np.zeros((max(n - 1, 0), 7))
@@ -326,9 +330,17 @@ class Context:
         its = np.zeros(max(n - 1, 0), dtype=np.uint32)
         ne = np.zeros(n, dtype=np.uint32)
         npl = np.zeros(n, dtype=np.uint32)
-        self._check(self.lib.loamgpu_odometry_host(self.h, _ptr(s), n, C.addressof(lp), C.addressof(fe),
-                                                   C.addressof(rp), _ptr(poses), _ptr(term), _ptr(its), _ptr(ne),
-                                                   _ptr(npl)))
+        if sweep_motions is None:
+            self._check(self.lib.loamgpu_odometry_host(self.h, _ptr(s), n, C.addressof(lp), C.addressof(fe),
+                                                       C.addressof(rp), _ptr(poses), _ptr(term), _ptr(its), _ptr(ne),
+                                                       _ptr(npl)))
+        else:
+            m = np.ascontiguousarray(sweep_motions, dtype=np.float64)
+            if m.shape != (n, 7):
+                raise ValueError("sweep_motions must be [n_scans, 7]")
+            self._check(self.lib.loamgpu_odometry_host_dewarped(self.h, _ptr(s), n, _ptr(m), C.addressof(lp),
+                                                                C.addressof(fe), C.addressof(rp), _ptr(poses), _ptr(term),
+                                                                _ptr(its), _ptr(ne), _ptr(npl)))
         return poses, term, its, ne, npl
 
     def odometry_host_ptr(self, scans_ptr: int, n_scans: int, lp, fe, rp, poses_ptr, term_ptr, iters_ptr, ne_ptr,
@@ -352,6 +364,14 @@ class Context:
         self._check(self.lib.loamgpu_odometry_device(self.h, scans_ptr, n_scans, C.addressof(lp), C.addressof(fe),
                                                      C.addressof(rp), poses_ptr, term_ptr, iters_ptr, ne_ptr,
                                                      np_ptr))
+
+
+    def odometry_device_dewarped_ptr(self, scans_ptr: int, n_scans: int, motions_ptr: int, lp, fe, rp, poses_ptr,
+                                     term_ptr, iters_ptr, ne_ptr, np_ptr):
+        """odometry_device_ptr on sweeps de-warped in the extraction kernel; motions_ptr = device [n_scans, 7] doubles."""
+        self._check(self.lib.loamgpu_odometry_device_dewarped(self.h, scans_ptr, n_scans, motions_ptr, C.addressof(lp),
+                                                              C.addressof(fe), C.addressof(rp), poses_ptr, term_ptr,
+                                                              iters_ptr, ne_ptr, np_ptr))
 
 
 class DeviceMap:

@@ -347,13 +347,15 @@ def registerFeatures(source: LoamFeatures, target, target_T_source_init: Pose3d,
     return Pose3d._from7(pose)
 
 
-def odometry(scans, lidar_params: LidarParams, fe_params=None, reg_params=None, device: int = 0):
+def odometry(scans, lidar_params: LidarParams, fe_params=None, reg_params=None, device: int = 0, sweep_motions=None):
     """Batched extract + scan-to-scan registration over a float32 [n_scans, R*P, 4] sequence
     (the README loop of the reference, run for the whole sequence in one call).
-    Returns (poses[n-1,7] as qx qy qz qw tx ty tz, termination, iterations, n_edge, n_planar)."""
+    Returns (poses[n-1,7] as qx qy qz qw tx ty tz, termination, iterations, n_edge, n_planar).
+    sweep_motions ([n_scans, 7] start_T_end per sweep, optional): de-warp every scan inside the extraction kernel."""
     fe_params = fe_params or FeatureExtractionParams()
     reg_params = reg_params or RegistrationParams()
     try:
-        return get_context(device).odometry_host(scans, lidar_params._c, fe_params._to_c(), reg_params._to_c())
+        return get_context(device).odometry_host(scans, lidar_params._c, fe_params._to_c(), reg_params._to_c(),
+                                                 sweep_motions)
     except _capi.LoamGpuError as e:
         raise _map_error(e) from None

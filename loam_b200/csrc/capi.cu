@@ -63,7 +63,7 @@ struct loamgpu_ctx {
   DevBuf edge_idx, planar_idx, edge_pts, planar_pts, feat_counts;
   DevBuf ge_hdr, ge_nodes, ge_sorted, ge_keys, ge_aux, gp_hdr, gp_nodes, gp_sorted, gp_keys, gp_aux;
   DevBuf state, rec_p, rec_a, rec_b, nearest, nn_idx, nn_cnt, active;
-  DevBuf big_scratch, misc, out_pose, out_term, out_iters, out_ne, out_np;
+  DevBuf big_scratch, misc, motions, out_pose, out_term, out_iters, out_ne, out_np;
   DevBuf det_est, det_upd, det_assoc_n, det_lm_iters, det_lm_cost, init_pose;
 
   // optional per-kernel-class timing (CUDA events on the launching stream)
@@ -229,13 +229,15 @@ int reserve_extract(loamgpu_ctx* ctx, const ExtractPlan& pl, uint32_t n_scans, u
 int run_extract(loamgpu_ctx* ctx, const ExtractPlan& pl, const void* dev_pts, int dtype, size_t stride,
                 const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe, uint32_t n_scans, uint64_t scan0,
                 uint32_t n_slots, uint32_t* n_edge_out, uint32_t* n_planar_out, const double* motion = nullptr,
-                double* dewarp_out = nullptr) {
+                double* dewarp_out = nullptr, const double* motions_dev = nullptr) {
   ExtractArgs a;
   fill_extract_args(a, pl, dev_pts, dtype, stride, lp, fe);
-  if (motion) {  // de-warp fused into the staging loop (strided loads; the bulk copy cannot transform)
+  const bool dewarp = motion != nullptr || motions_dev != nullptr;
+  if (dewarp) {  // de-warp fused into the staging loop (strided loads; the bulk copy cannot transform)
     a.dewarp = 1;
     a.use_bulk = 0;
-    memcpy(a.motion, motion, sizeof a.motion);
+    if (motion) memcpy(a.motion, motion, sizeof a.motion);
+    a.motions = motions_dev;  // one motion per scan of this launch (device), or null: `motion` for all
     a.dewarp_out = dewarp_out;
   }
   a.ring_edge = ctx->ring_edge.as<uint32_t>();
@@ -265,6 +267,12 @@ int run_extract(loamgpu_ctx* ctx, const ExtractPlan& pl, const void* dev_pts, in
   p.feat_counts = ctx->feat_counts.as<uint32_t>();
   p.n_edge_out = n_edge_out;
   p.n_planar_out = n_planar_out;
+  if (dewarp) {
+    p.dewarp = 1;
+    p.P = pl.P;
+    memcpy(p.motion, a.motion, sizeof p.motion);
+    p.motions = motions_dev;
+  }
   TIMED(LOAMGPU_K_PACK, launch_pack(p, n_scans, ctx->stream));
   return LOAMGPU_OK;
 }
@@ -519,7 +527,7 @@ void loamgpu_destroy(loamgpu_ctx* c) {
   DevBuf* bufs[] = {&c->scan_in[0], &c->scan_in[1], &c->ring_edge, &c->ring_planar, &c->ring_counts, &c->edge_idx,
                     &c->planar_idx, &c->edge_pts, &c->planar_pts, &c->feat_counts, &c->ge_hdr, &c->ge_nodes,
                     &c->ge_sorted, &c->ge_keys, &c->ge_aux, &c->gp_hdr, &c->gp_nodes, &c->gp_sorted, &c->gp_keys, &c->gp_aux, &c->state,
-                    &c->rec_p, &c->rec_a, &c->rec_b, &c->nearest, &c->nn_idx, &c->nn_cnt, &c->active, &c->misc, &c->out_pose, &c->out_term,
+                    &c->rec_p, &c->rec_a, &c->rec_b, &c->nearest, &c->nn_idx, &c->nn_cnt, &c->active, &c->misc, &c->motions, &c->out_pose, &c->out_term,
                     &c->out_iters, &c->out_ne, &c->out_np, &c->det_est, &c->det_upd, &c->det_assoc_n,
                     &c->det_lm_iters, &c->det_lm_cost, &c->init_pose, &c->big_scratch};
   for (DevBuf* b : bufs) b->release();
@@ -1208,12 +1216,14 @@ template <typename Fetch>
 static int odometry_core(loamgpu_ctx* ctx, uint64_t n_scans, const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe,
                          const loamgpu_reg_params* reg, double* poses_dev, int32_t* term_dev, uint32_t* iters_dev,
                          uint32_t* ne_dev, uint32_t* np_dev, OdometryMode mode, uint32_t chunk, bool short_lead,
-                         Fetch fetch) {
+                         Fetch fetch, const double* motions_dev = nullptr) {
   ExtractPlan pl;
   const uint64_t n_per = lp->scan_lines * lp->points_per_line;
   int rc = plan_extract(ctx, LOAMGPU_F32, 16, n_per, lp, fe, &pl);
   if (rc) return rc;
   if (n_per == 0) return fail(ctx, LOAMGPU_ERR_INVALID, "empty scans");
+  if (motions_dev && extract_smem_bytes(LOAMGPU_F64, pl.P, pl.S) > (size_t)ctx->max_smem_optin)
+    return fail(ctx, LOAMGPU_ERR_UNSUPPORTED, "points_per_line too large for one CTA's shared memory");
   RegP rp;
   rc = make_regp(ctx, reg, &rp);
   if (rc) return rc;
@@ -1230,7 +1240,7 @@ static int odometry_core(loamgpu_ctx* ctx, uint64_t n_scans, const loamgpu_lidar
     const float* d = nullptr;
     rc = fetch(0, 1, 0, &d);
     if (rc) return rc;
-    return run_extract(ctx, pl, d, LOAMGPU_F32, 16, lp, fe, 1, 0, n_slots, ne_dev, np_dev);
+    return run_extract(ctx, pl, d, LOAMGPU_F32, 16, lp, fe, 1, 0, n_slots, ne_dev, np_dev, nullptr, nullptr, motions_dev);
   }
   const uint64_t n_pairs = n_scans - 1;
   int buf = 0;
@@ -1250,7 +1260,8 @@ static int odometry_core(loamgpu_ctx* ctx, uint64_t n_scans, const loamgpu_lidar
     const float* d = nullptr;
     rc = fetch(s0, ns, buf, &d);
     if (rc) return rc;
-    rc = run_extract(ctx, pl, d, LOAMGPU_F32, 16, lp, fe, ns, s0, n_slots, ne_dev, np_dev);
+    rc = run_extract(ctx, pl, d, LOAMGPU_F32, 16, lp, fe, ns, s0, n_slots, ne_dev, np_dev, nullptr, nullptr,
+                     motions_dev ? motions_dev + 7 * s0 : nullptr);
     if (rc) return rc;
     CU(cudaEventRecord(ctx->ev_consumed[buf], ctx->stream));
     rc = run_register(ctx, rp, np, p0, n_slots, 1, pl.capE_scan, pl.capP_scan, nullptr, false);
@@ -1264,9 +1275,10 @@ static int odometry_core(loamgpu_ctx* ctx, uint64_t n_scans, const loamgpu_lidar
 
 extern "C" {
 
-int loamgpu_odometry_device(loamgpu_ctx* ctx, const float* scans_dev, uint64_t n_scans, const loamgpu_lidar_params* lp,
-                            const loamgpu_fe_params* fe, const loamgpu_reg_params* reg, double* poses_dev,
-                            int32_t* term_dev, uint32_t* iters_dev, uint32_t* ne_dev, uint32_t* np_dev) {
+static int odometry_device_impl(loamgpu_ctx* ctx, const float* scans_dev, uint64_t n_scans, const double* motions_dev,
+                                const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe,
+                                const loamgpu_reg_params* reg, double* poses_dev, int32_t* term_dev, uint32_t* iters_dev,
+                                uint32_t* ne_dev, uint32_t* np_dev) {
   if (!ctx) return LOAMGPU_ERR_INVALID;
   if (!lp || !fe || !reg) return fail(ctx, LOAMGPU_ERR_INVALID, "null parameter struct");
   if (n_scans == 0) return LOAMGPU_OK;
@@ -1281,7 +1293,24 @@ int loamgpu_odometry_device(loamgpu_ctx* ctx, const float* scans_dev, uint64_t n
   const int rc = chunk_for(ctx, kResident, n_scans, lp, fe, reg, &chunk);
   if (rc) return rc;
   return odometry_core(ctx, n_scans, lp, fe, reg, poses_dev, term_dev, iters_dev, ne_dev, np_dev, kResident, chunk,
-                       /*short_lead=*/false, fetch);
+                       /*short_lead=*/false, fetch, motions_dev);
+}
+
+int loamgpu_odometry_device(loamgpu_ctx* ctx, const float* scans_dev, uint64_t n_scans, const loamgpu_lidar_params* lp,
+                            const loamgpu_fe_params* fe, const loamgpu_reg_params* reg, double* poses_dev,
+                            int32_t* term_dev, uint32_t* iters_dev, uint32_t* ne_dev, uint32_t* np_dev) {
+  return odometry_device_impl(ctx, scans_dev, n_scans, nullptr, lp, fe, reg, poses_dev, term_dev, iters_dev, ne_dev,
+                              np_dev);
+}
+
+int loamgpu_odometry_device_dewarped(loamgpu_ctx* ctx, const float* scans_dev, uint64_t n_scans,
+                                     const double* start_T_end_dev, const loamgpu_lidar_params* lp,
+                                     const loamgpu_fe_params* fe, const loamgpu_reg_params* reg, double* poses_dev,
+                                     int32_t* term_dev, uint32_t* iters_dev, uint32_t* ne_dev, uint32_t* np_dev) {
+  if (!ctx) return LOAMGPU_ERR_INVALID;
+  if (n_scans && !start_T_end_dev) return fail(ctx, LOAMGPU_ERR_INVALID, "null start_T_end");
+  return odometry_device_impl(ctx, scans_dev, n_scans, start_T_end_dev, lp, fe, reg, poses_dev, term_dev, iters_dev,
+                              ne_dev, np_dev);
 }
 
 int loamgpu_synchronize(loamgpu_ctx* ctx) {
@@ -1297,7 +1326,7 @@ int loamgpu_synchronize(loamgpu_ctx* ctx) {
 static int odometry_host_impl(loamgpu_ctx* ctx, OdometryMode mode, const float* scans, uint64_t n_scans,
                               const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe, const loamgpu_reg_params* reg,
                               double* poses, int32_t* termination, uint32_t* iterations, uint32_t* n_edge,
-                              uint32_t* n_planar);
+                              uint32_t* n_planar, const double* motions = nullptr);
 
 extern "C" {
 
@@ -1306,6 +1335,18 @@ int loamgpu_odometry_host(loamgpu_ctx* ctx, const float* scans, uint64_t n_scans
                           uint32_t* iterations, uint32_t* n_edge, uint32_t* n_planar) {
   const int rc = odometry_host_impl(ctx, kHostSync, scans, n_scans, lp, fe, reg, poses, termination, iterations, n_edge,
                                     n_planar);
+  if (rc) return rc;
+  return loamgpu_synchronize(ctx);
+}
+
+int loamgpu_odometry_host_dewarped(loamgpu_ctx* ctx, const float* scans, uint64_t n_scans, const double* start_T_end,
+                                   const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe,
+                                   const loamgpu_reg_params* reg, double* poses, int32_t* termination,
+                                   uint32_t* iterations, uint32_t* n_edge, uint32_t* n_planar) {
+  if (!ctx) return LOAMGPU_ERR_INVALID;
+  if (n_scans && !start_T_end) return fail(ctx, LOAMGPU_ERR_INVALID, "null start_T_end");
+  const int rc = odometry_host_impl(ctx, kHostSync, scans, n_scans, lp, fe, reg, poses, termination, iterations, n_edge,
+                                    n_planar, start_T_end);
   if (rc) return rc;
   return loamgpu_synchronize(ctx);
 }
@@ -1322,7 +1363,7 @@ int loamgpu_odometry_host_async(loamgpu_ctx* ctx, const float* scans, uint64_t n
 static int odometry_host_impl(loamgpu_ctx* ctx, OdometryMode mode, const float* scans, uint64_t n_scans,
                               const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe, const loamgpu_reg_params* reg,
                               double* poses, int32_t* termination, uint32_t* iterations, uint32_t* n_edge,
-                              uint32_t* n_planar) {
+                              uint32_t* n_planar, const double* motions) {
   if (!ctx) return LOAMGPU_ERR_INVALID;
   if (!lp || !fe || !reg) return fail(ctx, LOAMGPU_ERR_INVALID, "null parameter struct");
   if (n_scans == 0) return LOAMGPU_OK;
@@ -1345,6 +1386,14 @@ static int odometry_host_impl(loamgpu_ctx* ctx, OdometryMode mode, const float* 
   CU(ctx->out_iters.reserve(std::max<uint64_t>(n_pairs, 1) * 4));
   CU(ctx->out_ne.reserve(n_scans * 4));
   CU(ctx->out_np.reserve(n_scans * 4));
+  const double* motions_dev = nullptr;
+  if (motions) {  // per-sweep motions for the fused de-warp: small, copied ahead of the first extract
+    for (uint64_t i = 0; i < 7 * n_scans; i++)
+      if (!std::isfinite(motions[i])) return fail(ctx, LOAMGPU_ERR_INVALID, "start_T_end is not finite");
+    CU(ctx->motions.reserve(n_scans * 56));
+    CU(cudaMemcpyAsync(ctx->motions.p, motions, n_scans * 56, cudaMemcpyHostToDevice, ctx->stream));
+    motions_dev = ctx->motions.as<double>();
+  }
   // Staging buffers are guarded by per-buffer events recorded right after the extract that consumed them, so the first
   // copies of this call may overlap the registration kernels of a previous, still running call.  Other entry points
   // use the staging memory on the compute stream without those events: after one of them, wait for all of it.
@@ -1367,7 +1416,7 @@ static int odometry_host_impl(loamgpu_ctx* ctx, OdometryMode mode, const float* 
   };
   int rc = odometry_core(ctx, n_scans, lp, fe, reg, ctx->out_pose.as<double>(), ctx->out_term.as<int32_t>(),
                          ctx->out_iters.as<uint32_t>(), ctx->out_ne.as<uint32_t>(), ctx->out_np.as<uint32_t>(), mode, chunk,
-                         short_lead, fetch);
+                         short_lead, fetch, motions_dev);
   if (rc) return rc;
   if (poses && n_pairs) CU(cudaMemcpyAsync(poses, ctx->out_pose.p, n_pairs * 56, cudaMemcpyDeviceToHost, ctx->stream));
   if (termination && n_pairs)

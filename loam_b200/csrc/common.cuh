@@ -51,6 +51,34 @@ __device__ __forceinline__ V3 pose_act(const double* pose, const V3& p) {
   const V3 r = quat_rotate(pose, p);
   return V3{r.x + pose[4], r.y + pose[5], r.z + pose[6]};
 }
+// De-warp of one point of an organised scan (extension).  mq = quaternion of start_T_end on the
+// hemisphere of Identity (dewarp_hemisphere), mt = its translation; column / P is the fraction of the sweep at which
+// the point was measured.  Every operation is an IEEE + - * / sqrt in a fixed order: the CPU definition replays it bit
+// for bit, and the extraction and pack kernels both call this one function.
+__device__ __forceinline__ void dewarp_hemisphere(const double* motion, double* mq) {
+  const bool flip = motion[3] < 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) mq[i] = flip ? -motion[i] : motion[i];
+}
+__device__ __forceinline__ V3 dewarp_point(const double* mq, const double* mt, uint32_t column, uint32_t P, const V3& p) {
+  const double s = (double)column / (double)P;
+  double pose[7];
+  pose[0] = dmul(s, mq[0]);
+  pose[1] = dmul(s, mq[1]);
+  pose[2] = dmul(s, mq[2]);
+  pose[3] = dadd(dsub(1.0, s), dmul(s, mq[3]));
+  const double nn = __dsqrt_rn(
+      dadd(dadd(dadd(dmul(pose[0], pose[0]), dmul(pose[1], pose[1])), dmul(pose[2], pose[2])), dmul(pose[3], pose[3])));
+  pose[0] = __ddiv_rn(pose[0], nn);
+  pose[1] = __ddiv_rn(pose[1], nn);
+  pose[2] = __ddiv_rn(pose[2], nn);
+  pose[3] = __ddiv_rn(pose[3], nn);
+  pose[4] = dmul(s, mt[0]);
+  pose[5] = dmul(s, mt[1]);
+  pose[6] = dmul(s, mt[2]);
+  return pose_act(pose, p);
+}
+
 // Eigen quaternion product a*b with (x,y,z,w) storage
 __device__ __forceinline__ void quat_mul(const double* a, const double* b, double* o) {
   const double w = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];

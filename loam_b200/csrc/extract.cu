@@ -77,39 +77,21 @@ __global__ void __launch_bounds__(kExtractThreads) extract_ring_kernel(ExtractAr
     }
     mbar_wait(bar, 0);
   } else {
-    double mq[4] = {0.0, 0.0, 0.0, 1.0};
+    double mq[4] = {0.0, 0.0, 0.0, 1.0}, mt[3] = {0.0, 0.0, 0.0};
     if constexpr (kDewarp) {
-      mq[0] = a.motion[0];
-      mq[1] = a.motion[1];
-      mq[2] = a.motion[2];
-      mq[3] = a.motion[3];
-      if (mq[3] < 0.0) {  // hemisphere of Identity
-        mq[0] = -mq[0];
-        mq[1] = -mq[1];
-        mq[2] = -mq[2];
-        mq[3] = -mq[3];
-      }
+      double mo[7];
+#pragma unroll
+      for (int i = 0; i < 7; i++) mo[i] = a.motions ? a.motions[(size_t)scan * 7 + i] : a.motion[i];
+      dewarp_hemisphere(mo, mq);
+      mt[0] = mo[4];
+      mt[1] = mo[5];
+      mt[2] = mo[6];
     }
     for (uint32_t j = tid; j < P; j += nthr) {
       const TIn* src = reinterpret_cast<const TIn*>(ring_src + (size_t)j * a.stride);
       T x = (T)src[0], y = (T)src[1], z = (T)src[2];
-      if constexpr (kDewarp) {  // operation order fixed, DESIGN.md §5c: the tests replay it on the CPU
-        const double s = (double)j / (double)P;
-        double pose[7];
-        pose[0] = dmul(s, mq[0]);
-        pose[1] = dmul(s, mq[1]);
-        pose[2] = dmul(s, mq[2]);
-        pose[3] = dadd(dsub(1.0, s), dmul(s, mq[3]));
-        const double nn = __dsqrt_rn(dadd(dadd(dadd(dmul(pose[0], pose[0]), dmul(pose[1], pose[1])), dmul(pose[2], pose[2])),
-                                          dmul(pose[3], pose[3])));
-        pose[0] = __ddiv_rn(pose[0], nn);
-        pose[1] = __ddiv_rn(pose[1], nn);
-        pose[2] = __ddiv_rn(pose[2], nn);
-        pose[3] = __ddiv_rn(pose[3], nn);
-        pose[4] = dmul(s, a.motion[4]);
-        pose[5] = dmul(s, a.motion[5]);
-        pose[6] = dmul(s, a.motion[6]);
-        const V3 m = pose_act(pose, V3{(double)x, (double)y, (double)z});
+      if constexpr (kDewarp) {
+        const V3 m = dewarp_point(mq, mt, j, P, V3{(double)x, (double)y, (double)z});
         x = (T)m.x;
         y = (T)m.y;
         z = (T)m.z;
@@ -339,6 +321,16 @@ __global__ void __launch_bounds__(256) pack_features_kernel(PackArgs a) {
   }
   __syncthreads();
   const unsigned char* base = a.pts + (size_t)scan * a.scan_stride_bytes;
+  double mq[4] = {0.0, 0.0, 0.0, 1.0}, mt[3] = {0.0, 0.0, 0.0};
+  if (a.dewarp) {
+    double mo[7];
+#pragma unroll
+    for (int i = 0; i < 7; i++) mo[i] = a.motions ? a.motions[(size_t)scan * 7 + i] : a.motion[i];
+    dewarp_hemisphere(mo, mq);
+    mt[0] = mo[4];
+    mt[1] = mo[5];
+    mt[2] = mo[6];
+  }
   for (uint32_t r = 0; r < R; r++) {
     for (int kind = 0; kind < 2; kind++) {
       const uint32_t n = offs[2 * (r + 1) + kind] - offs[2 * r + kind];
@@ -358,6 +350,10 @@ __global__ void __launch_bounds__(256) pack_features_kernel(PackArgs a) {
         } else {
           const double* d = reinterpret_cast<const double*>(rec);
           v = make_double4(d[0], d[1], d[2], 0.0);
+        }
+        if (a.dewarp) {  // the feature points of a de-warped extraction are the moved points
+          const V3 m = dewarp_point(mq, mt, id % a.P, a.P, V3{v.x, v.y, v.z});
+          v = make_double4(m.x, m.y, m.z, 0.0);
         }
         dst_pt[i] = v;
       }

@@ -49,7 +49,8 @@ struct ExtractArgs {
   // de-warp fused into the ring staging (extension): every point is moved into the frame of the sweep start by
   // interp(Identity, motion, column / P) before anything else looks at it
   int dewarp;
-  double motion[7];             // start_T_end: qx qy qz qw tx ty tz
+  double motion[7];             // start_T_end: qx qy qz qw tx ty tz (one motion for every scan of the launch)
+  const double* motions;        // or: device [scan][7], one motion per scan of the launch (overrides `motion`)
   double* dewarp_out;           // optional [scan][R*P][3] de-warped points
 };
 
@@ -72,6 +73,11 @@ struct PackArgs {
   uint32_t* feat_counts;        // [slot][2]
   uint32_t* n_edge_out;         // optional [global scan] feature counts for the caller
   uint32_t* n_planar_out;
+  // de-warped extraction: the gathered feature points are the moved points (same arithmetic as the extract kernel)
+  int dewarp;
+  uint32_t P;
+  double motion[7];
+  const double* motions;        // device [scan][7] or null (then `motion`)
 };
 
 size_t extract_smem_bytes(int dtype, uint32_t P, uint32_t S);

@@ -110,3 +110,45 @@ def test_dewarped_sweep_registers_onto_a_static_view(ctx):
     raw = L.registerFeatures(L.extractFeatures(moving, lpp), tgt, L.Pose3d.Identity())._to7()
     assert H.angular_distance(est[:4], ident[:4]) < 2e-3 and np.linalg.norm(est[4:]) < 1e-2, est
     assert H.angular_distance(raw[:4], ident[:4]) > 1e-2 and np.linalg.norm(raw[4:]) > 0.1, raw
+
+
+def test_sequence_with_per_sweep_motions_matches_oracle(ctx, oracle):
+    """loamgpu_odometry_host_dewarped: every scan de-warped with its own motion inside the extraction kernel, the moved
+    points carried to registration by the pack kernel.  Checked against the CPU chain orc_dewarp -> extract -> register."""
+    R, P, n = 32, 1024, 5
+    lp, fe, rp = LidarParams(R, P, 1.0, 120.0), FeParams.default(), RegParams.default()
+    motions = np.stack([synth.relative_pose(k, k + 1) for k in range(n)])
+    motions[2, :4] = -motions[2, :4]  # one on the far hemisphere
+    scans = np.stack([synth.make_warped_scan(R, P, k, synth.relative_pose(k, k + 1), sigma=0.01) for k in range(n)])
+    poses, term, its, ne, npl = ctx.odometry_host(scans, H.to_capi(lp), H.to_capi(fe), H.to_capi(rp), sweep_motions=motions)
+    feats = []
+    for k in range(n):
+        moved = oracle.dewarp(scans[k][:, :3].astype(np.float64), P, motions[k])
+        e, p = oracle.extract(moved, lp, fe)
+        assert ne[k] == len(e) and npl[k] == len(p), k
+        ge, gp, gm = ctx.extract_dewarped(scans[k], H.to_capi(lp), H.to_capi(fe), motions[k])
+        assert np.array_equal(ge, e) and np.array_equal(gp, p) and np.array_equal(gm, moved)
+        feats.append((moved[e], moved[p]))
+    for k in range(n - 1):
+        ref = oracle.register(feats[k + 1][0], feats[k + 1][1], feats[k][0], feats[k][1], None, rp)
+        assert H.angular_distance(ref[:4], poses[k][:4]) < 1e-6, k
+        assert np.abs(ref[4:] - poses[k][4:]).max() < 1e-5, k
+    # the single-pair path fed with the moved points the single-scan call returns agrees with the sequence call
+    one = ctx.register(feats[1][0], feats[1][1], feats[0][0], feats[0][1], [0, 0, 0, 1, 0, 0, 0], H.to_capi(rp))
+    assert H.angular_distance(one[:4], poses[0][:4]) < 1e-9 and np.abs(one[4:] - poses[0][4:]).max() < 1e-9
+
+
+def test_sequence_identity_motions_bit_identical_to_plain(ctx):
+    R, P, n = 16, 1800, 4
+    lp, fe, rp = LidarParams(R, P, 1.0, 120.0), FeParams.default(), RegParams.default()
+    scans = np.stack([synth.make_scan(R, P, k=k) for k in range(n)])
+    a = ctx.odometry_host(scans, H.to_capi(lp), H.to_capi(fe), H.to_capi(rp))
+    ident = np.tile(np.r_[0, 0, 0, 1.0, 0, 0, 0], (n, 1))
+    b = ctx.odometry_host(scans, H.to_capi(lp), H.to_capi(fe), H.to_capi(rp), sweep_motions=ident)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    with pytest.raises(_capi.LoamGpuError) as ei:
+        bad = ident.copy()
+        bad[1, 5] = np.inf
+        ctx.odometry_host(scans, H.to_capi(lp), H.to_capi(fe), H.to_capi(rp), sweep_motions=bad)
+    assert ei.value.code == _capi.ERR_INVALID
