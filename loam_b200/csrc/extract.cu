@@ -49,8 +49,8 @@ __host__ __device__ inline uint32_t rng_doubles(uint32_t P) {
 // T = scalar type of the staged ring (what the arithmetic widens from), TIn = scalar type of the caller's records.
 // They differ only for de-warping float input: the moved points are not float-representable, so the ring is staged
 // as doubles.
-template <typename T, typename TIn = T, bool kDewarp = false>
-__global__ void __launch_bounds__(kExtractThreads) extract_ring_kernel(ExtractArgs a) {
+template <typename T, typename TIn, bool kDewarp>
+__device__ __forceinline__ void extract_ring_body(const ExtractArgs& a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t P = a.P, N = a.N, S = a.S;
   const uint32_t ring = blockIdx.x, scan = blockIdx.y;
@@ -297,9 +297,22 @@ __global__ void __launch_bounds__(kExtractThreads) extract_ring_kernel(ExtractAr
   }
 }
 
+// The plain kernels (what every throughput path runs) and the de-warping ones are separate entry points so that the
+// register budget of one never shapes the other: plain 37-40 registers / 6 CTAs per SM; de-warping (24-byte staging
+// records, 41 KB of shared memory per 1024-column ring) capped for 5.
+template <typename T>
+__global__ void __launch_bounds__(kExtractThreads) extract_ring_kernel(ExtractArgs a) {
+  extract_ring_body<T, T, false>(a);
+}
+template <typename TIn>
+__global__ void __launch_bounds__(kExtractThreads, 5) extract_ring_dewarp_kernel(ExtractArgs a) {
+  extract_ring_body<double, TIn, true>(a);
+}
+
 // Pack per-ring pick lists into the scan-level feature arrays (reference output order:
 // line-major, sector-major, selection order) and gather the widened feature points
 // (featuresToEigen, features.h:188-198).  One CTA per scan.
+template <bool kDewarp>
 __global__ void __launch_bounds__(256) pack_features_kernel(PackArgs a) {
   extern __shared__ uint32_t offs[];  // [R+1][2]
   const uint32_t scan = blockIdx.x, R = a.R;
@@ -322,7 +335,7 @@ __global__ void __launch_bounds__(256) pack_features_kernel(PackArgs a) {
   __syncthreads();
   const unsigned char* base = a.pts + (size_t)scan * a.scan_stride_bytes;
   double mq[4] = {0.0, 0.0, 0.0, 1.0}, mt[3] = {0.0, 0.0, 0.0};
-  if (a.dewarp) {
+  if constexpr (kDewarp) {
     double mo[7];
 #pragma unroll
     for (int i = 0; i < 7; i++) mo[i] = a.motions ? a.motions[(size_t)scan * 7 + i] : a.motion[i];
@@ -351,7 +364,7 @@ __global__ void __launch_bounds__(256) pack_features_kernel(PackArgs a) {
           const double* d = reinterpret_cast<const double*>(rec);
           v = make_double4(d[0], d[1], d[2], 0.0);
         }
-        if (a.dewarp) {  // the feature points of a de-warped extraction are the moved points
+        if constexpr (kDewarp) {  // the feature points of a de-warped extraction are the moved points
           const V3 m = dewarp_point(mq, mt, id % a.P, a.P, V3{v.x, v.y, v.z});
           v = make_double4(m.x, m.y, m.z, 0.0);
         }
@@ -376,13 +389,13 @@ cudaError_t launch_extract(const ExtractArgs& a, uint32_t n_scans, cudaStream_t 
   cudaError_t err;
   if (a.dewarp) {  // double staging whatever the input type; strided loads (use_bulk is off)
     if (a.dtype == LOAMGPU_F32) {
-      err = cudaFuncSetAttribute(extract_ring_kernel<double, float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      err = cudaFuncSetAttribute(extract_ring_dewarp_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (err != cudaSuccess) return err;
-      extract_ring_kernel<double, float, true><<<grid, kExtractThreads, smem, st>>>(a);
+      extract_ring_dewarp_kernel<float><<<grid, kExtractThreads, smem, st>>>(a);
     } else {
-      err = cudaFuncSetAttribute(extract_ring_kernel<double, double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      err = cudaFuncSetAttribute(extract_ring_dewarp_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (err != cudaSuccess) return err;
-      extract_ring_kernel<double, double, true><<<grid, kExtractThreads, smem, st>>>(a);
+      extract_ring_dewarp_kernel<double><<<grid, kExtractThreads, smem, st>>>(a);
     }
     return cudaGetLastError();
   }
@@ -399,7 +412,10 @@ cudaError_t launch_extract(const ExtractArgs& a, uint32_t n_scans, cudaStream_t 
 }
 
 cudaError_t launch_pack(const PackArgs& a, uint32_t n_scans, cudaStream_t st) {
-  pack_features_kernel<<<n_scans, 256, (size_t)(a.R + 1) * 2 * sizeof(uint32_t), st>>>(a);
+  if (a.dewarp)
+    pack_features_kernel<true><<<n_scans, 256, (size_t)(a.R + 1) * 2 * sizeof(uint32_t), st>>>(a);
+  else
+    pack_features_kernel<false><<<n_scans, 256, (size_t)(a.R + 1) * 2 * sizeof(uint32_t), st>>>(a);
   return cudaGetLastError();
 }
 
