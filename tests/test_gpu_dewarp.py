@@ -152,3 +152,14 @@ def test_sequence_identity_motions_bit_identical_to_plain(ctx):
         bad[1, 5] = np.inf
         ctx.odometry_host(scans, H.to_capi(lp), H.to_capi(fe), H.to_capi(rp), sweep_motions=bad)
     assert ei.value.code == _capi.ERR_INVALID
+
+
+def test_golden_fixture_from_real_reference(ctx):
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "dewarp_golden.npz"))
+    for n in sorted({k.split("/")[0] for k in g.files}):
+        R, P = (int(v) for v in g[n + "/shape"])
+        lp, fe = LidarParams(R, P, 1.0, 120.0), FeParams.default()
+        e, p, moved = ctx.extract_dewarped(np.ascontiguousarray(g[n + "/scan"]), H.to_capi(lp), H.to_capi(fe), g[n + "/motion"])
+        assert np.array_equal(moved, g[n + "/moved"]), n
+        assert np.array_equal(e, g[n + "/edge"]) and np.array_equal(p, g[n + "/planar"]), n
