@@ -239,6 +239,7 @@ __global__ void __launch_bounds__(kBuildThreads, BUILD_MINBLOCKS) bvh_build_kern
     if (first == split) w |= kLeftLeaf;
     if (last == split + 1) w |= kRightLeaf;
     nodes[i].split = w;
+    nodes[i].pad = (uint32_t)j;  // the other end of the node's key range [min(i, j), max(i, j)]
     arrived[i] = 0;
   }
   __syncthreads();
@@ -316,6 +317,69 @@ __global__ void __launch_bounds__(kBuildThreads, BUILD_MINBLOCKS) bvh_build_kern
       if (!__syncthreads_or(pending)) break;
     }
   }
+}
+
+// ============================================================================ 4-wide collapse (KNN_WIDE4)
+
+// Box of the subtree [f, l] of one set: a single point is rounded outward like the build does, any other subtree is
+// the node that covers it (`idx`: node s for a left child, s + 1 for a right child — Karras' numbering).
+__device__ __forceinline__ void subtree_box(const BvhNode* __restrict__ nodes, const double4* __restrict__ sorted,
+                                            uint32_t f, uint32_t l, uint32_t idx, float* b) {
+  if (f == l) {
+    const double4 pt = sorted[f];
+    b[0] = __double2float_rd(pt.x); b[1] = __double2float_rd(pt.y); b[2] = __double2float_rd(pt.z);
+    b[3] = __double2float_ru(pt.x); b[4] = __double2float_ru(pt.y); b[5] = __double2float_ru(pt.z);
+  } else {
+    const float4* q = reinterpret_cast<const float4*>(nodes + idx);
+    const float4 va = q[0], vb = q[1];
+    b[0] = va.x; b[1] = va.y; b[2] = va.z;
+    b[3] = vb.x; b[4] = vb.y; b[5] = vb.z;
+  }
+}
+
+// One thread per internal node, after the build kernel of the same sets has finished (next launch on the stream).
+__global__ void __launch_bounds__(256) bvh_widen_kernel(BvhSetArrays g) {
+  const uint32_t set = blockIdx.y;
+  const uint32_t n = g.hdr[set].n;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < 2 || i + 1 >= n) return;
+  const BvhNode* nodes = g.nodes + (size_t)set * g.pt_cap;
+  const double4* sorted = g.sorted + (size_t)set * g.pt_cap;
+  const uint32_t other = nodes[i].pad;
+  const uint32_t first = min(i, other), last = max(i, other);
+  if (last - first < (uint32_t)kBvhLeaf) return;  // scanned as a leaf: its record is never read
+  const uint32_t s = nodes[i].split & kSplitMask;
+  BvhWide w;
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    w.box[c][0] = w.box[c][1] = w.box[c][2] = CUDART_INF_F;
+    w.box[c][3] = w.box[c][4] = w.box[c][5] = -CUDART_INF_F;
+  }
+  w.s = s;
+  w.sl = w.sr = 0;
+#pragma unroll
+  for (int k = 0; k < 5; k++) w.pad[k] = 0;
+  // side L = [first, s] (node s), side R = [s + 1, last] (node s + 1)
+  if (s - first < (uint32_t)kBvhLeaf) {
+    subtree_box(nodes, sorted, first, s, s, w.box[0]);
+  } else {
+    const uint32_t sl = nodes[s].split & kSplitMask;
+    w.sl = sl;
+    subtree_box(nodes, sorted, first, sl, sl, w.box[0]);
+    subtree_box(nodes, sorted, sl + 1, s, sl + 1, w.box[1]);
+  }
+  if (last - (s + 1) < (uint32_t)kBvhLeaf) {
+    subtree_box(nodes, sorted, s + 1, last, s + 1, w.box[2]);
+  } else {
+    const uint32_t sr = nodes[s + 1].split & kSplitMask;
+    w.sr = sr;
+    subtree_box(nodes, sorted, s + 1, sr, sr, w.box[2]);
+    subtree_box(nodes, sorted, sr + 1, last, sr + 1, w.box[3]);
+  }
+  uint4* dst = reinterpret_cast<uint4*>(g.wide + (size_t)set * g.pt_cap + i);
+  const uint4* src = reinterpret_cast<const uint4*>(&w);
+#pragma unroll
+  for (int k = 0; k < 8; k++) dst[k] = src[k];
 }
 
 // ============================================================================ exact k-NN (K4)
@@ -426,6 +490,7 @@ __device__ __forceinline__ double4 load_point(const double4* __restrict__ p) {
 // the exact test afterwards).  A subtree is skipped only when its box lower bound is STRICTLY above the current k-th
 // best (or the radius cut), so candidates that tie the k-th distance are still seen and resolved by index.
 constexpr int kBvhStack = 64;  // >= tree depth: 30 Morton bits + 32 position bits for duplicate codes
+constexpr int kBvhStackWide = 96;  // 4-wide walk: up to 3 pending subtrees per step, 31 steps deep
 
 template <int K>
 __device__ __forceinline__ void knn_bvh(const BvhHdr& h, const BvhNode* __restrict__ nodes,
@@ -524,6 +589,127 @@ __device__ __forceinline__ void knn_bvh(const BvhHdr& h, const BvhNode* __restri
     }
     if (!at_leaf) break;  // done
     // ---- leaf: fp64 distances in nanoflann's L2_Simple order, branch-free insertion
+#pragma unroll
+    for (int j = 0; j < kBvhLeaf; j++) {
+      const uint32_t p = first + j;
+      const double4 t = load_point(sorted + min(p, last));
+      double d2 = sqdist(qx, qy, qz, t.x, t.y, t.z);
+      uint32_t id = (uint32_t)__double_as_longlong(t.w);
+      const bool ok = p <= last && d2 <= d2_cut;
+      d2 = ok ? d2 : CUDART_INF;
+      id = ok ? id : 0xFFFFFFFFu;
+      tk.insert(d2, id);
+    }
+    bound = __double2float_ru(fmin(tk.kth(k), d2_cut));
+    have = false;
+  }
+}
+
+// Lower bound for one slot of a wide record (6 floats: lo xyz, hi xyz); empty slots (lo = +inf) give +inf.
+__device__ __forceinline__ float slot_lower_bound(const float* b, const QueryF& q) {
+  float s = 0.f;
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    const float g = fmax3_nonneg(__fsub_rd(b[d], q.hi[d]), __fsub_rd(q.lo[d], b[3 + d]));
+    s = __fmaf_rd(g, g, s);
+  }
+  return s;
+}
+
+// The same search over the 4-wide records: a pending subtree is (node index, first, last, lower bound); one step loads
+// ONE 128-byte record and decides two levels.  Near-first order as in the binary walk: the side whose nearer slot is
+// closer is entered, its farther slot and the other side's two slots stay pending (nearest on top of the stack).
+// Pruning is the same conservative strict test, leaves are scanned by the same code: results are identical.
+template <int K>
+__device__ __forceinline__ void knn_bvh_wide(const BvhHdr& h, const BvhNode* __restrict__ nodes,
+                                             const BvhWide* __restrict__ wide, const double4* __restrict__ sorted,
+                                             double qx, double qy, double qz, int k, double max_dist, TopK<K>& tk,
+                                             double d2_hint) {
+  tk.init();
+  if (h.n == 0) return;
+  const double d2_cut = fmin(max_dist > 0 ? max_dist * max_dist * (1.0 + 1e-12) : CUDART_INF, d2_hint);
+  QueryF q;
+  q.lo[0] = __double2float_rd(qx); q.hi[0] = __double2float_ru(qx);
+  q.lo[1] = __double2float_rd(qy); q.hi[1] = __double2float_ru(qy);
+  q.lo[2] = __double2float_rd(qz); q.hi[2] = __double2float_ru(qz);
+  float bound = __double2float_ru(d2_cut);
+  uint4 st[kBvhStackWide];  // (node index, first, last, lower bound)
+  int sp = 0;
+  uint32_t first = 0, last = h.n - 1, idx = 0;
+  bool have = true, done = false;
+  if (h.n > (uint32_t)kBvhLeaf) {
+    const BvhNode root = load_node(nodes);
+    if (box_lower_bound(root, q) > bound) return;
+  }
+  while (true) {
+    bool at_leaf = false;
+    while (!done && !at_leaf) {
+      if (!have) {
+        if (sp == 0) {
+          done = true;
+        } else {
+          --sp;
+          const uint4 e = st[sp];
+          if (__uint_as_float(e.w) <= bound) {
+            idx = e.x;
+            first = e.y;
+            last = e.z;
+            have = true;
+          }
+        }
+      } else if (last - first < (uint32_t)kBvhLeaf) {
+        at_leaf = true;
+      } else {
+        const uint4* rp = reinterpret_cast<const uint4*>(wide + idx);
+        uint4 r[7];  // 6 words of boxes + (s, sl, sr)
+#pragma unroll
+        for (int j = 0; j < 7; j++) r[j] = __ldg(rp + j);
+        float bx[24];
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+          bx[4 * j + 0] = __uint_as_float(r[j].x);
+          bx[4 * j + 1] = __uint_as_float(r[j].y);
+          bx[4 * j + 2] = __uint_as_float(r[j].z);
+          bx[4 * j + 3] = __uint_as_float(r[j].w);
+        }
+        const uint32_t s = r[6].x, sl = r[6].y, sr = r[6].z;
+        const bool l_leaf = s - first < (uint32_t)kBvhLeaf, r_leaf = last - (s + 1) < (uint32_t)kBvhLeaf;
+        // slot c: range [cf[c], cl[c]], node index ci[c] (unused for leaf-sized ranges and empty slots)
+        const uint32_t cf0 = first, cl0 = l_leaf ? s : sl, ci0 = sl;
+        const uint32_t cf1 = sl + 1, cl1 = s, ci1 = sl + 1;
+        const uint32_t cf2 = s + 1, cl2 = r_leaf ? last : sr, ci2 = sr;
+        const uint32_t cf3 = sr + 1, cl3 = last, ci3 = sr + 1;
+        // a side that is one leaf has no second slot: NaN fails every "<= bound" test and never sorts first
+        const float kNoSlot = __int_as_float(0x7FFFFFFF);
+        const float d0 = slot_lower_bound(bx + 0, q), d1 = l_leaf ? kNoSlot : slot_lower_bound(bx + 6, q);
+        const float d2 = slot_lower_bound(bx + 12, q), d3 = r_leaf ? kNoSlot : slot_lower_bound(bx + 18, q);
+        // order inside each side, then the sides by their nearer slot
+        const bool sw_l = d1 < d0, sw_r = d3 < d2;
+        const float ln = sw_l ? d1 : d0, lf = sw_l ? d0 : d1, rn = sw_r ? d3 : d2, rf = sw_r ? d2 : d3;
+        const uint4 e_ln = sw_l ? make_uint4(ci1, cf1, cl1, __float_as_uint(d1)) : make_uint4(ci0, cf0, cl0, __float_as_uint(d0));
+        const uint4 e_lf = sw_l ? make_uint4(ci0, cf0, cl0, __float_as_uint(d0)) : make_uint4(ci1, cf1, cl1, __float_as_uint(d1));
+        const uint4 e_rn = sw_r ? make_uint4(ci3, cf3, cl3, __float_as_uint(d3)) : make_uint4(ci2, cf2, cl2, __float_as_uint(d2));
+        const uint4 e_rf = sw_r ? make_uint4(ci2, cf2, cl2, __float_as_uint(d2)) : make_uint4(ci3, cf3, cl3, __float_as_uint(d3));
+        const bool right_side = rn < ln;
+        const uint4 near_n = right_side ? e_rn : e_ln, near_f = right_side ? e_rf : e_lf;
+        const uint4 far_n = right_side ? e_ln : e_rn, far_f = right_side ? e_lf : e_rf;
+        const float d_near_f = right_side ? rf : lf, d_far_n = right_side ? ln : rn, d_far_f = right_side ? lf : rf;
+        const float d_near_n = right_side ? rn : ln;
+        // pending subtrees, farthest first (the far side's slots are ordered; the near side's far slot may be
+        // farther than the far side's near slot: the stack order is a heuristic, pops re-test the bound anyway)
+        if (d_far_f <= bound) st[sp++] = far_f;
+        if (d_far_n <= bound) st[sp++] = far_n;
+        if (d_near_f <= bound) st[sp++] = near_f;
+        if (d_near_n <= bound) {
+          idx = near_n.x;
+          first = near_n.y;
+          last = near_n.z;
+        } else {
+          have = false;
+        }
+      }
+    }
+    if (!at_leaf) break;  // done
 #pragma unroll
     for (int j = 0; j < kBvhLeaf; j++) {
       const uint32_t p = first + j;

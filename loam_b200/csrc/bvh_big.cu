@@ -264,6 +264,7 @@ __global__ void __launch_bounds__(256) big_topology_kernel(const uint32_t* __res
   if (first == split) w |= kLeftLeaf; else parent[split] = (uint32_t)i;
   if (last == split + 1) w |= kRightLeaf; else parent[split + 1] = (uint32_t)i;
   nodes[i].split = w;
+  nodes[i].pad = (uint32_t)j;  // the other end of the node's key range
   counter[i] = 0;
   if (i == 0) parent[0] = 0xFFFFFFFFu;
 }

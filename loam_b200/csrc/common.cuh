@@ -138,6 +138,17 @@ struct BvhHdr {
   uint32_t n;  // points
   uint32_t pad[3];
 };
+// 4-wide collapse of the radix tree (KNN_WIDE4): the record of internal node i holds the boxes of the subtrees two
+// levels below it, so ONE dependent 128-byte load decides two levels of the descent (tools/sim_bvh.py: 18.1 -> 8.8
+// dependent loads per query on a 14k-point planar set, box tests 35 -> 32).  Node i covers [first, last]; its children
+// are L = [first, s] (node s) and R = [s + 1, last] (node s + 1).  A child of at most kBvhLeaf points is scanned as a
+// leaf and keeps ONE slot (its own box; the second slot of its side is empty: lo = +inf); otherwise its two slots are
+// its children [.., sl] (node sl) and [sl + 1, ..] (node sl + 1) — likewise sr for R.
+struct __align__(128) BvhWide {
+  float box[4][6];   // slot c: lo xyz, hi xyz (rounded outward); slots 0,1 = side L, slots 2,3 = side R
+  uint32_t s, sl, sr;
+  uint32_t pad[5];
+};
 struct __align__(32) BvhNode {
   float lo[3];
   uint32_t split;  // split position | kLeftLeaf | kRightLeaf

@@ -26,6 +26,9 @@ constexpr int kLmMinBlocks = LM_MINBLOCKS;
 #ifndef BUILD_MINBLOCKS
 #define BUILD_MINBLOCKS 1
 #endif
+#ifndef KNN_WIDE4
+#define KNN_WIDE4 0
+#endif
 constexpr int kBuildThreads = BUILD_THREADS;  // one CTA per feature set (single-CTA NN build)
 constexpr int kKnnSmall = 5;     // neighbour counts up to this use the 5-slot register top-k
 constexpr int kKnnRegMax = 8;    // ... up to this the 8-slot one
@@ -92,6 +95,7 @@ struct BvhSetArrays {
   uint2* keys;        // [n_sets][2][pt_cap]  radix-sort ping-pong scratch: (morton, original index)
   int* aux;           // [n_sets][pt_cap]     build scratch: per-node readiness
   uint32_t pt_cap;
+  BvhWide* wide;      // [n_sets][pt_cap]     optional 4-wide records (null: binary traversal only)
 };
 
 // Build NN structures for `n_sets` point sets.  Set s reads points

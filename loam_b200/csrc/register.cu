@@ -393,7 +393,7 @@ __device__ __forceinline__ uint32_t active_count(const uint32_t* active, uint32_
 }
 __device__ __forceinline__ uint32_t active_pair(const uint32_t* active, uint32_t i) { return active ? active[1 + i] : i; }
 
-template <int K>
+template <int K, bool kWide>
 __device__ __forceinline__ void assoc_knn_pair(const AssocArgs& a, int outer_iter, uint32_t pair) {
   const PairState* ps = a.state + pair;
   if (ps->status != -1) return;
@@ -443,8 +443,12 @@ __device__ __forceinline__ void assoc_knn_pair(const AssocArgs& a, int outer_ite
     d2_hint = worst;
   }
   TopK<K> tk;
-  knn_bvh<K>(g, gt.nodes + (size_t)tset * gt.pt_cap, gt.sorted + (size_t)tset * gt.pt_cap, q.x, q.y, q.z, k, md, tk,
-             d2_hint);
+  if constexpr (kWide)
+    knn_bvh_wide<K>(g, gt.nodes + (size_t)tset * gt.pt_cap, gt.wide + (size_t)tset * gt.pt_cap,
+                    gt.sorted + (size_t)tset * gt.pt_cap, q.x, q.y, q.z, k, md, tk, d2_hint);
+  else
+    knn_bvh<K>(g, gt.nodes + (size_t)tset * gt.pt_cap, gt.sorted + (size_t)tset * gt.pt_cap, q.x, q.y, q.z, k, md, tk,
+               d2_hint);
   const int m = radius_count(tk, k, md);
   a.rec_p[rec] = make_double4(q.x, q.y, q.z, 0.0);
   a.nn_cnt[rec] = (uint32_t)m;
@@ -453,10 +457,11 @@ __device__ __forceinline__ void assoc_knn_pair(const AssocArgs& a, int outer_ite
     if (j < k) out[j] = tk.id[j];
 }
 
-template <int K>
+template <int K, bool kWide>
 __global__ void __launch_bounds__(kKnnThreads, KNN_MINBLOCKS) assoc_knn_kernel(AssocArgs a, int outer_iter) {
   const uint32_t n_act = active_count(a.active, a.n_pairs);
-  for (uint32_t i = blockIdx.y; i < n_act; i += gridDim.y) assoc_knn_pair<K>(a, outer_iter, active_pair(a.active, i));
+  for (uint32_t i = blockIdx.y; i < n_act; i += gridDim.y)
+    assoc_knn_pair<K, kWide>(a, outer_iter, active_pair(a.active, i));
 }
 
 // K5: line / plane fit + guards for every source feature (associateEdges/associatePlanes, registration.cpp:39-57,
@@ -1235,6 +1240,9 @@ cudaError_t launch_bvh_build(const BvhBuildArgs& a_in, uint32_t n_sets, cudaStre
   cudaError_t err = cudaFuncSetAttribute(bvh_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
   bvh_build_kernel<<<n_sets, kBuildThreads, smem, st>>>(a);
+  err = cudaGetLastError();
+  if (err != cudaSuccess || a.g.wide == nullptr) return err;
+  bvh_widen_kernel<<<dim3((a.g.pt_cap + 255) / 256, n_sets), 256, 0, st>>>(a.g);
   return cudaGetLastError();
 }
 
@@ -1249,12 +1257,21 @@ cudaError_t launch_assoc_knn(const AssocArgs& a, uint32_t n_pairs, int outer_ite
   const uint32_t cap = a.capE_scan + a.capP_scan;
   dim3 grid((cap + kKnnThreads - 1) / kKnnThreads, pair_rows(n_pairs, outer_iter, a.active != nullptr, 16));
   const int kmax = a.rp.ke > a.rp.kp ? a.rp.ke : a.rp.kp;
-  if (kmax <= kKnnSmall)
-    assoc_knn_kernel<kKnnSmall><<<grid, kKnnThreads, 0, st>>>(a, outer_iter);
-  else if (kmax <= kKnnRegMax)
-    assoc_knn_kernel<kKnnRegMax><<<grid, kKnnThreads, 0, st>>>(a, outer_iter);
-  else
-    assoc_knn_kernel<kKnnMax><<<grid, kKnnThreads, 0, st>>>(a, outer_iter);
+  // 4-wide records exist for the sets this context builds itself (not for device-resident map targets)
+  const bool wide = !a.ext_target && a.ge.wide != nullptr && a.gp.wide != nullptr;
+  if (kmax <= kKnnSmall) {
+    if (wide)
+      assoc_knn_kernel<kKnnSmall, true><<<grid, kKnnThreads, 0, st>>>(a, outer_iter);
+    else
+      assoc_knn_kernel<kKnnSmall, false><<<grid, kKnnThreads, 0, st>>>(a, outer_iter);
+  } else if (kmax <= kKnnRegMax) {
+    if (wide)
+      assoc_knn_kernel<kKnnRegMax, true><<<grid, kKnnThreads, 0, st>>>(a, outer_iter);
+    else
+      assoc_knn_kernel<kKnnRegMax, false><<<grid, kKnnThreads, 0, st>>>(a, outer_iter);
+  } else {
+    assoc_knn_kernel<kKnnMax, false><<<grid, kKnnThreads, 0, st>>>(a, outer_iter);
+  }
   return cudaGetLastError();
 }
 
