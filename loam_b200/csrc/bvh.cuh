@@ -454,6 +454,9 @@ __device__ __forceinline__ float box_lower_bound(const BvhNode& b, const QueryF&
 #ifndef KNN_STACK4
 #define KNN_STACK4 1
 #endif
+#ifndef KNN_TWOPHASE
+#define KNN_TWOPHASE 0
+#endif
 // 32-byte records (node, point) are fetched with ONE 256-bit load (sm_100: ld.global.nc.v8.b32 / .v4.f64, SASS
 // LDG.E.256) instead of two 128-bit ones: half the load instructions of the traversal.  Both record arrays are
 // 32-byte aligned (cudaMalloc base + index * 32).
@@ -482,6 +485,50 @@ __device__ __forceinline__ double4 load_point(const double4* __restrict__ p) {
   return t;
 #else
   return *p;
+#endif
+}
+
+// Leaf scan shared by the binary and the 4-wide walk: the points [first, last] (at most kBvhLeaf) of the sorted copy.
+template <int K>
+__device__ __forceinline__ void scan_leaf(const double4* __restrict__ sorted, uint32_t first, uint32_t last, double qx,
+                                          double qy, double qz, double d2_cut, TopK<K>& tk) {
+  // ---- leaf: fp64 distances in nanoflann's L2_Simple order, branch-free insertion
+#if KNN_TWOPHASE
+  // (not measured yet — prepared for an A/B.)  Phase 1 computes the 8 distances and keeps, compacted, only the
+  // candidates that beat the K-th entry as it stands on entry (it can only improve, so this is a superset of what the
+  // network would accept; for everything else insert() is a no-op).  Phase 2 runs the insertion network once per kept
+  // candidate: a warp pays for the largest count among its lanes instead of 8 — all 8 on a query's first leaf,
+  // typically 2-4 on the following ones.
+  double cd[kBvhLeaf];
+  uint32_t ci[kBvhLeaf];
+  int cn = 0;
+  const double wd = tk.d[K - 1];
+  const uint32_t wi = tk.id[K - 1];
+#pragma unroll
+  for (int j = 0; j < kBvhLeaf; j++) {
+    const uint32_t p = first + j;
+    const double4 t = load_point(sorted + min(p, last));
+    const double d2 = sqdist(qx, qy, qz, t.x, t.y, t.z);
+    const uint32_t id = (uint32_t)__double_as_longlong(t.w);
+    if (p <= last && d2 <= d2_cut && TopK<K>::lt(d2, id, wd, wi)) {
+      cd[cn] = d2;
+      ci[cn] = id;
+      cn++;
+    }
+  }
+  for (int t = 0; t < cn; t++) tk.insert(cd[t], ci[t]);
+#else
+#pragma unroll
+  for (int j = 0; j < kBvhLeaf; j++) {
+    const uint32_t p = first + j;
+    const double4 t = load_point(sorted + min(p, last));
+    double d2 = sqdist(qx, qy, qz, t.x, t.y, t.z);
+    uint32_t id = (uint32_t)__double_as_longlong(t.w);
+    const bool ok = p <= last && d2 <= d2_cut;
+    d2 = ok ? d2 : CUDART_INF;
+    id = ok ? id : 0xFFFFFFFFu;
+    tk.insert(d2, id);
+  }
 #endif
 }
 
@@ -588,18 +635,7 @@ __device__ __forceinline__ void knn_bvh(const BvhHdr& h, const BvhNode* __restri
       }
     }
     if (!at_leaf) break;  // done
-    // ---- leaf: fp64 distances in nanoflann's L2_Simple order, branch-free insertion
-#pragma unroll
-    for (int j = 0; j < kBvhLeaf; j++) {
-      const uint32_t p = first + j;
-      const double4 t = load_point(sorted + min(p, last));
-      double d2 = sqdist(qx, qy, qz, t.x, t.y, t.z);
-      uint32_t id = (uint32_t)__double_as_longlong(t.w);
-      const bool ok = p <= last && d2 <= d2_cut;
-      d2 = ok ? d2 : CUDART_INF;
-      id = ok ? id : 0xFFFFFFFFu;
-      tk.insert(d2, id);
-    }
+    scan_leaf<K>(sorted, first, last, qx, qy, qz, d2_cut, tk);
     bound = __double2float_ru(fmin(tk.kth(k), d2_cut));
     have = false;
   }
@@ -710,17 +746,7 @@ __device__ __forceinline__ void knn_bvh_wide(const BvhHdr& h, const BvhNode* __r
       }
     }
     if (!at_leaf) break;  // done
-#pragma unroll
-    for (int j = 0; j < kBvhLeaf; j++) {
-      const uint32_t p = first + j;
-      const double4 t = load_point(sorted + min(p, last));
-      double d2 = sqdist(qx, qy, qz, t.x, t.y, t.z);
-      uint32_t id = (uint32_t)__double_as_longlong(t.w);
-      const bool ok = p <= last && d2 <= d2_cut;
-      d2 = ok ? d2 : CUDART_INF;
-      id = ok ? id : 0xFFFFFFFFu;
-      tk.insert(d2, id);
-    }
+    scan_leaf<K>(sorted, first, last, qx, qy, qz, d2_cut, tk);
     bound = __double2float_ru(fmin(tk.kth(k), d2_cut));
     have = false;
   }
