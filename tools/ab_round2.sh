@@ -1,14 +1,11 @@
 #!/bin/bash
-# First GPU call of the next round: the k-NN variants prepared (compiled, SASS inspected, not yet measured) at the end
-# of round 1.  Every variant runs the full GPU parity suite before its bench line.
-#   -DKNN_TWOPHASE=1               leaf scan in two phases: 8 distances + filter against the K-th entry, then the
-#                                  insertion network only for the kept candidates (leaf: 176 + 53 per kept candidate
-#                                  SASS instructions against 640, no spills)
-#   -DKNN_WIDE4=1                  4-wide walk (measured alone: k-NN -1 %, NN build +0.30 ms)
-#   -DKNN_TWOPHASE=1 -DKNN_WIDE4=1 both
+# A/B of the flag-gated k-NN variants kept in the tree (each: full GPU parity suite, then a 1024-scan bench line).
+# Round-1 results, 1024 pairs per launch, default 12.02 ms:
+#   -DKNN_WIDE4=1      4-wide walk: 11.88 ms, NN build +0.30 ms for the widening pass
+#   -DKNN_TWOPHASE=1   two-phase leaf scan: 12.33 ms (smoke parity only; the full suite has not run on it)
 mkdir -p gpurun_out
 i=0
-for flags in "" "-DKNN_TWOPHASE=1" "-DKNN_TWOPHASE=1 -DKNN_WIDE4=1" "-DKNN_TWOPHASE=1 -DKNN_MINBLOCKS=7"; do
+for flags in "" "-DKNN_WIDE4=1" "-DKNN_TWOPHASE=1" "-DKNN_TWOPHASE=1 -DKNN_WIDE4=1"; do
   i=$((i+1))
   LOAMGPU_NVCC_FLAGS="$flags" python loam_b200/build.py --force > /dev/null 2>&1 || { echo "build failed: $flags"; continue; }
   python -m pytest tests -m gpu -q --maxfail=5 > gpurun_out/pytest_r2ab$i.log 2>&1; echo "[$flags] $(tail -1 gpurun_out/pytest_r2ab$i.log)"
