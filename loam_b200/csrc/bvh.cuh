@@ -494,7 +494,7 @@ __device__ __forceinline__ void scan_leaf(const double4* __restrict__ sorted, ui
                                           double qy, double qz, double d2_cut, TopK<K>& tk) {
   // ---- leaf: fp64 distances in nanoflann's L2_Simple order, branch-free insertion
 #if KNN_TWOPHASE
-  // (not measured yet — prepared for an A/B.)  Phase 1 computes the 8 distances and keeps, compacted, only the
+  // (measured 2.6 % slower than the plain scan; kept for A/B.)  Phase 1 computes the 8 distances and keeps, compacted, only the
   // candidates that beat the K-th entry as it stands on entry (it can only improve, so this is a superset of what the
   // network would accept; for everything else insert() is a no-op).  Phase 2 runs the insertion network once per kept
   // candidate: a warp pays for the largest count among its lanes instead of 8 — all 8 on a query's first leaf,
