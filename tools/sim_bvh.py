@@ -201,6 +201,75 @@ def knn_wide(t, q, bound0, levels=2):
         cur = keep[0][1] if keep else None
 
 
+def morton_order(pts):
+    lo, hi = pts.min(0), pts.max(0)
+    q = np.clip(((pts - lo) * (1023.999 / max((hi - lo).max(), 1e-30))).astype(np.int64), 0, 1023)
+    code = np.zeros(len(pts), dtype=np.int64)
+    for b in range(10):
+        for a in range(3):
+            code |= ((q[:, a] >> b) & 1) << (3 * b + a)
+    return np.argsort(code, kind="stable")
+
+
+def knn_packet(t, qs, bound0):
+    """One walk for a whole warp of (Morton-adjacent) queries: a node is entered when ANY lane's conservative bound
+    allows it, every lane tests the same record (uniform loads, all lanes busy in the node steps), lanes the subtree
+    cannot help are masked in its leaf scans.  Each lane still sees every leaf it needs, so results are unchanged.
+    Counts per WARP: node steps, pops (each re-tests the popped subtree's box), leaf scans, and lane-leaf scans."""
+    nl = len(qs)
+    c = dict(steps=0, pop=0, leaves=0, lane_leaves=0, push=0)
+    best = [[] for _ in range(nl)]
+    bound = np.full(nl, bound0)
+    stack = []
+
+    def lbs(f, l):
+        lo, hi = t.box(f, l)
+        g = np.maximum(np.maximum(lo - qs, qs - hi), 0.0)
+        return (g * g).sum(1)
+
+    def leaf(f, l, want):
+        c["leaves"] += 1
+        c["lane_leaves"] += int(want.sum())
+        seg = t.pts[f:l + 1]
+        for i in np.nonzero(want)[0]:
+            d2 = ((seg - qs[i]) ** 2).sum(1)
+            b = best[i]
+            b.extend(d2.tolist())
+            b.sort()
+            del b[K:]
+            if len(b) == K:
+                bound[i] = min(bound[i], b[-1])
+
+    cur = (0, t.n - 1, lbs(0, t.n - 1))
+    while True:
+        if cur is None:
+            if not stack:
+                return c
+            f, l = stack.pop()
+            c["pop"] += 1
+            d = lbs(f, l)
+            if (d <= bound).any():
+                cur = (f, l, d)
+            continue
+        f, l, d = cur
+        if l - f < LEAF:
+            leaf(f, l, d <= bound)
+            cur = None
+            continue
+        a, b = t.children(f, l)
+        c["steps"] += 1
+        da = np.zeros(nl) if a[0] == a[1] else lbs(*a)
+        db = np.zeros(nl) if b[0] == b[1] else lbs(*b)
+        wa, wb = (da <= bound), (db <= bound)
+        # the side most lanes would enter first goes first
+        a_first = (da <= db).sum() * 2 >= nl
+        (n1, d1, w1), (n2, d2, w2) = ((a, da, wa), (b, db, wb)) if a_first else ((b, db, wb), (a, da, wa))
+        if w2.any():
+            stack.append(n2)
+            c["push"] += 1
+        cur = (n1[0], n1[1], d1) if w1.any() else None
+
+
 def main():
     nq = int(sys.argv[1]) if len(sys.argv) > 1 else 1500
     R, P = 64, 1024
@@ -229,6 +298,31 @@ def main():
                         acc[k_] += c[k_]
                 tot[kind] = {k_: round(v / len(qs), 2) for k_, v in acc.items()}
             print(json.dumps({"set": name, "n": len(T), "queries": len(qs), "bound": mode, **tot}))
+        # warp packets over the source set's own Morton order (what the kernel's lanes hold)
+        order = morton_order(Q)
+        n_warps = max(1, min(nq // 32, len(Q) // 32))
+        starts = rng.choice(len(Q) // 32, size=n_warps, replace=False) * 32
+        for mode in ("cold", "hint"):
+            acc = dict(steps=0, pop=0, leaves=0, lane_leaves=0, push=0)
+            solo = dict(steps=0, leaves=0)
+            for s0 in starts:
+                qw = Q[order[s0:s0 + 32]]
+                b0 = r * r
+                if mode == "hint":  # (a per-lane hint would be tighter; the packet uses each lane's own below)
+                    pass
+                cw = knn_packet(t, qw, b0)
+                for k_ in acc:
+                    acc[k_] += cw[k_]
+                for q in qw:
+                    cs = knn_binary(t, q, b0)
+                    solo["steps"] += cs["steps"]
+                    solo["leaves"] += cs["leaves"]
+            if mode == "hint":
+                continue
+            print(json.dumps({"set": name, "packet_per_warp": {k_: round(v / n_warps, 1) for k_, v in acc.items()},
+                              "solo_sum_per_warp": {k_: round(v / n_warps, 1) for k_, v in solo.items()},
+                              "solo_mean_per_lane": {k_: round(v / n_warps / 32, 2) for k_, v in solo.items()},
+                              "warps": int(n_warps)}))
 
 
 if __name__ == "__main__":
