@@ -132,8 +132,8 @@ __device__ __noinline__ double fit_plane(const double (&P)[KMAX][3], int K, V3& 
     s = sqrt(s);
     if (s > maxnorm) maxnorm = s;
   }
-  const double th = maxnorm * 2.220446049250313e-16 / (double)K;
-  const double threshold_helper = th * th;
+  const double th = maxnorm * 2.220446049250313e-16;
+  const double threshold_helper = th * th / (double)K;  // Eigen: abs2(maxnorm * eps) / rows
   int nonzero = size;
   for (int k = 0; k < size; k++) {
     int big = k;
@@ -260,8 +260,8 @@ __device__ __forceinline__ double fit_plane_reg(const double (&P)[KMAX][3], int 
     sq = sqrt(sq);
     if (sq > maxnorm) maxnorm = sq;
   }
-  const double th = maxnorm * 2.220446049250313e-16 / (double)K;
-  const double threshold_helper = th * th;
+  const double th = maxnorm * 2.220446049250313e-16;
+  const double threshold_helper = th * th / (double)K;  // Eigen: abs2(maxnorm * eps) / rows
   int nonzero = size;
 #pragma unroll
   for (int k = 0; k < 3; k++) {

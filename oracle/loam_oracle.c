@@ -377,8 +377,9 @@ static void colpiv_qr_solve3(const double* pts, uint32_t K, double* x) {
     s = sqrt(s);
     if (s > maxnorm) maxnorm = s;
   }
-  const double th = maxnorm * DBL_EPSILON / (double)K;
-  const double threshold_helper = th * th;
+  /* Eigen ColPivHouseholderQR::computeInPlace: abs2(maxnorm * eps) / rows — ONE division by the row count */
+  const double th = maxnorm * DBL_EPSILON;
+  const double threshold_helper = th * th / (double)K;
   int nonzero_pivots = size;
   for (int k = 0; k < size; k++) {
     /* pivot: remaining column with the biggest norm (recomputed directly) */
@@ -1039,6 +1040,55 @@ static void lm_solve(const resblock* rb, size_t M, double* x_user, int armed_fla
   free(r);
   free(J);
   free(work);
+}
+
+/* ------------------------------------------------------------------------ test hooks
+ * (tests/test_oracle_jacobians.py: the analytic derivatives and the LM step sequence are checked against torch
+ * float64 autograd of the literal functor expressions and against an independent QR-based model of the solver) */
+static resblock* blocks_from_flat(const int32_t* is_plane, const double* P, const double* A, const double* B, size_t M) {
+  resblock* rb = (resblock*)malloc(sizeof(resblock) * (M + 1));
+  for (size_t i = 0; i < M; i++) {
+    rb[i].is_plane = is_plane[i];
+    memcpy(rb[i].p, P + 3 * i, 3 * sizeof(double));
+    memcpy(rb[i].a, A + 3 * i, 3 * sizeof(double));
+    memcpy(rb[i].b, B + 3 * i, 3 * sizeof(double));
+  }
+  return rb;
+}
+
+/* one residual: value and 1x7 ambient Jacobian (x y z w tx ty tz); B = line point b, or (d, -, -) for a plane */
+double orc_residual_eval(int32_t is_plane, const double* p, const double* a, const double* b, const double* x,
+                         double* J7) {
+  resblock rb;
+  rb.is_plane = is_plane;
+  memcpy(rb.p, p, sizeof rb.p);
+  memcpy(rb.a, a, sizeof rb.a);
+  memcpy(rb.b, b, sizeof rb.b);
+  return residual_eval(&rb, x, J7);
+}
+
+/* whole problem at x: cost; optional corrected residuals r[M], corrected tangent Jacobian J[M][6], gradient g[6] */
+double orc_problem_eval(const int32_t* is_plane, const double* P, const double* A, const double* B, uint64_t M,
+                        const double* x, double* r, double* J, double* g) {
+  resblock* rb = blocks_from_flat(is_plane, P, A, B, (size_t)M);
+  double* rr = r ? r : (J ? (double*)malloc(sizeof(double) * (M + 1)) : NULL);
+  double gg[6];
+  const double c = problem_eval(rb, (size_t)M, x, J ? rr : NULL, J, J ? (g ? g : gg) : NULL);
+  if (rr && rr != r) free(rr);
+  free(rb);
+  return c;
+}
+
+void orc_manifold_plus(const double* x, const double* delta, double* out) { manifold_plus(x, delta, out); }
+
+/* the restated ceres::Solve on explicit residual blocks; x (7) in/out; returns LM iterations recorded */
+uint32_t orc_lm_solve(const int32_t* is_plane, const double* P, const double* A, const double* B, uint64_t M,
+                      double* x, int armed_flag, double* cost2) {
+  resblock* rb = blocks_from_flat(is_plane, P, A, B, (size_t)M);
+  uint32_t it = 0;
+  lm_solve(rb, (size_t)M, x, armed_flag, &it, cost2);
+  free(rb);
+  return it;
 }
 
 typedef uint32_t (*knn_fn)(const void* ctx, const double* pts, uint64_t n, const double* q, uint32_t k, double md,

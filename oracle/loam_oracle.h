@@ -125,6 +125,16 @@ int orc_register(const double* src_edge, uint64_t n_se, const double* src_planar
                  const double* init_pose, const orc_reg_params* rp, double* out_pose, orc_detail* detail,
                  int use_kdtree, int armed_flag);
 
+/* test hooks (tests/test_oracle_jacobians.py): one residual with its 1x7 ambient Jacobian, the whole problem at an
+ * iterate (corrected residuals, corrected tangent Jacobian [M][6], gradient), the manifold Plus, and the restated
+ * ceres::Solve on explicit residual blocks.  is_plane[i] != 0: A = normal, B[0] = d;  else A, B = line points. */
+double orc_residual_eval(int32_t is_plane, const double* p, const double* a, const double* b, const double* x, double* J7);
+double orc_problem_eval(const int32_t* is_plane, const double* P, const double* A, const double* B, uint64_t M,
+                        const double* x, double* r, double* J, double* g);
+void orc_manifold_plus(const double* x, const double* delta, double* out);
+uint32_t orc_lm_solve(const int32_t* is_plane, const double* P, const double* A, const double* B, uint64_t M,
+                      double* x, int armed_flag, double* cost2);
+
 #ifdef __cplusplus
 }
 #endif

@@ -100,6 +100,13 @@ class Oracle:
         L.orc_point_to_plane.restype = f64
         L.orc_point_to_plane.argtypes = [C.c_void_p, C.c_void_p, f64]
         L.orc_quat_angular_distance.restype = f64
+        L.orc_residual_eval.restype = f64
+        L.orc_residual_eval.argtypes = [i32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_problem_eval.restype = f64
+        L.orc_problem_eval.argtypes = [C.c_void_p] * 4 + [u64] + [C.c_void_p] * 4
+        L.orc_manifold_plus.argtypes = [C.c_void_p] * 3
+        L.orc_lm_solve.restype = u32
+        L.orc_lm_solve.argtypes = [C.c_void_p] * 4 + [u64, C.c_void_p, C.c_int, C.c_void_p]
 
     # ---- features ----
     def curvature(self, xyz, lp: LidarParams, fe: FeParams):
@@ -204,6 +211,43 @@ class Oracle:
     def angular_distance(self, q1, q2):
         q1, q2 = (np.ascontiguousarray(v, dtype=np.float64) for v in (q1, q2))
         return self.lib.orc_quat_angular_distance(q1.ctypes, q2.ctypes)
+
+    # ---- test hooks: residuals / Jacobians / the restated ceres::Solve on explicit residual blocks ----
+    @staticmethod
+    def _blocks(is_plane, P, A, B):
+        k = np.ascontiguousarray(is_plane, dtype=np.int32)
+        P, A, B = (np.ascontiguousarray(np.asarray(v, dtype=np.float64).reshape(len(k), 3)) for v in (P, A, B))
+        return k, P, A, B
+
+    def residual_eval(self, is_plane, p, a, b, x):
+        p, a, b, x = (np.ascontiguousarray(v, dtype=np.float64) for v in (p, a, b, x))
+        J7 = np.empty(7)
+        r = self.lib.orc_residual_eval(int(is_plane), p.ctypes.data, a.ctypes.data, b.ctypes.data, x.ctypes.data,
+                                       J7.ctypes.data)
+        return r, J7
+
+    def problem_eval(self, is_plane, P, A, B, x):
+        k, P, A, B = self._blocks(is_plane, P, A, B)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        M = len(k)
+        r, J, g = np.empty(M), np.empty((M, 6)), np.empty(6)
+        cost = self.lib.orc_problem_eval(k.ctypes.data, P.ctypes.data, A.ctypes.data, B.ctypes.data, M, x.ctypes.data,
+                                         r.ctypes.data, J.ctypes.data, g.ctypes.data)
+        return cost, r, J, g
+
+    def manifold_plus(self, x, delta):
+        x, delta = (np.ascontiguousarray(v, dtype=np.float64) for v in (x, delta))
+        out = np.empty(7)
+        self.lib.orc_manifold_plus(x.ctypes.data, delta.ctypes.data, out.ctypes.data)
+        return out
+
+    def lm_solve(self, is_plane, P, A, B, x0=None, armed_flag=True):
+        k, P, A, B = self._blocks(is_plane, P, A, B)
+        x = np.array([0, 0, 0, 1, 0, 0, 0.0] if x0 is None else x0, dtype=np.float64)
+        cost2 = np.zeros(2)
+        it = self.lib.orc_lm_solve(k.ctypes.data, P.ctypes.data, A.ctypes.data, B.ctypes.data, len(k), x.ctypes.data,
+                                   1 if armed_flag else 0, cost2.ctypes.data)
+        return x, int(it), cost2
 
     # ---- registration ----
     def register(self, src_edge, src_planar, tgt_edge, tgt_planar, init_pose=None, rp: RegParams | None = None,
