@@ -86,6 +86,14 @@ __global__ void __launch_bounds__(kBuildThreads, BUILD_MINBLOCKS) bvh_build_kern
     h.n = n;
     h.pad[0] = h.pad[1] = h.pad[2] = 0;
     *hdr = h;
+    if (a.g.quant && n == 0) {
+      BvhQuant q;
+      q.org[0] = q.org[1] = q.org[2] = 0.0;
+      q.inv_cell = q.inv_cell2 = 1.0;
+      q.n_rec = 0;
+      q.pad = 0;
+      a.g.quant[set] = q;
+    }
   }
   if (n == 0) return;
 
@@ -108,6 +116,23 @@ __global__ void __launch_bounds__(kBuildThreads, BUILD_MINBLOCKS) bvh_build_kern
   }
   // one scale for all axes (cubic cells); the ordering only has to be spatially coherent, not exact
   const double scale = emax > 0 ? 1023.999 / emax : 0.0;
+  // 16-bit grid of the compact records: origin a margin below the box (float-rounded box corners stay inside),
+  // 65534 cells across the longest axis plus the margins
+  if (tid == 0 && a.g.quant) {
+    double amax = emax;
+    for (int d = 0; d < 3; d++) amax = fmax(amax, fmax(fabs(lo[d]), fabs(hi[d])));
+    const double qmargin = 1e-6 * amax + 1e-9;
+    const double qinv = 65534.0 / (emax + 2.0 * qmargin);
+    BvhQuant q;
+    q.org[0] = lo[0] - qmargin;
+    q.org[1] = lo[1] - qmargin;
+    q.org[2] = lo[2] - qmargin;
+    q.inv_cell = qinv;
+    q.inv_cell2 = qinv * qinv * (1.0 + 1e-12);
+    q.n_rec = 0;  // (sets of at most kBvhLeaf points keep 0; larger ones get their count at the end)
+    q.pad = 0;
+    a.g.quant[set] = q;
+  }
 
   // ---- Morton keys (thread-contiguous chunks: the radix passes below need a fixed item -> thread map)
   const uint32_t chunk = (n + nthr - 1) / nthr;
@@ -317,69 +342,93 @@ __global__ void __launch_bounds__(kBuildThreads, BUILD_MINBLOCKS) bvh_build_kern
       if (!__syncthreads_or(pending)) break;
     }
   }
-}
 
-// ============================================================================ 4-wide collapse (KNN_WIDE4)
-
-// Box of the subtree [f, l] of one set: a single point is rounded outward like the build does, any other subtree is
-// the node that covers it (`idx`: node s for a left child, s + 1 for a right child — Karras' numbering).
-__device__ __forceinline__ void subtree_box(const BvhNode* __restrict__ nodes, const double4* __restrict__ sorted,
-                                            uint32_t f, uint32_t l, uint32_t idx, float* b) {
-  if (f == l) {
-    const double4 pt = sorted[f];
-    b[0] = __double2float_rd(pt.x); b[1] = __double2float_rd(pt.y); b[2] = __double2float_rd(pt.z);
-    b[3] = __double2float_ru(pt.x); b[4] = __double2float_ru(pt.y); b[5] = __double2float_ru(pt.z);
-  } else {
-    const float4* q = reinterpret_cast<const float4*>(nodes + idx);
-    const float4 va = q[0], vb = q[1];
-    b[0] = va.x; b[1] = va.y; b[2] = va.z;
-    b[3] = vb.x; b[4] = vb.y; b[5] = vb.z;
+  // ---- compact traversal records (common.cuh: BvhRec).  Internal node i is "big" when it covers more than kBvhLeaf
+  // points; big nodes are numbered in index order (the root, node 0, gets record 0) and each writes one record with its
+  // children's boxes on the 16-bit grid.  The records overlay this set's sort scratch, which is dead by now.
+  if (a.g.quant == nullptr || n <= (uint32_t)kBvhLeaf) return;
+  __syncthreads();
+  uint32_t* cid = reinterpret_cast<uint32_t*>(arrived);  // readiness flags are dead: record number per big node
+  BvhRec* recs = reinterpret_cast<BvhRec*>(keyA);
+  const uint32_t rec_cap = a.g.pt_cap / 2;
+  const uint32_t per = (n_int + nthr - 1) / nthr;
+  const uint32_t b0 = min(tid * per, n_int), b1 = min(b0 + per, n_int);
+  auto node_range = [&](uint32_t i, uint32_t& first, uint32_t& last) {
+    const uint32_t other = __ldcg(&nodes[i].pad);
+    first = min(i, other);
+    last = max(i, other);
+  };
+  uint32_t cnt_big = 0;
+  for (uint32_t i = b0; i < b1; i++) {
+    uint32_t f, l;
+    node_range(i, f, l);
+    cnt_big += (l - f >= (uint32_t)kBvhLeaf) ? 1u : 0u;
   }
-}
-
-// One thread per internal node, after the build kernel of the same sets has finished (next launch on the stream).
-__global__ void __launch_bounds__(256) bvh_widen_kernel(BvhSetArrays g) {
-  const uint32_t set = blockIdx.y;
-  const uint32_t n = g.hdr[set].n;
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n < 2 || i + 1 >= n) return;
-  const BvhNode* nodes = g.nodes + (size_t)set * g.pt_cap;
-  const double4* sorted = g.sorted + (size_t)set * g.pt_cap;
-  const uint32_t other = nodes[i].pad;
-  const uint32_t first = min(i, other), last = max(i, other);
-  if (last - first < (uint32_t)kBvhLeaf) return;  // scanned as a leaf: its record is never read
-  const uint32_t s = nodes[i].split & kSplitMask;
-  BvhWide w;
+  uint32_t incl = cnt_big;
 #pragma unroll
-  for (int c = 0; c < 4; c++) {
-    w.box[c][0] = w.box[c][1] = w.box[c][2] = CUDART_INF_F;
-    w.box[c][3] = w.box[c][4] = w.box[c][5] = -CUDART_INF_F;
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((int)lane >= o) incl += t;
   }
-  w.s = s;
-  w.sl = w.sr = 0;
+  if (lane == 31) s_scan[warp] = incl;
+  __syncthreads();
+  uint32_t base = 0, total = 0;
+  for (uint32_t w = 0; w < (nthr >> 5); w++) {
+    if (w < warp) base += s_scan[w];
+    total += s_scan[w];
+  }
+  if (total > rec_cap) {  // degenerate tree (long chains): this set keeps the general traversal only
+    if (tid == 0) a.g.quant[set].n_rec = kNoRecs;
+    return;
+  }
+  uint32_t run = base + incl - cnt_big;
+  for (uint32_t i = b0; i < b1; i++) {
+    uint32_t f, l;
+    node_range(i, f, l);
+    if (l - f >= (uint32_t)kBvhLeaf) __stcg(cid + i, run++);
+  }
+  __syncthreads();
+  // (the grid was written by thread 0 before the sort; barriers since)
+  const double qorg[3] = {__ldcg(&a.g.quant[set].org[0]), __ldcg(&a.g.quant[set].org[1]), __ldcg(&a.g.quant[set].org[2])};
+  const double qinv = __ldcg(&a.g.quant[set].inv_cell);
+  auto quant_lo = [&](float v, int d) -> uint32_t {
+    const double t = ((double)v - qorg[d]) * qinv;
+    return (uint32_t)fmin(fmax(floor(t - 1e-6), 0.0), 65535.0);
+  };
+  auto quant_hi = [&](float v, int d) -> uint32_t {
+    const double t = ((double)v - qorg[d]) * qinv;
+    return (uint32_t)fmin(fmax(ceil(t + 1e-6), 0.0), 65535.0);
+  };
+  for (uint32_t i = b0; i < b1; i++) {
+    uint32_t f, l;
+    node_range(i, f, l);
+    if (l - f < (uint32_t)kBvhLeaf) continue;
+    const uint32_t sp = __ldcg(&nodes[i].split) & kSplitMask;
+    BvhRec r;
 #pragma unroll
-  for (int k = 0; k < 5; k++) w.pad[k] = 0;
-  // side L = [first, s] (node s), side R = [s + 1, last] (node s + 1)
-  if (s - first < (uint32_t)kBvhLeaf) {
-    subtree_box(nodes, sorted, first, s, s, w.box[0]);
-  } else {
-    const uint32_t sl = nodes[s].split & kSplitMask;
-    w.sl = sl;
-    subtree_box(nodes, sorted, first, sl, sl, w.box[0]);
-    subtree_box(nodes, sorted, sl + 1, s, sl + 1, w.box[1]);
-  }
-  if (last - (s + 1) < (uint32_t)kBvhLeaf) {
-    subtree_box(nodes, sorted, s + 1, last, s + 1, w.box[2]);
-  } else {
-    const uint32_t sr = nodes[s + 1].split & kSplitMask;
-    w.sr = sr;
-    subtree_box(nodes, sorted, s + 1, sr, sr, w.box[2]);
-    subtree_box(nodes, sorted, sr + 1, last, sr + 1, w.box[3]);
-  }
-  uint4* dst = reinterpret_cast<uint4*>(g.wide + (size_t)set * g.pt_cap + i);
-  const uint4* src = reinterpret_cast<const uint4*>(&w);
+    for (int c = 0; c < 2; c++) {
+      const uint32_t cf = c == 0 ? f : sp + 1, cl = c == 0 ? sp : l;
+      float clo[3], chi[3];
+      if (cf == cl) {  // a single point has no node record: its own coordinates, rounded outward
+        const double4 pt = sorted[cf];
+        clo[0] = __double2float_rd(pt.x); chi[0] = __double2float_ru(pt.x);
+        clo[1] = __double2float_rd(pt.y); chi[1] = __double2float_ru(pt.y);
+        clo[2] = __double2float_rd(pt.z); chi[2] = __double2float_ru(pt.z);
+      } else {
+        const float4* q = reinterpret_cast<const float4*>(nodes + sp + c);
+        const float4 va = __ldcg(q), vb = __ldcg(q + 1);
+        clo[0] = va.x; clo[1] = va.y; clo[2] = va.z;
+        chi[0] = vb.x; chi[1] = vb.y; chi[2] = vb.z;
+      }
 #pragma unroll
-  for (int k = 0; k < 8; k++) dst[k] = src[k];
+      for (int d = 0; d < 3; d++) r.box[3 * c + d] = quant_lo(clo[d], d) | (quant_hi(chi[d], d) << 16);
+      r.ref[c] = (cl - cf < (uint32_t)kBvhLeaf) ? (kRefLeaf | ((cl - cf) << 24) | cf) : __ldcg(cid + sp + c);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(recs + __ldcg(cid + i));
+    dst[0] = make_uint4(r.box[0], r.box[1], r.box[2], r.box[3]);
+    dst[1] = make_uint4(r.box[4], r.box[5], r.ref[0], r.ref[1]);
+  }
+  if (tid == 0) a.g.quant[set].n_rec = total;
 }
 
 // ============================================================================ exact k-NN (K4)
@@ -454,9 +503,6 @@ __device__ __forceinline__ float box_lower_bound(const BvhNode& b, const QueryF&
 #ifndef KNN_STACK4
 #define KNN_STACK4 1
 #endif
-#ifndef KNN_TWOPHASE
-#define KNN_TWOPHASE 0
-#endif
 // 32-byte records (node, point) are fetched with ONE 256-bit load (sm_100: ld.global.nc.v8.b32 / .v4.f64, SASS
 // LDG.E.256) instead of two 128-bit ones: half the load instructions of the traversal.  Both record arrays are
 // 32-byte aligned (cudaMalloc base + index * 32).
@@ -488,36 +534,11 @@ __device__ __forceinline__ double4 load_point(const double4* __restrict__ p) {
 #endif
 }
 
-// Leaf scan shared by the binary and the 4-wide walk: the points [first, last] (at most kBvhLeaf) of the sorted copy.
+// Leaf scan shared by the global and the shared-memory walk: the points [first, last] (at most kBvhLeaf) of the sorted copy.
 template <int K>
 __device__ __forceinline__ void scan_leaf(const double4* __restrict__ sorted, uint32_t first, uint32_t last, double qx,
                                           double qy, double qz, double d2_cut, TopK<K>& tk) {
   // ---- leaf: fp64 distances in nanoflann's L2_Simple order, branch-free insertion
-#if KNN_TWOPHASE
-  // (measured 2.6 % slower than the plain scan; kept for A/B.)  Phase 1 computes the 8 distances and keeps, compacted, only the
-  // candidates that beat the K-th entry as it stands on entry (it can only improve, so this is a superset of what the
-  // network would accept; for everything else insert() is a no-op).  Phase 2 runs the insertion network once per kept
-  // candidate: a warp pays for the largest count among its lanes instead of 8 — all 8 on a query's first leaf,
-  // typically 2-4 on the following ones.
-  double cd[kBvhLeaf];
-  uint32_t ci[kBvhLeaf];
-  int cn = 0;
-  const double wd = tk.d[K - 1];
-  const uint32_t wi = tk.id[K - 1];
-#pragma unroll
-  for (int j = 0; j < kBvhLeaf; j++) {
-    const uint32_t p = first + j;
-    const double4 t = load_point(sorted + min(p, last));
-    const double d2 = sqdist(qx, qy, qz, t.x, t.y, t.z);
-    const uint32_t id = (uint32_t)__double_as_longlong(t.w);
-    if (p <= last && d2 <= d2_cut && TopK<K>::lt(d2, id, wd, wi)) {
-      cd[cn] = d2;
-      ci[cn] = id;
-      cn++;
-    }
-  }
-  for (int t = 0; t < cn; t++) tk.insert(cd[t], ci[t]);
-#else
 #pragma unroll
   for (int j = 0; j < kBvhLeaf; j++) {
     const uint32_t p = first + j;
@@ -529,7 +550,6 @@ __device__ __forceinline__ void scan_leaf(const double4* __restrict__ sorted, ui
     id = ok ? id : 0xFFFFFFFFu;
     tk.insert(d2, id);
   }
-#endif
 }
 
 // Exact k nearest neighbours of (qx,qy,qz) among the points of one set, restricted to candidates that can pass the
@@ -537,7 +557,6 @@ __device__ __forceinline__ void scan_leaf(const double4* __restrict__ sorted, ui
 // the exact test afterwards).  A subtree is skipped only when its box lower bound is STRICTLY above the current k-th
 // best (or the radius cut), so candidates that tie the k-th distance are still seen and resolved by index.
 constexpr int kBvhStack = 64;  // >= tree depth: 30 Morton bits + 32 position bits for duplicate codes
-constexpr int kBvhStackWide = 96;  // 4-wide walk: up to 3 pending subtrees per step, 31 steps deep
 
 template <int K>
 __device__ __forceinline__ void knn_bvh(const BvhHdr& h, const BvhNode* __restrict__ nodes,
@@ -641,42 +660,68 @@ __device__ __forceinline__ void knn_bvh(const BvhHdr& h, const BvhNode* __restri
   }
 }
 
-// Lower bound for one slot of a wide record (6 floats: lo xyz, hi xyz); empty slots (lo = +inf) give +inf.
-__device__ __forceinline__ float slot_lower_bound(const float* b, const QueryF& q) {
+// ---------------------------------------------------------------------------- the same search over compact records
+// The batched association kernel keeps a target set's compact records (common.cuh: BvhRec) in SHARED memory, so a
+// node step costs two LDS.128 (29 cycles) instead of two dependent global loads (L1 hit 32, L2 hit ~250 cycles; 37 % of
+// them missed L1 in the global walk: profiles/r1_kernels_full_v29.md) and the state of a walk is one 32-bit child
+// reference.  Box tests run on the set's 16-bit grid: the query's cell coordinates are rounded outward to integers
+// (below / above), a box corner c is decoded as the float 2^23 + c by OR-ing it into the mantissa of 8388608.0f, and
+// the differences of those integers are exact in fp32.  gap^2 is summed with round-down FMAs and compared with the
+// pruning bound converted to cells^2 and rounded up: a subtree is skipped only when its true distance is strictly
+// above the bound, exactly as in knn_bvh — the results are identical, whatever the tree looks like.
+struct QueryG {  // 2^23 + floor / ceil of the query's cell coordinate, clamped to +-2^22 cells
+  float lo[3], hi[3];
+};
+
+__device__ __forceinline__ void query_grid(const BvhQuant* __restrict__ Q, double qx, double qy, double qz, QueryG& g) {
+  const double q[3] = {qx, qy, qz};
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    const double t = (q[d] - Q->org[d]) * Q->inv_cell;
+    const double e = 1e-6 + fabs(t) * 1e-12;  // covers the rounding of t itself
+    // clamping is conservative: a clamped coordinate lies between the true one and every box (cells 0 .. 65535)
+    const double lo = fmin(fmax(floor(t - e), -4194304.0), 4194304.0);
+    const double hi = fmin(fmax(ceil(t + e), -4194304.0), 4194304.0);
+    g.lo[d] = (float)(8388608.0 + lo);  // integers below 2^24: exact
+    g.hi[d] = (float)(8388608.0 + hi);
+  }
+}
+
+// lower bound, in cells^2, of the squared distance from the query to the box packed in (wx, wy, wz)
+__device__ __forceinline__ float rec_lower_bound(uint32_t wx, uint32_t wy, uint32_t wz, const QueryG& g) {
+  const uint32_t w[3] = {wx, wy, wz};
   float s = 0.f;
 #pragma unroll
   for (int d = 0; d < 3; d++) {
-    const float g = fmax3_nonneg(__fsub_rd(b[d], q.hi[d]), __fsub_rd(q.lo[d], b[3 + d]));
-    s = __fmaf_rd(g, g, s);
+    const float blo = __uint_as_float(0x4B000000u | (w[d] & 0xFFFFu));  // 2^23 + lo cell
+    const float bhi = __uint_as_float(0x4B000000u | (w[d] >> 16));      // 2^23 + hi cell
+    const float gap = fmax3_nonneg(blo - g.hi[d], g.lo[d] - bhi);      // exact integer differences
+    s = __fmaf_rd(gap, gap, s);
   }
   return s;
 }
 
-// The same search over the 4-wide records: a pending subtree is (node index, first, last, lower bound); one step loads
-// ONE 128-byte record and decides two levels.  Near-first order as in the binary walk: the side whose nearer slot is
-// closer is entered, its farther slot and the other side's two slots stay pending (nearest on top of the stack).
-// Pruning is the same conservative strict test, leaves are scanned by the same code: results are identical.
+__device__ __forceinline__ void load_rec_shared(uint32_t saddr, uint4& r0, uint4& r1) {
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r0.x), "=r"(r0.y), "=r"(r0.z), "=r"(r0.w) : "r"(saddr));
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r1.x), "=r"(r1.y), "=r"(r1.z), "=r"(r1.w) : "r"(saddr + 16u));
+}
+
+// s_recs: shared-memory address of the set's record 0; n_pts: points of the set; Q: its grid (shared or global memory)
 template <int K>
-__device__ __forceinline__ void knn_bvh_wide(const BvhHdr& h, const BvhNode* __restrict__ nodes,
-                                             const BvhWide* __restrict__ wide, const double4* __restrict__ sorted,
-                                             double qx, double qy, double qz, int k, double max_dist, TopK<K>& tk,
-                                             double d2_hint) {
+__device__ __forceinline__ void knn_compact(uint32_t s_recs, uint32_t n_pts, const BvhQuant* __restrict__ Q,
+                                            const double4* __restrict__ sorted, double qx, double qy, double qz, int k,
+                                            double max_dist, TopK<K>& tk, double d2_hint) {
   tk.init();
-  if (h.n == 0) return;
+  if (n_pts == 0) return;
   const double d2_cut = fmin(max_dist > 0 ? max_dist * max_dist * (1.0 + 1e-12) : CUDART_INF, d2_hint);
-  QueryF q;
-  q.lo[0] = __double2float_rd(qx); q.hi[0] = __double2float_ru(qx);
-  q.lo[1] = __double2float_rd(qy); q.hi[1] = __double2float_ru(qy);
-  q.lo[2] = __double2float_rd(qz); q.hi[2] = __double2float_ru(qz);
-  float bound = __double2float_ru(d2_cut);
-  uint4 st[kBvhStackWide];  // (node index, first, last, lower bound)
+  QueryG g;
+  query_grid(Q, qx, qy, qz, g);
+  const double inv2 = Q->inv_cell2;
+  float bound = __double2float_ru(d2_cut * inv2);  // cells^2; a subtree is pruned when its lower bound > bound
+  uint2 st[kBvhStack];                             // pending subtrees: (child reference, lower bound)
   int sp = 0;
-  uint32_t first = 0, last = h.n - 1, idx = 0;
+  uint32_t cur = n_pts > (uint32_t)kBvhLeaf ? 0u : (kRefLeaf | ((n_pts - 1u) << 24));
   bool have = true, done = false;
-  if (h.n > (uint32_t)kBvhLeaf) {
-    const BvhNode root = load_node(nodes);
-    if (box_lower_bound(root, q) > bound) return;
-  }
   while (true) {
     bool at_leaf = false;
     while (!done && !at_leaf) {
@@ -685,69 +730,35 @@ __device__ __forceinline__ void knn_bvh_wide(const BvhHdr& h, const BvhNode* __r
           done = true;
         } else {
           --sp;
-          const uint4 e = st[sp];
-          if (__uint_as_float(e.w) <= bound) {
-            idx = e.x;
-            first = e.y;
-            last = e.z;
+          const uint2 e = st[sp];
+          if (__uint_as_float(e.y) <= bound) {
+            cur = e.x;
             have = true;
           }
         }
-      } else if (last - first < (uint32_t)kBvhLeaf) {
+      } else if (cur & kRefLeaf) {
         at_leaf = true;
       } else {
-        const uint4* rp = reinterpret_cast<const uint4*>(wide + idx);
-        uint4 r[7];  // 6 words of boxes + (s, sl, sr)
-#pragma unroll
-        for (int j = 0; j < 7; j++) r[j] = __ldg(rp + j);
-        float bx[24];
-#pragma unroll
-        for (int j = 0; j < 6; j++) {
-          bx[4 * j + 0] = __uint_as_float(r[j].x);
-          bx[4 * j + 1] = __uint_as_float(r[j].y);
-          bx[4 * j + 2] = __uint_as_float(r[j].z);
-          bx[4 * j + 3] = __uint_as_float(r[j].w);
+        uint4 r0, r1;  // (Lx Ly Lz Rx) (Ry Rz refL refR)
+        load_rec_shared(s_recs + cur * (uint32_t)sizeof(BvhRec), r0, r1);
+        const float dl = rec_lower_bound(r0.x, r0.y, r0.z, g);
+        const float dr = rec_lower_bound(r0.w, r1.x, r1.y, g);
+        const bool right_first = dr < dl;
+        const float dn = right_first ? dr : dl, df = right_first ? dl : dr;
+        if (df <= bound) {  // far child stays pending
+          st[sp] = make_uint2(right_first ? r1.z : r1.w, __float_as_uint(df));
+          sp++;
         }
-        const uint32_t s = r[6].x, sl = r[6].y, sr = r[6].z;
-        const bool l_leaf = s - first < (uint32_t)kBvhLeaf, r_leaf = last - (s + 1) < (uint32_t)kBvhLeaf;
-        // slot c: range [cf[c], cl[c]], node index ci[c] (unused for leaf-sized ranges and empty slots)
-        const uint32_t cf0 = first, cl0 = l_leaf ? s : sl, ci0 = sl;
-        const uint32_t cf1 = sl + 1, cl1 = s, ci1 = sl + 1;
-        const uint32_t cf2 = s + 1, cl2 = r_leaf ? last : sr, ci2 = sr;
-        const uint32_t cf3 = sr + 1, cl3 = last, ci3 = sr + 1;
-        // a side that is one leaf has no second slot: NaN fails every "<= bound" test and never sorts first
-        const float kNoSlot = __int_as_float(0x7FFFFFFF);
-        const float d0 = slot_lower_bound(bx + 0, q), d1 = l_leaf ? kNoSlot : slot_lower_bound(bx + 6, q);
-        const float d2 = slot_lower_bound(bx + 12, q), d3 = r_leaf ? kNoSlot : slot_lower_bound(bx + 18, q);
-        // order inside each side, then the sides by their nearer slot
-        const bool sw_l = d1 < d0, sw_r = d3 < d2;
-        const float ln = sw_l ? d1 : d0, lf = sw_l ? d0 : d1, rn = sw_r ? d3 : d2, rf = sw_r ? d2 : d3;
-        const uint4 e_ln = sw_l ? make_uint4(ci1, cf1, cl1, __float_as_uint(d1)) : make_uint4(ci0, cf0, cl0, __float_as_uint(d0));
-        const uint4 e_lf = sw_l ? make_uint4(ci0, cf0, cl0, __float_as_uint(d0)) : make_uint4(ci1, cf1, cl1, __float_as_uint(d1));
-        const uint4 e_rn = sw_r ? make_uint4(ci3, cf3, cl3, __float_as_uint(d3)) : make_uint4(ci2, cf2, cl2, __float_as_uint(d2));
-        const uint4 e_rf = sw_r ? make_uint4(ci2, cf2, cl2, __float_as_uint(d2)) : make_uint4(ci3, cf3, cl3, __float_as_uint(d3));
-        const bool right_side = rn < ln;
-        const uint4 near_n = right_side ? e_rn : e_ln, near_f = right_side ? e_rf : e_lf;
-        const uint4 far_n = right_side ? e_ln : e_rn, far_f = right_side ? e_lf : e_rf;
-        const float d_near_f = right_side ? rf : lf, d_far_n = right_side ? ln : rn, d_far_f = right_side ? lf : rf;
-        const float d_near_n = right_side ? rn : ln;
-        // pending subtrees, farthest first (the far side's slots are ordered; the near side's far slot may be
-        // farther than the far side's near slot: the stack order is a heuristic, pops re-test the bound anyway)
-        if (d_far_f <= bound) st[sp++] = far_f;
-        if (d_far_n <= bound) st[sp++] = far_n;
-        if (d_near_f <= bound) st[sp++] = near_f;
-        if (d_near_n <= bound) {
-          idx = near_n.x;
-          first = near_n.y;
-          last = near_n.z;
-        } else {
+        if (dn <= bound)
+          cur = right_first ? r1.w : r1.z;
+        else
           have = false;
-        }
       }
     }
     if (!at_leaf) break;  // done
-    scan_leaf<K>(sorted, first, last, qx, qy, qz, d2_cut, tk);
-    bound = __double2float_ru(fmin(tk.kth(k), d2_cut));
+    const uint32_t first = cur & 0x00FFFFFFu;
+    scan_leaf<K>(sorted, first, first + ((cur >> 24) & 7u), qx, qy, qz, d2_cut, tk);
+    bound = __double2float_ru(fmin(tk.kth(k), d2_cut) * inv2);
     have = false;
   }
 }

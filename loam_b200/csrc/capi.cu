@@ -62,7 +62,7 @@ struct loamgpu_ctx {
   DevBuf ring_edge, ring_planar, ring_counts;
   DevBuf edge_idx, planar_idx, edge_pts, planar_pts, feat_counts;
   DevBuf ge_hdr, ge_nodes, ge_sorted, ge_keys, ge_aux, gp_hdr, gp_nodes, gp_sorted, gp_keys, gp_aux;
-  DevBuf ge_wide, gp_wide;                 // 4-wide records (KNN_WIDE4)
+  DevBuf ge_quant, gp_quant, leftover;     // compact-record grids per set; pairs left to the general k-NN kernel
   DevBuf state, rec_p, rec_a, rec_b, nearest, nn_idx, nn_cnt, active;
   DevBuf big_scratch, misc, motions, out_pose, out_term, out_iters, out_ne, out_np;
   DevBuf det_est, det_upd, det_assoc_n, det_lm_iters, det_lm_cost, init_pose;
@@ -307,10 +307,9 @@ int reserve_register(loamgpu_ctx* ctx, uint32_t n_pairs, uint32_t capE, uint32_t
   CU(ctx->gp_hdr.reserve(n_sets * sizeof(BvhHdr)));
   CU(ctx->ge_nodes.reserve(n_sets * capE * sizeof(BvhNode)));
   CU(ctx->gp_nodes.reserve(n_sets * capP * sizeof(BvhNode)));
-#if KNN_WIDE4
-  CU(ctx->ge_wide.reserve(n_sets * capE * sizeof(BvhWide)));
-  CU(ctx->gp_wide.reserve(n_sets * capP * sizeof(BvhWide)));
-#endif
+  CU(ctx->ge_quant.reserve(n_sets * sizeof(BvhQuant)));
+  CU(ctx->gp_quant.reserve(n_sets * sizeof(BvhQuant)));
+  CU(ctx->leftover.reserve(((size_t)n_pairs + 1) * 4));
   CU(ctx->ge_aux.reserve(n_sets * capE * 4));
   CU(ctx->gp_aux.reserve(n_sets * capP * 4));
   CU(ctx->ge_sorted.reserve(n_sets * capE * 32));
@@ -336,7 +335,7 @@ BvhSetArrays bvh_arrays(loamgpu_ctx* ctx, bool planar, uint32_t cap) {
   g.keys = (planar ? ctx->gp_keys : ctx->ge_keys).as<uint2>();
   g.aux = (planar ? ctx->gp_aux : ctx->ge_aux).as<int>();
   g.pt_cap = cap;
-  g.wide = KNN_WIDE4 ? (planar ? ctx->gp_wide : ctx->ge_wide).as<BvhWide>() : nullptr;
+  g.quant = (planar ? ctx->gp_quant : ctx->ge_quant).as<BvhQuant>();
   return g;
 }
 
@@ -347,7 +346,7 @@ BvhSetArrays map_arrays(const loamgpu_map* m, int kind) {
   g.sorted = m->sorted[kind].as<double4>();
   g.keys = m->keys[kind].as<uint2>();
   g.aux = nullptr;
-  g.wide = nullptr;
+  g.quant = nullptr;
   g.pt_cap = (uint32_t)std::max<uint64_t>(m->n[kind], 1);
   return g;
 }
@@ -417,6 +416,7 @@ int run_register(loamgpu_ctx* ctx, const RegP& rp, uint32_t n_pairs, uint64_t pa
   aa.nearest = detail ? ctx->nearest.as<int32_t>() : nullptr;
   aa.nn_idx = ctx->nn_idx.as<uint32_t>();
   aa.nn_cnt = ctx->nn_cnt.as<uint32_t>();
+  aa.leftover = ctx->leftover.as<uint32_t>();
   aa.nn_stride = (uint32_t)std::max(rp.ke, rp.kp);
   aa.morton_queries = ctx->morton_queries;
   if (map) {
@@ -533,7 +533,7 @@ void loamgpu_destroy(loamgpu_ctx* c) {
   cudaDeviceSynchronize();
   DevBuf* bufs[] = {&c->scan_in[0], &c->scan_in[1], &c->ring_edge, &c->ring_planar, &c->ring_counts, &c->edge_idx,
                     &c->planar_idx, &c->edge_pts, &c->planar_pts, &c->feat_counts, &c->ge_hdr, &c->ge_nodes,
-                    &c->ge_sorted, &c->ge_keys, &c->ge_aux, &c->gp_hdr, &c->gp_nodes, &c->gp_sorted, &c->gp_keys, &c->gp_aux, &c->ge_wide, &c->gp_wide, &c->state,
+                    &c->ge_sorted, &c->ge_keys, &c->ge_aux, &c->gp_hdr, &c->gp_nodes, &c->gp_sorted, &c->gp_keys, &c->gp_aux, &c->ge_quant, &c->gp_quant, &c->leftover, &c->state,
                     &c->rec_p, &c->rec_a, &c->rec_b, &c->nearest, &c->nn_idx, &c->nn_cnt, &c->active, &c->misc, &c->motions, &c->out_pose, &c->out_term,
                     &c->out_iters, &c->out_ne, &c->out_np, &c->det_est, &c->det_upd, &c->det_assoc_n,
                     &c->det_lm_iters, &c->det_lm_cost, &c->init_pose, &c->big_scratch};
@@ -1200,7 +1200,7 @@ static uint32_t pick_chunk(loamgpu_ctx* ctx, OdometryMode mode, uint64_t n_scans
   const uint64_t cap = (uint64_t)capE + capP;
   // per pair: k-NN lists, residual records, two NN structures (nodes, sorted copy, sort keys, flags), feature slots
   // (indices + widened points), ring pick lists, and for host calls two staging copies of the scan
-  const uint64_t per_pair = cap * ((uint64_t)nn_stride * 4 + 4 + 96 + 84 + 36 + 4 + (KNN_WIDE4 ? sizeof(BvhWide) : 0)) +
+  const uint64_t per_pair = cap * ((uint64_t)nn_stride * 4 + 4 + 96 + 84 + 36 + 4 ) +
                             (mode == kResident ? 0 : 2 * n_per * 16);
   if (ctx->mem_budget && per_pair)  // (queried once at context creation: cudaMemGetInfo per call is far too slow)
     want = std::min<uint64_t>(want, std::max<uint64_t>(32, ctx->mem_budget / per_pair));

@@ -138,21 +138,29 @@ struct BvhHdr {
   uint32_t n;  // points
   uint32_t pad[3];
 };
-// 4-wide collapse of the radix tree (KNN_WIDE4): the record of internal node i holds the boxes of the subtrees two
-// levels below it, so ONE dependent 128-byte load decides two levels of the descent (tools/sim_bvh.py: 18.1 -> 8.8
-// dependent loads per query on a 14k-point planar set, box tests 35 -> 32).  Node i covers [first, last]; its children
-// are L = [first, s] (node s) and R = [s + 1, last] (node s + 1).  A child of at most kBvhLeaf points is scanned as a
-// leaf and keeps ONE slot (its own box; the second slot of its side is empty: lo = +inf); otherwise its two slots are
-// its children [.., sl] (node sl) and [sl + 1, ..] (node sl + 1) — likewise sr for R.
-struct __align__(128) BvhWide {
-  float box[4][6];   // slot c: lo xyz, hi xyz (rounded outward); slots 0,1 = side L, slots 2,3 = side R
-  uint32_t s, sl, sr;
-  uint32_t pad[5];
-};
 struct __align__(32) BvhNode {
   float lo[3];
   uint32_t split;  // split position | kLeftLeaf | kRightLeaf
   float hi[3];
+  uint32_t pad;    // the other end of the node's key range (node i covers [min(i, pad), max(i, pad)])
+};
+// Compact traversal records: what the batched k-NN kernel keeps in SHARED MEMORY while it walks one target set.  One
+// record per internal node that covers more than kBvhLeaf points (~ n / 4.6 of them), holding the boxes of its two
+// children on a 16-bit grid over the set's bounding box (rounded outward: a lower bound stays a lower bound) and what
+// each child is: another record, or a run of <= kBvhLeaf points of the Morton-sorted copy to scan.  32 bytes per
+// record, so a 64x1024 scan's two sets (2.4 k + 14.3 k points) take ~120 KB.  Written by the build kernel into the
+// (then dead) sort scratch of the set.
+constexpr uint32_t kRefLeaf = 0x80000000u;   // child ref: kRefLeaf | (count - 1) << 24 | first point  /  record index
+constexpr uint32_t kNoRecs = 0xFFFFFFFFu;    // BvhQuant::n_rec of a set without compact records (multi-CTA build, overflow)
+struct __align__(16) BvhRec {
+  uint32_t box[6];  // [axis] child L, [3 + axis] child R: lo | hi << 16 (grid cells)
+  uint32_t ref[2];  // child L, child R
+};
+struct BvhQuant {   // grid of one set: cell index of coordinate x on axis d = (x - org[d]) * inv_cell
+  double org[3];
+  double inv_cell;
+  double inv_cell2;  // inv_cell^2 (1 + 1e-12): squared metres -> squared cells, never rounded below the exact value
+  uint32_t n_rec;    // records of this set (0: at most kBvhLeaf points, scanned directly)
   uint32_t pad;
 };
 

@@ -26,9 +26,6 @@ constexpr int kLmMinBlocks = LM_MINBLOCKS;
 #ifndef BUILD_MINBLOCKS
 #define BUILD_MINBLOCKS 1
 #endif
-#ifndef KNN_WIDE4
-#define KNN_WIDE4 0
-#endif
 constexpr int kBuildThreads = BUILD_THREADS;  // one CTA per feature set (single-CTA NN build)
 constexpr int kKnnSmall = 5;     // neighbour counts up to this use the 5-slot register top-k
 constexpr int kKnnRegMax = 8;    // ... up to this the 8-slot one
@@ -92,11 +89,17 @@ struct BvhSetArrays {
   BvhHdr* hdr;        // [n_sets]
   BvhNode* nodes;     // [n_sets][pt_cap]     internal nodes 0 .. n-2, root = 0
   double4* sorted;    // [n_sets][pt_cap]     (x,y,z, bits(original index)), Morton order
-  uint2* keys;        // [n_sets][2][pt_cap]  radix-sort ping-pong scratch: (morton, original index)
-  int* aux;           // [n_sets][pt_cap]     build scratch: per-node readiness
+  uint2* keys;        // [n_sets][2][pt_cap]  radix-sort ping-pong scratch: (morton, original index); after the build
+                      //                      the first pt_cap / 2 BvhRec slots of a set's scratch hold its compact records
+  int* aux;           // [n_sets][pt_cap]     build scratch: per-node readiness, then compact record numbers
   uint32_t pt_cap;
-  BvhWide* wide;      // [n_sets][pt_cap]     optional 4-wide records (null: binary traversal only)
+  BvhQuant* quant;    // [n_sets]             grid + record count of the compact records (null: none, e.g. map targets)
 };
+// compact records of set `set` (they overlay its sort scratch)
+__host__ __device__ inline const BvhRec* bvh_recs(const BvhSetArrays& g, uint32_t set) {
+  return reinterpret_cast<const BvhRec*>(g.keys + (size_t)set * 2 * g.pt_cap);
+}
+__host__ __device__ inline uint32_t bvh_rec_cap(const BvhSetArrays& g) { return g.pt_cap / 2; }
 
 // Build NN structures for `n_sets` point sets.  Set s reads points
 // pts[(slot0 + s) % n_slots][0 .. counts[((slot0+s) % n_slots)*2 + kind]).
@@ -129,15 +132,19 @@ struct AssocArgs {
   int src_offset;          // 1 for sequence odometry; explicit-pair calls use slots 1 (src) / 0 (tgt)
   BvhSetArrays ge, gp;     // NN structures: set `pair` = target of the pair, set `pair + src_offset` = its source
   PairState* state;        // [pair]
-  double4* rec_p;          // [pair][capE+capP]  transformed point, w = 0 invalid / 1 edge / 2 plane
+  double4* rec_p;          // [pair][capE+capP]  transformed point, w = 0 invalid / 1 edge / 2 plane (after the fit kernel)
   double4* rec_a;          // [pair][capE+capP]  edge: line point a ; plane: normal, w = d
   double4* rec_b;          // [pair][capE]       edge: line point b
+  // Per-source-feature arrays (rec_*, nn_*) are in QUERY order: edge feature at position m of the source set's Morton
+  // order -> slot m, planar -> slot capE + m.  The k-NN kernel stores the feature's original index in rec_p.w; the fit
+  // kernel replaces it by the residual kind.  (Threads walk the queries in that order, so every write coalesces.)
   uint32_t* nn_idx;        // [pair][capE+capP][nn_stride] neighbour indices of the current outer iteration
   uint32_t* nn_cnt;        // [pair][capE+capP]            neighbours inside the radius
   uint32_t nn_stride;      // max(num_edge_neighbors, num_plane_neighbors)
   int morton_queries;      // 1: walk the source set in its Morton order (default), 0: original order
   uint32_t n_pairs;        // pairs of this launch
   const uint32_t* active;  // [0] = number of pairs still iterating, [1..] their indices; null = all, in order
+  uint32_t* leftover;      // [0] = count, [1..] pairs the shared-memory k-NN kernel left to the general one
   int32_t* nearest;        // optional [outer_iter][pair][capE+capP] nearest target index or -1 (detail)
   // external target (device-resident local map): when ext_target != 0 every pair registers onto set 0 of te / tp,
   // whose points in original order are te_pts / tp_pts; ge / gp then hold only the source sets (set = pair)

@@ -393,36 +393,25 @@ __device__ __forceinline__ uint32_t active_count(const uint32_t* active, uint32_
 }
 __device__ __forceinline__ uint32_t active_pair(const uint32_t* active, uint32_t i) { return active ? active[1 + i] : i; }
 
-template <int K, bool kWide>
-__device__ __forceinline__ void assoc_knn_pair(const AssocArgs& a, int outer_iter, uint32_t pair) {
-  const PairState* ps = a.state + pair;
-  if (ps->status != -1) return;
-  const uint32_t src_slot = (uint32_t)((a.pair0 + pair + a.src_offset) % a.n_slots);
-  const uint32_t nE = a.feat_counts[src_slot * 2], nP = a.feat_counts[src_slot * 2 + 1];
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nE + nP) return;
-  const bool is_plane = i >= nE;
-  double est[7];
-#pragma unroll
-  for (int j = 0; j < 7; j++) est[j] = ps->est[j];
+// Shared by both association kernels: one source feature (Morton position `m` of its kind in the source set) of one
+// pair.  `search` runs the k-NN of the transformed point in the target's structure.
+template <int K, typename Search>
+__device__ __forceinline__ void assoc_knn_query(const AssocArgs& a, int outer_iter, uint32_t pair, const double* est,
+                                                uint32_t src_slot, bool is_plane, uint32_t m, Search&& search) {
   const BvhSetArrays& gs = is_plane ? a.gp : a.ge;
   const uint32_t src_set = pair + (uint32_t)a.src_offset;
   double4 sp;
   if (a.morton_queries) {
-    sp = gs.sorted[(size_t)src_set * gs.pt_cap + (is_plane ? i - nE : i)];
+    sp = gs.sorted[(size_t)src_set * gs.pt_cap + m];
   } else {  // A/B switch: source features in their original order
-    sp = is_plane ? a.planar_pts[(size_t)src_slot * a.capP_scan + (i - nE)] : a.edge_pts[(size_t)src_slot * a.capE_scan + i];
-    sp.w = __longlong_as_double((long long)(is_plane ? i - nE : i));
+    sp = is_plane ? a.planar_pts[(size_t)src_slot * a.capP_scan + m] : a.edge_pts[(size_t)src_slot * a.capE_scan + m];
+    sp.w = __longlong_as_double((long long)m);
   }
-  const uint32_t li = (uint32_t)__double_as_longlong(sp.w);  // original index of this source feature
   const V3 q = pose_act(est, V3{sp.x, sp.y, sp.z});
-  const BvhSetArrays& gt = a.ext_target ? (is_plane ? a.tp : a.te) : gs;  // the target's structure
-  const uint32_t tset = a.ext_target ? 0u : pair;
-  const BvhHdr g = gt.hdr[tset];
   const int k = is_plane ? a.rp.kp : a.rp.ke;
   const double md = is_plane ? a.rp.rp : a.rp.re;
   const size_t cap_src = (size_t)a.capE_scan + a.capP_scan;
-  const size_t rec = (size_t)pair * cap_src + (is_plane ? a.capE_scan + li : li);
+  const size_t rec = (size_t)pair * cap_src + (is_plane ? a.capE_scan + m : m);  // query order (kernels.h: AssocArgs)
   uint32_t* out = a.nn_idx + rec * (size_t)a.nn_stride;
   // From the second outer iteration on, the previous neighbours give a bound before the search starts: k target
   // points lie within max_j |q - p_j|, so the k-th nearest distance cannot exceed it (the estimate moved by
@@ -443,25 +432,128 @@ __device__ __forceinline__ void assoc_knn_pair(const AssocArgs& a, int outer_ite
     d2_hint = worst;
   }
   TopK<K> tk;
-  if constexpr (kWide)
-    knn_bvh_wide<K>(g, gt.nodes + (size_t)tset * gt.pt_cap, gt.wide + (size_t)tset * gt.pt_cap,
-                    gt.sorted + (size_t)tset * gt.pt_cap, q.x, q.y, q.z, k, md, tk, d2_hint);
-  else
-    knn_bvh<K>(g, gt.nodes + (size_t)tset * gt.pt_cap, gt.sorted + (size_t)tset * gt.pt_cap, q.x, q.y, q.z, k, md, tk,
-               d2_hint);
-  const int m = radius_count(tk, k, md);
-  a.rec_p[rec] = make_double4(q.x, q.y, q.z, 0.0);
-  a.nn_cnt[rec] = (uint32_t)m;
+  search(q, k, md, d2_hint, tk);
+  const int cnt = radius_count(tk, k, md);
+  a.rec_p[rec] = make_double4(q.x, q.y, q.z, sp.w);  // w: original index of the source feature (for the fit kernel)
+  a.nn_cnt[rec] = (uint32_t)cnt;
 #pragma unroll
   for (int j = 0; j < K; j++)
     if (j < k) out[j] = tk.id[j];
 }
 
-template <int K, bool kWide>
-__global__ void __launch_bounds__(kKnnThreads, KNN_MINBLOCKS) assoc_knn_kernel(AssocArgs a, int outer_iter) {
+// General kernel: one query per thread, walks the target's node records in global memory (any target: this context's
+// sets, device-resident maps, neighbour counts up to 32).  Also takes the pairs the shared-memory kernel left over.
+template <int K>
+__device__ __forceinline__ void assoc_knn_pair(const AssocArgs& a, int outer_iter, uint32_t pair) {
+  const PairState* ps = a.state + pair;
+  if (ps->status != -1) return;
+  const uint32_t src_slot = (uint32_t)((a.pair0 + pair + a.src_offset) % a.n_slots);
+  const uint32_t nE = a.feat_counts[src_slot * 2], nP = a.feat_counts[src_slot * 2 + 1];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nE + nP) return;
+  const bool is_plane = i >= nE;
+  double est[7];
+#pragma unroll
+  for (int j = 0; j < 7; j++) est[j] = ps->est[j];
+  const BvhSetArrays& gt = a.ext_target ? (is_plane ? a.tp : a.te) : (is_plane ? a.gp : a.ge);  // the target's structure
+  const uint32_t tset = a.ext_target ? 0u : pair;
+  const BvhHdr g = gt.hdr[tset];
+  assoc_knn_query<K>(a, outer_iter, pair, est, src_slot, is_plane, is_plane ? i - nE : i,
+                     [&](const V3& q, int k, double md, double d2_hint, TopK<K>& tk) {
+                       knn_bvh<K>(g, gt.nodes + (size_t)tset * gt.pt_cap, gt.sorted + (size_t)tset * gt.pt_cap, q.x, q.y,
+                                  q.z, k, md, tk, d2_hint);
+                     });
+}
+
+template <int K>
+__global__ void __launch_bounds__(kKnnThreads, KNN_MINBLOCKS) assoc_knn_kernel(AssocArgs a, int outer_iter,
+                                                                              const uint32_t* list) {
+  // `list` = a.active (pairs still iterating) or a.leftover (pairs the shared-memory kernel skipped); null = all
+  const uint32_t n_act = active_count(list, a.n_pairs);
+  for (uint32_t i = blockIdx.y; i < n_act; i += gridDim.y) assoc_knn_pair<K>(a, outer_iter, active_pair(list, i));
+}
+
+// Batched kernel (sequence odometry, explicit batches): ONE persistent 1024-thread CTA per SM takes (pair, slice)
+// items; for each it bulk-copies the compact records of the pair's target sets (edge, planar: ~120 KB for a 64x1024
+// scan) into shared memory once, then its 32 warps pull 32-query chunks of the pair's source features (Morton order)
+// from a shared counter and walk the records there (bvh.cuh: knn_compact).  Pairs whose records do not fit, or whose
+// sets have none, go to a.leftover and are done by the general kernel right after.
+constexpr int kKnnCtaThreads = 1024;
+template <int K>
+__global__ void __launch_bounds__(kKnnCtaThreads, 1) assoc_knn_smem_kernel(AssocArgs a, int outer_iter, uint32_t n_slices,
+                                                                          uint32_t max_recs) {
+  extern __shared__ __align__(128) unsigned char knn_smem[];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ uint32_t s_next;
+  __shared__ BvhQuant s_q[2];
+  __shared__ double s_est[7];
+  const uint32_t tid = threadIdx.x, lane = tid & 31;
+  if (tid == 0) mbar_init(&s_bar, 1);
+  __syncthreads();
+  uint32_t phase = 0;
+  const uint32_t s_base = smem_u32(knn_smem);
   const uint32_t n_act = active_count(a.active, a.n_pairs);
-  for (uint32_t i = blockIdx.y; i < n_act; i += gridDim.y)
-    assoc_knn_pair<K, kWide>(a, outer_iter, active_pair(a.active, i));
+  const uint32_t n_items = n_act * n_slices;
+  for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const uint32_t pair = active_pair(a.active, item / n_slices), slice = item % n_slices;
+    const PairState* ps = a.state + pair;
+    if (ps->status != -1) continue;  // (CTA-uniform, like every exit below)
+    const uint32_t src_slot = (uint32_t)((a.pair0 + pair + a.src_offset) % a.n_slots);
+    const uint32_t nE = a.feat_counts[src_slot * 2], nP = a.feat_counts[src_slot * 2 + 1];
+    const uint32_t recE = a.ge.quant[pair].n_rec, recP = a.gp.quant[pair].n_rec;
+    if (recE == kNoRecs || recP == kNoRecs || recE + recP > max_recs) {
+      if (slice == 0 && tid == 0) a.leftover[1 + atomicAdd(a.leftover, 1u)] = pair;
+      continue;
+    }
+    // chunks of 32 queries: edge chunks first, then planar chunks; this item's share [c_lo, c_hi)
+    const uint32_t chE = (nE + 31) / 32, chAll = chE + (nP + 31) / 32;
+    const uint32_t per = (chAll + n_slices - 1) / n_slices;
+    const uint32_t c_lo = min(slice * per, chAll), c_hi = min(c_lo + per, chAll);
+    if (c_lo >= c_hi) continue;
+    const bool need_e = c_lo < chE && recE > 0, need_p = c_hi > chE && recP > 0;
+    __syncthreads();  // everyone is done with the previous item's records, grids and counter
+    if (tid == 0) {
+      s_next = c_lo;
+      const uint32_t bytes = (need_e ? recE : 0u) * (uint32_t)sizeof(BvhRec) + (need_p ? recP : 0u) * (uint32_t)sizeof(BvhRec);
+      if (bytes) {
+        mbar_expect_tx(&s_bar, bytes);
+        const BvhRec* src[2] = {bvh_recs(a.ge, pair), bvh_recs(a.gp, pair)};
+        const uint32_t cnt[2] = {need_e ? recE : 0u, need_p ? recP : 0u}, off[2] = {0u, recE};
+        for (int kind = 0; kind < 2; kind++)  // (pieces of at most 32 KB per bulk copy)
+          for (uint32_t r = 0; r < cnt[kind]; r += 1024) {
+            const uint32_t nr = min(1024u, cnt[kind] - r);
+            bulk_g2s(knn_smem + (size_t)(off[kind] + r) * sizeof(BvhRec), src[kind] + r, nr * (uint32_t)sizeof(BvhRec),
+                     &s_bar);
+          }
+      }
+    }
+    if (tid < 2) s_q[tid] = (tid ? a.gp : a.ge).quant[pair];
+    if (tid >= 32 && tid < 39) s_est[tid - 32] = ps->est[tid - 32];
+    __syncthreads();
+    if (need_e || need_p) {
+      mbar_wait(&s_bar, phase);
+      phase ^= 1u;
+    }
+    const uint32_t nTe = a.ge.hdr[pair].n, nTp = a.gp.hdr[pair].n;  // points of the target sets
+    for (;;) {
+      uint32_t c = 0;
+      if (lane == 0) c = atomicAdd(&s_next, 1u);
+      c = __shfl_sync(0xffffffffu, c, 0);
+      if (c >= c_hi) break;
+      const bool is_plane = c >= chE;
+      const uint32_t m = (is_plane ? c - chE : c) * 32 + lane;
+      if (m >= (is_plane ? nP : nE)) continue;
+      const BvhSetArrays& gt = is_plane ? a.gp : a.ge;
+      const uint32_t s_recs = s_base + (is_plane ? recE : 0u) * (uint32_t)sizeof(BvhRec);
+      const uint32_t n_pts = is_plane ? nTp : nTe;
+      const BvhQuant* Q = s_q + (is_plane ? 1 : 0);
+      const double4* sorted = gt.sorted + (size_t)pair * gt.pt_cap;
+      assoc_knn_query<K>(a, outer_iter, pair, s_est, src_slot, is_plane, m,
+                         [&](const V3& q, int k, double md, double d2_hint, TopK<K>& tk) {
+                           knn_compact<K>(s_recs, n_pts, Q, sorted, q.x, q.y, q.z, k, md, tk, d2_hint);
+                         });
+    }
+  }
 }
 
 // K5: line / plane fit + guards for every source feature (associateEdges/associatePlanes, registration.cpp:39-57,
@@ -479,9 +571,12 @@ __device__ __forceinline__ void assoc_fit_pair(const AssocArgs& a, int outer_ite
   const bool is_plane = active && i >= nE;
   bool ok = false;
   if (active) {
-    const uint32_t li = is_plane ? i - nE : i;
+    const uint32_t pos = is_plane ? i - nE : i;  // query order (kernels.h: AssocArgs)
     const size_t cap_src = (size_t)a.capE_scan + a.capP_scan;
-    const size_t rec = (size_t)pair * cap_src + (is_plane ? a.capE_scan + li : li);
+    const size_t rec = (size_t)pair * cap_src + (is_plane ? a.capE_scan + pos : pos);
+    // the k-NN kernel left the feature's original index in rec_p.w; this kernel replaces it by the residual kind
+    double* rec_w = reinterpret_cast<double*>(a.rec_p + rec) + 3;
+    const uint32_t li = (uint32_t)__double_as_longlong(*rec_w);
     const int m = (int)a.nn_cnt[rec];
     const uint32_t* nn = a.nn_idx + rec * (size_t)a.nn_stride;
     const int need = is_plane ? a.rp.min_plane : a.rp.min_line;
@@ -509,7 +604,7 @@ __device__ __forceinline__ void assoc_fit_pair(const AssocArgs& a, int outer_ite
         if (!(1.7976931348623157e308 < a.rp.min_cond)) {
           ok = true;
           a.rec_a[rec] = make_double4(la.x, la.y, la.z, 0.0);
-          a.rec_b[(size_t)pair * a.capE_scan + li] = make_double4(lb.x, lb.y, lb.z, 0.0);
+          a.rec_b[(size_t)pair * a.capE_scan + pos] = make_double4(lb.x, lb.y, lb.z, 0.0);
         }
       } else {
         V3 nrm;
@@ -521,7 +616,7 @@ __device__ __forceinline__ void assoc_fit_pair(const AssocArgs& a, int outer_ite
         }
       }
     }
-    if (ok) reinterpret_cast<double*>(a.rec_p + rec)[3] = is_plane ? 2.0 : 1.0;  // w: 0 invalid / 1 edge / 2 plane
+    *rec_w = ok ? (is_plane ? 2.0 : 1.0) : 0.0;  // w: 0 invalid / 1 edge / 2 plane
     if (a.nearest) a.nearest[((size_t)outer_iter * a.n_pairs + pair) * cap_src + (is_plane ? a.capE_scan + li : li)] =
         ok ? (int32_t)nn[0] : -1;
   }
@@ -1240,9 +1335,6 @@ cudaError_t launch_bvh_build(const BvhBuildArgs& a_in, uint32_t n_sets, cudaStre
   cudaError_t err = cudaFuncSetAttribute(bvh_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
   bvh_build_kernel<<<n_sets, kBuildThreads, smem, st>>>(a);
-  err = cudaGetLastError();
-  if (err != cudaSuccess || a.g.wide == nullptr) return err;
-  bvh_widen_kernel<<<dim3((a.g.pt_cap + 255) / 256, n_sets), 256, 0, st>>>(a.g);
   return cudaGetLastError();
 }
 
@@ -1252,27 +1344,66 @@ static uint32_t pair_rows(uint32_t n_pairs, int outer_iter, bool has_list, uint3
   return (outer_iter < 2 || !has_list) ? n_pairs : std::min(n_pairs, late_rows);
 }
 
+template <int K>
+static cudaError_t launch_knn_general(const AssocArgs& a, dim3 grid, int outer_iter, const uint32_t* list, cudaStream_t st) {
+  assoc_knn_kernel<K><<<grid, kKnnThreads, 0, st>>>(a, outer_iter, list);
+  return cudaGetLastError();
+}
+
+// Shared-memory budget of the batched k-NN kernel (bytes of compact records per CTA).  What is not given to shared
+// memory stays L1 (leaf points, traversal stacks).  $LOAMGPU_KNN_SMEM_KB overrides; 0 switches the kernel off.
+static uint32_t knn_smem_budget(int optin) {
+  static const long env = []() { const char* e = getenv("LOAMGPU_KNN_SMEM_KB"); return e ? atol(e) : -1L; }();
+  const long kb = env >= 0 ? env : 176;
+  return (uint32_t)std::min<long>(kb * 1024, (long)optin - 2048);
+}
+
 cudaError_t launch_assoc_knn(const AssocArgs& a, uint32_t n_pairs, int outer_iter, cudaStream_t st) {
   if (n_pairs == 0) return cudaSuccess;
   const uint32_t cap = a.capE_scan + a.capP_scan;
-  dim3 grid((cap + kKnnThreads - 1) / kKnnThreads, pair_rows(n_pairs, outer_iter, a.active != nullptr, 16));
+  const uint32_t grid_x = (cap + kKnnThreads - 1) / kKnnThreads;
   const int kmax = a.rp.ke > a.rp.kp ? a.rp.ke : a.rp.kp;
-  // 4-wide records exist for the sets this context builds itself (not for device-resident map targets)
-  const bool wide = !a.ext_target && a.ge.wide != nullptr && a.gp.wide != nullptr;
-  if (kmax <= kKnnSmall) {
-    if (wide)
-      assoc_knn_kernel<kKnnSmall, true><<<grid, kKnnThreads, 0, st>>>(a, outer_iter);
-    else
-      assoc_knn_kernel<kKnnSmall, false><<<grid, kKnnThreads, 0, st>>>(a, outer_iter);
-  } else if (kmax <= kKnnRegMax) {
-    if (wide)
-      assoc_knn_kernel<kKnnRegMax, true><<<grid, kKnnThreads, 0, st>>>(a, outer_iter);
-    else
-      assoc_knn_kernel<kKnnRegMax, false><<<grid, kKnnThreads, 0, st>>>(a, outer_iter);
-  } else {
-    assoc_knn_kernel<kKnnMax, false><<<grid, kKnnThreads, 0, st>>>(a, outer_iter);
+  static int n_sm = 0, optin = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   }
-  return cudaGetLastError();
+  static const uint32_t min_pairs = []() { const char* e = getenv("LOAMGPU_KNN_SMEM_MIN_PAIRS"); return e ? (uint32_t)atol(e) : 16u; }();
+  const uint32_t budget = knn_smem_budget(optin);
+  // The batched kernel needs this context's own sets (compact records), Morton-ordered queries, register-resident
+  // top-k lists and enough pairs to fill the SMs; everything else takes the general kernel alone.
+  const bool batched = !a.ext_target && a.morton_queries && a.ge.quant && a.gp.quant && a.leftover && kmax <= kKnnRegMax &&
+                       n_pairs >= min_pairs && budget >= 32 * 1024;
+  const uint32_t* list = a.active;
+  uint32_t rows = pair_rows(n_pairs, outer_iter, a.active != nullptr, 16);
+  if (batched) {
+    cudaError_t err = cudaMemsetAsync(a.leftover, 0, sizeof(uint32_t), st);
+    if (err != cudaSuccess) return err;
+    // items per launch ~ 6 per SM: whole waves of similar items, still few copies of a pair's records
+    const uint32_t n_slices = std::min<uint32_t>(16u, std::max<uint32_t>(1u, (6u * (uint32_t)n_sm + n_pairs - 1) / n_pairs));
+    const uint32_t grid = std::min<uint32_t>((uint32_t)n_sm, rows * n_slices);
+    const uint32_t max_recs = budget / (uint32_t)sizeof(BvhRec);
+    if (kmax <= kKnnSmall) {
+      err = cudaFuncSetAttribute(assoc_knn_smem_kernel<kKnnSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+      if (err != cudaSuccess) return err;
+      assoc_knn_smem_kernel<kKnnSmall><<<grid, kKnnCtaThreads, budget, st>>>(a, outer_iter, n_slices, max_recs);
+    } else {
+      err = cudaFuncSetAttribute(assoc_knn_smem_kernel<kKnnRegMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+      if (err != cudaSuccess) return err;
+      assoc_knn_smem_kernel<kKnnRegMax><<<grid, kKnnCtaThreads, budget, st>>>(a, outer_iter, n_slices, max_recs);
+    }
+    err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
+    // whatever it left over (normally nothing): a short strided grid of the general kernel
+    list = a.leftover;
+    rows = std::min<uint32_t>(n_pairs, 32u);
+  }
+  const dim3 grid(grid_x, rows);
+  if (kmax <= kKnnSmall) return launch_knn_general<kKnnSmall>(a, grid, outer_iter, list, st);
+  if (kmax <= kKnnRegMax) return launch_knn_general<kKnnRegMax>(a, grid, outer_iter, list, st);
+  return launch_knn_general<kKnnMax>(a, grid, outer_iter, list, st);
 }
 
 cudaError_t launch_assoc_fit(const AssocArgs& a, uint32_t n_pairs, int outer_iter, cudaStream_t st) {

@@ -140,7 +140,7 @@ def test_scan_to_scan_on_lidar_shapes(ctx, oracle, shape):
         assert np.array_equal(det["plane_assoc"][i], do.plane_assoc[i])
 
 
-def test_python_module_mirror(ctx, scene):
+def test_python_module_mirror(ctx, oracle, scene):
     import loam_b200 as loam
     ed, pl = scene
     sTt = H.REG_SCENARIOS[0][1]
@@ -150,7 +150,8 @@ def test_python_module_mirror(ctx, scene):
     pose = loam.registerFeatures(src, tgt, loam.Pose3d(), loam.RegistrationParams(), detail)
     ang, t = H.pose_error(sTt, pose._to7())
     assert ang < 1e-4 and np.all(np.abs(t) < 1e-4)
-    assert detail.termination_type == loam.CONVERGED and len(detail.iteration_info) == 3
+    _, do = oracle.register(H.transform(ed, sTt), H.transform(pl, sTt), ed, pl, want_detail=True)
+    assert detail.termination_type == loam.CONVERGED and len(detail.iteration_info) == do.n_iters >= 2
     info = detail.iteration_info[0]
     assert len(info.plane_associations) > 8000 and isinstance(info.edge_associations[0], tuple)
     # left composition of each recorded update reproduces the next recorded estimate (registration-inl.h:65)
