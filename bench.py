@@ -39,8 +39,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "extract+register scans/sec at 64x1024"
 UNIT = "scans/s"
+README_MS_PER_SCAN = 16.5  # the reference's only published figure: ~3.5 ms extract + ~13 ms register (README.md:31)
+
+
+def metric_name(a):
+    """BASELINE.json's metric, quoted on the shape actually run (the default is its 64x1024 headline)."""
+    return f"extract+register scans/sec at {a.rings}x{a.cols}"
 K_NEIGH = 5
 
 
@@ -57,6 +62,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline leg")
     ap.add_argument("--ref-pairs", type=int, default=0, help="--impl reference: pairs per step (0 = 2 x host cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the block of the other named BASELINE.json configs")
     return ap.parse_args()
 
 
@@ -168,29 +174,67 @@ def _cpu_extract(scan, lp, fe, orc, ref):
     return xyz[e], xyz[p]
 
 
-def cpu_pairs_time(scans, lp, fe, rp, orc, ref):
-    """Single-thread time of extract(every scan once) + register(each consecutive pair)."""
+def cpu_pairs_time(scans, lp, fe, rp, orc, ref, results=None):
+    """Single-thread time of extract(every scan once) + register(each consecutive pair).  `results` (optional dict)
+    receives what the CPU computed: feature counts per scan and pose / termination / outer iterations per pair."""
     t0 = time.perf_counter()
     feats = [_cpu_extract(s, lp, fe, orc, ref) for s in scans]
+    out = []
     for k in range(len(scans) - 1):
-        orc.register(feats[k + 1][0], feats[k + 1][1], feats[k][0], feats[k][1], None, rp)
-    return time.perf_counter() - t0
+        if results is None:
+            orc.register(feats[k + 1][0], feats[k + 1][1], feats[k][0], feats[k][1], None, rp)
+        else:
+            out.append(orc.register(feats[k + 1][0], feats[k + 1][1], feats[k][0], feats[k][1], None, rp,
+                                    want_detail=True))
+    dt = time.perf_counter() - t0
+    if results is not None:
+        results["n_edge"] = np.array([len(f[0]) for f in feats])
+        results["n_planar"] = np.array([len(f[1]) for f in feats])
+        results["poses"] = np.array([o[0] for o in out])
+        results["termination"] = np.array([o[1].termination for o in out])
+        results["iterations"] = np.array([o[1].n_iters for o in out])
+    return dt
 
 
 def cpu_baseline_leg(a, host_scans):
-    """Bounded single-core sample of the same workload: the first n+1 scans of rank 0's segment."""
+    """Bounded single-core sample of the same workload: the first n+1 scans of rank 0's segment.  Returns the
+    cpu_baseline object and the CPU results of those pairs (bench.py compares the GPU's with them: parity_check)."""
     lp, fe, rp, orc, ref = _cpu_setup(a)
     probe = 3
     t_probe = cpu_pairs_time(host_scans[:probe + 1], lp, fe, rp, orc, ref)  # also warms caches
     per_pair = t_probe / probe
     n = int(max(4, min(len(host_scans) - 1, a.cpu_seconds / max(per_pair, 1e-6))))
-    t = cpu_pairs_time(host_scans[:n + 1], lp, fe, rp, orc, ref)
+    res = {}
+    t = cpu_pairs_time(host_scans[:n + 1], lp, fe, rp, orc, ref, results=res)
     # every scan of a long sequence is extracted once and registered once: scans/s = pairs / time
-    return {"value": n / t, "unit": UNIT, "cores": 1, "kind": "port",
+    base = {"value": n / t, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": f"first {n} pairs ({n + 1} scans) of rank 0's segment, {t:.1f} s on one core; extract = "
                       f"{'real reference features code (oracle/_ref)' if ref is not None else 'oracle port'}, "
                       f"register = restated CPU port (Ceres/nanoflann absent)",
-            "ms_per_scan": 1e3 * t / n}
+            "ms_per_scan": 1e3 * t / n,
+            # the only published number for this path, always printed beside the restated CPU figure (BASELINE.md §4)
+            "reference_readme": {"ms_per_scan": README_MS_PER_SCAN, "scans_per_s": 1e3 / README_MS_PER_SCAN,
+                                 "source": "README.md:31 of the reference: ~3.5 ms extractFeatures + ~13 ms "
+                                           "registerFeatures, Ouster-64, author's laptop, 1 thread"}}
+    return base, res
+
+
+def parity_check(cpu, poses, term, iters, ne, npl, index_check):
+    """GPU results of this very run against the CPU oracle on the cpu_baseline sample (same pairs, same inputs)."""
+    n = len(cpu["poses"])
+    dq = np.abs(np.sum(cpu["poses"][:, :4] * poses[:n, :4], axis=1))
+    rad = 2.0 * np.arccos(np.minimum(1.0, dq))
+    out = {"pairs": int(n), "max_rad": float(rad.max()), "max_m": float(np.abs(cpu["poses"][:, 4:] - poses[:n, 4:]).max()),
+           "terminations_equal": bool(np.array_equal(cpu["termination"], term[:n])),
+           "outer_iterations_equal": bool(np.array_equal(cpu["iterations"], iters[:n])),
+           "feature_counts_equal": bool(np.array_equal(cpu["n_edge"], ne[:n + 1]) and
+                                        np.array_equal(cpu["n_planar"], npl[:n + 1])),
+           "indices_equal": index_check, "tolerance": {"rad": 1e-6, "m": 1e-5},
+           "against": "CPU oracle: real reference feature code + restated registration (parity with the real Ceres "
+                      "solve itself is unpinned, DESIGN.md §7)"}
+    out["ok"] = bool(out["max_rad"] < 1e-6 and out["max_m"] < 1e-5 and out["terminations_equal"] and
+                     out["outer_iterations_equal"] and out["feature_counts_equal"] and index_check["equal"])
+    return out
 
 
 def reference_arm(a):
@@ -227,7 +271,7 @@ def reference_arm(a):
     sample = (f"{pairs} pairs/step ({per} per thread + halo scan) of the same synthetic sequence; extract = "
               f"{'real reference features code (oracle/_ref)' if ref is not None else 'oracle port'}, register = "
               f"restated CPU port (Ceres 2.2.0 / nanoflann 1.5.5 are not in the image)")
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+    line = {"impl": "reference", "metric": metric_name(a), "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(a), "rings": a.rings, "cols": a.cols, "host_threads": cores,
@@ -256,6 +300,160 @@ def algorithmic_bytes(n_points, ne, npl, iters, k=K_NEIGH):
         "lm": int((iters * S).sum()) * 48,
         "misc": 0,
     }
+
+
+class Seq:
+    """One synthetic sequence segment on one GPU: device-resident scans, their pinned host mirror, result buffers."""
+
+    def __init__(self, torch, synth, dev, R, P, scan_lo, n):
+        self.R, self.P, self.n, self.n_points = R, P, n, R * P
+        self.d_scans = synth.make_scans_torch(R, P, scan_lo, n, dev)
+        self.h_scans = torch.empty(self.d_scans.shape, dtype=torch.float32, pin_memory=True)
+        self.h_scans.copy_(self.d_scans)
+        mk = lambda shape, dt, **kw: torch.zeros(shape, dtype=dt, **kw)  # noqa: E731
+        self.d = [mk((n - 1, 7), torch.float64, device=dev), mk(n - 1, torch.int32, device=dev),
+                  mk(n - 1, torch.int32, device=dev), mk(n, torch.int32, device=dev), mk(n, torch.int32, device=dev)]
+        self.h = [mk((n - 1, 7), torch.float64, pin_memory=True), mk(n - 1, torch.int32, pin_memory=True),
+                  mk(n - 1, torch.int32, pin_memory=True), mk(n, torch.int32, pin_memory=True),
+                  mk(n, torch.int32, pin_memory=True)]
+        torch.cuda.synchronize()
+
+
+def time_sequence(torch, ctx, stream, seq, lp, fe, rp, steps, warmup, barrier, max_over_ranks, profile=True):
+    """`steps` timed passes over `seq`: device-resident (CUDA events on the launching stream) and through the
+    host-buffer calls (wall clock around K asynchronous calls + one wait, and around K synchronous calls)."""
+    n = seq.n
+    dp, hp = [t.data_ptr() for t in seq.d], [t.data_ptr() for t in seq.h]
+
+    def step_device():
+        ctx.odometry_device_ptr(seq.d_scans.data_ptr(), n, lp, fe, rp, *dp)
+
+    def step_host():
+        ctx.odometry_host_ptr(seq.h_scans.data_ptr(), n, lp, fe, rp, *hp)
+
+    def step_host_async():
+        ctx.odometry_host_async_ptr(seq.h_scans.data_ptr(), n, lp, fe, rp, *hp)
+
+    for _ in range(warmup):
+        step_device()
+    barrier()
+    ctx.kernel_times()  # reset accumulators
+    ctx.set_profiling(profile)
+    launches0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    out = {"dev_ms": max_over_ranks(e0.elapsed_time(e1)), "launches": ctx.launch_count - launches0,
+           "ktimes": ctx.kernel_times()}
+    ctx.set_profiling(False)
+    # (a) the way a recording is streamed through: K asynchronous calls (pinned host scans in, results out to pinned
+    #     host memory, all copies inside the timed region), one wait at the end — the copies of a call overlap the
+    #     kernels of the previous one;  (b) every call waited for before the next one starts.
+    for _ in range(max(1, min(warmup, 2))):  # both forms (they use different chunk sizes: buffers grow once)
+        step_host()
+        step_host_async()
+    ctx.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step_host_async()
+    ctx.synchronize()
+    torch.cuda.synchronize()
+    out["e2e_ms"] = max_over_ranks(1e3 * (time.perf_counter() - t0))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step_host()
+    torch.cuda.synchronize()
+    out["e2e_sync_ms"] = max_over_ranks(1e3 * (time.perf_counter() - t0))
+    barrier()
+    assert np.array_equal(seq.h[0].numpy(), seq.d[0].cpu().numpy()), "host and device entry points disagree"
+    return out
+
+
+def traffic_per_launch(dom, dom_n, shape, n, steps):
+    """Per-launch DRAM bytes of the dominant kernel class from the committed `ncu --set full` capture — only when that
+    capture was taken on the shape being run (profiles/traffic.json names its shape and the commit it was taken at)."""
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(tp):
+        return None, None, None
+    try:
+        tj = json.load(open(tp))
+        if list(tj.get("shape", [64, 1024])) != list(shape):
+            return None, None, f"no capture for {shape[0]}x{shape[1]} (profiles/traffic.json: {tj.get('shape')})"
+        units = n if tj.get("unit", {}).get(dom) == "scan" else n - 1
+        per_unit = tj.get("per_unit", {}).get(dom)
+        traffic = per_unit * units * steps / max(dom_n, 1) if per_unit else None
+        return traffic, tj.get("_limiter", {}).get(dom), f"ncu --set full capture at commit {tj.get('commit', '?')}"
+    except Exception:
+        return None, None, None
+
+
+def other_configs(torch, synth, _capi, ctx, stream, dev, a, barrier, max_over_ranks):
+    """The other named configs of BASELINE.json on this GPU (3 timed steps each after 3 warm-ups): 16x1800, 128x2048
+    and scan-to-local-map.  Parity for these shapes is what the -m gpu tests cover; here they are measured."""
+    out = {}
+    fe, rp = _capi.default_fe_params(), _capi.default_reg_params()
+    for name, R, P, n in (("16x1800", 16, 1800, 1024), ("128x2048", 128, 2048, 256)):
+        seq = Seq(torch, synth, dev, R, P, 0, n)
+        lp = _capi.CLidarParams(R, P, 1.0, 120.0)
+        t = time_sequence(torch, ctx, stream, seq, lp, fe, rp, 3, 3, barrier, max_over_ranks, profile=False)
+        it = seq.h[2].numpy()
+        out[name] = {"metric": f"extract+register scans/sec at {R}x{P}", "scans_per_step": n, "steps": 3, "warmup": 3,
+                     "value": 3 * n / (t["dev_ms"] / 1e3), "e2e": 3 * n / (t["e2e_ms"] / 1e3),
+                     "e2e_each_call_waited": 3 * n / (t["e2e_sync_ms"] / 1e3), "unit": UNIT,
+                     "ms_per_step": t["dev_ms"] / 3, "mean_edge": float(seq.h[3].numpy().mean()),
+                     "mean_planar": float(seq.h[4].numpy().mean()), "mean_outer_iterations": float(it.mean()),
+                     "h2d_bytes_per_step": int(n * R * P * 16)}
+        del seq
+        torch.cuda.empty_cache()
+    # scan-to-local-map (config 5): target = features of 20 accumulated 128x2048 scans (max 400 planar / 60 edge per
+    # sector) in the frame of scan 0, resident on the device; source = one 64x1024 scan; one C-ABI call per registration
+    R, P, n_map = 128, 2048, 20
+    lp = _capi.CLidarParams(R, P, 1.0, 120.0)
+    fe_map = _capi.default_fe_params()
+    fe_map.max_planar_feats_per_sector, fe_map.max_edge_feats_per_sector = 400, 60
+
+    def moved(points, pose):
+        q, tr = np.asarray(pose[:4]), np.asarray(pose[4:7])
+        uv = 2.0 * np.cross(q[:3], points)
+        return (points + q[3] * uv + np.cross(q[:3], uv) + tr).astype(np.float32).astype(np.float64)
+
+    te, tp = [], []
+    for k in range(n_map):
+        sc = synth.make_scan(R, P, k=k)
+        e, p = ctx.extract(sc, lp, fe_map)
+        xyz = sc[:, :3].astype(np.float64)
+        te.append(moved(xyz[e], synth.relative_pose(0, k)))
+        tp.append(moved(xyz[p], synth.relative_pose(0, k)))
+    te, tp = np.concatenate(te), np.concatenate(tp)
+    sc = synth.make_scan(64, 1024, k=n_map)
+    e, p = ctx.extract(sc, _capi.CLidarParams(64, 1024, 1.0, 120.0), fe)
+    se, sp = sc[:, :3].astype(np.float64)[e], sc[:, :3].astype(np.float64)[p]
+    init, gt = synth.relative_pose(0, n_map - 1), synth.relative_pose(0, n_map)
+    t0 = time.perf_counter()
+    m = ctx.map_create(te, tp)
+    create_ms = 1e3 * (time.perf_counter() - t0)
+    for _ in range(3):
+        pose = ctx.register_to_map(m, se, sp, init, rp)
+    ts = []
+    for _ in range(10):
+        t0 = time.perf_counter()
+        pose = ctx.register_to_map(m, se, sp, init, rp)
+        ts.append(1e3 * (time.perf_counter() - t0))
+    m.close()
+    dq = abs(float(np.dot(pose[:4], gt[:4])))
+    out["scan_to_map"] = {"metric": "scan-to-local-map registrations/sec (one host-buffer call each)",
+                          "target_points": int(len(te) + len(tp)), "source_points": int(len(se) + len(sp)),
+                          "value": 1e3 / float(np.median(ts)), "unit": "registrations/s",
+                          "register_to_map_ms": float(np.median(ts)), "map_create_ms": create_ms,
+                          "error_vs_ground_truth": {"rad": 2.0 * float(np.arccos(min(1.0, dq))),
+                                                    "m": float(np.abs(pose[4:] - gt[4:]).max())}}
+    return out
 
 
 def ours(a):
@@ -302,20 +500,7 @@ def ours(a):
         ctx.set_chunk_pairs(a.chunk_pairs)
 
     # this rank's scans of the synthetic sequence (generated on the device, then mirrored to pinned host)
-    d_scans = synth.make_scans_torch(R, P, shard.scan_lo, n, dev)
-    h_scans = torch.empty(d_scans.shape, dtype=torch.float32, pin_memory=True)
-    h_scans.copy_(d_scans)
-    d_pose = torch.zeros((n - 1, 7), dtype=torch.float64, device=dev)
-    d_term = torch.zeros(n - 1, dtype=torch.int32, device=dev)
-    d_iter = torch.zeros(n - 1, dtype=torch.int32, device=dev)
-    d_ne = torch.zeros(n, dtype=torch.int32, device=dev)
-    d_np = torch.zeros(n, dtype=torch.int32, device=dev)
-    h_pose = torch.zeros((n - 1, 7), dtype=torch.float64, pin_memory=True)
-    h_term = torch.zeros(n - 1, dtype=torch.int32, pin_memory=True)
-    h_iter = torch.zeros(n - 1, dtype=torch.int32, pin_memory=True)
-    h_ne = torch.zeros(n, dtype=torch.int32, pin_memory=True)
-    h_np = torch.zeros(n, dtype=torch.int32, pin_memory=True)
-    torch.cuda.synchronize()
+    seq = Seq(torch, synth, dev, R, P, shard.scan_lo, n)
 
     # a dedicated non-default stream: the library treats a NULL stream handle as "use the context's own stream",
     # and the CUDA events below must sit on the stream the kernels are launched on
@@ -323,95 +508,33 @@ def ours(a):
     assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
 
-    def step_device():
-        ctx.odometry_device_ptr(d_scans.data_ptr(), n, lp, fe, rp, d_pose.data_ptr(), d_term.data_ptr(),
-                                d_iter.data_ptr(), d_ne.data_ptr(), d_np.data_ptr())
-
-    def step_host():
-        ctx.odometry_host_ptr(h_scans.data_ptr(), n, lp, fe, rp, h_pose.data_ptr(), h_term.data_ptr(),
-                              h_iter.data_ptr(), h_ne.data_ptr(), h_np.data_ptr())
-
-    # ---------------- device-resident timing (value)
-    for _ in range(a.warmup):
-        step_device()
-    barrier()
-    ctx.kernel_times()  # reset accumulators
-    ctx.set_profiling(True)
     sampler = ClockSampler(physical_gpu_index(local)) if rank == 0 else None
     if sampler:
         sampler.start()
-    launches0 = ctx.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(stream)
-    for _ in range(a.steps):
-        step_device()
-    e1.record(stream)
-    barrier()
-    dev_ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = ctx.launch_count - launches0
-    ktimes = ctx.kernel_times()
-    ctx.set_profiling(False)
-
-    # ---------------- end-to-end timing through the host-buffer C-ABI call (e2e)
-    # (a) the way a recording is streamed through: K asynchronous calls (pinned host scans in, results out to pinned
-    #     host memory, all copies inside the timed region), one wait at the end — the copies of a call overlap the
-    #     kernels of the previous one;  (b) every call waited for before the next one starts.
-    def step_host_async():
-        ctx.odometry_host_async_ptr(h_scans.data_ptr(), n, lp, fe, rp, h_pose.data_ptr(), h_term.data_ptr(),
-                                    h_iter.data_ptr(), h_ne.data_ptr(), h_np.data_ptr())
-
-    for _ in range(max(1, min(a.warmup, 2))):  # both forms (they use different chunk sizes: buffers grow once)
-        step_host()
-        step_host_async()
-    ctx.synchronize()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(a.steps):
-        step_host_async()
-    ctx.synchronize()
-    torch.cuda.synchronize()
-    t_host = time.perf_counter() - t0
-    barrier()
-    e2e_ms = max_over_ranks(1e3 * t_host)
-    t0 = time.perf_counter()
-    for _ in range(a.steps):
-        step_host()
-    torch.cuda.synchronize()
-    t_sync = time.perf_counter() - t0
-    barrier()
-    e2e_sync_ms = max_over_ranks(1e3 * t_sync)
+    t = time_sequence(torch, ctx, stream, seq, lp, fe, rp, a.steps, a.warmup, barrier, max_over_ranks)
     if sampler:
         sampler.stop_flag.set()
         sampler.join(timeout=2)
+    dev_ms, e2e_ms, e2e_sync_ms, ktimes, launches = t["dev_ms"], t["e2e_ms"], t["e2e_sync_ms"], t["ktimes"], t["launches"]
 
     # results of the last step (host copies from the e2e call)
-    ne, npl = h_ne.numpy().astype(np.int64), h_np.numpy().astype(np.int64)
-    iters, term = h_iter.numpy().astype(np.int64), h_term.numpy()
-    assert np.array_equal(h_pose.numpy(), d_pose.cpu().numpy()), "host and device entry points disagree"
+    h_pose, h_term, h_iter, h_ne, h_np = (x.numpy() for x in seq.h)
+    ne, npl = h_ne.astype(np.int64), h_np.astype(np.int64)
+    iters, term = h_iter.astype(np.int64), h_term
 
+    rc = 0
     if rank == 0:
         peak, peak_src = peaks()
         ab = algorithmic_bytes(n_points, ne, npl, iters)
         dom = max(ktimes, key=lambda k: ktimes[k][0])
         dom_ms, dom_n = ktimes[dom]
         achieved = (ab[dom] * a.steps / 1e9) / (dom_ms / 1e3) if dom_ms > 0 else 0.0
-        traffic, limiter = None, None
-        tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):  # per-launch DRAM bytes and the limiter named by the committed `ncu --set full` capture
-            try:
-                tj = json.load(open(tp))
-                limiter = tj.get("_limiter", {}).get(dom)
-                units = n if tj.get("unit", {}).get(dom) == "scan" else n - 1
-                per_unit = tj.get("per_unit", {}).get(dom)
-                traffic = per_unit * units * a.steps / max(dom_n, 1) if per_unit else None
-            except Exception:
-                traffic = None
+        traffic, limiter, traffic_src = traffic_per_launch(dom, dom_n, (R, P), n, a.steps)
         total_scans = a.scans * world * a.steps  # halo scans (extracted by two ranks) are counted once
         kernel_ms_total = sum(v[0] for v in ktimes.values())
         whole = sum(ab.values()) * a.steps
         line = {
-            "metric": METRIC, "value": total_scans / (dev_ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "metric": metric_name(a), "value": total_scans / (dev_ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(a), "rings": R, "cols": P, "scans_per_step_per_gpu": a.scans,
@@ -428,7 +551,8 @@ def ours(a):
                     "value_each_call_waited": total_scans / (e2e_sync_ms / 1e3)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ab[dom] * a.steps / max(dom_n, 1),
                          "avg_launch_ms": dom_ms / max(dom_n, 1), "launches": dom_n,
                          "whole_path_GBps": (whole / 1e9) / (dev_ms / 1e3),
@@ -443,14 +567,34 @@ def ours(a):
         if sampler:
             line["clocks"] = sampler.summary()
         if world == 1 and not a.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_leg(a, h_scans.numpy())
+            host = seq.h_scans.numpy()
+            line["cpu_baseline"], cpu = cpu_baseline_leg(a, host)
+            # feature indices of the first scans through the single-scan entry point against the reference's feature code
+            lp_o, fe_o, _, orc, ref = _cpu_setup(a)
+            eq = True
+            for k in range(2):
+                xyz = host[k][:, :3].astype(np.float64)
+                ce, cp = (ref.extract(xyz, lp_o, fe_o) if ref is not None else orc.extract(xyz, lp_o, fe_o))
+                ge, gp = ctx.extract(host[k], lp, fe)
+                eq = eq and np.array_equal(ce, ge) and np.array_equal(cp, gp)
+            line["parity_check"] = parity_check(cpu, h_pose, term, iters, ne, npl, {
+                "scans": 2, "equal": bool(eq),
+                "against": "real reference feature code (oracle/_ref)" if ref is not None else "oracle port"})
+            if not line["parity_check"]["ok"]:
+                rc = 3
+        if world == 1 and not a.no_configs:
+            del seq
+            torch.cuda.empty_cache()
+            line["configs"] = other_configs(torch, synth, _capi, ctx, stream, dev, a, barrier, max_over_ranks)
         print(json.dumps(line), flush=True)
+        if rc:
+            sys.stderr.write("bench.py: PARITY VIOLATION " + json.dumps(line["parity_check"]) + "\n")
     ctx.set_stream(None)
     ctx.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    return 0
+    return rc
 
 
 def main():

@@ -38,7 +38,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     cmd = [nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
            "-fmad=false", "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"),
-           "-I", os.path.join(HERE, "csrc"), "-o", LIB] + SRC
+           "-I", os.path.join(HERE, "csrc"), "-o", LIB] + SRC + ["-ldl"]
     cmd[1:1] = os.environ.get("LOAMGPU_NVCC_FLAGS", "").split()
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
@@ -51,5 +51,35 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def python_module_path() -> str:
+    import sysconfig
+    return os.path.join(HERE, "loam_python" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def build_python_module(force: bool = False) -> str:
+    """The pybind11 module `loam_python` (python/loam_b200_bindings.cpp) next to the package, linked against
+    lib/libloamgpu.so through an $ORIGIN rpath.  Host code only (g++): the kernels live in libloamgpu.so."""
+    import sysconfig
+
+    import pybind11
+    out = python_module_path()
+    src = os.path.join(ROOT, "python", "loam_b200_bindings.cpp")
+    deps = [src, LIB] + [os.path.join(ROOT, "include", "loam", f) for f in
+                         ("common.h", "features.h", "registration.h", "geometry.h", "detail/gpu.h")]
+    if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+        return out
+    cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden",
+           "-I", pybind11.get_include(), "-I", sysconfig.get_paths()["include"], "-I", os.path.join(ROOT, "include"),
+           "-I", os.path.join(ROOT, "include", "loam_compat"), src, "-o", out, "-L", os.path.dirname(LIB), "-lloamgpu",
+           "-Wl,-rpath,$ORIGIN/lib"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building the loam_python module")
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--python" in sys.argv:
+        print(build_python_module(force="--force" in sys.argv))

@@ -706,11 +706,25 @@ __device__ __forceinline__ void load_rec_shared(uint32_t saddr, uint4& r0, uint4
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r1.x), "=r"(r1.y), "=r"(r1.z), "=r"(r1.w) : "r"(saddr + 16u));
 }
 
+// Top of the traversal stack in shared memory (KNN_SMEM_STACK = entries per thread, a power of two; 0 = local memory
+// only).  Every push also goes to the thread's local-memory stack (a store nobody waits for); the newest
+// KNN_SMEM_STACK entries additionally sit in a ring in shared memory, where a pop costs an LDS instead of a
+// local-memory load that missed L1 (8 % of the stall samples of the first shared-memory version).  `s_stack` is the
+// shared address of this thread's slot 0; slot e lives kKnnStackPitch bytes further (conflict-free across a warp).
+#ifndef KNN_SMEM_STACK
+#define KNN_SMEM_STACK 0
+#endif
+#ifndef KNN_PREFETCH
+#define KNN_PREFETCH 0
+#endif
+constexpr uint32_t kKnnStackPitch = 1024u * 8u;
+
 // s_recs: shared-memory address of the set's record 0; n_pts: points of the set; Q: its grid (shared or global memory)
 template <int K>
-__device__ __forceinline__ void knn_compact(uint32_t s_recs, uint32_t n_pts, const BvhQuant* __restrict__ Q,
-                                            const double4* __restrict__ sorted, double qx, double qy, double qz, int k,
-                                            double max_dist, TopK<K>& tk, double d2_hint) {
+__device__ __forceinline__ void knn_compact(uint32_t s_recs, uint32_t s_stack, uint32_t n_pts,
+                                            const BvhQuant* __restrict__ Q, const double4* __restrict__ sorted,
+                                            double qx, double qy, double qz, int k, double max_dist, TopK<K>& tk,
+                                            double d2_hint) {
   tk.init();
   if (n_pts == 0) return;
   const double d2_cut = fmin(max_dist > 0 ? max_dist * max_dist * (1.0 + 1e-12) : CUDART_INF, d2_hint);
@@ -720,6 +734,11 @@ __device__ __forceinline__ void knn_compact(uint32_t s_recs, uint32_t n_pts, con
   float bound = __double2float_ru(d2_cut * inv2);  // cells^2; a subtree is pruned when its lower bound > bound
   uint2 st[kBvhStack];                             // pending subtrees: (child reference, lower bound)
   int sp = 0;
+#if KNN_SMEM_STACK
+  int ring_lo = 0;  // entries [ring_lo, sp) are intact in the shared-memory ring
+#else
+  (void)s_stack;
+#endif
   uint32_t cur = n_pts > (uint32_t)kBvhLeaf ? 0u : (kRefLeaf | ((n_pts - 1u) << 24));
   bool have = true, done = false;
   while (true) {
@@ -730,7 +749,15 @@ __device__ __forceinline__ void knn_compact(uint32_t s_recs, uint32_t n_pts, con
           done = true;
         } else {
           --sp;
-          const uint2 e = st[sp];
+          uint2 e;
+#if KNN_SMEM_STACK
+          if (sp >= ring_lo)
+            asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];"
+                         : "=r"(e.x), "=r"(e.y)
+                         : "r"(s_stack + (uint32_t)(sp & (KNN_SMEM_STACK - 1)) * kKnnStackPitch));
+          else
+#endif
+            e = st[sp];
           if (__uint_as_float(e.y) <= bound) {
             cur = e.x;
             have = true;
@@ -738,6 +765,13 @@ __device__ __forceinline__ void knn_compact(uint32_t s_recs, uint32_t n_pts, con
         }
       } else if (cur & kRefLeaf) {
         at_leaf = true;
+#if KNN_PREFETCH
+        {  // the leaf's points are needed once every lane of the warp stands on a leaf: start fetching them now
+          const char* p = reinterpret_cast<const char*>(sorted + (cur & 0x00FFFFFFu));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 128));
+        }
+#endif
       } else {
         uint4 r0, r1;  // (Lx Ly Lz Rx) (Ry Rz refL refR)
         load_rec_shared(s_recs + cur * (uint32_t)sizeof(BvhRec), r0, r1);
@@ -746,7 +780,13 @@ __device__ __forceinline__ void knn_compact(uint32_t s_recs, uint32_t n_pts, con
         const bool right_first = dr < dl;
         const float dn = right_first ? dr : dl, df = right_first ? dl : dr;
         if (df <= bound) {  // far child stays pending
-          st[sp] = make_uint2(right_first ? r1.z : r1.w, __float_as_uint(df));
+          const uint2 e = make_uint2(right_first ? r1.z : r1.w, __float_as_uint(df));
+          st[sp] = e;
+#if KNN_SMEM_STACK
+          asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(s_stack + (uint32_t)(sp & (KNN_SMEM_STACK - 1)) * kKnnStackPitch),
+                       "r"(e.x), "r"(e.y));
+          ring_lo = max(min(ring_lo, sp), sp - (KNN_SMEM_STACK - 1));
+#endif
           sp++;
         }
         if (dn <= bound)
@@ -757,7 +797,7 @@ __device__ __forceinline__ void knn_compact(uint32_t s_recs, uint32_t n_pts, con
     }
     if (!at_leaf) break;  // done
     const uint32_t first = cur & 0x00FFFFFFu;
-    scan_leaf<K>(sorted, first, first + ((cur >> 24) & 7u), qx, qy, qz, d2_cut, tk);
+    scan_leaf<K>(sorted, first, first + ((cur >> 24) & 15u), qx, qy, qz, d2_cut, tk);
     bound = __double2float_ru(fmin(tk.kth(k), d2_cut) * inv2);
     have = false;
   }

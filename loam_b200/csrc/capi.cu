@@ -9,6 +9,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges cost one pointer test when no tool is attached
+
 #include "kernels.h"
 #include "loamgpu.h"
 
@@ -41,6 +43,13 @@ struct DevBuf {
 };
 
 thread_local std::string g_create_err;
+
+// NVTX range around one C-ABI call (tracing): visible in Nsight Systems / Compute timelines
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+#define API_RANGE() NvtxRange _nvtx_range(__func__)
 
 }  // namespace
 
@@ -679,6 +688,7 @@ int loamgpu_extract(loamgpu_ctx* ctx, const void* pts, int dtype, size_t stride,
                     const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe, uint32_t* edge_idx,
                     uint64_t edge_cap, uint64_t* n_edge, uint32_t* planar_idx, uint64_t planar_cap,
                     uint64_t* n_planar) {
+  API_RANGE();
   return extract_one(ctx, pts, dtype, stride, n_points, lp, fe, nullptr, edge_idx, edge_cap, n_edge, planar_idx,
                      planar_cap, n_planar, nullptr);
 }
@@ -687,6 +697,7 @@ int loamgpu_extract_dewarped(loamgpu_ctx* ctx, const void* pts, int dtype, size_
                              const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe, const double* start_T_end,
                              uint32_t* edge_idx, uint64_t edge_cap, uint64_t* n_edge, uint32_t* planar_idx,
                              uint64_t planar_cap, uint64_t* n_planar, double* dewarped_xyz) {
+  API_RANGE();
   if (!ctx) return LOAMGPU_ERR_INVALID;
   if (!start_T_end) return fail(ctx, LOAMGPU_ERR_INVALID, "null start_T_end");
   return extract_one(ctx, pts, dtype, stride, n_points, lp, fe, start_T_end, edge_idx, edge_cap, n_edge, planar_idx,
@@ -723,11 +734,13 @@ static int curvature_or_mask(loamgpu_ctx* ctx, const void* pts, int dtype, size_
 
 int loamgpu_curvature(loamgpu_ctx* ctx, const void* pts, int dtype, size_t stride, uint64_t n_points,
                       const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe, double* curvature) {
+  API_RANGE();
   return curvature_or_mask(ctx, pts, dtype, stride, n_points, lp, fe, curvature, nullptr);
 }
 
 int loamgpu_valid_mask(loamgpu_ctx* ctx, const void* pts, int dtype, size_t stride, uint64_t n_points,
                        const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe, uint8_t* mask) {
+  API_RANGE();
   return curvature_or_mask(ctx, pts, dtype, stride, n_points, lp, fe, nullptr, mask);
 }
 
@@ -871,6 +884,7 @@ int loamgpu_register(loamgpu_ctx* ctx, const double* src_edge, uint64_t n_se, co
                      const double* tgt_edge, uint64_t n_te, const double* tgt_planar, uint64_t n_tp,
                      const double init_pose[7], const loamgpu_reg_params* params, double out_pose[7],
                      loamgpu_detail* detail) {
+  API_RANGE();
   if (!ctx) return LOAMGPU_ERR_INVALID;
   if (!init_pose || !out_pose) return fail(ctx, LOAMGPU_ERR_INVALID, "null pose pointer");
   if ((n_se && !src_edge) || (n_sp && !src_planar) || (n_te && !tgt_edge) || (n_tp && !tgt_planar))
@@ -899,6 +913,7 @@ int loamgpu_extract_batch(loamgpu_ctx* ctx, const void* pts, int dtype, size_t s
                           uint32_t* edge_idx,
                           uint64_t edge_cap, uint32_t* n_edge, uint32_t* planar_idx, uint64_t planar_cap,
                           uint32_t* n_planar) {
+  API_RANGE();
   if (!ctx) return LOAMGPU_ERR_INVALID;
   if (!lp || !fe) return fail(ctx, LOAMGPU_ERR_INVALID, "null parameter struct");
   if (n_scans == 0) return LOAMGPU_OK;
@@ -949,6 +964,7 @@ int loamgpu_register_pairs(loamgpu_ctx* ctx, uint64_t n_pairs, const double* src
                            const uint64_t* n_tgt_edge, const double* tgt_planar, const uint64_t* n_tgt_planar,
                            const double* init_poses, const loamgpu_reg_params* params, double* out_poses,
                            int32_t* termination, uint32_t* iterations) {
+  API_RANGE();
   if (!ctx) return LOAMGPU_ERR_INVALID;
   if (n_pairs == 0) return LOAMGPU_OK;
   if (!n_src_edge || !n_src_planar || !n_tgt_edge || !n_tgt_planar || !out_poses)
@@ -1024,6 +1040,7 @@ int loamgpu_register_pairs(loamgpu_ctx* ctx, uint64_t n_pairs, const double* src
 
 int loamgpu_map_create(loamgpu_ctx* ctx, const double* edge, uint64_t n_edge, const double* planar, uint64_t n_planar,
                        loamgpu_map** out) {
+  API_RANGE();
   if (!ctx || !out) return LOAMGPU_ERR_INVALID;
   *out = nullptr;
   if ((n_edge && !edge) || (n_planar && !planar)) return fail(ctx, LOAMGPU_ERR_INVALID, "null feature buffer");
@@ -1074,6 +1091,7 @@ int loamgpu_map_size(const loamgpu_map* m, uint64_t* n_edge, uint64_t* n_planar)
 
 int loamgpu_map_update(loamgpu_ctx* ctx, loamgpu_map* m, const double* edge, uint64_t n_edge, const double* planar,
                        uint64_t n_planar, const double pose[7], uint64_t max_edge, uint64_t max_planar) {
+  API_RANGE();
   if (!ctx || !m) return LOAMGPU_ERR_INVALID;
   if ((n_edge && !edge) || (n_planar && !planar)) return fail(ctx, LOAMGPU_ERR_INVALID, "null feature buffer");
   if (m->device != ctx->device) return fail(ctx, LOAMGPU_ERR_INVALID, "map belongs to another device");
@@ -1111,6 +1129,7 @@ int loamgpu_map_update(loamgpu_ctx* ctx, loamgpu_map* m, const double* edge, uin
 int loamgpu_register_to_map(loamgpu_ctx* ctx, const loamgpu_map* map, const double* src_edge, uint64_t n_se,
                             const double* src_planar, uint64_t n_sp, const double init_pose[7],
                             const loamgpu_reg_params* params, double out_pose[7], loamgpu_detail* detail) {
+  API_RANGE();
   if (!ctx || !map) return LOAMGPU_ERR_INVALID;
   if (!init_pose || !out_pose) return fail(ctx, LOAMGPU_ERR_INVALID, "null pose pointer");
   if ((n_se && !src_edge) || (n_sp && !src_planar)) return fail(ctx, LOAMGPU_ERR_INVALID, "null feature buffer");
@@ -1124,6 +1143,7 @@ int loamgpu_register_to_map(loamgpu_ctx* ctx, const loamgpu_map* map, const doub
 
 int loamgpu_knn(loamgpu_ctx* ctx, const double* targets, uint64_t n_t, const double* queries, uint64_t n_q, uint32_t k,
                 double max_dist, uint32_t* idx_out, uint32_t* count_out) {
+  API_RANGE();
   if (!ctx) return LOAMGPU_ERR_INVALID;
   if (k == 0 || k > (uint32_t)kKnnMax) return fail(ctx, LOAMGPU_ERR_UNSUPPORTED, "k must be in [1, 32]");
   if ((n_t && !targets) || (n_q && (!queries || !idx_out || !count_out)))
@@ -1307,6 +1327,7 @@ static int odometry_device_impl(loamgpu_ctx* ctx, const float* scans_dev, uint64
 int loamgpu_odometry_device(loamgpu_ctx* ctx, const float* scans_dev, uint64_t n_scans, const loamgpu_lidar_params* lp,
                             const loamgpu_fe_params* fe, const loamgpu_reg_params* reg, double* poses_dev,
                             int32_t* term_dev, uint32_t* iters_dev, uint32_t* ne_dev, uint32_t* np_dev) {
+  API_RANGE();
   return odometry_device_impl(ctx, scans_dev, n_scans, nullptr, lp, fe, reg, poses_dev, term_dev, iters_dev, ne_dev,
                               np_dev);
 }
@@ -1315,6 +1336,7 @@ int loamgpu_odometry_device_dewarped(loamgpu_ctx* ctx, const float* scans_dev, u
                                      const double* start_T_end_dev, const loamgpu_lidar_params* lp,
                                      const loamgpu_fe_params* fe, const loamgpu_reg_params* reg, double* poses_dev,
                                      int32_t* term_dev, uint32_t* iters_dev, uint32_t* ne_dev, uint32_t* np_dev) {
+  API_RANGE();
   if (!ctx) return LOAMGPU_ERR_INVALID;
   if (n_scans && !start_T_end_dev) return fail(ctx, LOAMGPU_ERR_INVALID, "null start_T_end");
   return odometry_device_impl(ctx, scans_dev, n_scans, start_T_end_dev, lp, fe, reg, poses_dev, term_dev, iters_dev,
@@ -1322,6 +1344,7 @@ int loamgpu_odometry_device_dewarped(loamgpu_ctx* ctx, const float* scans_dev, u
 }
 
 int loamgpu_synchronize(loamgpu_ctx* ctx) {
+  API_RANGE();
   if (!ctx) return LOAMGPU_ERR_INVALID;
   CU(cudaSetDevice(ctx->device));
   CU(cudaStreamSynchronize(ctx->copy_stream));
@@ -1341,6 +1364,7 @@ extern "C" {
 int loamgpu_odometry_host(loamgpu_ctx* ctx, const float* scans, uint64_t n_scans, const loamgpu_lidar_params* lp,
                           const loamgpu_fe_params* fe, const loamgpu_reg_params* reg, double* poses, int32_t* termination,
                           uint32_t* iterations, uint32_t* n_edge, uint32_t* n_planar) {
+  API_RANGE();
   const int rc = odometry_host_impl(ctx, kHostSync, scans, n_scans, lp, fe, reg, poses, termination, iterations, n_edge,
                                     n_planar);
   if (rc) return rc;
@@ -1351,6 +1375,7 @@ int loamgpu_odometry_host_dewarped(loamgpu_ctx* ctx, const float* scans, uint64_
                                    const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe,
                                    const loamgpu_reg_params* reg, double* poses, int32_t* termination,
                                    uint32_t* iterations, uint32_t* n_edge, uint32_t* n_planar) {
+  API_RANGE();
   if (!ctx) return LOAMGPU_ERR_INVALID;
   if (n_scans && !start_T_end) return fail(ctx, LOAMGPU_ERR_INVALID, "null start_T_end");
   const int rc = odometry_host_impl(ctx, kHostSync, scans, n_scans, lp, fe, reg, poses, termination, iterations, n_edge,
@@ -1362,6 +1387,7 @@ int loamgpu_odometry_host_dewarped(loamgpu_ctx* ctx, const float* scans, uint64_
 int loamgpu_odometry_host_async(loamgpu_ctx* ctx, const float* scans, uint64_t n_scans, const loamgpu_lidar_params* lp,
                                 const loamgpu_fe_params* fe, const loamgpu_reg_params* reg, double* poses,
                                 int32_t* termination, uint32_t* iterations, uint32_t* n_edge, uint32_t* n_planar) {
+  API_RANGE();
   return odometry_host_impl(ctx, kHostAsync, scans, n_scans, lp, fe, reg, poses, termination, iterations, n_edge,
                             n_planar);
 }

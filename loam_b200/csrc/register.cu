@@ -491,7 +491,10 @@ __global__ void __launch_bounds__(kKnnCtaThreads, 1) assoc_knn_smem_kernel(Assoc
   if (tid == 0) mbar_init(&s_bar, 1);
   __syncthreads();
   uint32_t phase = 0;
-  const uint32_t s_base = smem_u32(knn_smem);
+  // dynamic shared memory: [traversal-stack ring: KNN_SMEM_STACK x 1024 x 8 bytes][compact records]
+  const uint32_t s_stack = smem_u32(knn_smem) + tid * 8u;
+  unsigned char* const rec_smem = knn_smem + (size_t)KNN_SMEM_STACK * kKnnStackPitch;
+  const uint32_t s_base = smem_u32(rec_smem);
   const uint32_t n_act = active_count(a.active, a.n_pairs);
   const uint32_t n_items = n_act * n_slices;
   for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -522,7 +525,7 @@ __global__ void __launch_bounds__(kKnnCtaThreads, 1) assoc_knn_smem_kernel(Assoc
         for (int kind = 0; kind < 2; kind++)  // (pieces of at most 32 KB per bulk copy)
           for (uint32_t r = 0; r < cnt[kind]; r += 1024) {
             const uint32_t nr = min(1024u, cnt[kind] - r);
-            bulk_g2s(knn_smem + (size_t)(off[kind] + r) * sizeof(BvhRec), src[kind] + r, nr * (uint32_t)sizeof(BvhRec),
+            bulk_g2s(rec_smem + (size_t)(off[kind] + r) * sizeof(BvhRec), src[kind] + r, nr * (uint32_t)sizeof(BvhRec),
                      &s_bar);
           }
       }
@@ -550,7 +553,7 @@ __global__ void __launch_bounds__(kKnnCtaThreads, 1) assoc_knn_smem_kernel(Assoc
       const double4* sorted = gt.sorted + (size_t)pair * gt.pt_cap;
       assoc_knn_query<K>(a, outer_iter, pair, s_est, src_slot, is_plane, m,
                          [&](const V3& q, int k, double md, double d2_hint, TopK<K>& tk) {
-                           knn_compact<K>(s_recs, n_pts, Q, sorted, q.x, q.y, q.z, k, md, tk, d2_hint);
+                           knn_compact<K>(s_recs, s_stack, n_pts, Q, sorted, q.x, q.y, q.z, k, md, tk, d2_hint);
                          });
     }
   }
@@ -1384,7 +1387,9 @@ cudaError_t launch_assoc_knn(const AssocArgs& a, uint32_t n_pairs, int outer_ite
     // items per launch ~ 6 per SM: whole waves of similar items, still few copies of a pair's records
     const uint32_t n_slices = std::min<uint32_t>(16u, std::max<uint32_t>(1u, (6u * (uint32_t)n_sm + n_pairs - 1) / n_pairs));
     const uint32_t grid = std::min<uint32_t>((uint32_t)n_sm, rows * n_slices);
-    const uint32_t max_recs = budget / (uint32_t)sizeof(BvhRec);
+    const uint32_t ring = (uint32_t)KNN_SMEM_STACK * kKnnStackPitch;  // traversal-stack ring in front of the records
+    if (budget <= ring + 32 * 1024) return cudaErrorInvalidConfiguration;
+    const uint32_t max_recs = (budget - ring) / (uint32_t)sizeof(BvhRec);
     if (kmax <= kKnnSmall) {
       err = cudaFuncSetAttribute(assoc_knn_smem_kernel<kKnnSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
       if (err != cudaSuccess) return err;

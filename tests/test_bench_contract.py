@@ -57,7 +57,7 @@ import pytest
 @pytest.mark.gpu
 def test_our_arm_line_has_the_contract_keys():
     lines = run_bench(["--steps", "2", "--warmup", "1", "--scans", "12", "--rings", "16", "--cols", "512",
-                       "--cpu-seconds", "0.5"])
+                       "--cpu-seconds", "0.5", "--no-configs"])
     d = json.loads(lines[-1])
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
@@ -74,3 +74,11 @@ def test_our_arm_line_has_the_contract_keys():
     assert cb["cores"] == 1 and cb["kind"] == "port" and cb["value"] > 0 and "pairs" in cb["sample"]
     assert abs(sum(d["kernel_share"].values()) - 1.0) < 1e-9
     assert "workload" in d["config"] and "l2" in d["config"]
+    assert d["metric"] == "extract+register scans/sec at 16x512"
+    assert cb["reference_readme"]["ms_per_scan"] == 16.5
+    # the run checks its own results against the CPU oracle on the cpu_baseline sample (non-zero exit on violation)
+    pc = d["parity_check"]
+    assert pc["ok"] and pc["pairs"] >= 4 and pc["max_rad"] < 1e-6 and pc["max_m"] < 1e-5
+    assert pc["terminations_equal"] and pc["outer_iterations_equal"] and pc["feature_counts_equal"]
+    assert pc["indices_equal"]["equal"]
+    assert r["traffic"] is None  # no ncu capture exists for this shape: never a number measured on another one
