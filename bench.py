@@ -63,6 +63,8 @@ def parse():
     ap.add_argument("--ref-pairs", type=int, default=0, help="--impl reference: pairs per step (0 = 2 x host cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the block of the other named BASELINE.json configs")
+    ap.add_argument("--point-bytes", type=int, default=16, choices=[12, 16],
+                    help="bytes per float record of the headline run: 16 = {x,y,z,.} (SURVEY §8d spec, default), 12 = packed xyz")
     return ap.parse_args()
 
 
@@ -167,6 +169,8 @@ def _cpu_setup(a):
 def _cpu_extract(scan, lp, fe, orc, ref):
     """One scan through the reference's feature code (real sources when oracle/_ref exists)."""
     if ref is not None:
+        if scan.shape[1] == 3:  # packed xyz records: the reference shim reads 16-byte FieldAccessor points
+            scan = np.concatenate([scan, np.zeros((len(scan), 1), np.float32)], axis=1)
         _, _, e, p = ref.extract_timed_f32x4(scan, lp, fe, reps=1)
     else:
         e, p = orc.extract(scan[:, :3].astype(np.float64), lp, fe)
@@ -305,9 +309,11 @@ def algorithmic_bytes(n_points, ne, npl, iters, k=K_NEIGH):
 class Seq:
     """One synthetic sequence segment on one GPU: device-resident scans, their pinned host mirror, result buffers."""
 
-    def __init__(self, torch, synth, dev, R, P, scan_lo, n):
-        self.R, self.P, self.n, self.n_points = R, P, n, R * P
+    def __init__(self, torch, synth, dev, R, P, scan_lo, n, point_bytes=16):
+        self.R, self.P, self.n, self.n_points, self.point_bytes = R, P, n, R * P, point_bytes
         self.d_scans = synth.make_scans_torch(R, P, scan_lo, n, dev)
+        if point_bytes == 12:  # packed xyz records: the fourth float of a sensor record is never read
+            self.d_scans = self.d_scans[:, :, :3].contiguous()
         self.h_scans = torch.empty(self.d_scans.shape, dtype=torch.float32, pin_memory=True)
         self.h_scans.copy_(self.d_scans)
         mk = lambda shape, dt, **kw: torch.zeros(shape, dtype=dt, **kw)  # noqa: E731
@@ -326,13 +332,13 @@ def time_sequence(torch, ctx, stream, seq, lp, fe, rp, steps, warmup, barrier, m
     dp, hp = [t.data_ptr() for t in seq.d], [t.data_ptr() for t in seq.h]
 
     def step_device():
-        ctx.odometry_device_ptr(seq.d_scans.data_ptr(), n, lp, fe, rp, *dp)
+        ctx.odometry_device_ptr(seq.d_scans.data_ptr(), n, lp, fe, rp, *dp, stride=seq.point_bytes)
 
     def step_host():
-        ctx.odometry_host_ptr(seq.h_scans.data_ptr(), n, lp, fe, rp, *hp)
+        ctx.odometry_host_ptr(seq.h_scans.data_ptr(), n, lp, fe, rp, *hp, stride=seq.point_bytes)
 
     def step_host_async():
-        ctx.odometry_host_async_ptr(seq.h_scans.data_ptr(), n, lp, fe, rp, *hp)
+        ctx.odometry_host_async_ptr(seq.h_scans.data_ptr(), n, lp, fe, rp, *hp, stride=seq.point_bytes)
 
     for _ in range(warmup):
         step_device()
@@ -500,7 +506,7 @@ def ours(a):
         ctx.set_chunk_pairs(a.chunk_pairs)
 
     # this rank's scans of the synthetic sequence (generated on the device, then mirrored to pinned host)
-    seq = Seq(torch, synth, dev, R, P, shard.scan_lo, n)
+    seq = Seq(torch, synth, dev, R, P, shard.scan_lo, n, a.point_bytes)
 
     # a dedicated non-default stream: the library treats a NULL stream handle as "use the context's own stream",
     # and the CUDA events below must sit on the stream the kernels are launched on
@@ -539,12 +545,13 @@ def ours(a):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(a), "rings": R, "cols": P, "scans_per_step_per_gpu": a.scans,
                        "params": "default FeatureExtractionParams / RegistrationParams, identity init",
-                       "l2": f"inputs larger than L2 ({n * n_points * 16 / 2**20:.0f} MiB of scans per step per GPU)",
+                       "point_bytes": a.point_bytes,
+                       "l2": f"inputs larger than L2 ({n * n_points * a.point_bytes / 2**20:.0f} MiB of scans per step per GPU)",
                        "sharding": "contiguous sequence segments per rank, no data-path collective",
                        "host_affinity": (f"each rank bound to its GPU's NUMA-local CPUs ({numa_cpus})" if numa_cpus
                                          else "unbound")},
             "e2e": {"value": total_scans / (e2e_ms / 1e3), "unit": UNIT,
-                    "h2d_bytes_per_step": int(world * n * n_points * 16),
+                    "h2d_bytes_per_step": int(world * n * n_points * a.point_bytes),
                     "d2h_bytes_per_step": int(world * ((n - 1) * (56 + 4 + 4) + n * 8)),
                     "ms_per_step": e2e_ms / a.steps,
                     "mode": "K asynchronous host-buffer calls (loamgpu_odometry_host_async), one wait after the last",

@@ -244,6 +244,22 @@ int loamgpu_odometry_device(loamgpu_ctx* ctx, const float* scans_dev, uint64_t n
                             const loamgpu_lidar_params* lidar, const loamgpu_fe_params* fe,
                             const loamgpu_reg_params* reg, double* poses_dev, int32_t* termination_dev,
                             uint32_t* iterations_dev, uint32_t* n_edge_dev, uint32_t* n_planar_dev);
+/* The same three calls on float records of `stride_bytes` = 12 (packed x y z: numpy (N,3) float32, PCL-style packed
+ * clouds) or 16 (x y z + one unused float).  The fourth float of a sensor record is never read, so a host that can
+ * hand over packed xyz moves 25 % fewer bytes through the host-to-device copy that bounds the host-buffer calls;
+ * the extraction kernel stages 12-byte rings with one bulk copy just like float4 ones.  Results are identical. */
+int loamgpu_odometry_host_strided(loamgpu_ctx* ctx, const void* scans, size_t stride_bytes, uint64_t n_scans,
+                                  const loamgpu_lidar_params* lidar, const loamgpu_fe_params* fe,
+                                  const loamgpu_reg_params* reg, double* poses, int32_t* termination,
+                                  uint32_t* iterations, uint32_t* n_edge, uint32_t* n_planar);
+int loamgpu_odometry_host_async_strided(loamgpu_ctx* ctx, const void* scans, size_t stride_bytes, uint64_t n_scans,
+                                        const loamgpu_lidar_params* lidar, const loamgpu_fe_params* fe,
+                                        const loamgpu_reg_params* reg, double* poses, int32_t* termination,
+                                        uint32_t* iterations, uint32_t* n_edge, uint32_t* n_planar);
+int loamgpu_odometry_device_strided(loamgpu_ctx* ctx, const void* scans_dev, size_t stride_bytes, uint64_t n_scans,
+                                    const loamgpu_lidar_params* lidar, const loamgpu_fe_params* fe,
+                                    const loamgpu_reg_params* reg, double* poses_dev, int32_t* termination_dev,
+                                    uint32_t* iterations_dev, uint32_t* n_edge_dev, uint32_t* n_planar_dev);
 /* EXTENSION: the sequence calls on sweeps that still need de-warping.  start_T_end is
  * [n_scans][7] (qx qy qz qw tx ty tz): the sensor motion during sweep s, e.g. the previous pair's
  * estimate under a constant-velocity model, or an IMU / wheel-odometry prediction.  Every scan is

@@ -28,6 +28,7 @@ SYMBOLS = [
     "loamgpu_map_destroy", "loamgpu_map_size", "loamgpu_map_update", "loamgpu_register_to_map",
     "loamgpu_extract_batch", "loamgpu_register_pairs", "loamgpu_odometry_host_async", "loamgpu_synchronize",
     "loamgpu_extract_dewarped", "loamgpu_odometry_host_dewarped", "loamgpu_odometry_device_dewarped",
+    "loamgpu_odometry_host_strided", "loamgpu_odometry_host_async_strided", "loamgpu_odometry_device_strided",
 ]
 KERNEL_CLASSES = ["extract", "pack", "nn_build", "knn", "lm", "misc", "fit"]
 
@@ -104,6 +105,9 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     lib.loamgpu_odometry_host_async.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.loamgpu_synchronize.argtypes = [vp]
     lib.loamgpu_odometry_device.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, vp, vp, vp]
+    for f in (lib.loamgpu_odometry_host_strided, lib.loamgpu_odometry_host_async_strided,
+              lib.loamgpu_odometry_device_strided):
+        f.argtypes = [vp, vp, C.c_size_t, u64, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.loamgpu_odometry_host_dewarped.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.loamgpu_odometry_device_dewarped.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     _lib = lib
@@ -325,46 +329,52 @@ class Context:
         kernel (loamgpu_odometry_host_dewarped)."""
         s = np.ascontiguousarray(scans, dtype=np.float32)
         n = s.shape[0]
+        if s.ndim != 3 or s.shape[2] not in (3, 4):
+            raise ValueError("scans must be [n_scans, points, 3 or 4] float32 records")
+        stride = 4 * s.shape[2]  # packed xyz (12 bytes) or float4 (16 bytes)
         poses = np.zeros((max(n - 1, 0), 7))
         term = np.zeros(max(n - 1, 0), dtype=np.int32)
         its = np.zeros(max(n - 1, 0), dtype=np.uint32)
         ne = np.zeros(n, dtype=np.uint32)
         npl = np.zeros(n, dtype=np.uint32)
         if sweep_motions is None:
-            self._check(self.lib.loamgpu_odometry_host(self.h, _ptr(s), n, C.addressof(lp), C.addressof(fe),
-                                                       C.addressof(rp), _ptr(poses), _ptr(term), _ptr(its), _ptr(ne),
-                                                       _ptr(npl)))
+            self._check(self.lib.loamgpu_odometry_host_strided(self.h, _ptr(s), stride, n, C.addressof(lp),
+                                                               C.addressof(fe), C.addressof(rp), _ptr(poses), _ptr(term),
+                                                               _ptr(its), _ptr(ne), _ptr(npl)))
         else:
             m = np.ascontiguousarray(sweep_motions, dtype=np.float64)
             if m.shape != (n, 7):
                 raise ValueError("sweep_motions must be [n_scans, 7]")
+            if stride != 16:
+                raise ValueError("the de-warping sequence call takes float4 records")
             self._check(self.lib.loamgpu_odometry_host_dewarped(self.h, _ptr(s), n, _ptr(m), C.addressof(lp),
                                                                 C.addressof(fe), C.addressof(rp), _ptr(poses), _ptr(term),
                                                                 _ptr(its), _ptr(ne), _ptr(npl)))
         return poses, term, its, ne, npl
 
     def odometry_host_ptr(self, scans_ptr: int, n_scans: int, lp, fe, rp, poses_ptr, term_ptr, iters_ptr, ne_ptr,
-                          np_ptr):
-        self._check(self.lib.loamgpu_odometry_host(self.h, scans_ptr, n_scans, C.addressof(lp), C.addressof(fe),
-                                                   C.addressof(rp), poses_ptr, term_ptr, iters_ptr, ne_ptr, np_ptr))
+                          np_ptr, stride: int = 16):
+        """`stride` = bytes per float record: 16 (x y z .) or 12 (packed x y z)."""
+        self._check(self.lib.loamgpu_odometry_host_strided(self.h, scans_ptr, stride, n_scans, C.addressof(lp),
+                                                           C.addressof(fe), C.addressof(rp), poses_ptr, term_ptr,
+                                                           iters_ptr, ne_ptr, np_ptr))
 
     def odometry_host_async_ptr(self, scans_ptr: int, n_scans: int, lp, fe, rp, poses_ptr, term_ptr, iters_ptr, ne_ptr,
-                                np_ptr):
+                                np_ptr, stride: int = 16):
         """Enqueue only (page-locked host buffers, valid until synchronize()); consecutive calls pipeline."""
-        self._check(self.lib.loamgpu_odometry_host_async(self.h, scans_ptr, n_scans, C.addressof(lp), C.addressof(fe),
-                                                         C.addressof(rp), poses_ptr, term_ptr, iters_ptr, ne_ptr,
-                                                         np_ptr))
+        self._check(self.lib.loamgpu_odometry_host_async_strided(self.h, scans_ptr, stride, n_scans, C.addressof(lp),
+                                                                 C.addressof(fe), C.addressof(rp), poses_ptr, term_ptr,
+                                                                 iters_ptr, ne_ptr, np_ptr))
 
     def synchronize(self):
         self._check(self.lib.loamgpu_synchronize(self.h))
 
     def odometry_device_ptr(self, scans_ptr: int, n_scans: int, lp, fe, rp, poses_ptr, term_ptr, iters_ptr, ne_ptr,
-                            np_ptr):
+                            np_ptr, stride: int = 16):
         """All pointers are device addresses (e.g. torch tensor .data_ptr()); asynchronous on the context stream."""
-        self._check(self.lib.loamgpu_odometry_device(self.h, scans_ptr, n_scans, C.addressof(lp), C.addressof(fe),
-                                                     C.addressof(rp), poses_ptr, term_ptr, iters_ptr, ne_ptr,
-                                                     np_ptr))
-
+        self._check(self.lib.loamgpu_odometry_device_strided(self.h, scans_ptr, stride, n_scans, C.addressof(lp),
+                                                             C.addressof(fe), C.addressof(rp), poses_ptr, term_ptr,
+                                                             iters_ptr, ne_ptr, np_ptr))
 
     def odometry_device_dewarped_ptr(self, scans_ptr: int, n_scans: int, motions_ptr: int, lp, fe, rp, poses_ptr,
                                      term_ptr, iters_ptr, ne_ptr, np_ptr):

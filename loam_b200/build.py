@@ -68,7 +68,9 @@ def build_python_module(force: bool = False) -> str:
                          ("common.h", "features.h", "registration.h", "geometry.h", "detail/gpu.h")]
     if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
         return out
-    cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden",
+    # (plain g++, not $CXX: this image exports a wrapper there that links libstdc++ statically, and a module with its
+    # own copy of the iostream machinery next to the shared one crashes on the first formatted exception message)
+    cmd = [os.environ.get("LOAMGPU_CXX", "g++"), "-O2", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden",
            "-I", pybind11.get_include(), "-I", sysconfig.get_paths()["include"], "-I", os.path.join(ROOT, "include"),
            "-I", os.path.join(ROOT, "include", "loam_compat"), src, "-o", out, "-L", os.path.dirname(LIB), "-lloamgpu",
            "-Wl,-rpath,$ORIGIN/lib"]

@@ -191,7 +191,7 @@ int plan_extract(loamgpu_ctx* ctx, int dtype, size_t stride, uint64_t n_points, 
   pl->capP_ring = (uint32_t)std::min<uint64_t>((uint64_t)pl->S * ((uint64_t)pl->maxP + 1), P);
   pl->capE_scan = pl->R * pl->capE_ring;
   pl->capP_scan = pl->R * pl->capP_ring;
-  pl->smem = extract_smem_bytes(dtype, pl->P, pl->S);
+  pl->smem = extract_smem_bytes(dtype, pl->P, pl->S, dtype == LOAMGPU_F32 && stride == 12 ? 12 : 0);
   if (pl->smem > (size_t)ctx->max_smem_optin)
     return fail(ctx, LOAMGPU_ERR_UNSUPPORTED, "points_per_line too large for one CTA's shared memory");
   return LOAMGPU_OK;
@@ -204,7 +204,7 @@ void fill_extract_args(ExtractArgs& a, const ExtractPlan& pl, const void* dev_pt
   a.scan_stride_bytes = (uint64_t)pl.R * pl.P * stride;
   a.stride = (uint32_t)stride;
   a.dtype = dtype;
-  const size_t rec = dtype == LOAMGPU_F32 ? 16 : 24;
+  const size_t rec = dtype == LOAMGPU_F32 ? (stride == 12 ? 12 : 16) : 24;  // staging record (launch_extract)
   a.use_bulk = (stride == rec) && (((size_t)pl.P * rec) % 16 == 0) && (((uintptr_t)dev_pts) % 16 == 0) &&
                (a.scan_stride_bytes % 16 == 0);
   a.R = pl.R;
@@ -1211,7 +1211,7 @@ int loamgpu_knn(loamgpu_ctx* ctx, const double* targets, uint64_t n_t, const dou
 enum OdometryMode { kResident = 0, kHostSync = 1, kHostAsync = 2 };
 
 static uint32_t pick_chunk(loamgpu_ctx* ctx, OdometryMode mode, uint64_t n_scans, uint64_t n_per, uint32_t capE,
-                           uint32_t capP, uint32_t nn_stride) {
+                           uint32_t capP, uint32_t nn_stride, size_t pt_stride) {
   const uint64_t n_pairs_max = std::max<uint64_t>(n_scans, 2) - 1;
   if (ctx->chunk_pairs) return (uint32_t)std::min<uint64_t>(ctx->chunk_pairs, n_pairs_max);
   // host-async: at least two chunks per typical call, so the copy of a chunk runs under the extract AND the
@@ -1221,22 +1221,22 @@ static uint32_t pick_chunk(loamgpu_ctx* ctx, OdometryMode mode, uint64_t n_scans
   // per pair: k-NN lists, residual records, two NN structures (nodes, sorted copy, sort keys, flags), feature slots
   // (indices + widened points), ring pick lists, and for host calls two staging copies of the scan
   const uint64_t per_pair = cap * ((uint64_t)nn_stride * 4 + 4 + 96 + 84 + 36 + 4 ) +
-                            (mode == kResident ? 0 : 2 * n_per * 16);
+                            (mode == kResident ? 0 : 2 * n_per * pt_stride);
   if (ctx->mem_budget && per_pair)  // (queried once at context creation: cudaMemGetInfo per call is far too slow)
     want = std::min<uint64_t>(want, std::max<uint64_t>(32, ctx->mem_budget / per_pair));
   return (uint32_t)std::min<uint64_t>(want, n_pairs_max);
 }
 
 static int chunk_for(loamgpu_ctx* ctx, OdometryMode mode, uint64_t n_scans, const loamgpu_lidar_params* lp,
-                     const loamgpu_fe_params* fe, const loamgpu_reg_params* reg, uint32_t* chunk) {
+                     const loamgpu_fe_params* fe, const loamgpu_reg_params* reg, size_t pt_stride, uint32_t* chunk) {
   ExtractPlan pl;
   RegP rp;
   const uint64_t n_per = lp->scan_lines * lp->points_per_line;
-  int rc = plan_extract(ctx, LOAMGPU_F32, 16, n_per, lp, fe, &pl);
+  int rc = plan_extract(ctx, LOAMGPU_F32, pt_stride, n_per, lp, fe, &pl);
   if (rc) return rc;
   rc = make_regp(ctx, reg, &rp);
   if (rc) return rc;
-  *chunk = pick_chunk(ctx, mode, n_scans, n_per, pl.capE_scan, pl.capP_scan, (uint32_t)std::max(rp.ke, rp.kp));
+  *chunk = pick_chunk(ctx, mode, n_scans, n_per, pl.capE_scan, pl.capP_scan, (uint32_t)std::max(rp.ke, rp.kp), pt_stride);
   return LOAMGPU_OK;
 }
 
@@ -1244,10 +1244,10 @@ template <typename Fetch>
 static int odometry_core(loamgpu_ctx* ctx, uint64_t n_scans, const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe,
                          const loamgpu_reg_params* reg, double* poses_dev, int32_t* term_dev, uint32_t* iters_dev,
                          uint32_t* ne_dev, uint32_t* np_dev, OdometryMode mode, uint32_t chunk, bool short_lead,
-                         Fetch fetch, const double* motions_dev = nullptr) {
+                         Fetch fetch, const double* motions_dev = nullptr, size_t pt_stride = 16) {
   ExtractPlan pl;
   const uint64_t n_per = lp->scan_lines * lp->points_per_line;
-  int rc = plan_extract(ctx, LOAMGPU_F32, 16, n_per, lp, fe, &pl);
+  int rc = plan_extract(ctx, LOAMGPU_F32, pt_stride, n_per, lp, fe, &pl);
   if (rc) return rc;
   if (n_per == 0) return fail(ctx, LOAMGPU_ERR_INVALID, "empty scans");
   if (motions_dev && extract_smem_bytes(LOAMGPU_F64, pl.P, pl.S) > (size_t)ctx->max_smem_optin)
@@ -1268,7 +1268,7 @@ static int odometry_core(loamgpu_ctx* ctx, uint64_t n_scans, const loamgpu_lidar
     const float* d = nullptr;
     rc = fetch(0, 1, 0, &d);
     if (rc) return rc;
-    return run_extract(ctx, pl, d, LOAMGPU_F32, 16, lp, fe, 1, 0, n_slots, ne_dev, np_dev, nullptr, nullptr, motions_dev);
+    return run_extract(ctx, pl, d, LOAMGPU_F32, pt_stride, lp, fe, 1, 0, n_slots, ne_dev, np_dev, nullptr, nullptr, motions_dev);
   }
   const uint64_t n_pairs = n_scans - 1;
   int buf = 0;
@@ -1288,7 +1288,7 @@ static int odometry_core(loamgpu_ctx* ctx, uint64_t n_scans, const loamgpu_lidar
     const float* d = nullptr;
     rc = fetch(s0, ns, buf, &d);
     if (rc) return rc;
-    rc = run_extract(ctx, pl, d, LOAMGPU_F32, 16, lp, fe, ns, s0, n_slots, ne_dev, np_dev, nullptr, nullptr,
+    rc = run_extract(ctx, pl, d, LOAMGPU_F32, pt_stride, lp, fe, ns, s0, n_slots, ne_dev, np_dev, nullptr, nullptr,
                      motions_dev ? motions_dev + 7 * s0 : nullptr);
     if (rc) return rc;
     CU(cudaEventRecord(ctx->ev_consumed[buf], ctx->stream));
@@ -1303,33 +1303,44 @@ static int odometry_core(loamgpu_ctx* ctx, uint64_t n_scans, const loamgpu_lidar
 
 extern "C" {
 
-static int odometry_device_impl(loamgpu_ctx* ctx, const float* scans_dev, uint64_t n_scans, const double* motions_dev,
-                                const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe,
+static int odometry_device_impl(loamgpu_ctx* ctx, const void* scans_dev, size_t pt_stride, uint64_t n_scans,
+                                const double* motions_dev, const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe,
                                 const loamgpu_reg_params* reg, double* poses_dev, int32_t* term_dev, uint32_t* iters_dev,
                                 uint32_t* ne_dev, uint32_t* np_dev) {
   if (!ctx) return LOAMGPU_ERR_INVALID;
   if (!lp || !fe || !reg) return fail(ctx, LOAMGPU_ERR_INVALID, "null parameter struct");
+  if (pt_stride != 12 && pt_stride != 16)
+    return fail(ctx, LOAMGPU_ERR_UNSUPPORTED, "sequence calls take float records of 12 (x y z) or 16 (x y z .) bytes");
   if (n_scans == 0) return LOAMGPU_OK;
   if (!scans_dev) return fail(ctx, LOAMGPU_ERR_INVALID, "null scan buffer");
   CU(cudaSetDevice(ctx->device));
   const uint64_t n_per = lp->scan_lines * lp->points_per_line;
   auto fetch = [&](uint64_t s0, uint32_t, int, const float** out) {
-    *out = scans_dev + s0 * n_per * 4;
+    *out = reinterpret_cast<const float*>(static_cast<const unsigned char*>(scans_dev) + s0 * n_per * pt_stride);
     return (int)LOAMGPU_OK;
   };
   uint32_t chunk = 0;
-  const int rc = chunk_for(ctx, kResident, n_scans, lp, fe, reg, &chunk);
+  const int rc = chunk_for(ctx, kResident, n_scans, lp, fe, reg, pt_stride, &chunk);
   if (rc) return rc;
   return odometry_core(ctx, n_scans, lp, fe, reg, poses_dev, term_dev, iters_dev, ne_dev, np_dev, kResident, chunk,
-                       /*short_lead=*/false, fetch, motions_dev);
+                       /*short_lead=*/false, fetch, motions_dev, pt_stride);
 }
 
 int loamgpu_odometry_device(loamgpu_ctx* ctx, const float* scans_dev, uint64_t n_scans, const loamgpu_lidar_params* lp,
                             const loamgpu_fe_params* fe, const loamgpu_reg_params* reg, double* poses_dev,
                             int32_t* term_dev, uint32_t* iters_dev, uint32_t* ne_dev, uint32_t* np_dev) {
   API_RANGE();
-  return odometry_device_impl(ctx, scans_dev, n_scans, nullptr, lp, fe, reg, poses_dev, term_dev, iters_dev, ne_dev,
+  return odometry_device_impl(ctx, scans_dev, 16, n_scans, nullptr, lp, fe, reg, poses_dev, term_dev, iters_dev, ne_dev,
                               np_dev);
+}
+
+int loamgpu_odometry_device_strided(loamgpu_ctx* ctx, const void* scans_dev, size_t stride_bytes, uint64_t n_scans,
+                                    const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe,
+                                    const loamgpu_reg_params* reg, double* poses_dev, int32_t* term_dev,
+                                    uint32_t* iters_dev, uint32_t* ne_dev, uint32_t* np_dev) {
+  API_RANGE();
+  return odometry_device_impl(ctx, scans_dev, stride_bytes, n_scans, nullptr, lp, fe, reg, poses_dev, term_dev, iters_dev,
+                              ne_dev, np_dev);
 }
 
 int loamgpu_odometry_device_dewarped(loamgpu_ctx* ctx, const float* scans_dev, uint64_t n_scans,
@@ -1339,7 +1350,7 @@ int loamgpu_odometry_device_dewarped(loamgpu_ctx* ctx, const float* scans_dev, u
   API_RANGE();
   if (!ctx) return LOAMGPU_ERR_INVALID;
   if (n_scans && !start_T_end_dev) return fail(ctx, LOAMGPU_ERR_INVALID, "null start_T_end");
-  return odometry_device_impl(ctx, scans_dev, n_scans, start_T_end_dev, lp, fe, reg, poses_dev, term_dev, iters_dev,
+  return odometry_device_impl(ctx, scans_dev, 16, n_scans, start_T_end_dev, lp, fe, reg, poses_dev, term_dev, iters_dev,
                               ne_dev, np_dev);
 }
 
@@ -1354,10 +1365,10 @@ int loamgpu_synchronize(loamgpu_ctx* ctx) {
 
 }  // extern "C"
 
-static int odometry_host_impl(loamgpu_ctx* ctx, OdometryMode mode, const float* scans, uint64_t n_scans,
+static int odometry_host_impl(loamgpu_ctx* ctx, OdometryMode mode, const void* scans, uint64_t n_scans,
                               const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe, const loamgpu_reg_params* reg,
                               double* poses, int32_t* termination, uint32_t* iterations, uint32_t* n_edge,
-                              uint32_t* n_planar, const double* motions = nullptr);
+                              uint32_t* n_planar, const double* motions = nullptr, size_t pt_stride = 16);
 
 extern "C" {
 
@@ -1392,23 +1403,46 @@ int loamgpu_odometry_host_async(loamgpu_ctx* ctx, const float* scans, uint64_t n
                             n_planar);
 }
 
+int loamgpu_odometry_host_strided(loamgpu_ctx* ctx, const void* scans, size_t stride_bytes, uint64_t n_scans,
+                                  const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe,
+                                  const loamgpu_reg_params* reg, double* poses, int32_t* termination,
+                                  uint32_t* iterations, uint32_t* n_edge, uint32_t* n_planar) {
+  API_RANGE();
+  const int rc = odometry_host_impl(ctx, kHostSync, scans, n_scans, lp, fe, reg, poses, termination, iterations, n_edge,
+                                    n_planar, nullptr, stride_bytes);
+  if (rc) return rc;
+  return loamgpu_synchronize(ctx);
+}
+
+int loamgpu_odometry_host_async_strided(loamgpu_ctx* ctx, const void* scans, size_t stride_bytes, uint64_t n_scans,
+                                        const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe,
+                                        const loamgpu_reg_params* reg, double* poses, int32_t* termination,
+                                        uint32_t* iterations, uint32_t* n_edge, uint32_t* n_planar) {
+  API_RANGE();
+  return odometry_host_impl(ctx, kHostAsync, scans, n_scans, lp, fe, reg, poses, termination, iterations, n_edge,
+                            n_planar, nullptr, stride_bytes);
+}
+
 }  // extern "C"
 
-static int odometry_host_impl(loamgpu_ctx* ctx, OdometryMode mode, const float* scans, uint64_t n_scans,
+static int odometry_host_impl(loamgpu_ctx* ctx, OdometryMode mode, const void* scans_v, uint64_t n_scans,
                               const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe, const loamgpu_reg_params* reg,
                               double* poses, int32_t* termination, uint32_t* iterations, uint32_t* n_edge,
-                              uint32_t* n_planar, const double* motions) {
+                              uint32_t* n_planar, const double* motions, size_t pt_stride) {
   if (!ctx) return LOAMGPU_ERR_INVALID;
   if (!lp || !fe || !reg) return fail(ctx, LOAMGPU_ERR_INVALID, "null parameter struct");
+  if (pt_stride != 12 && pt_stride != 16)
+    return fail(ctx, LOAMGPU_ERR_UNSUPPORTED, "sequence calls take float records of 12 (x y z) or 16 (x y z .) bytes");
+  const unsigned char* scans = static_cast<const unsigned char*>(scans_v);
   if (n_scans == 0) return LOAMGPU_OK;
   if (!scans) return fail(ctx, LOAMGPU_ERR_INVALID, "null scan buffer");
   CU(cudaSetDevice(ctx->device));
   const uint64_t n_per = lp->scan_lines * lp->points_per_line;
-  const size_t scan_bytes = (size_t)n_per * 16;
+  const size_t scan_bytes = (size_t)n_per * pt_stride;
   const uint64_t n_pairs = n_scans - 1;
   uint32_t chunk = 0;
   {
-    const int rc = chunk_for(ctx, mode, n_scans, lp, fe, reg, &chunk);
+    const int rc = chunk_for(ctx, mode, n_scans, lp, fe, reg, pt_stride, &chunk);
     if (rc) return rc;
   }
   // The first copy of a call is exposed unless kernels of a previous asynchronous call are still running: a
@@ -1440,7 +1474,7 @@ static int odometry_host_impl(loamgpu_ctx* ctx, OdometryMode mode, const float* 
     // copy stream: wait until the previous user of this staging buffer is done, copy, signal the compute stream
     cudaError_t e = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[buf], 0);
     if (e == cudaSuccess)
-      e = cudaMemcpyAsync(ctx->scan_in[buf].p, scans + s0 * n_per * 4, (size_t)ns * scan_bytes,
+      e = cudaMemcpyAsync(ctx->scan_in[buf].p, scans + s0 * scan_bytes, (size_t)ns * scan_bytes,
                           cudaMemcpyHostToDevice, ctx->copy_stream);
     if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_copied[buf], ctx->copy_stream);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[buf], 0);
@@ -1450,7 +1484,7 @@ static int odometry_host_impl(loamgpu_ctx* ctx, OdometryMode mode, const float* 
   };
   int rc = odometry_core(ctx, n_scans, lp, fe, reg, ctx->out_pose.as<double>(), ctx->out_term.as<int32_t>(),
                          ctx->out_iters.as<uint32_t>(), ctx->out_ne.as<uint32_t>(), ctx->out_np.as<uint32_t>(), mode, chunk,
-                         short_lead, fetch, motions_dev);
+                         short_lead, fetch, motions_dev, pt_stride);
   if (rc) return rc;
   if (poses && n_pairs) CU(cudaMemcpyAsync(poses, ctx->out_pose.p, n_pairs * 56, cudaMemcpyDeviceToHost, ctx->stream));
   if (termination && n_pairs)

@@ -26,17 +26,11 @@ namespace loamgpu {
 
 namespace {
 
-template <typename T>
-struct Rec;  // packed staging record in shared memory
-template <>
-struct Rec<float> {
-  static constexpr int kBytes = 16;  // float4-shaped
-  static constexpr int kElems = 4;
-};
-template <>
-struct Rec<double> {
-  static constexpr int kBytes = 24;  // Eigen::Vector3d-shaped
-  static constexpr int kElems = 3;
+// packed staging record in shared memory: kE scalars of type T per point (x, y, z first)
+template <typename T, int kE>
+struct Rec {
+  static constexpr int kBytes = (int)sizeof(T) * kE;  // float x 4: sensor-driver float4 records; float x 3: packed xyz;
+  static constexpr int kElems = kE;                   // double x 3: Eigen::Vector3d-shaped
 };
 
 // the range buffer is reused for the walk state (P bytes, padded to 16), the pick list (P uint16) and the
@@ -49,7 +43,7 @@ __host__ __device__ inline uint32_t rng_doubles(uint32_t P) {
 // T = scalar type of the staged ring (what the arithmetic widens from), TIn = scalar type of the caller's records.
 // They differ only for de-warping float input: the moved points are not float-representable, so the ring is staged
 // as doubles.
-template <typename T, typename TIn, bool kDewarp>
+template <typename T, typename TIn, bool kDewarp, int kE>
 __device__ __forceinline__ void extract_ring_body(const ExtractArgs& a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t P = a.P, N = a.N, S = a.S;
@@ -57,8 +51,8 @@ __device__ __forceinline__ void extract_ring_body(const ExtractArgs& a) {
   const uint32_t tid = threadIdx.x, nthr = blockDim.x;
 
   // ---- shared memory carve-up (see extract_smem_bytes) ----
-  T* stage = reinterpret_cast<T*>(smem);                                       // P * Rec<T>::kBytes
-  double* rng = reinterpret_cast<double*>(smem + (size_t)P * Rec<T>::kBytes);  // ranges; later the walk state + pick list
+  T* stage = reinterpret_cast<T*>(smem);                                       // P * Rec<T, kE>::kBytes
+  double* rng = reinterpret_cast<double*>(smem + (((size_t)P * Rec<T, kE>::kBytes + 7) & ~(size_t)7));  // ranges; later the walk state + pick list
   double* cur = rng + rng_doubles(P);                                          // P doubles
   uint8_t* mask = reinterpret_cast<uint8_t*>(cur + P);                         // P bytes
   uint64_t* bar = reinterpret_cast<uint64_t*>(mask + ((P + 15) & ~15u));       // 8-byte aligned mbarrier
@@ -71,7 +65,7 @@ __device__ __forceinline__ void extract_ring_body(const ExtractArgs& a) {
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
     if (tid == 0) {
-      const uint32_t bytes = P * Rec<T>::kBytes;
+      const uint32_t bytes = P * Rec<T, kE>::kBytes;
       mbar_expect_tx(bar, bytes);
       bulk_g2s(stage, ring_src, bytes, bar);
     }
@@ -102,18 +96,18 @@ __device__ __forceinline__ void extract_ring_body(const ExtractArgs& a) {
           o[2] = m.z;
         }
       }
-      stage[j * Rec<T>::kElems + 0] = x;
-      stage[j * Rec<T>::kElems + 1] = y;
-      stage[j * Rec<T>::kElems + 2] = z;
+      stage[j * Rec<T, kE>::kElems + 0] = x;
+      stage[j * Rec<T, kE>::kElems + 1] = y;
+      stage[j * Rec<T, kE>::kElems + 2] = z;
     }
     __syncthreads();
   }
 
   // ---- phase B: ranges ----
   for (uint32_t j = tid; j < P; j += nthr) {
-    const double x = (double)stage[j * Rec<T>::kElems + 0];
-    const double y = (double)stage[j * Rec<T>::kElems + 1];
-    const double z = (double)stage[j * Rec<T>::kElems + 2];
+    const double x = (double)stage[j * Rec<T, kE>::kElems + 0];
+    const double y = (double)stage[j * Rec<T, kE>::kElems + 1];
+    const double z = (double)stage[j * Rec<T, kE>::kElems + 2];
     rng[j] = point_range(x, y, z);
   }
   __syncthreads();
@@ -126,12 +120,12 @@ __device__ __forceinline__ void extract_ring_body(const ExtractArgs& a) {
     const bool ring_edge = (j < N) || ((uint64_t)j >= hi_edge);
     double c = -1.0;
     if (!ring_edge) {
-      double dx = dmul(m2n, (double)stage[j * Rec<T>::kElems + 0]);
-      double dy = dmul(m2n, (double)stage[j * Rec<T>::kElems + 1]);
-      double dz = dmul(m2n, (double)stage[j * Rec<T>::kElems + 2]);
+      double dx = dmul(m2n, (double)stage[j * Rec<T, kE>::kElems + 0]);
+      double dy = dmul(m2n, (double)stage[j * Rec<T, kE>::kElems + 1]);
+      double dz = dmul(m2n, (double)stage[j * Rec<T, kE>::kElems + 2]);
       for (uint32_t k = 1; k <= N; k++) {
-        const T* lo = stage + (size_t)(j - k) * Rec<T>::kElems;
-        const T* hi = stage + (size_t)(j + k) * Rec<T>::kElems;
+        const T* lo = stage + (size_t)(j - k) * Rec<T, kE>::kElems;
+        const T* hi = stage + (size_t)(j + k) * Rec<T, kE>::kElems;
         dx = dadd(dadd(dx, (double)lo[0]), (double)hi[0]);
         dy = dadd(dadd(dy, (double)lo[1]), (double)hi[1]);
         dz = dadd(dadd(dz, (double)lo[2]), (double)hi[2]);
@@ -300,13 +294,13 @@ __device__ __forceinline__ void extract_ring_body(const ExtractArgs& a) {
 // The plain kernels (what every throughput path runs) and the de-warping ones are separate entry points so that the
 // register budget of one never shapes the other: plain 37-40 registers / 6 CTAs per SM; de-warping (24-byte staging
 // records, 41 KB of shared memory per 1024-column ring) capped for 5.
-template <typename T>
+template <typename T, int kE>
 __global__ void __launch_bounds__(kExtractThreads) extract_ring_kernel(ExtractArgs a) {
-  extract_ring_body<T, T, false>(a);
+  extract_ring_body<T, T, false, kE>(a);
 }
 template <typename TIn>
 __global__ void __launch_bounds__(kExtractThreads, 5) extract_ring_dewarp_kernel(ExtractArgs a) {
-  extract_ring_body<double, TIn, true>(a);
+  extract_ring_body<double, TIn, true, 3>(a);
 }
 
 // Pack per-ring pick lists into the scan-level feature arrays (reference output order:
@@ -376,39 +370,35 @@ __global__ void __launch_bounds__(256) pack_features_kernel(PackArgs a) {
 
 }  // namespace
 
-size_t extract_smem_bytes(int dtype, uint32_t P, uint32_t S) {
+size_t extract_smem_bytes(int dtype, uint32_t P, uint32_t S, uint32_t stage_bytes) {
   (void)S;
-  const size_t rec = dtype == LOAMGPU_F32 ? 16 : 24;
-  size_t b = (size_t)P * rec + 8 * (size_t)rng_doubles(P) + 8 * (size_t)P + ((P + 15) & ~15u) + 8 + 16;
+  const size_t rec = stage_bytes ? stage_bytes : (dtype == LOAMGPU_F32 ? 16 : 24);
+  size_t b = (((size_t)P * rec + 7) & ~(size_t)7) + 8 * (size_t)rng_doubles(P) + 8 * (size_t)P + ((P + 15) & ~15u) + 8 + 16;
   return (b + 127) & ~(size_t)127;
 }
 
+template <typename K>
+static cudaError_t launch_extract_as(K kernel, const ExtractArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
+  cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  kernel<<<grid, kExtractThreads, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_extract(const ExtractArgs& a, uint32_t n_scans, cudaStream_t st) {
-  const size_t smem = extract_smem_bytes(a.dewarp ? (int)LOAMGPU_F64 : a.dtype, a.P, a.S);
-  dim3 grid(a.R, n_scans);
-  cudaError_t err;
+  const dim3 grid(a.R, n_scans);
   if (a.dewarp) {  // double staging whatever the input type; strided loads (use_bulk is off)
-    if (a.dtype == LOAMGPU_F32) {
-      err = cudaFuncSetAttribute(extract_ring_dewarp_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (err != cudaSuccess) return err;
-      extract_ring_dewarp_kernel<float><<<grid, kExtractThreads, smem, st>>>(a);
-    } else {
-      err = cudaFuncSetAttribute(extract_ring_dewarp_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (err != cudaSuccess) return err;
-      extract_ring_dewarp_kernel<double><<<grid, kExtractThreads, smem, st>>>(a);
-    }
-    return cudaGetLastError();
+    const size_t smem = extract_smem_bytes(LOAMGPU_F64, a.P, a.S, 24);
+    return a.dtype == LOAMGPU_F32 ? launch_extract_as(extract_ring_dewarp_kernel<float>, a, grid, smem, st)
+                                  : launch_extract_as(extract_ring_dewarp_kernel<double>, a, grid, smem, st);
   }
   if (a.dtype == LOAMGPU_F32) {
-    err = cudaFuncSetAttribute(extract_ring_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return err;
-    extract_ring_kernel<float><<<grid, kExtractThreads, smem, st>>>(a);
-  } else {
-    err = cudaFuncSetAttribute(extract_ring_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return err;
-    extract_ring_kernel<double><<<grid, kExtractThreads, smem, st>>>(a);
+    // packed xyz records (12 bytes) are staged as they are: one bulk copy of 12 P bytes, and three-float records
+    // read without shared-memory bank conflicts; every other float layout is staged as float4
+    if (a.stride == 12) return launch_extract_as(extract_ring_kernel<float, 3>, a, grid, extract_smem_bytes(a.dtype, a.P, a.S, 12), st);
+    return launch_extract_as(extract_ring_kernel<float, 4>, a, grid, extract_smem_bytes(a.dtype, a.P, a.S, 16), st);
   }
-  return cudaGetLastError();
+  return launch_extract_as(extract_ring_kernel<double, 3>, a, grid, extract_smem_bytes(a.dtype, a.P, a.S, 24), st);
 }
 
 cudaError_t launch_pack(const PackArgs& a, uint32_t n_scans, cudaStream_t st) {

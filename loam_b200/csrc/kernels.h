@@ -80,7 +80,8 @@ struct PackArgs {
   const double* motions;        // device [scan][7] or null (then `motion`)
 };
 
-size_t extract_smem_bytes(int dtype, uint32_t P, uint32_t S);
+// stage_bytes: staging record size in shared memory (0 = the default of the dtype: float4 / 3 doubles)
+size_t extract_smem_bytes(int dtype, uint32_t P, uint32_t S, uint32_t stage_bytes = 0);
 cudaError_t launch_extract(const ExtractArgs& a, uint32_t n_scans, cudaStream_t st);
 cudaError_t launch_pack(const PackArgs& a, uint32_t n_scans, cudaStream_t st);
 

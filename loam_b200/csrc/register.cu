@@ -1357,7 +1357,7 @@ static cudaError_t launch_knn_general(const AssocArgs& a, dim3 grid, int outer_i
 // memory stays L1 (leaf points, traversal stacks).  $LOAMGPU_KNN_SMEM_KB overrides; 0 switches the kernel off.
 static uint32_t knn_smem_budget(int optin) {
   static const long env = []() { const char* e = getenv("LOAMGPU_KNN_SMEM_KB"); return e ? atol(e) : -1L; }();
-  const long kb = env >= 0 ? env : 176;
+  const long kb = env >= 0 ? env : 128;
   return (uint32_t)std::min<long>(kb * 1024, (long)optin - 2048);
 }
 

@@ -123,3 +123,48 @@ def test_async_host_calls_pipeline_without_changing_results(ctx):
         assert np.array_equal(ref[1][0], outs[0][0].numpy())
     finally:
         ctx.set_chunk_pairs(0)  # back to automatic
+
+
+@pytest.mark.parametrize("shape", [(16, 512), (8, 250), (5, 333)])
+def test_packed_xyz_records_give_identical_results(ctx, shape):
+    """12-byte {x,y,z} float records (loamgpu_odometry_*_strided): host, asynchronous host and device-resident calls
+    and the single-scan entry point all equal the float4 path bit for bit — also for ring lengths whose 12-byte rows
+    are not 16-byte multiples (no bulk copy) and odd ring lengths (staging buffer alignment)."""
+    import torch
+    R, P = shape
+    n = 5
+    lp, fe, rp = _capi.CLidarParams(R, P, 1.0, 120.0), _capi.default_fe_params(), _capi.default_reg_params()
+    scans4 = np.stack([synth.make_scan(R, P, k=k) for k in range(n)])
+    scans3 = np.ascontiguousarray(scans4[:, :, :3])
+    ref = ctx.odometry_host(scans4, lp, fe, rp)
+    got = ctx.odometry_host(scans3, lp, fe, rp)
+    for a, b in zip(ref, got):
+        assert np.array_equal(a, b)
+    e4, p4 = ctx.extract(scans4[1], lp, fe)
+    e3, p3 = ctx.extract(scans3[1], lp, fe)
+    assert np.array_equal(e4, e3) and np.array_equal(p4, p3) and len(p4) == ref[4][1]
+    # device-resident and asynchronous host variants
+    dev = torch.device("cuda", 0)
+    d_scans = torch.from_numpy(scans3).to(dev)
+    outs = [torch.zeros((n - 1, 7), dtype=torch.float64, device=dev), torch.zeros(n - 1, dtype=torch.int32, device=dev),
+            torch.zeros(n - 1, dtype=torch.int32, device=dev), torch.zeros(n, dtype=torch.int32, device=dev),
+            torch.zeros(n, dtype=torch.int32, device=dev)]
+    torch.cuda.synchronize()
+    ctx.odometry_device_ptr(d_scans.data_ptr(), n, lp, fe, rp, *(t.data_ptr() for t in outs), stride=12)
+    ctx.synchronize()
+    assert np.array_equal(outs[0].cpu().numpy(), ref[0]) and np.array_equal(outs[3].cpu().numpy(), ref[3].astype(np.int32))
+    h_scans = torch.from_numpy(scans3).pin_memory()
+    h_outs = [torch.zeros((n - 1, 7), dtype=torch.float64).pin_memory(), torch.zeros(n - 1, dtype=torch.int32).pin_memory(),
+              torch.zeros(n - 1, dtype=torch.int32).pin_memory(), torch.zeros(n, dtype=torch.int32).pin_memory(),
+              torch.zeros(n, dtype=torch.int32).pin_memory()]
+    ctx.odometry_host_async_ptr(h_scans.data_ptr(), n, lp, fe, rp, *(t.data_ptr() for t in h_outs), stride=12)
+    ctx.synchronize()
+    assert np.array_equal(h_outs[0].numpy(), ref[0]) and np.array_equal(h_outs[1].numpy(), ref[1])
+
+
+def test_strided_calls_reject_other_record_sizes(ctx):
+    lp, fe, rp = _capi.CLidarParams(4, 64, 1.0, 120.0), _capi.default_fe_params(), _capi.default_reg_params()
+    buf = np.zeros((2, 256, 5), dtype=np.float32)
+    with pytest.raises(_capi.LoamGpuError) as ei:
+        ctx.odometry_host_ptr(buf.ctypes.data, 2, lp, fe, rp, None, None, None, None, None, stride=20)
+    assert ei.value.code == _capi.ERR_UNSUPPORTED
