@@ -276,6 +276,22 @@ int loamgpu_odometry_device_dewarped(loamgpu_ctx* ctx, const float* scans_dev, u
                                      int32_t* termination_dev, uint32_t* iterations_dev, uint32_t* n_edge_dev,
                                      uint32_t* n_planar_dev);
 
+/* ------------------------------------------------------- one sequence over several GPUs of one box
+ * ("one host thread + one loamgpu_ctx + one stream set per GPU"; the reference's README loop shards by scan
+ * pair, README.md:46-59.)  Pair k depends only on scans k and k+1: the pair range is cut into contiguous blocks, one
+ * per entry of `devices` (a device may be listed more than once); every block's device extracts its own scans plus
+ * one halo scan.  No collective, no peer traffic; results are identical to loamgpu_odometry_host_strided on one
+ * device, whatever the split.  Host buffers as for loamgpu_odometry_host_strided. */
+typedef struct loamgpu_multi loamgpu_multi;
+int loamgpu_multi_create(const int* devices, int n_devices, loamgpu_multi** out);
+void loamgpu_multi_destroy(loamgpu_multi* m);
+const char* loamgpu_multi_last_error(const loamgpu_multi* m);
+int loamgpu_multi_device_count(const loamgpu_multi* m);
+int loamgpu_multi_odometry_host(loamgpu_multi* m, const void* scans, size_t stride_bytes, uint64_t n_scans,
+                                const loamgpu_lidar_params* lidar, const loamgpu_fe_params* fe,
+                                const loamgpu_reg_params* reg, double* poses, int32_t* termination,
+                                uint32_t* iterations, uint32_t* n_edge, uint32_t* n_planar);
+
 /* pairs processed per internal chunk by the sequence / batch calls; 0 (default) = automatic: 1024 for
  * device-resident calls, 512 for asynchronous and 256 for synchronous host calls and explicit batches,
  * bounded by a share of the free device memory */

@@ -7,7 +7,7 @@ include/loamgpu.h.  There is no CPU path in this package.
 from .api import (FeatureExtractionParams, LidarParams, LoamFeatures, Pose3d, Quaterniond, RegistrationDetail,
                   RegistrationIterationInfo, RegistrationParams, RegistrationTerminationType, computeCurvature,
                   computeValidPoints, extractFeatures, extractFeatureIndices, registerFeatures, odometry,
-                  get_context, LocalMap, extractFeaturesDewarped)
+                  get_context, release_context, get_multi_context, LocalMap, extractFeaturesDewarped)
 
 CONVERGED = RegistrationTerminationType.CONVERGED
 MAX_ITER = RegistrationTerminationType.MAX_ITER
@@ -18,5 +18,5 @@ __all__ = [
     "RegistrationDetail", "RegistrationIterationInfo", "RegistrationTerminationType", "extractFeatures",
     "computeCurvature", "computeValidPoints", "registerFeatures", "extractFeatureIndices", "odometry",
     "extractFeaturesDewarped",
-    "get_context", "LocalMap", "CONVERGED", "MAX_ITER", "INSUFFICIENT_ASSOCIATIONS",
+    "get_context", "release_context", "get_multi_context", "LocalMap", "CONVERGED", "MAX_ITER", "INSUFFICIENT_ASSOCIATIONS",
 ]

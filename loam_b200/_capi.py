@@ -29,6 +29,8 @@ SYMBOLS = [
     "loamgpu_extract_batch", "loamgpu_register_pairs", "loamgpu_odometry_host_async", "loamgpu_synchronize",
     "loamgpu_extract_dewarped", "loamgpu_odometry_host_dewarped", "loamgpu_odometry_device_dewarped",
     "loamgpu_odometry_host_strided", "loamgpu_odometry_host_async_strided", "loamgpu_odometry_device_strided",
+    "loamgpu_multi_create", "loamgpu_multi_destroy", "loamgpu_multi_last_error", "loamgpu_multi_device_count",
+    "loamgpu_multi_odometry_host",
 ]
 KERNEL_CLASSES = ["extract", "pack", "nn_build", "knn", "lm", "misc", "fit"]
 
@@ -110,6 +112,13 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         f.argtypes = [vp, vp, C.c_size_t, u64, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.loamgpu_odometry_host_dewarped.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.loamgpu_odometry_device_dewarped.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.loamgpu_multi_create.argtypes = [vp, C.c_int, C.POINTER(C.c_void_p)]
+    lib.loamgpu_multi_destroy.argtypes = [vp]
+    lib.loamgpu_multi_destroy.restype = None
+    lib.loamgpu_multi_last_error.argtypes = [vp]
+    lib.loamgpu_multi_last_error.restype = C.c_char_p
+    lib.loamgpu_multi_device_count.argtypes = [vp]
+    lib.loamgpu_multi_odometry_host.argtypes = [vp, vp, C.c_size_t, u64, vp, vp, vp, vp, vp, vp, vp, vp]
     _lib = lib
     return lib
 
@@ -137,6 +146,16 @@ def _xyz64(points):
     if a.size == 0:
         return np.zeros((0, 3), dtype=np.float64)
     return np.ascontiguousarray(a.reshape(len(a), -1)[:, :3])
+
+
+def _check_scan_size(s, lp):
+    """validateLidarScan (common.h:104-113) for a [n_scans, points, C] array: the C-ABI sequence calls take the scan size
+    from the lidar parameters, so a mismatch must be caught before any pointer arithmetic."""
+    want = int(lp.scan_lines) * int(lp.points_per_line)
+    if s.shape[1] != want:
+        raise LoamGpuError(ERR_SIZE_MISMATCH,
+                           f"LOAM: provided lidar scan size ( {s.shape[1]})  does not match provided lidar parameters "
+                           f"({int(lp.scan_lines)} x {int(lp.points_per_line)})")
 
 
 class Context:
@@ -332,6 +351,7 @@ class Context:
         if s.ndim != 3 or s.shape[2] not in (3, 4):
             raise ValueError("scans must be [n_scans, points, 3 or 4] float32 records")
         stride = 4 * s.shape[2]  # packed xyz (12 bytes) or float4 (16 bytes)
+        _check_scan_size(s, lp)
         poses = np.zeros((max(n - 1, 0), 7))
         term = np.zeros(max(n - 1, 0), dtype=np.int32)
         its = np.zeros(max(n - 1, 0), dtype=np.uint32)
@@ -382,6 +402,52 @@ class Context:
         self._check(self.lib.loamgpu_odometry_device_dewarped(self.h, scans_ptr, n_scans, motions_ptr, C.addressof(lp),
                                                               C.addressof(fe), C.addressof(rp), poses_ptr, term_ptr,
                                                               iters_ptr, ne_ptr, np_ptr))
+
+
+class MultiContext:
+    """One sequence over several GPUs of one box (loamgpu_multi_*): contiguous pair blocks, one host thread + context per
+    device, no collective.  `devices` may name a device more than once."""
+
+    def __init__(self, devices):
+        self.lib = load_library()
+        self.devices = [int(d) for d in devices]
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        h = C.c_void_p()
+        rc = self.lib.loamgpu_multi_create(arr, len(self.devices), C.byref(h))
+        if rc != OK:
+            raise LoamGpuError(rc, self.lib.loamgpu_last_error(None).decode())
+        self.h = h
+
+    def odometry_host(self, scans: np.ndarray, lp, fe, rp):
+        s = np.ascontiguousarray(scans, dtype=np.float32)
+        if s.ndim != 3 or s.shape[2] not in (3, 4):
+            raise ValueError("scans must be [n_scans, points, 3 or 4] float32 records")
+        n = s.shape[0]
+        _check_scan_size(s, lp)
+        poses = np.zeros((max(n - 1, 0), 7))
+        term = np.zeros(max(n - 1, 0), dtype=np.int32)
+        its = np.zeros(max(n - 1, 0), dtype=np.uint32)
+        ne, npl = np.zeros(n, dtype=np.uint32), np.zeros(n, dtype=np.uint32)
+        self.odometry_host_ptr(s.ctypes.data, n, lp, fe, rp, poses.ctypes.data, term.ctypes.data, its.ctypes.data,
+                               ne.ctypes.data, npl.ctypes.data, stride=4 * s.shape[2])
+        return poses, term, its, ne, npl
+
+    def odometry_host_ptr(self, scans_ptr, n_scans, lp, fe, rp, poses_ptr, term_ptr, iters_ptr, ne_ptr, np_ptr, stride=16):
+        rc = self.lib.loamgpu_multi_odometry_host(self.h, scans_ptr, stride, n_scans, C.addressof(lp), C.addressof(fe),
+                                                  C.addressof(rp), poses_ptr, term_ptr, iters_ptr, ne_ptr, np_ptr)
+        if rc != OK:
+            raise LoamGpuError(rc, self.lib.loamgpu_multi_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.loamgpu_multi_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class DeviceMap:

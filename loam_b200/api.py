@@ -202,19 +202,44 @@ class RegistrationDetail:
 
 
 # ----------------------------------------------------------------------------------------------- context
-_ctx_lock = threading.Lock()
-_ctxs: dict = {}
+_tls = threading.local()
+
+
+class _ThreadContexts:
+    """This thread's contexts, one per device.  Lives in threading.local(): when the thread ends the object is collected
+    and its contexts (each owns device workspaces) are closed, like the C++ side's thread_local ThreadContext."""
+
+    def __init__(self):
+        self.by_device = {}
+
+    def __del__(self):
+        for c in self.by_device.values():
+            try:
+                c.close()
+            except Exception:
+                pass
 
 
 def get_context(device: int = 0) -> _capi.Context:
     """Per-(thread, device) context: the reference is stateless/re-entrant; so are these calls."""
-    key = (threading.get_ident(), device)
-    with _ctx_lock:
-        c = _ctxs.get(key)
-        if c is None:
-            c = _capi.Context(device)
-            _ctxs[key] = c
-        return c
+    tc = getattr(_tls, "contexts", None)
+    if tc is None:
+        tc = _tls.contexts = _ThreadContexts()
+    c = tc.by_device.get(device)
+    if c is None:
+        c = tc.by_device[device] = _capi.Context(device)
+    return c
+
+
+def release_context(device=None):
+    """Close this thread's context(s) now (device=None: all of them) instead of at thread exit."""
+    tc = getattr(_tls, "contexts", None)
+    if tc is None:
+        return
+    for d in list(tc.by_device) if device is None else [device]:
+        c = tc.by_device.pop(d, None)
+        if c is not None:
+            c.close()
 
 
 def _as_cloud(input_scan):
@@ -347,14 +372,36 @@ def registerFeatures(source: LoamFeatures, target, target_T_source_init: Pose3d,
     return Pose3d._from7(pose)
 
 
-def odometry(scans, lidar_params: LidarParams, fe_params=None, reg_params=None, device: int = 0, sweep_motions=None):
-    """Batched extract + scan-to-scan registration over a float32 [n_scans, R*P, 4] sequence
-    (the README loop of the reference, run for the whole sequence in one call).
+_multi_lock = threading.Lock()
+_multis: dict = {}
+
+
+def get_multi_context(devices) -> _capi.MultiContext:
+    """One cached set of per-device contexts per (thread, device list)."""
+    key = (threading.get_ident(), tuple(int(d) for d in devices))
+    with _multi_lock:
+        m = _multis.get(key)
+        if m is None:
+            m = _capi.MultiContext(key[1])
+            _multis[key] = m
+        return m
+
+
+def odometry(scans, lidar_params: LidarParams, fe_params=None, reg_params=None, device: int = 0, sweep_motions=None,
+             devices=None):
+    """Batched extract + scan-to-scan registration over a float32 [n_scans, R*P, 4] (or packed [n_scans, R*P, 3])
+    sequence (the README loop of the reference, run for the whole sequence in one call).
     Returns (poses[n-1,7] as qx qy qz qw tx ty tz, termination, iterations, n_edge, n_planar).
-    sweep_motions ([n_scans, 7] start_T_end per sweep, optional): de-warp every scan inside the extraction kernel."""
+    sweep_motions ([n_scans, 7] start_T_end per sweep, optional): de-warp every scan inside the extraction kernel.
+    devices (list of CUDA device indices, optional): shard the pairs of the sequence over several GPUs of this box —
+    contiguous pair blocks, one host thread and context per device, no collective; same results as one device."""
     fe_params = fe_params or FeatureExtractionParams()
     reg_params = reg_params or RegistrationParams()
     try:
+        if devices is not None and len(devices) > 0:
+            if sweep_motions is not None:
+                raise ValueError("sweep_motions is not supported together with devices=")
+            return get_multi_context(devices).odometry_host(scans, lidar_params._c, fe_params._to_c(), reg_params._to_c())
         return get_context(device).odometry_host(scans, lidar_params._c, fe_params._to_c(), reg_params._to_c(),
                                                  sweep_motions)
     except _capi.LoamGpuError as e:

@@ -62,7 +62,21 @@ constexpr int kRadixBits = 4;
 constexpr int kRadixBins = 1 << kRadixBits;
 constexpr int kMortonBits = 30;
 
+// -DBUILD_TIMING: set 0 prints the clock64 cycles of each phase (one line per launch)
+#ifdef BUILD_TIMING
+#define BT_MARK(i) \
+  do {             \
+    __syncthreads(); \
+    if (threadIdx.x == 0) bt[i] = clock64(); \
+  } while (0)
+#else
+#define BT_MARK(i)
+#endif
 __global__ void __launch_bounds__(kBuildThreads, BUILD_MINBLOCKS) bvh_build_kernel(BvhBuildArgs a) {
+#ifdef BUILD_TIMING
+  long long bt[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  BT_MARK(0);
+#endif
   // dynamic shared memory: [0, kRadixBins*kBuildThreads) radix counters during the sort; afterwards, when the set
   // fits (a.smem_tree), the sorted Morton codes (n words) and behind them one readiness byte per node
   extern __shared__ uint32_t s_cnt[];
@@ -134,6 +148,7 @@ __global__ void __launch_bounds__(kBuildThreads, BUILD_MINBLOCKS) bvh_build_kern
     a.g.quant[set] = q;
   }
 
+  BT_MARK(1);
   // ---- Morton keys (thread-contiguous chunks: the radix passes below need a fixed item -> thread map)
   const uint32_t chunk = (n + nthr - 1) / nthr;
   const uint32_t c0 = min(tid * chunk, n), c1 = min(c0 + chunk, n);
@@ -146,6 +161,7 @@ __global__ void __launch_bounds__(kBuildThreads, BUILD_MINBLOCKS) bvh_build_kern
   }
   __syncthreads();
 
+  BT_MARK(2);
   // ---- stable LSD radix sort, 4 bits per pass.  Rank of an item = items with a smaller digit + items with the
   // same digit owned by earlier threads + earlier items of the same digit in this thread's own chunk.
   uint2* src = keyA;
@@ -210,6 +226,7 @@ __global__ void __launch_bounds__(kBuildThreads, BUILD_MINBLOCKS) bvh_build_kern
     dst = t;
   }
 
+  BT_MARK(3);
   // ---- Morton-ordered point copy
   for (uint32_t i = tid; i < n; i += nthr) {
     const uint32_t id = src[i].y;
@@ -220,6 +237,7 @@ __global__ void __launch_bounds__(kBuildThreads, BUILD_MINBLOCKS) bvh_build_kern
 
   if (n < 2) return;  // a single point has no internal node; knn_bvh scans it directly
 
+  BT_MARK(4);
   const bool in_smem = a.smem_tree != 0;
   uint32_t* s_codes = s_cnt;
   uint8_t* s_ready = reinterpret_cast<uint8_t*>(s_cnt + max((uint32_t)(kRadixBins * kBuildThreads), a.g.pt_cap));
@@ -269,6 +287,7 @@ __global__ void __launch_bounds__(kBuildThreads, BUILD_MINBLOCKS) bvh_build_kern
   }
   __syncthreads();
 
+  BT_MARK(5);
   // ---- boxes, bottom-up in passes: a node is merged from its children once both were merged in an EARLIER pass
   // (ready[] holds the 1-based pass in which a node was merged, 0 = not yet), so one barrier per pass separates a
   // box from its readers.  A thread tracks its own pending nodes in a register bit mask and only revisits those.
@@ -346,6 +365,7 @@ __global__ void __launch_bounds__(kBuildThreads, BUILD_MINBLOCKS) bvh_build_kern
   // ---- compact traversal records (common.cuh: BvhRec).  Internal node i is "big" when it covers more than kBvhLeaf
   // points; big nodes are numbered in index order (the root, node 0, gets record 0) and each writes one record with its
   // children's boxes on the 16-bit grid.  The records overlay this set's sort scratch, which is dead by now.
+  BT_MARK(6);
   if (a.g.quant == nullptr || n <= (uint32_t)kBvhLeaf) return;
   __syncthreads();
   uint32_t* cid = reinterpret_cast<uint32_t*>(arrived);  // readiness flags are dead: record number per big node
@@ -429,6 +449,420 @@ __global__ void __launch_bounds__(kBuildThreads, BUILD_MINBLOCKS) bvh_build_kern
     dst[1] = make_uint4(r.box[4], r.box[5], r.ref[0], r.ref[1]);
   }
   if (tid == 0) a.g.quant[set].n_rec = total;
+#ifdef BUILD_TIMING
+  BT_MARK(7);
+  if (tid == 0 && set == 0)
+    printf("BT n %u: bbox %lld morton %lld sort %lld gather %lld codes+topology %lld boxes %lld compact %lld total %lld\n", n,
+           bt[1] - bt[0], bt[2] - bt[1], bt[3] - bt[2], bt[4] - bt[3], bt[5] - bt[4], bt[6] - bt[5], bt[7] - bt[6],
+           bt[7] - bt[0]);
+#endif
+}
+
+// ============================================================================ build, shared-memory version (K3)
+// The same structure (Morton-sorted copy, node split words + boxes for the general walk, compact records for the batched
+// walk) for sets of up to kSbMaxPoints points, with every intermediate kept in SHARED memory.  Measured on the first
+// kernel (-DBUILD_TIMING, 14.3 k points, 763 k cycles): sort 28 % (4-bit passes, (key, index) pairs ping-ponged through
+// global memory), boxes 28 % (~28 level-synchronous passes over all n nodes with L2 round trips), topology 17 %,
+// compaction 13 %.  Here:
+//   * codes stay in shared memory indexed by point; the sort permutes 16-bit point numbers only, 8 bits per pass
+//     (3 passes for 24-bit codes): a warp owns a contiguous block of the current order and ranks 32 keys at a time with
+//     __match_any_sync, per-(digit, warp) counters in shared memory, one block-wide scan per pass — stable, so the
+//     order equals the first kernel's;
+//   * node ranges / splits live in shared memory; nodes INSIDE a subtree of at most kBvhLeaf points get neither a
+//     split nor a box (no walk ever reads them: such subtrees are scanned as leaves);
+//   * boxes are merged bottom-up over the BIG nodes only (~n / 4.6 of them, ~14 levels instead of ~28): a big node
+//     whose child is a leaf-sized subtree takes that child's box straight from its <= kBvhLeaf points (and stores it
+//     for the general walk), big children are waited for pass by pass with readiness bytes in shared memory;
+//   * the compact records are written in the same sweep.
+constexpr int kSbThreads = 1024;
+constexpr int kSbMaxPer = 24;                               // sorted positions a thread carries in registers
+constexpr uint32_t kSbMaxPoints = kSbMaxPer * kSbThreads;   // 24,576
+__host__ __device__ inline size_t sb_smem_bytes(uint32_t cap) {
+  const size_t capA = (cap + 15) & ~(size_t)15;
+  return 8 * capA + (capA > 16384 ? capA : 16384) + 64;  // codes | two 16-bit arrays | counters / readiness bytes
+}
+
+__global__ void __launch_bounds__(kSbThreads, 1) bvh_build_smem_kernel(BvhBuildArgs a) {
+  extern __shared__ __align__(16) unsigned char sb_smem[];
+  __shared__ double s_red[33];
+  __shared__ uint32_t s_scan[kSbThreads / 32];
+  const uint32_t set = blockIdx.x;
+  const uint32_t slot = (uint32_t)((a.slot0 + set) % a.n_slots);
+  const uint32_t n = a.counts[slot * 2 + a.kind];
+  const double4* pts = a.pts + (size_t)slot * a.pt_stride;
+  BvhNode* nodes = a.g.nodes + (size_t)set * a.g.pt_cap;
+  double4* sorted = a.g.sorted + (size_t)set * a.g.pt_cap;
+  const uint32_t tid = threadIdx.x, nthr = kSbThreads, lane = tid & 31, warp = tid >> 5;
+  const size_t capA = ((size_t)a.g.pt_cap + 15) & ~(size_t)15;
+  uint32_t* s_code = reinterpret_cast<uint32_t*>(sb_smem);              // [capA] codes: by point, after the sort by position
+  uint16_t* s_p0 = reinterpret_cast<uint16_t*>(s_code + capA);          // [capA] sort ping / node: other end of its range
+  uint16_t* s_p1 = s_p0 + capA;                                         // [capA] sort pong / node: split position
+  uint16_t* s_hist = s_p1 + capA;                                       // [256][32] sort counters; later readiness bytes
+#ifdef BUILD_TIMING
+  long long bt[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  BT_MARK(0);
+#endif
+  if (tid == 0) {
+    BvhHdr h;
+    h.n = n;
+    h.pad[0] = h.pad[1] = h.pad[2] = 0;
+    a.g.hdr[set] = h;
+    if (a.g.quant && n == 0) {
+      BvhQuant q;
+      q.org[0] = q.org[1] = q.org[2] = 0.0;
+      q.inv_cell = q.inv_cell2 = 1.0;
+      q.n_rec = 0;
+      q.pad = 0;
+      a.g.quant[set] = q;
+    }
+  }
+  if (n == 0) return;
+
+  // ---- bounding box, Morton scale, grid of the compact records (as in bvh_build_kernel)
+  double lo[3] = {CUDART_INF, CUDART_INF, CUDART_INF}, hi[3] = {-CUDART_INF, -CUDART_INF, -CUDART_INF};
+  for (uint32_t i = tid; i < n; i += nthr) {
+    const double4 p = pts[i];
+    lo[0] = fmin(lo[0], p.x);
+    lo[1] = fmin(lo[1], p.y);
+    lo[2] = fmin(lo[2], p.z);
+    hi[0] = fmax(hi[0], p.x);
+    hi[1] = fmax(hi[1], p.y);
+    hi[2] = fmax(hi[2], p.z);
+  }
+  double emax = 0;
+  for (int d = 0; d < 3; d++) {
+    lo[d] = block_reduce_minmax(lo[d], false, s_red);
+    hi[d] = block_reduce_minmax(hi[d], true, s_red);
+    emax = fmax(emax, hi[d] - lo[d]);
+  }
+  const double scale = emax > 0 ? 1023.999 / emax : 0.0;
+  if (tid == 0 && a.g.quant) {
+    double amax = emax;
+    for (int d = 0; d < 3; d++) amax = fmax(amax, fmax(fabs(lo[d]), fabs(hi[d])));
+    const double qmargin = 1e-6 * amax + 1e-9;
+    const double qinv = 65534.0 / (emax + 2.0 * qmargin);
+    BvhQuant q;
+    q.org[0] = lo[0] - qmargin;
+    q.org[1] = lo[1] - qmargin;
+    q.org[2] = lo[2] - qmargin;
+    q.inv_cell = qinv;
+    q.inv_cell2 = qinv * qinv * (1.0 + 1e-12);
+    q.n_rec = 0;
+    q.pad = 0;
+    a.g.quant[set] = q;
+  }
+  BT_MARK(1);
+
+  // ---- Morton codes (only as many bits as a set of n points needs, see bvh_build_kernel), identity order
+  int bits_axis = 6;
+  while (bits_axis < 10 && (1u << (2 * (bits_axis - 1))) < n) bits_axis++;
+  const int key_shift = 3 * (10 - bits_axis);
+  const int sort_bits = 3 * bits_axis;
+  for (uint32_t i = tid; i < n; i += nthr) {
+    const double4 p = pts[i];
+    const uint32_t ix = (uint32_t)fmin(fmax((p.x - lo[0]) * scale, 0.0), 1023.0);
+    const uint32_t iy = (uint32_t)fmin(fmax((p.y - lo[1]) * scale, 0.0), 1023.0);
+    const uint32_t iz = (uint32_t)fmin(fmax((p.z - lo[2]) * scale, 0.0), 1023.0);
+    s_code[i] = (spread10(ix) | (spread10(iy) << 1) | (spread10(iz) << 2)) >> key_shift;
+    s_p0[i] = (uint16_t)i;
+  }
+  __syncthreads();
+  BT_MARK(2);
+
+  // ---- stable LSD radix sort of the order, 8 bits per pass.  Counters are laid out [warp][digit] (a warp's group
+  // leaders hit different banks); lanes with the same digit find each other with 8 ballots (__match_any_sync measured
+  // ~10x slower here: its latency grows with the number of distinct values, up to 32 per batch of 8-bit digits).
+  {
+    uint16_t* src = s_p0;
+    uint16_t* dst = s_p1;
+    const uint32_t blk = (((n + 31) / 32) + 31) & ~31u;  // positions per warp: whole batches of 32
+    const uint32_t w_lo = min(warp * blk, n), w_hi = min(w_lo + blk, n);
+    const unsigned lt_mask = (1u << lane) - 1u;
+    uint16_t* my_hist = s_hist + warp * 256;
+    auto same_digit = [&](uint32_t dg, bool in) -> unsigned {  // lanes of this batch whose digit equals mine
+      unsigned peers = __ballot_sync(0xffffffffu, in);
+#pragma unroll
+      for (int b = 0; b < 8; b++) {
+        const bool bit = (dg >> b) & 1u;
+        const unsigned m = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? m : ~m;
+      }
+      return peers;
+    };
+    for (int shift = 0; shift < sort_bits; shift += 8) {
+      reinterpret_cast<uint4*>(s_hist)[tid] = make_uint4(0, 0, 0, 0);  // 32 x 256 counters = 1024 x 16 bytes
+      __syncthreads();
+      for (uint32_t b = w_lo; b < w_hi; b += 32) {
+        const uint32_t pos = b + lane;
+        const bool in = pos < w_hi;
+        const uint32_t dg = in ? (s_code[src[pos]] >> shift) & 255u : 0u;
+        const unsigned peers = same_digit(dg, in);
+        if (in && (peers & lt_mask) == 0u) my_hist[dg] += (uint16_t)__popc(peers);  // the group's first lane
+        __syncwarp();
+      }
+      __syncthreads();
+      {  // exclusive scan of the counters in (digit, warp) order: thread t takes digit t / 4, warps 8 (t % 4) .. + 7
+        const uint32_t dgt = tid >> 2, w0 = (tid & 3u) * 8u;
+        uint32_t c[8], tot = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          c[j] = s_hist[(w0 + j) * 256 + dgt];
+          tot += c[j];
+        }
+        uint32_t inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+          if ((int)lane >= o) inc += t;
+        }
+        if (lane == 31) s_scan[warp] = inc;
+        __syncthreads();
+        uint32_t run = inc - tot;
+        for (uint32_t w = 0; w < warp; w++) run += s_scan[w];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          s_hist[(w0 + j) * 256 + dgt] = (uint16_t)run;
+          run += c[j];
+        }
+      }
+      __syncthreads();
+      for (uint32_t b = w_lo; b < w_hi; b += 32) {
+        const uint32_t pos = b + lane;
+        const bool in = pos < w_hi;
+        const uint16_t e = in ? src[pos] : (uint16_t)0;
+        const uint32_t dg = in ? (s_code[e] >> shift) & 255u : 0u;
+        const unsigned peers = same_digit(dg, in);
+        if (in) dst[(uint32_t)my_hist[dg] + (uint32_t)__popc(peers & lt_mask)] = e;
+        __syncwarp();  // every lane has read its group's base
+        if (in && (peers & lt_mask) == 0u) my_hist[dg] += (uint16_t)__popc(peers);
+        __syncwarp();
+      }
+      __syncthreads();
+      uint16_t* t = src;
+      src = dst;
+      dst = t;
+    }
+    if (src != s_p0) {  // final order into s_p0
+      for (uint32_t i = tid; i < n; i += nthr) s_p0[i] = src[i];
+      __syncthreads();
+    }
+  }
+  BT_MARK(3);
+
+  // ---- Morton-ordered point copy; codes permuted in place (through registers) into sorted order
+  {
+    uint32_t c[kSbMaxPer];
+#pragma unroll
+    for (int j = 0; j < kSbMaxPer; j++) {
+      const uint32_t pos = tid + (uint32_t)j * nthr;
+      c[j] = pos < n ? s_code[s_p0[pos]] : 0u;
+    }
+    for (uint32_t pos = tid; pos < n; pos += nthr) {
+      const uint32_t id = s_p0[pos];
+      const double4 p = pts[id];
+      sorted[pos] = make_double4(p.x, p.y, p.z, __longlong_as_double((long long)id));
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kSbMaxPer; j++) {
+      const uint32_t pos = tid + (uint32_t)j * nthr;
+      if (pos < n) s_code[pos] = c[j];
+    }
+  }
+  __syncthreads();
+  BT_MARK(4);
+  if (n <= (uint32_t)kBvhLeaf) return;  // scanned directly by every walk: no nodes, no records (n_rec stays 0)
+
+  // ---- binary radix tree (Karras): range of every internal node, split of the big ones
+  uint16_t* s_other = s_p0;  // (the order is dead: both 16-bit arrays now describe nodes)
+  uint16_t* s_split = s_p1;
+  auto delta = [&](int i, int j) -> int {  // common-prefix length of keys i and j, -1 outside the array
+    if (j < 0 || j >= (int)n) return -1;
+    const uint32_t ci = s_code[i], cj = s_code[j];
+    return ci != cj ? __clz(ci ^ cj) : 32 + __clz((uint32_t)i ^ (uint32_t)j);
+  };
+  const uint32_t n_int = n - 1;
+  for (uint32_t t = tid; t < n_int; t += nthr) {
+    const int i = (int)t;
+    const int d = delta(i, i + 1) - delta(i, i - 1) >= 0 ? 1 : -1;
+    const int dmin = delta(i, i - d);
+    int lmax = 2;
+    while (delta(i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int st = lmax >> 1; st >= 1; st >>= 1)
+      if (delta(i, i + (l + st) * d) > dmin) l += st;
+    const int j = i + l * d;
+    uint32_t w = 0;
+    int split = 0;
+    if (l >= kBvhLeaf) {  // more than kBvhLeaf points: a node the walks expand
+      const int dnode = delta(i, j);
+      int sp = 0;
+      for (int div = 2;; div <<= 1) {
+        const int st = (l + div - 1) / div;
+        if (delta(i, i + (sp + st) * d) > dnode) sp += st;
+        if (st <= 1) break;
+      }
+      split = i + sp * d + min(d, 0);
+      w = (uint32_t)split;
+      if (min(i, j) == split) w |= kLeftLeaf;
+      if (max(i, j) == split + 1) w |= kRightLeaf;
+    }
+    s_other[i] = (uint16_t)j;
+    s_split[i] = (uint16_t)split;
+    nodes[i].split = w;
+    nodes[i].pad = (uint32_t)j;
+  }
+  __syncthreads();
+  BT_MARK(5);
+
+  // ---- number the big nodes in index order (the root, node 0, is number 0) and list them
+  uint16_t* s_cid = reinterpret_cast<uint16_t*>(s_code);  // (codes are dead) node -> number
+  uint16_t* s_big = s_cid + capA;                          // number -> node
+  uint8_t* s_ready = reinterpret_cast<uint8_t*>(s_hist);   // per number: pass in which its box was merged (0: not yet)
+  const uint32_t per = (n_int + nthr - 1) / nthr;
+  const uint32_t b0 = min(tid * per, n_int), b1 = min(b0 + per, n_int);
+  auto is_big = [&](uint32_t i) -> bool {
+    const int o = (int)s_other[i];
+    return abs(o - (int)i) >= kBvhLeaf;
+  };
+  uint32_t cnt_big = 0;
+  for (uint32_t i = b0; i < b1; i++) cnt_big += is_big(i) ? 1u : 0u;
+  uint32_t incl = cnt_big;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((int)lane >= o) incl += t;
+  }
+  if (lane == 31) s_scan[warp] = incl;
+  __syncthreads();
+  uint32_t base = 0, n_big = 0;
+  for (uint32_t w = 0; w < (nthr >> 5); w++) {
+    if (w < warp) base += s_scan[w];
+    n_big += s_scan[w];
+  }
+  __syncthreads();  // (everyone has read the codes' last users' data: s_cid / s_big overwrite s_code)
+  {
+    uint32_t run = base + incl - cnt_big;
+    for (uint32_t i = b0; i < b1; i++)
+      if (is_big(i)) {
+        s_cid[i] = (uint16_t)run;
+        s_big[run] = (uint16_t)i;
+        s_ready[run] = 0;
+        run++;
+      }
+  }
+  __syncthreads();
+
+  // ---- boxes of the big nodes, bottom-up in passes (thread t owns numbers t, t + 1024, ...)
+  auto child_box = [&](uint32_t cf, uint32_t cl, uint32_t cnode, bool store, float* blo, float* bhi) {
+    if (cl - cf < (uint32_t)kBvhLeaf) {  // a leaf-sized subtree: straight from its points
+      double plo[3] = {CUDART_INF, CUDART_INF, CUDART_INF}, phi[3] = {-CUDART_INF, -CUDART_INF, -CUDART_INF};
+#pragma unroll
+      for (int k = 0; k < kBvhLeaf; k++) {
+        const double4 pt = sorted[min(cf + (uint32_t)k, cl)];
+        plo[0] = fmin(plo[0], pt.x); phi[0] = fmax(phi[0], pt.x);
+        plo[1] = fmin(plo[1], pt.y); phi[1] = fmax(phi[1], pt.y);
+        plo[2] = fmin(plo[2], pt.z); phi[2] = fmax(phi[2], pt.z);
+      }
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        blo[k] = __double2float_rd(plo[k]);
+        bhi[k] = __double2float_ru(phi[k]);
+      }
+      if (store && cf != cl) {  // the general walk tests this child through its node record
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          nodes[cnode].lo[k] = blo[k];
+          nodes[cnode].hi[k] = bhi[k];
+        }
+      }
+    } else {
+      const float4* q = reinterpret_cast<const float4*>(nodes + cnode);
+      const float4 va = __ldcg(q), vb = __ldcg(q + 1);
+      blo[0] = va.x; blo[1] = va.y; blo[2] = va.z;
+      bhi[0] = vb.x; bhi[1] = vb.y; bhi[2] = vb.z;
+    }
+  };
+  const uint32_t mine = tid < n_big ? (n_big - tid + nthr - 1) / nthr : 0u;  // (at most 24: n_big < n <= 24,576)
+  {
+    uint32_t pend = mine >= 32 ? 0xffffffffu : ((1u << mine) - 1u);
+    for (uint32_t pass = 1;; pass++) {
+      uint32_t m = pend;
+      while (m) {
+        const int k = __ffs((int)m) - 1;
+        m &= m - 1;
+        const uint32_t num = tid + (uint32_t)k * nthr;
+        const uint32_t i = s_big[num];
+        const uint32_t o = s_other[i], sp = s_split[i];
+        const uint32_t f = min(i, o), l = max(i, o);
+        // big children must have been merged in an EARLIER pass (one barrier per pass separates writers from readers)
+        bool ok = true;
+        if (sp - f >= (uint32_t)kBvhLeaf) {
+          const uint32_t r = s_ready[s_cid[sp]];
+          ok = ok && r != 0 && r < pass;
+        }
+        if (l - (sp + 1) >= (uint32_t)kBvhLeaf) {
+          const uint32_t r = s_ready[s_cid[sp + 1]];
+          ok = ok && r != 0 && r < pass;
+        }
+        if (!ok) continue;
+        float llo[3], lhi[3], rlo[3], rhi[3];
+        child_box(f, sp, sp, true, llo, lhi);
+        child_box(sp + 1, l, sp + 1, true, rlo, rhi);
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+          nodes[i].lo[q] = fminf(llo[q], rlo[q]);
+          nodes[i].hi[q] = fmaxf(lhi[q], rhi[q]);
+        }
+        s_ready[num] = (uint8_t)min(pass, 255u);
+        pend &= ~(1u << k);
+      }
+      if (!__syncthreads_or(pend != 0)) break;
+    }
+  }
+  BT_MARK(6);
+
+  // ---- compact records (common.cuh: BvhRec), one per big node, numbered as above
+  if (a.g.quant == nullptr) return;
+  const uint32_t rec_cap = a.g.pt_cap / 2;
+  if (n_big > rec_cap) {  // degenerate tree (long chains): this set keeps the general walk only
+    if (tid == 0) a.g.quant[set].n_rec = kNoRecs;
+    return;
+  }
+  BvhRec* recs = reinterpret_cast<BvhRec*>(a.g.keys + (size_t)set * 2 * a.g.pt_cap);
+  const double qorg[3] = {__ldcg(&a.g.quant[set].org[0]), __ldcg(&a.g.quant[set].org[1]), __ldcg(&a.g.quant[set].org[2])};
+  const double qinv = __ldcg(&a.g.quant[set].inv_cell);
+  for (uint32_t num = tid; num < n_big; num += nthr) {
+    const uint32_t i = s_big[num];
+    const uint32_t o = s_other[i], sp = s_split[i];
+    const uint32_t f = min(i, o), l = max(i, o);
+    uint32_t box[6], ref[2];
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      const uint32_t cf = c == 0 ? f : sp + 1, cl = c == 0 ? sp : l;
+      float blo[3], bhi[3];
+      child_box(cf, cl, sp + (uint32_t)c, false, blo, bhi);
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        const double tl = ((double)blo[d] - qorg[d]) * qinv, th = ((double)bhi[d] - qorg[d]) * qinv;
+        const uint32_t ql = (uint32_t)fmin(fmax(floor(tl - 1e-6), 0.0), 65535.0);
+        const uint32_t qh = (uint32_t)fmin(fmax(ceil(th + 1e-6), 0.0), 65535.0);
+        box[3 * c + d] = ql | (qh << 16);
+      }
+      ref[c] = (cl - cf < (uint32_t)kBvhLeaf) ? (kRefLeaf | ((cl - cf) << 24) | cf) : (uint32_t)s_cid[sp + c];
+    }
+    uint4* dst = reinterpret_cast<uint4*>(recs + num);
+    dst[0] = make_uint4(box[0], box[1], box[2], box[3]);
+    dst[1] = make_uint4(box[4], box[5], ref[0], ref[1]);
+  }
+  if (tid == 0) a.g.quant[set].n_rec = n_big;
+#ifdef BUILD_TIMING
+  BT_MARK(7);
+  if (tid == 0 && set == 0)
+    printf("BT n %u: bbox %lld morton %lld sort %lld gather %lld topology %lld boxes %lld compact %lld total %lld\n", n,
+           bt[1] - bt[0], bt[2] - bt[1], bt[3] - bt[2], bt[4] - bt[3], bt[5] - bt[4], bt[6] - bt[5], bt[7] - bt[6],
+           bt[7] - bt[0]);
+#endif
 }
 
 // ============================================================================ exact k-NN (K4)

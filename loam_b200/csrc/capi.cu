@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges cost one pointer test when no tool is attached
@@ -1495,3 +1496,101 @@ static int odometry_host_impl(loamgpu_ctx* ctx, OdometryMode mode, const void* s
   if (n_planar) CU(cudaMemcpyAsync(n_planar, ctx->out_np.p, n_scans * 4, cudaMemcpyDeviceToHost, ctx->stream));
   return LOAMGPU_OK;
 }
+
+// =============================================================================================== multi-GPU
+// One sequence over several GPUs of one box: pair k depends only on scans k and k + 1, so the pair range is
+// cut into contiguous blocks, one per device; each device extracts its own scans plus one halo scan (the first scan of
+// the next block) and no feature set ever crosses GPUs.  One host thread + one context (own streams, own buffers) per
+// device, no collective anywhere: the only cross-device data are the result rows each thread writes into its own slice
+// of the caller's arrays.  Results are identical to the single-device call, whatever the split.
+struct loamgpu_multi {
+  std::vector<loamgpu_ctx*> ctx;  // one per entry of `devices` (a device may appear more than once)
+  std::string err;
+};
+
+extern "C" {
+
+int loamgpu_multi_create(const int* devices, int n_devices, loamgpu_multi** out) {
+  if (!out) return LOAMGPU_ERR_INVALID;
+  *out = nullptr;
+  if (!devices || n_devices <= 0) {
+    g_create_err = "loamgpu_multi_create: empty device list";
+    return LOAMGPU_ERR_INVALID;
+  }
+  loamgpu_multi* m = new loamgpu_multi();
+  for (int i = 0; i < n_devices; i++) {
+    loamgpu_ctx* c = nullptr;
+    const int rc = loamgpu_create(devices[i], &c);
+    if (rc != LOAMGPU_OK) {
+      for (loamgpu_ctx* p : m->ctx) loamgpu_destroy(p);
+      delete m;
+      return rc;  // (message in loamgpu_last_error(NULL))
+    }
+    m->ctx.push_back(c);
+  }
+  *out = m;
+  return LOAMGPU_OK;
+}
+
+void loamgpu_multi_destroy(loamgpu_multi* m) {
+  if (!m) return;
+  for (loamgpu_ctx* c : m->ctx) loamgpu_destroy(c);
+  delete m;
+}
+
+const char* loamgpu_multi_last_error(const loamgpu_multi* m) { return m ? m->err.c_str() : g_create_err.c_str(); }
+
+int loamgpu_multi_device_count(const loamgpu_multi* m) { return m ? (int)m->ctx.size() : 0; }
+
+int loamgpu_multi_odometry_host(loamgpu_multi* m, const void* scans, size_t stride_bytes, uint64_t n_scans,
+                                const loamgpu_lidar_params* lp, const loamgpu_fe_params* fe,
+                                const loamgpu_reg_params* reg, double* poses, int32_t* termination, uint32_t* iterations,
+                                uint32_t* n_edge, uint32_t* n_planar) {
+  if (!m) return LOAMGPU_ERR_INVALID;
+  NvtxRange range(__func__);
+  m->err.clear();
+  if (!lp || !fe || !reg) {
+    m->err = "null parameter struct";
+    return LOAMGPU_ERR_INVALID;
+  }
+  if (n_scans == 0) return LOAMGPU_OK;
+  const uint64_t n_pairs = n_scans - 1;
+  const uint64_t n_per = lp->scan_lines * lp->points_per_line;
+  const size_t G = m->ctx.size();
+  // contiguous pair blocks: device g takes pairs [g * per, (g + 1) * per) and scans [g * per, (g + 1) * per] (halo)
+  const uint64_t per = n_pairs ? (n_pairs + G - 1) / G : 0;
+  std::vector<int> rc(G, LOAMGPU_OK);
+  std::vector<std::thread> workers;
+  auto work = [&](size_t g) {
+    const uint64_t p_lo = std::min<uint64_t>(g * per, n_pairs), p_hi = std::min<uint64_t>(p_lo + per, n_pairs);
+    uint64_t s_lo = p_lo, ns = p_hi > p_lo ? p_hi - p_lo + 1 : 0;
+    if (n_pairs == 0) {  // a single scan: device 0 extracts it
+      s_lo = 0;
+      ns = g == 0 ? 1 : 0;
+    }
+    if (ns == 0) return;
+    const unsigned char* base = static_cast<const unsigned char*>(scans) + s_lo * n_per * stride_bytes;
+    // feature counts of a halo scan are written by both neighbours (same values): each device writes its own scans
+    // except the halo, the last device also its final scan
+    const bool last = p_hi == n_pairs;
+    std::vector<uint32_t> ne(ns), np(ns);
+    rc[g] = loamgpu_odometry_host_strided(m->ctx[g], base, stride_bytes, ns, lp, fe, reg, poses ? poses + 7 * p_lo : nullptr,
+                                          termination ? termination + p_lo : nullptr,
+                                          iterations ? iterations + p_lo : nullptr, ne.data(), np.data());
+    if (rc[g] != LOAMGPU_OK) return;
+    const uint64_t own = last || n_pairs == 0 ? ns : ns - 1;
+    if (n_edge) memcpy(n_edge + s_lo, ne.data(), own * sizeof(uint32_t));
+    if (n_planar) memcpy(n_planar + s_lo, np.data(), own * sizeof(uint32_t));
+  };
+  for (size_t g = 1; g < G; g++) workers.emplace_back(work, g);
+  work(0);
+  for (std::thread& t : workers) t.join();
+  for (size_t g = 0; g < G; g++)
+    if (rc[g] != LOAMGPU_OK) {
+      m->err = std::string("device slot ") + std::to_string(g) + ": " + loamgpu_last_error(m->ctx[g]);
+      return rc[g];
+    }
+  return LOAMGPU_OK;
+}
+
+}  // extern "C"

@@ -1327,12 +1327,21 @@ __global__ void finish_pairs_kernel(const PairState* st, uint32_t n, double* pos
 cudaError_t launch_bvh_build(const BvhBuildArgs& a_in, uint32_t n_sets, cudaStream_t st) {
   if (n_sets == 0) return cudaSuccess;
   BvhBuildArgs a = a_in;
-  const size_t sort_bytes = (size_t)kRadixBins * kBuildThreads * sizeof(uint32_t);
-  // radix counters, reused after the sort for the sorted codes; + one readiness byte per node
-  const size_t tree_bytes = std::max(sort_bytes, (size_t)a.g.pt_cap * 4) + a.g.pt_cap + 16;
   int dev = 0, optin = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  static const bool legacy = []() { const char* e = getenv("LOAMGPU_BUILD_LEGACY"); return e && atoi(e) != 0; }();
+  // sets whose intermediates fit in shared memory (16-bit point numbers, 8 bytes per point + counters)
+  if (!legacy && a.g.pt_cap <= kSbMaxPoints && sb_smem_bytes(a.g.pt_cap) + 1024 <= (size_t)optin) {
+    const size_t smem = sb_smem_bytes(a.g.pt_cap);
+    cudaError_t err = cudaFuncSetAttribute(bvh_build_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    bvh_build_smem_kernel<<<n_sets, kSbThreads, smem, st>>>(a);
+    return cudaGetLastError();
+  }
+  const size_t sort_bytes = (size_t)kRadixBins * kBuildThreads * sizeof(uint32_t);
+  // radix counters, reused after the sort for the sorted codes; + one readiness byte per node
+  const size_t tree_bytes = std::max(sort_bytes, (size_t)a.g.pt_cap * 4) + a.g.pt_cap + 16;
   a.smem_tree = tree_bytes + 4096 <= (size_t)optin;  // (the kernel also has ~2.4 KB of static shared memory)
   const size_t smem = a.smem_tree ? tree_bytes : sort_bytes;
   cudaError_t err = cudaFuncSetAttribute(bvh_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
