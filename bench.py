@@ -462,6 +462,36 @@ def other_configs(torch, synth, _capi, ctx, stream, dev, a, barrier, max_over_ra
     return out
 
 
+def single_call_block(host_scans, R, P):
+    """ONE loam::extractFeatures + ONE loam::registerFeatures call per scan through the C++ API (include/loam/*.h),
+    the reference's own usage pattern and what its README figure (3.5 + 13 ms) is quoted on.  Timed by the C++ program
+    tests/cpp/bench_single_call (host vectors in, features / pose out, every copy inside the timed call)."""
+    import subprocess
+    import tempfile
+    exe = os.path.join(ROOT, "tests", "cpp", "bench_single_call")
+    if not os.path.exists(exe):
+        r = subprocess.run(["make", "-C", os.path.dirname(exe), "build"], capture_output=True, text=True)
+        if r.returncode != 0:
+            return {"unavailable": "tests/cpp/bench_single_call does not build: " + r.stderr[-200:]}
+    scans = host_scans[:2]
+    if scans.shape[2] == 3:
+        scans = np.concatenate([scans, np.zeros(scans.shape[:2] + (1,), np.float32)], axis=2)
+    with tempfile.NamedTemporaryFile(suffix=".bin") as f:
+        np.ascontiguousarray(scans, dtype=np.float32).tofile(f.name)
+        r = subprocess.run([exe, f.name, str(R), str(P), "40"], capture_output=True, text=True, timeout=300)
+    if r.returncode != 0:
+        return {"unavailable": "bench_single_call failed: " + (r.stderr or r.stdout)[-200:]}
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    out = {"extract_ms": d["extract_ms"], "register_ms": d["register_ms"],
+           "register_with_detail_ms": d["register_with_detail_ms"], "outer_iterations": d["outer_iterations"],
+           "scans_per_s": 1e3 / (d["extract_ms"] + d["register_ms"]), "shape": [R, P],
+           "api": "loam::extractFeatures(std::vector<PointF>) + loam::registerFeatures(LoamFeatures<PointF>) "
+                  "(include/loam/*.h over the C-ABI), host buffers, median of 40 calls"}
+    if (R, P) == (64, 1024):  # the README figure is for a 64-ring Ouster scan
+        out["vs_readme"] = README_MS_PER_SCAN / (d["extract_ms"] + d["register_ms"])
+    return out
+
+
 def ours(a):
     import torch
     import torch.distributed as dist
@@ -590,6 +620,7 @@ def ours(a):
             if not line["parity_check"]["ok"]:
                 rc = 3
         if world == 1 and not a.no_configs:
+            line["single_call"] = single_call_block(seq.h_scans.numpy(), R, P)
             del seq
             torch.cuda.empty_cache()
             line["configs"] = other_configs(torch, synth, _capi, ctx, stream, dev, a, barrier, max_over_ranks)

@@ -475,14 +475,19 @@ __global__ void __launch_bounds__(kBuildThreads, BUILD_MINBLOCKS) bvh_build_kern
 //     for the general walk), big children are waited for pass by pass with readiness bytes in shared memory;
 //   * the compact records are written in the same sweep.
 constexpr int kSbThreads = 1024;
-constexpr int kSbMaxPer = 24;                               // sorted positions a thread carries in registers
-constexpr uint32_t kSbMaxPoints = kSbMaxPer * kSbThreads;   // 24,576
+constexpr int kSbMaxPer = 20;                               // sorted positions a thread carries in registers
+constexpr uint32_t kSbMaxPoints = kSbMaxPer * kSbThreads;   // 20,480
 __host__ __device__ inline size_t sb_smem_bytes(uint32_t cap) {
   const size_t capA = (cap + 15) & ~(size_t)15;
-  return 8 * capA + (capA > 16384 ? capA : 16384) + 64;  // codes | two 16-bit arrays | counters / readiness bytes
+  // codes (later: node -> number) | two 16-bit arrays (order; later node ranges, splits) | sort counters (later: the
+  // list of big nodes + their readiness bytes)
+  return 8 * capA + (3 * capA > 32768 ? 3 * capA : 32768) + 64;
 }
 
-__global__ void __launch_bounds__(kSbThreads, 1) bvh_build_smem_kernel(BvhBuildArgs a) {
+// grid (sets, kinds): row 0 builds `a0`'s sets, row 1 (when launched) `a1`'s — the edge and the planar sets of the same
+// scans in one launch (short edge CTAs fill in around the long planar ones; one launch less per chunk / call)
+__global__ void __launch_bounds__(kSbThreads, 1) bvh_build_smem_kernel(BvhBuildArgs a0, BvhBuildArgs a1) {
+  const BvhBuildArgs& a = blockIdx.y ? a1 : a0;
   extern __shared__ __align__(16) unsigned char sb_smem[];
   __shared__ double s_red[33];
   __shared__ uint32_t s_scan[kSbThreads / 32];
@@ -497,7 +502,7 @@ __global__ void __launch_bounds__(kSbThreads, 1) bvh_build_smem_kernel(BvhBuildA
   uint32_t* s_code = reinterpret_cast<uint32_t*>(sb_smem);              // [capA] codes: by point, after the sort by position
   uint16_t* s_p0 = reinterpret_cast<uint16_t*>(s_code + capA);          // [capA] sort ping / node: other end of its range
   uint16_t* s_p1 = s_p0 + capA;                                         // [capA] sort pong / node: split position
-  uint16_t* s_hist = s_p1 + capA;                                       // [256][32] sort counters; later readiness bytes
+  uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_p1 + capA);          // [32 warps][256 digits] sort counters
 #ifdef BUILD_TIMING
   long long bt[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   BT_MARK(0);
@@ -520,6 +525,7 @@ __global__ void __launch_bounds__(kSbThreads, 1) bvh_build_smem_kernel(BvhBuildA
 
   // ---- bounding box, Morton scale, grid of the compact records (as in bvh_build_kernel)
   double lo[3] = {CUDART_INF, CUDART_INF, CUDART_INF}, hi[3] = {-CUDART_INF, -CUDART_INF, -CUDART_INF};
+#pragma unroll 4
   for (uint32_t i = tid; i < n; i += nthr) {
     const double4 p = pts[i];
     lo[0] = fmin(lo[0], p.x);
@@ -558,6 +564,7 @@ __global__ void __launch_bounds__(kSbThreads, 1) bvh_build_smem_kernel(BvhBuildA
   while (bits_axis < 10 && (1u << (2 * (bits_axis - 1))) < n) bits_axis++;
   const int key_shift = 3 * (10 - bits_axis);
   const int sort_bits = 3 * bits_axis;
+#pragma unroll 4
   for (uint32_t i = tid; i < n; i += nthr) {
     const double4 p = pts[i];
     const uint32_t ix = (uint32_t)fmin(fmax((p.x - lo[0]) * scale, 0.0), 1023.0);
@@ -578,7 +585,7 @@ __global__ void __launch_bounds__(kSbThreads, 1) bvh_build_smem_kernel(BvhBuildA
     const uint32_t blk = (((n + 31) / 32) + 31) & ~31u;  // positions per warp: whole batches of 32
     const uint32_t w_lo = min(warp * blk, n), w_hi = min(w_lo + blk, n);
     const unsigned lt_mask = (1u << lane) - 1u;
-    uint16_t* my_hist = s_hist + warp * 256;
+    uint32_t* my_hist = s_hist + warp * 256;
     auto same_digit = [&](uint32_t dg, bool in) -> unsigned {  // lanes of this batch whose digit equals mine
       unsigned peers = __ballot_sync(0xffffffffu, in);
 #pragma unroll
@@ -590,16 +597,11 @@ __global__ void __launch_bounds__(kSbThreads, 1) bvh_build_smem_kernel(BvhBuildA
       return peers;
     };
     for (int shift = 0; shift < sort_bits; shift += 8) {
-      reinterpret_cast<uint4*>(s_hist)[tid] = make_uint4(0, 0, 0, 0);  // 32 x 256 counters = 1024 x 16 bytes
+#pragma unroll
+      for (int j = 0; j < 2; j++) reinterpret_cast<uint4*>(s_hist)[tid + j * kSbThreads] = make_uint4(0, 0, 0, 0);
       __syncthreads();
-      for (uint32_t b = w_lo; b < w_hi; b += 32) {
-        const uint32_t pos = b + lane;
-        const bool in = pos < w_hi;
-        const uint32_t dg = in ? (s_code[src[pos]] >> shift) & 255u : 0u;
-        const unsigned peers = same_digit(dg, in);
-        if (in && (peers & lt_mask) == 0u) my_hist[dg] += (uint16_t)__popc(peers);  // the group's first lane
-        __syncwarp();
-      }
+      // counting needs no order: shared-memory atomics (the kernel is issue-bound here: 14 k keys x instructions per key)
+      for (uint32_t pos = w_lo + lane; pos < w_hi; pos += 32) atomicAdd(&my_hist[(s_code[src[pos]] >> shift) & 255u], 1u);
       __syncthreads();
       {  // exclusive scan of the counters in (digit, warp) order: thread t takes digit t / 4, warps 8 (t % 4) .. + 7
         const uint32_t dgt = tid >> 2, w0 = (tid & 3u) * 8u;
@@ -621,20 +623,21 @@ __global__ void __launch_bounds__(kSbThreads, 1) bvh_build_smem_kernel(BvhBuildA
         for (uint32_t w = 0; w < warp; w++) run += s_scan[w];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-          s_hist[(w0 + j) * 256 + dgt] = (uint16_t)run;
+          s_hist[(w0 + j) * 256 + dgt] = run;
           run += c[j];
         }
       }
       __syncthreads();
+      // scattering must be stable: rank inside the batch by lane order among equal digits, batches in order
       for (uint32_t b = w_lo; b < w_hi; b += 32) {
         const uint32_t pos = b + lane;
         const bool in = pos < w_hi;
         const uint16_t e = in ? src[pos] : (uint16_t)0;
         const uint32_t dg = in ? (s_code[e] >> shift) & 255u : 0u;
         const unsigned peers = same_digit(dg, in);
-        if (in) dst[(uint32_t)my_hist[dg] + (uint32_t)__popc(peers & lt_mask)] = e;
+        if (in) dst[my_hist[dg] + (uint32_t)__popc(peers & lt_mask)] = e;
         __syncwarp();  // every lane has read its group's base
-        if (in && (peers & lt_mask) == 0u) my_hist[dg] += (uint16_t)__popc(peers);
+        if (in && (peers & lt_mask) == 0u) my_hist[dg] += (uint32_t)__popc(peers);
         __syncwarp();
       }
       __syncthreads();
@@ -657,10 +660,20 @@ __global__ void __launch_bounds__(kSbThreads, 1) bvh_build_smem_kernel(BvhBuildA
       const uint32_t pos = tid + (uint32_t)j * nthr;
       c[j] = pos < n ? s_code[s_p0[pos]] : 0u;
     }
-    for (uint32_t pos = tid; pos < n; pos += nthr) {
-      const uint32_t id = s_p0[pos];
-      const double4 p = pts[id];
-      sorted[pos] = make_double4(p.x, p.y, p.z, __longlong_as_double((long long)id));
+    for (uint32_t pos0 = tid; pos0 < n; pos0 += 4 * nthr) {  // four independent gathers in flight per thread
+      double4 p[4];
+      uint32_t id[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const uint32_t pos = pos0 + (uint32_t)u * nthr;
+        id[u] = s_p0[min(pos, n - 1)];
+        p[u] = pts[id[u]];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const uint32_t pos = pos0 + (uint32_t)u * nthr;
+        if (pos < n) sorted[pos] = make_double4(p[u].x, p[u].y, p[u].z, __longlong_as_double((long long)id[u]));
+      }
     }
     __syncthreads();
 #pragma unroll
@@ -673,9 +686,16 @@ __global__ void __launch_bounds__(kSbThreads, 1) bvh_build_smem_kernel(BvhBuildA
   BT_MARK(4);
   if (n <= (uint32_t)kBvhLeaf) return;  // scanned directly by every walk: no nodes, no records (n_rec stays 0)
 
-  // ---- binary radix tree (Karras): range of every internal node, split of the big ones
-  uint16_t* s_other = s_p0;  // (the order is dead: both 16-bit arrays now describe nodes)
-  uint16_t* s_split = s_p1;
+  // ---- binary radix tree (Karras).  Nodes of at most kBvhLeaf points need no split and no box (no walk expands them),
+  // and they are 4 of 5 nodes: a first sweep over ALL nodes only finds each node's range, giving up after three probes
+  // once the range is known to exceed kBvhLeaf points (a warp pays for its slowest lane: with the full searches in this
+  // sweep every warp paid for its biggest node, 118 k cycles on 14.3 k points).  The big nodes are then numbered and
+  // finish their searches densely packed, one thread per big node.
+  uint16_t* s_other = s_p0;  // (the order is dead: both 16-bit arrays now describe nodes) other end of the range
+  uint16_t* s_split = s_p1;  // split position (big nodes)
+  uint16_t* s_big = reinterpret_cast<uint16_t*>(s_hist);     // (the counters are dead) number -> node   [capA]
+  uint8_t* s_ready = reinterpret_cast<uint8_t*>(s_big + capA);  // per number: pass in which its box was completed
+  constexpr uint16_t kBigPending = 0xFFFFu;
   auto delta = [&](int i, int j) -> int {  // common-prefix length of keys i and j, -1 outside the array
     if (j < 0 || j >= (int)n) return -1;
     const uint32_t ci = s_code[i], cj = s_code[j];
@@ -687,46 +707,23 @@ __global__ void __launch_bounds__(kSbThreads, 1) bvh_build_smem_kernel(BvhBuildA
     const int d = delta(i, i + 1) - delta(i, i - 1) >= 0 ? 1 : -1;
     const int dmin = delta(i, i - d);
     int lmax = 2;
-    while (delta(i, i + lmax * d) > dmin) lmax <<= 1;
-    int l = 0;
-    for (int st = lmax >> 1; st >= 1; st >>= 1)
-      if (delta(i, i + (l + st) * d) > dmin) l += st;
-    const int j = i + l * d;
-    uint32_t w = 0;
-    int split = 0;
-    if (l >= kBvhLeaf) {  // more than kBvhLeaf points: a node the walks expand
-      const int dnode = delta(i, j);
-      int sp = 0;
-      for (int div = 2;; div <<= 1) {
-        const int st = (l + div - 1) / div;
-        if (delta(i, i + (sp + st) * d) > dnode) sp += st;
-        if (st <= 1) break;
-      }
-      split = i + sp * d + min(d, 0);
-      w = (uint32_t)split;
-      if (min(i, j) == split) w |= kLeftLeaf;
-      if (max(i, j) == split + 1) w |= kRightLeaf;
+    while (lmax < 2 * kBvhLeaf && delta(i, i + lmax * d) > dmin) lmax <<= 1;
+    uint16_t other = kBigPending;
+    if (lmax < 2 * kBvhLeaf) {  // the range ends within lmax - 1 < kBvhLeaf steps: a leaf-sized node
+      int l = 0;
+      for (int st = lmax >> 1; st >= 1; st >>= 1)
+        if (delta(i, i + (l + st) * d) > dmin) l += st;
+      if (l < kBvhLeaf) other = (uint16_t)(i + l * d);  // (else: big after all — leaf sizes that are no power of two)
     }
-    s_other[i] = (uint16_t)j;
-    s_split[i] = (uint16_t)split;
-    nodes[i].split = w;
-    nodes[i].pad = (uint32_t)j;
+    s_other[i] = other;
   }
   __syncthreads();
-  BT_MARK(5);
 
   // ---- number the big nodes in index order (the root, node 0, is number 0) and list them
-  uint16_t* s_cid = reinterpret_cast<uint16_t*>(s_code);  // (codes are dead) node -> number
-  uint16_t* s_big = s_cid + capA;                          // number -> node
-  uint8_t* s_ready = reinterpret_cast<uint8_t*>(s_hist);   // per number: pass in which its box was merged (0: not yet)
   const uint32_t per = (n_int + nthr - 1) / nthr;
   const uint32_t b0 = min(tid * per, n_int), b1 = min(b0 + per, n_int);
-  auto is_big = [&](uint32_t i) -> bool {
-    const int o = (int)s_other[i];
-    return abs(o - (int)i) >= kBvhLeaf;
-  };
   uint32_t cnt_big = 0;
-  for (uint32_t i = b0; i < b1; i++) cnt_big += is_big(i) ? 1u : 0u;
+  for (uint32_t i = b0; i < b1; i++) cnt_big += s_other[i] == kBigPending ? 1u : 0u;
   uint32_t incl = cnt_big;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -740,89 +737,162 @@ __global__ void __launch_bounds__(kSbThreads, 1) bvh_build_smem_kernel(BvhBuildA
     if (w < warp) base += s_scan[w];
     n_big += s_scan[w];
   }
-  __syncthreads();  // (everyone has read the codes' last users' data: s_cid / s_big overwrite s_code)
   {
     uint32_t run = base + incl - cnt_big;
     for (uint32_t i = b0; i < b1; i++)
-      if (is_big(i)) {
-        s_cid[i] = (uint16_t)run;
-        s_big[run] = (uint16_t)i;
-        s_ready[run] = 0;
-        run++;
-      }
+      if (s_other[i] == kBigPending) s_big[run++] = (uint16_t)i;
   }
   __syncthreads();
 
-  // ---- boxes of the big nodes, bottom-up in passes (thread t owns numbers t, t + 1024, ...)
-  auto child_box = [&](uint32_t cf, uint32_t cl, uint32_t cnode, bool store, float* blo, float* bhi) {
-    if (cl - cf < (uint32_t)kBvhLeaf) {  // a leaf-sized subtree: straight from its points
-      double plo[3] = {CUDART_INF, CUDART_INF, CUDART_INF}, phi[3] = {-CUDART_INF, -CUDART_INF, -CUDART_INF};
+  // ---- full range + split searches of the big nodes, one thread per node
+  for (uint32_t num = tid; num < n_big; num += nthr) {
+    const int i = (int)s_big[num];
+    const int d = delta(i, i + 1) - delta(i, i - 1) >= 0 ? 1 : -1;
+    const int dmin = delta(i, i - d);
+    int lmax = 2;
+    while (delta(i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int st = lmax >> 1; st >= 1; st >>= 1)
+      if (delta(i, i + (l + st) * d) > dmin) l += st;
+    const int j = i + l * d;
+    const int dnode = delta(i, j);
+    int sp = 0;
+    for (int div = 2;; div <<= 1) {
+      const int st = (l + div - 1) / div;
+      if (delta(i, i + (sp + st) * d) > dnode) sp += st;
+      if (st <= 1) break;
+    }
+    const int split = i + sp * d + min(d, 0);
+    uint32_t w = (uint32_t)split;
+    if (min(i, j) == split) w |= kLeftLeaf;
+    if (max(i, j) == split + 1) w |= kRightLeaf;
+    s_other[i] = (uint16_t)j;
+    s_split[i] = (uint16_t)split;
+    nodes[i].split = w;
+    nodes[i].pad = (uint32_t)j;
+  }
+  __syncthreads();
+  BT_MARK(5);
+
+  // ---- boxes.  Thread t owns the big nodes numbered t, t + 1024, ...  Pass 1: every big node takes the boxes of its
+  // LEAF-SIZED children straight from their points (all loads independent; stored in the child's node record for the
+  // general walk) — a node without big children is complete, the others keep the partial union in their record.
+  // Later passes: a pending node whose big children were completed in an EARLIER pass merges them in (one L2 round trip
+  // per pass, over the ~half of the big nodes that have a big child).
+  uint16_t* s_cid = reinterpret_cast<uint16_t*>(s_code);  // (codes are dead) node -> number
+  auto small_box = [&](uint32_t cf, uint32_t cl, uint32_t cnode, float* blo, float* bhi) {
+    double plo[3] = {CUDART_INF, CUDART_INF, CUDART_INF}, phi[3] = {-CUDART_INF, -CUDART_INF, -CUDART_INF};
 #pragma unroll
-      for (int k = 0; k < kBvhLeaf; k++) {
-        const double4 pt = sorted[min(cf + (uint32_t)k, cl)];
-        plo[0] = fmin(plo[0], pt.x); phi[0] = fmax(phi[0], pt.x);
-        plo[1] = fmin(plo[1], pt.y); phi[1] = fmax(phi[1], pt.y);
-        plo[2] = fmin(plo[2], pt.z); phi[2] = fmax(phi[2], pt.z);
-      }
+    for (int k = 0; k < kBvhLeaf; k++) {
+      const double4 pt = sorted[min(cf + (uint32_t)k, cl)];
+      plo[0] = fmin(plo[0], pt.x); phi[0] = fmax(phi[0], pt.x);
+      plo[1] = fmin(plo[1], pt.y); phi[1] = fmax(phi[1], pt.y);
+      plo[2] = fmin(plo[2], pt.z); phi[2] = fmax(phi[2], pt.z);
+    }
 #pragma unroll
-      for (int k = 0; k < 3; k++) {
-        blo[k] = __double2float_rd(plo[k]);
-        bhi[k] = __double2float_ru(phi[k]);
-      }
-      if (store && cf != cl) {  // the general walk tests this child through its node record
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          nodes[cnode].lo[k] = blo[k];
-          nodes[cnode].hi[k] = bhi[k];
-        }
-      }
-    } else {
-      const float4* q = reinterpret_cast<const float4*>(nodes + cnode);
-      const float4 va = __ldcg(q), vb = __ldcg(q + 1);
-      blo[0] = va.x; blo[1] = va.y; blo[2] = va.z;
-      bhi[0] = vb.x; bhi[1] = vb.y; bhi[2] = vb.z;
+    for (int k = 0; k < 3; k++) {
+      blo[k] = __double2float_rd(plo[k]);
+      bhi[k] = __double2float_ru(phi[k]);
+    }
+    if (cf != cl) {  // (a single point has no node record; split word 0: never expanded)
+      float4* q = reinterpret_cast<float4*>(nodes + cnode);
+      q[0] = make_float4(blo[0], blo[1], blo[2], 0.f);
+      q[1] = make_float4(bhi[0], bhi[1], bhi[2], 0.f);
     }
   };
-  const uint32_t mine = tid < n_big ? (n_big - tid + nthr - 1) / nthr : 0u;  // (at most 24: n_big < n <= 24,576)
-  {
-    uint32_t pend = mine >= 32 ? 0xffffffffu : ((1u << mine) - 1u);
-    for (uint32_t pass = 1;; pass++) {
-      uint32_t m = pend;
-      while (m) {
-        const int k = __ffs((int)m) - 1;
-        m &= m - 1;
-        const uint32_t num = tid + (uint32_t)k * nthr;
-        const uint32_t i = s_big[num];
-        const uint32_t o = s_other[i], sp = s_split[i];
-        const uint32_t f = min(i, o), l = max(i, o);
-        // big children must have been merged in an EARLIER pass (one barrier per pass separates writers from readers)
-        bool ok = true;
-        if (sp - f >= (uint32_t)kBvhLeaf) {
-          const uint32_t r = s_ready[s_cid[sp]];
-          ok = ok && r != 0 && r < pass;
-        }
-        if (l - (sp + 1) >= (uint32_t)kBvhLeaf) {
-          const uint32_t r = s_ready[s_cid[sp + 1]];
-          ok = ok && r != 0 && r < pass;
-        }
-        if (!ok) continue;
-        float llo[3], lhi[3], rlo[3], rhi[3];
-        child_box(f, sp, sp, true, llo, lhi);
-        child_box(sp + 1, l, sp + 1, true, rlo, rhi);
+  auto load_box = [&](uint32_t node, float* blo, float* bhi) {
+    const float4* q = reinterpret_cast<const float4*>(nodes + node);
+    const float4 va = __ldcg(q), vb = __ldcg(q + 1);
+    blo[0] = va.x; blo[1] = va.y; blo[2] = va.z;
+    bhi[0] = vb.x; bhi[1] = vb.y; bhi[2] = vb.z;
+  };
+  auto store_box = [&](uint32_t node, const float* blo, const float* bhi) {  // (keeps the split word and the range end)
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      nodes[node].lo[k] = blo[k];
+      nodes[node].hi[k] = bhi[k];
+    }
+  };
+  const uint32_t mine = tid < n_big ? (n_big - tid + nthr - 1) / nthr : 0u;  // (at most 20: n_big < n <= 20,480)
+  uint32_t pend = 0;
+  for (uint32_t k = 0; k < mine; k++) {  // pass 1
+    const uint32_t num = tid + k * nthr;
+    const uint32_t i = s_big[num];
+    const uint32_t o = s_other[i], sp = s_split[i];
+    const uint32_t f = min(i, o), l = max(i, o);
+    s_cid[i] = (uint16_t)num;
+    const bool lbig = sp - f >= (uint32_t)kBvhLeaf, rbig = l - (sp + 1) >= (uint32_t)kBvhLeaf;
+    float blo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, bhi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+    float clo[3], chi[3];
+    if (!lbig) {
+      small_box(f, sp, sp, clo, chi);
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        blo[q] = fminf(blo[q], clo[q]);
+        bhi[q] = fmaxf(bhi[q], chi[q]);
+      }
+    }
+    if (!rbig) {
+      small_box(sp + 1, l, sp + 1, clo, chi);
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        blo[q] = fminf(blo[q], clo[q]);
+        bhi[q] = fmaxf(bhi[q], chi[q]);
+      }
+    }
+    store_box(i, blo, bhi);
+    const bool complete = !lbig && !rbig;
+    s_ready[num] = complete ? 1 : 0;
+    if (!complete) pend |= 1u << k;
+  }
+  __syncthreads();
+  for (uint32_t pass = 2; __syncthreads_or(pend != 0); pass++) {
+    uint32_t m = pend;
+    while (m) {
+      const int k = __ffs((int)m) - 1;
+      m &= m - 1;
+      const uint32_t num = tid + (uint32_t)k * nthr;
+      const uint32_t i = s_big[num];
+      const uint32_t o = s_other[i], sp = s_split[i];
+      const uint32_t f = min(i, o), l = max(i, o);
+      const bool lbig = sp - f >= (uint32_t)kBvhLeaf, rbig = l - (sp + 1) >= (uint32_t)kBvhLeaf;
+      bool ok = true;
+      if (lbig) {
+        const uint32_t r = s_ready[s_cid[sp]];
+        ok = ok && r != 0 && r < pass;
+      }
+      if (rbig) {
+        const uint32_t r = s_ready[s_cid[sp + 1]];
+        ok = ok && r != 0 && r < pass;
+      }
+      if (!ok) continue;
+      float blo[3], bhi[3], clo[3], chi[3];
+      load_box(i, blo, bhi);  // the partial union of pass 1
+      if (lbig) {
+        load_box(sp, clo, chi);
 #pragma unroll
         for (int q = 0; q < 3; q++) {
-          nodes[i].lo[q] = fminf(llo[q], rlo[q]);
-          nodes[i].hi[q] = fmaxf(lhi[q], rhi[q]);
+          blo[q] = fminf(blo[q], clo[q]);
+          bhi[q] = fmaxf(bhi[q], chi[q]);
         }
-        s_ready[num] = (uint8_t)min(pass, 255u);
-        pend &= ~(1u << k);
       }
-      if (!__syncthreads_or(pend != 0)) break;
+      if (rbig) {
+        load_box(sp + 1, clo, chi);
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+          blo[q] = fminf(blo[q], clo[q]);
+          bhi[q] = fmaxf(bhi[q], chi[q]);
+        }
+      }
+      store_box(i, blo, bhi);
+      s_ready[num] = (uint8_t)min(pass, 255u);
+      pend &= ~(1u << k);
     }
   }
   BT_MARK(6);
 
-  // ---- compact records (common.cuh: BvhRec), one per big node, numbered as above
+  // ---- compact records (common.cuh: BvhRec), one per big node, numbered as above: the children's boxes are in their
+  // node records by now (single points: the point itself)
   if (a.g.quant == nullptr) return;
   const uint32_t rec_cap = a.g.pt_cap / 2;
   if (n_big > rec_cap) {  // degenerate tree (long chains): this set keeps the general walk only
@@ -841,7 +911,14 @@ __global__ void __launch_bounds__(kSbThreads, 1) bvh_build_smem_kernel(BvhBuildA
     for (int c = 0; c < 2; c++) {
       const uint32_t cf = c == 0 ? f : sp + 1, cl = c == 0 ? sp : l;
       float blo[3], bhi[3];
-      child_box(cf, cl, sp + (uint32_t)c, false, blo, bhi);
+      if (cf == cl) {
+        const double4 pt = sorted[cf];
+        blo[0] = __double2float_rd(pt.x); bhi[0] = __double2float_ru(pt.x);
+        blo[1] = __double2float_rd(pt.y); bhi[1] = __double2float_ru(pt.y);
+        blo[2] = __double2float_rd(pt.z); bhi[2] = __double2float_ru(pt.z);
+      } else {
+        load_box(sp + (uint32_t)c, blo, bhi);
+      }
 #pragma unroll
       for (int d = 0; d < 3; d++) {
         const double tl = ((double)blo[d] - qorg[d]) * qinv, th = ((double)bhi[d] - qorg[d]) * qinv;

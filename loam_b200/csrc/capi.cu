@@ -43,6 +43,31 @@ struct DevBuf {
   }
 };
 
+// page-locked host staging (results of the single-scan / single-pair calls come back through it in one piece)
+struct HostBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = bytes + bytes / 4 + 4096;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
 thread_local std::string g_create_err;
 
 // NVTX range around one C-ABI call (tracing): visible in Nsight Systems / Compute timelines
@@ -75,7 +100,8 @@ struct loamgpu_ctx {
   DevBuf ge_quant, gp_quant, leftover;     // compact-record grids per set; pairs left to the general k-NN kernel
   DevBuf state, rec_p, rec_a, rec_b, nearest, nn_idx, nn_cnt, active;
   DevBuf big_scratch, misc, motions, out_pose, out_term, out_iters, out_ne, out_np;
-  DevBuf det_est, det_upd, det_assoc_n, det_lm_iters, det_lm_cost, init_pose;
+  DevBuf det_est, det_upd, det_assoc_n, det_lm_iters, det_lm_cost, init_pose, reg_in;
+  HostBuf pinned;                          // staging of the single-call entry points
 
   // optional per-kernel-class timing (CUDA events on the launching stream)
   struct ProfRec {
@@ -390,21 +416,25 @@ int run_register(loamgpu_ctx* ctx, const RegP& rp, uint32_t n_pairs, uint64_t pa
                  uint32_t init_stride = 0) {
   // sets to build = feature slots pair0 .. pair0 + n_sets - 1 (without a map: + the last pair's source set)
   const uint32_t n_sets = n_sets_or_0 ? n_sets_or_0 : n_pairs + (map ? 0u : 1u);
-  BvhBuildArgs gb;
+  BvhBuildArgs gb, gbp;
   memset(&gb, 0, sizeof gb);
   gb.counts = ctx->feat_counts.as<uint32_t>();
   gb.slot0 = pair0;
   gb.n_slots = n_slots;
+  gbp = gb;
   gb.pts = ctx->edge_pts.as<double4>();
   gb.pt_stride = capE;
   gb.kind = 0;
   gb.g = bvh_arrays(ctx, false, capE);
-  TIMED(LOAMGPU_K_GRID, launch_bvh_build(gb, n_sets, ctx->stream));
-  gb.pts = ctx->planar_pts.as<double4>();
-  gb.pt_stride = capP;
-  gb.kind = 1;
-  gb.g = bvh_arrays(ctx, true, capP);
-  TIMED(LOAMGPU_K_GRID, launch_bvh_build(gb, n_sets, ctx->stream));
+  gbp.pts = ctx->planar_pts.as<double4>();
+  gbp.pt_stride = capP;
+  gbp.kind = 1;
+  gbp.g = bvh_arrays(ctx, true, capP);
+  {  // edge and planar sets in one launch when both take the shared-memory build
+    ProfScope ps(ctx, LOAMGPU_K_GRID);
+    ctx->launches--;  // (the launcher counts its own kernels)
+    CU(launch_bvh_build2(gb, gbp, n_sets, ctx->stream, &ctx->launches));
+  }
   TIMED(LOAMGPU_K_MISC, launch_init_pairs(ctx->state.as<PairState>(), n_pairs, init_pose_dev, init_stride, ctx->stream));
 
   AssocArgs aa;
@@ -473,10 +503,13 @@ int run_register(loamgpu_ctx* ctx, const RegP& rp, uint32_t n_pairs, uint64_t pa
     if (single_call) {
       // one pair: ask the device whether it is still iterating instead of launching up to max_iterations x 3 kernels
       // that would find nothing to do (the wait costs less than the idle launches; batches keep launching ahead)
-      int32_t status = -1;
-      CU(cudaMemcpyAsync(&status, &ctx->state.as<PairState>()->status, sizeof status, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(ctx->pinned.reserve(256));
+      volatile int32_t* status = reinterpret_cast<volatile int32_t*>(ctx->pinned.as<unsigned char>() + 192);
+      *status = -1;
+      CU(cudaMemcpyAsync(const_cast<int32_t*>(status), &ctx->state.as<PairState>()->status, sizeof(int32_t),
+                         cudaMemcpyDeviceToHost, ctx->stream));
       CU(cudaStreamSynchronize(ctx->stream));
-      if (status != -1) break;
+      if (*status != -1) break;
       continue;
     }
     TIMED(LOAMGPU_K_MISC, launch_compact_active(aa.state, n_pairs, ctx->active.as<uint32_t>(), ctx->stream));
@@ -546,8 +579,9 @@ void loamgpu_destroy(loamgpu_ctx* c) {
                     &c->ge_sorted, &c->ge_keys, &c->ge_aux, &c->gp_hdr, &c->gp_nodes, &c->gp_sorted, &c->gp_keys, &c->gp_aux, &c->ge_quant, &c->gp_quant, &c->leftover, &c->state,
                     &c->rec_p, &c->rec_a, &c->rec_b, &c->nearest, &c->nn_idx, &c->nn_cnt, &c->active, &c->misc, &c->motions, &c->out_pose, &c->out_term,
                     &c->out_iters, &c->out_ne, &c->out_np, &c->det_est, &c->det_upd, &c->det_assoc_n,
-                    &c->det_lm_iters, &c->det_lm_cost, &c->init_pose, &c->big_scratch};
+                    &c->det_lm_iters, &c->det_lm_cost, &c->init_pose, &c->big_scratch, &c->reg_in};
   for (DevBuf* b : bufs) b->release();
+  c->pinned.release();
   for (int i = 0; i < 2; i++) {
     if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
     if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]);
@@ -671,15 +705,20 @@ static int extract_one(loamgpu_ctx* ctx, const void* pts, int dtype, size_t stri
   if (rc) return rc;
   if (d_dewarped)
     CU(cudaMemcpyAsync(dewarped_xyz, d_dewarped, (size_t)n_points * 24, cudaMemcpyDeviceToHost, ctx->stream));
-  uint32_t counts[2];
-  CU(cudaMemcpyAsync(counts, ctx->feat_counts.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  // counts and both index lists (full capacity) come back through page-locked staging with ONE wait; the lists are a
+  // few tens of KB, cheaper to over-copy than to wait for the counts first
+  const size_t eb = (size_t)pl.capE_scan * 4, pb = (size_t)pl.capP_scan * 4;
+  CU(ctx->pinned.reserve(16 + eb + pb));
+  unsigned char* h = ctx->pinned.as<unsigned char>();
+  CU(cudaMemcpyAsync(h, ctx->feat_counts.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(h + 16, ctx->edge_idx.p, eb, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(h + 16 + eb, ctx->planar_idx.p, pb, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  const uint32_t* counts = reinterpret_cast<const uint32_t*>(h);
   if (counts[0] > edge_cap || counts[1] > planar_cap || (counts[0] && !edge_idx) || (counts[1] && !planar_idx))
     return fail(ctx, LOAMGPU_ERR_INVALID, "output index buffers too small");
-  if (counts[0]) CU(cudaMemcpyAsync(edge_idx, ctx->edge_idx.p, 4 * (size_t)counts[0], cudaMemcpyDeviceToHost, ctx->stream));
-  if (counts[1])
-    CU(cudaMemcpyAsync(planar_idx, ctx->planar_idx.p, 4 * (size_t)counts[1], cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
+  if (counts[0]) memcpy(edge_idx, h + 16, 4 * (size_t)counts[0]);
+  if (counts[1]) memcpy(planar_idx, h + 16 + eb, 4 * (size_t)counts[1]);
   *n_edge = counts[0];
   *n_planar = counts[1];
   return LOAMGPU_OK;
@@ -789,50 +828,92 @@ static int register_core(loamgpu_ctx* ctx, const double* src_edge, uint64_t n_se
     CU(ctx->det_lm_cost.reserve((size_t)det_iters * 16));
     CU(cudaMemsetAsync(ctx->det_assoc_n.p, 0, (size_t)det_iters * 8, ctx->stream));
   }
-  std::vector<double> he((size_t)n_slots * capE * 4), hp((size_t)n_slots * capP * 4);
-  if (!map) {
-    widen(tgt_edge, n_te, he, 0);
-    widen(tgt_planar, n_tp, hp, 0);
+  // Inputs: the four packed n x 3 clouds go up as they are (no host-side widening pass, 25 % fewer bytes) into a scratch
+  // buffer and one small kernel widens them into the double4 feature slots; counts and the initial pose travel in one
+  // small page-locked block.
+  const uint64_t n_in[4] = {map ? 0 : n_te, map ? 0 : n_tp, n_se, n_sp};
+  const double* in[4] = {tgt_edge, tgt_planar, src_edge, src_planar};
+  uint64_t off[4], total = 0;
+  for (int k = 0; k < 4; k++) {
+    off[k] = total;
+    total += n_in[k];
   }
-  widen(src_edge, n_se, he, map ? 0 : capE);
-  widen(src_planar, n_sp, hp, map ? 0 : capP);
-  const uint32_t counts[4] = {(uint32_t)(map ? n_se : n_te), (uint32_t)(map ? n_sp : n_tp), (uint32_t)n_se,
-                              (uint32_t)n_sp};
-  CU(cudaMemcpyAsync(ctx->edge_pts.p, he.data(), he.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->planar_pts.p, hp.data(), hp.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->feat_counts.p, counts, 16, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->init_pose.p, init_pose, 56, cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx->reg_in.reserve(std::max<uint64_t>(total, 1) * 24));
+  const size_t cap_src = (size_t)capE + capP;
+  const size_t head_bytes = 128, det_rows = want_detail ? det_iters : 0;
+  // page-locked block: [0,16) counts, [16,72) init pose | results: [128 ..) pose 56, term 4, iters 4, status 4, then
+  // the detail rows (est, update, assoc counts, lm iterations, lm costs) and the nearest-neighbour table
+  const size_t res_off = head_bytes, det_off = res_off + 128;
+  const size_t det_bytes = det_rows * (56 + 56 + 8 + 4 + 16);
+  const size_t near_off = det_off + ((det_bytes + 15) & ~(size_t)15);
+  CU(ctx->pinned.reserve(near_off + det_rows * cap_src * 4 + 16));
+  unsigned char* hpin = ctx->pinned.as<unsigned char>();
+  {
+    uint32_t* counts = reinterpret_cast<uint32_t*>(hpin);
+    counts[0] = (uint32_t)(map ? n_se : n_te);
+    counts[1] = (uint32_t)(map ? n_sp : n_tp);
+    counts[2] = (uint32_t)n_se;
+    counts[3] = (uint32_t)n_sp;
+    memcpy(hpin + 16, init_pose, 56);
+  }
+  for (int k = 0; k < 4; k++)
+    if (n_in[k])
+      CU(cudaMemcpyAsync(ctx->reg_in.as<double>() + 3 * off[k], in[k], n_in[k] * 24, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->feat_counts.p, hpin, 16, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->init_pose.p, hpin + 16, 56, cudaMemcpyHostToDevice, ctx->stream));
+  {
+    WidenArgs wa;
+    memset(&wa, 0, sizeof wa);
+    double4* de = ctx->edge_pts.as<double4>();
+    double4* dp = ctx->planar_pts.as<double4>();
+    double4* dst[4] = {de, dp, map ? de : de + capE, map ? dp : dp + capP};  // slot 0 = target, slot 1 = source
+    for (int k = 0; k < 4; k++) {
+      wa.src[k] = ctx->reg_in.as<double>() + 3 * off[k];
+      wa.dst[k] = dst[k];
+      wa.n[k] = (uint32_t)n_in[k];
+    }
+    TIMED(LOAMGPU_K_MISC, launch_widen(wa, ctx->stream));
+  }
   rc = run_register(ctx, rp, 1, 0, n_slots, map ? 0 : 1, capE, capP, ctx->init_pose.as<double>(), want_detail, map,
                     /*single_call=*/true);
   if (rc) return rc;
   TIMED(LOAMGPU_K_MISC, launch_finish_pairs(ctx->state.as<PairState>(), 1, ctx->out_pose.as<double>(),
                                             ctx->out_term.as<int32_t>(), ctx->out_iters.as<uint32_t>(), ctx->stream));
+  // results (and, if asked for, every detail row of capacity) through the page-locked block with ONE wait
+  CU(cudaMemcpyAsync(hpin + res_off, ctx->out_pose.p, 56, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(hpin + res_off + 56, ctx->out_term.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(hpin + res_off + 60, ctx->out_iters.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  unsigned char* hdet = hpin + det_off;
+  if (want_detail) {
+    CU(cudaMemcpyAsync(hdet, ctx->det_est.p, det_rows * 56, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(hdet + det_rows * 56, ctx->det_upd.p, det_rows * 56, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(hdet + det_rows * 112, ctx->det_assoc_n.p, det_rows * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(hdet + det_rows * 120, ctx->det_lm_iters.p, det_rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(hdet + det_rows * 124, ctx->det_lm_cost.p, det_rows * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  memcpy(out_pose, hpin + res_off, 56);
   int32_t term = 1;
   uint32_t iters = 0;
-  CU(cudaMemcpyAsync(out_pose, ctx->out_pose.p, 56, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaMemcpyAsync(&term, ctx->out_term.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaMemcpyAsync(&iters, ctx->out_iters.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
+  memcpy(&term, hpin + res_off + 56, 4);
+  memcpy(&iters, hpin + res_off + 60, 4);
   if (want_detail) {
     detail->n_iters = iters;
     detail->termination = term;
     const uint32_t rows = std::min<uint32_t>(iters, detail->max_iters_cap);
-    std::vector<uint32_t> assoc_n((size_t)std::max<uint32_t>(rows, 1) * 2);
     if (rows) {
-      if (detail->iter_est) CU(cudaMemcpy(detail->iter_est, ctx->det_est.p, (size_t)rows * 56, cudaMemcpyDeviceToHost));
-      if (detail->iter_update)
-        CU(cudaMemcpy(detail->iter_update, ctx->det_upd.p, (size_t)rows * 56, cudaMemcpyDeviceToHost));
-      if (detail->lm_iters)
-        CU(cudaMemcpy(detail->lm_iters, ctx->det_lm_iters.p, (size_t)rows * 4, cudaMemcpyDeviceToHost));
-      if (detail->lm_cost) CU(cudaMemcpy(detail->lm_cost, ctx->det_lm_cost.p, (size_t)rows * 16, cudaMemcpyDeviceToHost));
-      CU(cudaMemcpy(assoc_n.data(), ctx->det_assoc_n.p, (size_t)rows * 8, cudaMemcpyDeviceToHost));
-      const size_t cap_src = (size_t)capE + capP;
-      std::vector<int32_t> nearest((size_t)rows * cap_src);
-      CU(cudaMemcpy(nearest.data(), ctx->nearest.p, nearest.size() * 4, cudaMemcpyDeviceToHost));
+      if (detail->iter_est) memcpy(detail->iter_est, hdet, (size_t)rows * 56);
+      if (detail->iter_update) memcpy(detail->iter_update, hdet + det_rows * 56, (size_t)rows * 56);
+      if (detail->lm_iters) memcpy(detail->lm_iters, hdet + det_rows * 120, (size_t)rows * 4);
+      if (detail->lm_cost) memcpy(detail->lm_cost, hdet + det_rows * 124, (size_t)rows * 16);
+      // nearest-neighbour table: only the rows that were recorded (second, usually much smaller, wait)
+      int32_t* nearest = reinterpret_cast<int32_t*>(hpin + near_off);
+      CU(cudaMemcpyAsync(nearest, ctx->nearest.p, (size_t)rows * cap_src * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
       for (uint32_t it = 0; it < rows; it++) {
         // association lists in source-index order (registration.cpp:59,100)
         uint32_t ne = 0, np = 0;
-        const int32_t* row = nearest.data() + (size_t)it * cap_src;
+        const int32_t* row = nearest + (size_t)it * cap_src;
         for (uint64_t i = 0; i < n_se; i++)
           if (row[i] >= 0) {
             if (detail->edge_assoc && ne < detail->n_src_edge) {

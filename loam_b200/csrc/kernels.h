@@ -115,6 +115,9 @@ struct BvhBuildArgs {
   int smem_tree;           // set by launch_bvh_build: sorted codes + readiness flags fit in shared memory
 };
 cudaError_t launch_bvh_build(const BvhBuildArgs& a, uint32_t n_sets, cudaStream_t st);
+// the edge and the planar sets of the same slots in one launch when both fit the shared-memory build (else two launches)
+cudaError_t launch_bvh_build2(const BvhBuildArgs& edge, const BvhBuildArgs& planar, uint32_t n_sets, cudaStream_t st,
+                              uint64_t* launches);
 
 // Multi-CTA build of ONE large set (bvh_big.cu): same layout as launch_bvh_build produces for set 0 of `g`
 // (g.hdr, g.nodes, g.sorted; g.keys is the sort scratch).  `scratch` holds bvh_big_scratch_bytes(n) bytes.
@@ -194,6 +197,13 @@ struct KnnArgs {
 };
 cudaError_t launch_knn(const KnnArgs& a, cudaStream_t st);
 
+// Widen up to four packed n x 3 double clouds (device) into double4 feature slots (featuresToEigen, features.h:188-198)
+struct WidenArgs {
+  const double* src[4];
+  double4* dst[4];
+  uint32_t n[4];
+};
+cudaError_t launch_widen(const WidenArgs& a, cudaStream_t s);
 // p <- pose * p for n double4 points in place (map insertion: scan frame -> map frame, Pose3d::act, geometry.cpp:21)
 cudaError_t launch_transform_points(double4* pts, uint32_t n, const double* pose_dev, cudaStream_t s);
 // init poses: null = identity for every pair; init_stride 0 = the same pose for every pair, 7 = one pose per pair

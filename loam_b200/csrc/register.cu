@@ -1310,6 +1310,13 @@ __global__ void transform_points_kernel(double4* pts, uint32_t n, const double* 
   pts[i] = make_double4(q.x, q.y, q.z, 0.0);
 }
 
+__global__ void widen_kernel(WidenArgs a) {
+  const uint32_t seg = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n[seg]) return;
+  const double* s = a.src[seg] + 3 * (size_t)i;
+  a.dst[seg][i] = make_double4(s[0], s[1], s[2], 0.0);
+}
+
 __global__ void finish_pairs_kernel(const PairState* st, uint32_t n, double* poses, int32_t* term, uint32_t* iters) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -1324,21 +1331,27 @@ __global__ void finish_pairs_kernel(const PairState* st, uint32_t n, double* pos
 
 // ============================================================================ host launchers
 
+static bool sb_fits(const BvhBuildArgs& a, int optin) {
+  static const bool legacy = []() { const char* e = getenv("LOAMGPU_BUILD_LEGACY"); return e && atoi(e) != 0; }();
+  // sets whose intermediates fit in shared memory (16-bit point numbers, 8 bytes per point + counters)
+  return !legacy && a.g.pt_cap <= kSbMaxPoints && sb_smem_bytes(a.g.pt_cap) + 1024 <= (size_t)optin;
+}
+
+static cudaError_t launch_sb(const BvhBuildArgs& a0, const BvhBuildArgs& a1, uint32_t n_sets, uint32_t kinds, cudaStream_t st) {
+  const size_t smem = std::max(sb_smem_bytes(a0.g.pt_cap), kinds > 1 ? sb_smem_bytes(a1.g.pt_cap) : (size_t)0);
+  cudaError_t err = cudaFuncSetAttribute(bvh_build_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  bvh_build_smem_kernel<<<dim3(n_sets, kinds), kSbThreads, smem, st>>>(a0, a1);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_bvh_build(const BvhBuildArgs& a_in, uint32_t n_sets, cudaStream_t st) {
   if (n_sets == 0) return cudaSuccess;
   BvhBuildArgs a = a_in;
   int dev = 0, optin = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  static const bool legacy = []() { const char* e = getenv("LOAMGPU_BUILD_LEGACY"); return e && atoi(e) != 0; }();
-  // sets whose intermediates fit in shared memory (16-bit point numbers, 8 bytes per point + counters)
-  if (!legacy && a.g.pt_cap <= kSbMaxPoints && sb_smem_bytes(a.g.pt_cap) + 1024 <= (size_t)optin) {
-    const size_t smem = sb_smem_bytes(a.g.pt_cap);
-    cudaError_t err = cudaFuncSetAttribute(bvh_build_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return err;
-    bvh_build_smem_kernel<<<n_sets, kSbThreads, smem, st>>>(a);
-    return cudaGetLastError();
-  }
+  if (sb_fits(a, optin)) return launch_sb(a, a, n_sets, 1, st);
   const size_t sort_bytes = (size_t)kRadixBins * kBuildThreads * sizeof(uint32_t);
   // radix counters, reused after the sort for the sorted codes; + one readiness byte per node
   const size_t tree_bytes = std::max(sort_bytes, (size_t)a.g.pt_cap * 4) + a.g.pt_cap + 16;
@@ -1348,6 +1361,22 @@ cudaError_t launch_bvh_build(const BvhBuildArgs& a_in, uint32_t n_sets, cudaStre
   if (err != cudaSuccess) return err;
   bvh_build_kernel<<<n_sets, kBuildThreads, smem, st>>>(a);
   return cudaGetLastError();
+}
+
+cudaError_t launch_bvh_build2(const BvhBuildArgs& edge, const BvhBuildArgs& planar, uint32_t n_sets, cudaStream_t st,
+                              uint64_t* launches) {
+  if (n_sets == 0) return cudaSuccess;
+  int dev = 0, optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (sb_fits(edge, optin) && sb_fits(planar, optin)) {
+    if (launches) *launches += 1;
+    return launch_sb(edge, planar, n_sets, 2, st);
+  }
+  if (launches) *launches += 2;
+  cudaError_t err = launch_bvh_build(edge, n_sets, st);
+  if (err != cudaSuccess) return err;
+  return launch_bvh_build(planar, n_sets, st);
 }
 
 // Rows of pair-indexed grids: every pair in the first two outer iterations (nearly all are still active), a short
@@ -1478,6 +1507,13 @@ cudaError_t launch_knn(const KnnArgs& a, cudaStream_t st) {
     knn_kernel<kKnnRegMax><<<blocks, 128, 0, st>>>(a);
   else
     knn_kernel<kKnnMax><<<blocks, 128, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_widen(const WidenArgs& a, cudaStream_t st) {
+  const uint32_t nmax = std::max(std::max(a.n[0], a.n[1]), std::max(a.n[2], a.n[3]));
+  if (nmax == 0) return cudaSuccess;
+  widen_kernel<<<dim3((nmax + 255) / 256, 4), 256, 0, st>>>(a);
   return cudaGetLastError();
 }
 
