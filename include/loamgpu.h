@@ -17,6 +17,17 @@
  *   - feature / correspondence indices are uint32.
  *   - a context is bound to one device and one stream; use one context per thread/GPU
  *     (the reference is stateless and re-entrant; contexts give the same property).
+ *   - every entry point opens an NVTX range named after itself (Nsight timelines).
+ *
+ * Limits the reference does not have (LOAMGPU_ERR_UNSUPPORTED, never a silent fallback):
+ *   - one ring is staged in one CTA's shared memory: points_per_line <= ~8,900 (packed xyz floats),
+ *     ~7,700 (float4), ~5,700 (doubles) on a B200 (227 KB per SM), and <= 65,535 in any case;
+ *   - num_edge_neighbors, num_plane_neighbors <= 32; neighbor_points <= 16; total points < 2^32;
+ *   - the sequence calls take float records of 12 or 16 bytes.
+ * Sizes that change the kernels used, not the results: feature sets of up to 20,480 points take the
+ * shared-memory NN build, pairs whose two target sets hold up to ~18 k points the shared-memory k-NN
+ * walk ($LOAMGPU_KNN_SMEM_KB, default 128); larger ones run the general kernels, targets of >= 60,000
+ * points ($LOAMGPU_BIG_TARGET_MIN) the multi-CTA build.
  */
 #ifndef LOAMGPU_H
 #define LOAMGPU_H
@@ -293,7 +304,7 @@ int loamgpu_multi_odometry_host(loamgpu_multi* m, const void* scans, size_t stri
                                 uint32_t* iterations, uint32_t* n_edge, uint32_t* n_planar);
 
 /* pairs processed per internal chunk by the sequence / batch calls; 0 (default) = automatic: 1024 for
- * device-resident calls, 512 for asynchronous and 256 for synchronous host calls and explicit batches,
+ * device-resident and asynchronous host calls, 256 for synchronous host calls and explicit batches,
  * bounded by a share of the free device memory */
 int loamgpu_set_chunk_pairs(loamgpu_ctx* ctx, uint32_t pairs);
 

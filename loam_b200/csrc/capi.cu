@@ -91,6 +91,7 @@ struct loamgpu_ctx {
   uint32_t lm_cluster = 0;          // 0 = automatic (see run_register)
   uint64_t mem_budget = 0;          // bytes the automatic chunk size may plan with (a third of the memory free at creation, <= 24 GB)
   bool staging_unguarded = true;    // scan_in[] was last used outside the event-guarded odometry_host pipeline
+  int stage_buf = 0;                // staging buffer the next chunk of a host sequence call copies into (alternates ACROSS calls)
   uint64_t big_target_min = 60000;  // targets at least this large get the multi-CTA NN build ($LOAMGPU_BIG_TARGET_MIN)
 
   DevBuf scan_in[2];                       // H2D staging of scans
@@ -513,6 +514,16 @@ int run_register(loamgpu_ctx* ctx, const RegP& rp, uint32_t n_pairs, uint64_t pa
       continue;
     }
     TIMED(LOAMGPU_K_MISC, launch_compact_active(aa.state, n_pairs, ctx->active.as<uint32_t>(), ctx->stream));
+    // Idle iterations cost four empty launches each; with the default of 10 that is noise, but a caller may set a
+    // large max_iterations as "run until converged" (valid in the reference).  Beyond 16 iterations the host asks, at
+    // iterations 8, 16, 32, ..., how many pairs still iterate and stops enqueuing when none does.
+    if (rp.max_iterations > 16 && it + 1 >= 8 && ((it + 1) & it) == 0) {
+      CU(ctx->pinned.reserve(256));
+      volatile uint32_t* left = reinterpret_cast<volatile uint32_t*>(ctx->pinned.as<unsigned char>() + 200);
+      CU(cudaMemcpyAsync(const_cast<uint32_t*>(left), ctx->active.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+      if (*left == 0) break;
+    }
   }
   return LOAMGPU_OK;
 }
@@ -1180,6 +1191,9 @@ int loamgpu_map_update(loamgpu_ctx* ctx, loamgpu_map* m, const double* edge, uin
   CU(cudaSetDevice(ctx->device));
   const double* add[2] = {edge, planar};
   const uint64_t n_add[2] = {n_edge, n_planar}, cap[2] = {max_edge, max_planar};
+  // the point arrays change below: until build_map has succeeded again the old NN structures describe nothing
+  // (a failure on the way leaves the map unusable for registration instead of walking a stale tree)
+  m->built = false;
   if (pose) {
     CU(ctx->init_pose.reserve(56));
     CU(cudaMemcpyAsync(ctx->init_pose.p, pose, 56, cudaMemcpyHostToDevice, ctx->stream));
@@ -1296,9 +1310,11 @@ static uint32_t pick_chunk(loamgpu_ctx* ctx, OdometryMode mode, uint64_t n_scans
                            uint32_t capP, uint32_t nn_stride, size_t pt_stride) {
   const uint64_t n_pairs_max = std::max<uint64_t>(n_scans, 2) - 1;
   if (ctx->chunk_pairs) return (uint32_t)std::min<uint64_t>(ctx->chunk_pairs, n_pairs_max);
-  // host-async: at least two chunks per typical call, so the copy of a chunk runs under the extract AND the
-  // registration of the previous one (a single 1023-pair chunk per call measured 32.1k scans/s, 512 + 511: 35.7k)
-  uint64_t want = mode == kHostSync ? 256 : mode == kHostAsync ? 512 : 1024;
+  // Asynchronous host calls: the staging buffers alternate ACROSS calls, so even a call made of one chunk copies into
+  // the buffer the previous call is not reading and its copy runs under the previous call's kernels: full-size chunks
+  // (measured, 12 calls of 1024 float4 scans: 44.7 k scans/s with 1024-pair chunks, 42.3 k with 512, 40.2 k with 256).
+  // A synchronous host call exposes the copy of its first chunk and is fastest with 256.
+  uint64_t want = mode == kHostSync ? 256 : 1024;
   const uint64_t cap = (uint64_t)capE + capP;
   // per pair: k-NN lists, residual records, two NN structures (nodes, sorted copy, sort keys, flags), feature slots
   // (indices + widened points), ring pick lists, and for host calls two staging copies of the scan
@@ -1353,7 +1369,9 @@ static int odometry_core(loamgpu_ctx* ctx, uint64_t n_scans, const loamgpu_lidar
     return run_extract(ctx, pl, d, LOAMGPU_F32, pt_stride, lp, fe, 1, 0, n_slots, ne_dev, np_dev, nullptr, nullptr, motions_dev);
   }
   const uint64_t n_pairs = n_scans - 1;
-  int buf = 0;
+  // the two staging buffers alternate across calls too: an asynchronous call made of ONE chunk then still copies into
+  // the buffer the previous call is not reading, i.e. under the previous call's kernels
+  int buf = ctx->stage_buf;
   // A synchronous host call starts with a shorter chunk (`lead` pairs, then x`ramp` up to the full size): the H2D copy
   // of the first chunk is the only one that cannot hide behind kernels.  Copying a scan takes ~0.6x the time of
   // processing it (55 GB/s measured), so longer ramps expose more than they save; 128 -> 256 measured best
@@ -1380,6 +1398,7 @@ static int odometry_core(loamgpu_ctx* ctx, uint64_t n_scans, const loamgpu_lidar
           launch_finish_pairs(ctx->state.as<PairState>(), np, poses_dev ? poses_dev + 7 * p0 : nullptr,
                               term_dev ? term_dev + p0 : nullptr, iters_dev ? iters_dev + p0 : nullptr, ctx->stream));
   }
+  ctx->stage_buf = buf;
   return LOAMGPU_OK;
 }
 

@@ -33,11 +33,15 @@ struct Rec {
   static constexpr int kElems = kE;                   // double x 3: Eigen::Vector3d-shaped
 };
 
-// the range buffer is reused for the walk state (P bytes, padded to 16), the pick list (P uint16) and the
-// neighbour-priority bits (P uint32)
-__host__ __device__ inline uint32_t rng_doubles(uint32_t P) {
-  const uint32_t need = ((P + 15) & ~15u) + 2 * ((P + 1) & ~1u) + 4 * P;
-  return max(P, (need + 7) / 8);
+// Shared memory of one ring: [staging records | P doubles | P mask bytes | mbarrier].  The doubles hold the ranges
+// while the mask is derived and the curvature afterwards; once the curvature is known the staged points are dead and
+// their space holds the selection's walk state (P state bytes, P uint16 pick list, P uint32 neighbour-priority words).
+// (Round 1 kept ranges and curvature in separate arrays: 33 KB per 1024-column ring and 6 resident rings per SM; this
+// layout needs 21 KB with packed xyz records, 25 KB with float4 records.)
+__host__ __device__ inline uint32_t walk_bytes(uint32_t P) { return ((P + 15) & ~15u) + 2 * ((P + 1) & ~1u) + 4 * P; }
+__host__ __device__ inline size_t stage_bytes(uint32_t P, uint32_t rec) {
+  const size_t a = (size_t)P * rec, b = walk_bytes(P);
+  return ((a > b ? a : b) + 15) & ~(size_t)15;
 }
 
 // T = scalar type of the staged ring (what the arithmetic widens from), TIn = scalar type of the caller's records.
@@ -51,9 +55,8 @@ __device__ __forceinline__ void extract_ring_body(const ExtractArgs& a) {
   const uint32_t tid = threadIdx.x, nthr = blockDim.x;
 
   // ---- shared memory carve-up (see extract_smem_bytes) ----
-  T* stage = reinterpret_cast<T*>(smem);                                       // P * Rec<T, kE>::kBytes
-  double* rng = reinterpret_cast<double*>(smem + (((size_t)P * Rec<T, kE>::kBytes + 7) & ~(size_t)7));  // ranges; later the walk state + pick list
-  double* cur = rng + rng_doubles(P);                                          // P doubles
+  T* stage = reinterpret_cast<T*>(smem);                                       // P * Rec<T, kE>::kBytes; later the walk state
+  double* cur = reinterpret_cast<double*>(smem + stage_bytes(P, Rec<T, kE>::kBytes));  // ranges, then curvature
   uint8_t* mask = reinterpret_cast<uint8_t*>(cur + P);                         // P bytes
   uint64_t* bar = reinterpret_cast<uint64_t*>(mask + ((P + 15) & ~15u));       // 8-byte aligned mbarrier
 
@@ -103,18 +106,40 @@ __device__ __forceinline__ void extract_ring_body(const ExtractArgs& a) {
     __syncthreads();
   }
 
-  // ---- phase B: ranges ----
+  // ---- phase B: ranges (into the curvature buffer), ring-edge part of the mask ----
+  // P - N wraps exactly like the reference's size_t arithmetic when P < N (features-inl.h:66-67)
+  const uint64_t hi_edge = (uint64_t)P - (uint64_t)N;
   for (uint32_t j = tid; j < P; j += nthr) {
     const double x = (double)stage[j * Rec<T, kE>::kElems + 0];
     const double y = (double)stage[j * Rec<T, kE>::kElems + 1];
     const double z = (double)stage[j * Rec<T, kE>::kElems + 2];
-    rng[j] = point_range(x, y, z);
+    cur[j] = point_range(x, y, z);
+    mask[j] = ((j < N) || ((uint64_t)j >= hi_edge)) ? 0 : 1;  // CHECK 1
   }
   __syncthreads();
 
-  // ---- phase C: curvature + mask ----
-  // P - N wraps exactly like the reference's size_t arithmetic when P < N (features-inl.h:66-67)
-  const uint64_t hi_edge = (uint64_t)P - (uint64_t)N;
+  // ---- phase C: validity mask from the ranges, then the curvature over them ----
+  for (uint32_t j = tid; j < P; j += nthr) {
+    if ((j < N) || ((uint64_t)j >= hi_edge)) continue;  // CHECK 1 handled above
+    const double r = cur[j], rn = cur[j + 1], rp = cur[j - 1];
+    if (r < a.min_range || r > a.max_range) {  // CHECK 2
+      mask[j] = 0;
+      for (uint32_t k = 1; k <= N; k++) {
+        mask[j + k] = 0;
+        mask[j - k] = 0;
+      }
+    } else if (dsub(rn, r) > a.occ) {  // CHECK 3 case 1
+      for (uint32_t k = 1; k <= N; k++) mask[j + k] = 0;
+    } else if (dsub(r, rn) > a.occ) {  // CHECK 3 case 2
+      for (uint32_t k = 0; k < N; k++) mask[j - k] = 0;
+    } else {  // CHECK 4
+      const double diff_next = fabs(dsub(rp, r));
+      const double diff_prev = fabs(dsub(rn, r));
+      const double lim = dmul(a.par, r);
+      if (diff_next > lim && diff_prev > lim) mask[j] = 0;
+    }
+  }
+  __syncthreads();  // the ranges are dead: the curvature takes their place
   const double m2n = -(2.0 * (double)N);
   for (uint32_t j = tid; j < P; j += nthr) {
     const bool ring_edge = (j < N) || ((uint64_t)j >= hi_edge);
@@ -133,30 +158,8 @@ __device__ __forceinline__ void extract_ring_body(const ExtractArgs& a) {
       c = dadd(dadd(dmul(dx, dx), dmul(dy, dy)), dmul(dz, dz));
     }
     cur[j] = c;
-    mask[j] = ring_edge ? 0 : 1;
   }
-  __syncthreads();
-  for (uint32_t j = tid; j < P; j += nthr) {
-    if ((j < N) || ((uint64_t)j >= hi_edge)) continue;  // CHECK 1 handled above
-    const double r = rng[j], rn = rng[j + 1], rp = rng[j - 1];
-    if (r < a.min_range || r > a.max_range) {  // CHECK 2
-      mask[j] = 0;
-      for (uint32_t k = 1; k <= N; k++) {
-        mask[j + k] = 0;
-        mask[j - k] = 0;
-      }
-    } else if (dsub(rn, r) > a.occ) {  // CHECK 3 case 1
-      for (uint32_t k = 1; k <= N; k++) mask[j + k] = 0;
-    } else if (dsub(r, rn) > a.occ) {  // CHECK 3 case 2
-      for (uint32_t k = 0; k < N; k++) mask[j - k] = 0;
-    } else {  // CHECK 4
-      const double diff_next = fabs(dsub(rp, r));
-      const double diff_prev = fabs(dsub(rn, r));
-      const double lim = dmul(a.par, r);
-      if (diff_next > lim && diff_prev > lim) mask[j] = 0;
-    }
-  }
-  __syncthreads();
+  __syncthreads();  // (also: the staged points are dead from here on)
 
   if (a.curv_out != nullptr || a.mask_out != nullptr) {  // secondary entry points stop here
     const size_t base = (size_t)scan * a.R * P + (size_t)ring * P;
@@ -175,7 +178,7 @@ __device__ __forceinline__ void extract_ring_body(const ExtractArgs& a) {
   // (= the reference's selection order), truncated to max+1, and only the accepted picks invalidate neighbours.
   // Walks run in the reference's order (sector-major, edge before planar) because each sees the mask left by the
   // previous ones, including suppression that spills across a sector boundary (features-inl.h:148-151).
-  uint8_t* st = reinterpret_cast<uint8_t*>(rng);                  // walk state per column (rng is dead now)
+  uint8_t* st = reinterpret_cast<uint8_t*>(stage);                // walk state per column (the staged points are dead)
   uint16_t* plist = reinterpret_cast<uint16_t*>(st + ((P + 15) & ~15u));  // columns picked in the current walk
   uint32_t* hp = reinterpret_cast<uint32_t*>(plist + ((P + 1) & ~1u));    // higher-priority-neighbour bits per column
   __shared__ uint32_t s_m, s_base[2];
@@ -294,8 +297,11 @@ __device__ __forceinline__ void extract_ring_body(const ExtractArgs& a) {
 // The plain kernels (what every throughput path runs) and the de-warping ones are separate entry points so that the
 // register budget of one never shapes the other: plain 37-40 registers / 6 CTAs per SM; de-warping (24-byte staging
 // records, 41 KB of shared memory per 1024-column ring) capped for 5.
+// float records: 8 resident rings per SM (32 registers; 21-25 KB of shared memory per 1024-column ring) — measured
+// 4.04 -> 3.70 ms per 1024 float4 scans against the 40 registers / 6 rings the compiler picks unconstrained; a minimum
+// of 1 lets it take far more registers and runs at 6.4 ms
 template <typename T, int kE>
-__global__ void __launch_bounds__(kExtractThreads) extract_ring_kernel(ExtractArgs a) {
+__global__ void __launch_bounds__(kExtractThreads, sizeof(T) == 4 ? 8 : 6) extract_ring_kernel(ExtractArgs a) {
   extract_ring_body<T, T, false, kE>(a);
 }
 template <typename TIn>
@@ -370,10 +376,10 @@ __global__ void __launch_bounds__(256) pack_features_kernel(PackArgs a) {
 
 }  // namespace
 
-size_t extract_smem_bytes(int dtype, uint32_t P, uint32_t S, uint32_t stage_bytes) {
+size_t extract_smem_bytes(int dtype, uint32_t P, uint32_t S, uint32_t rec_bytes) {
   (void)S;
-  const size_t rec = stage_bytes ? stage_bytes : (dtype == LOAMGPU_F32 ? 16 : 24);
-  size_t b = (((size_t)P * rec + 7) & ~(size_t)7) + 8 * (size_t)rng_doubles(P) + 8 * (size_t)P + ((P + 15) & ~15u) + 8 + 16;
+  const uint32_t rec = rec_bytes ? rec_bytes : (dtype == LOAMGPU_F32 ? 16 : 24);
+  const size_t b = stage_bytes(P, rec) + 8 * (size_t)P + ((P + 15) & ~15u) + 8 + 16;
   return (b + 127) & ~(size_t)127;
 }
 

@@ -632,7 +632,7 @@ __device__ __forceinline__ void assoc_fit_pair(const AssocArgs& a, int outer_ite
 }
 
 #ifndef FIT_MINBLOCKS
-#define FIT_MINBLOCKS 6
+#define FIT_MINBLOCKS 7
 #endif
 template <int KMAX>
 __global__ void __launch_bounds__(kAssocThreads, FIT_MINBLOCKS) assoc_fit_kernel(AssocArgs a, int outer_iter) {

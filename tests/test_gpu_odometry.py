@@ -168,3 +168,19 @@ def test_strided_calls_reject_other_record_sizes(ctx):
     with pytest.raises(_capi.LoamGpuError) as ei:
         ctx.odometry_host_ptr(buf.ctypes.data, 2, lp, fe, rp, None, None, None, None, None, stride=20)
     assert ei.value.code == _capi.ERR_UNSUPPORTED
+
+
+def test_large_max_iterations_stops_enqueuing_once_every_pair_is_done(ctx):
+    """max_iterations as "run until converged" (valid in the reference) must not enqueue thousands of
+    empty launches: beyond 16 iterations the host checks the active count at iterations 8, 16, 32, ..."""
+    R, P, n = 16, 512, 6
+    lp, fe, rp = _capi.CLidarParams(R, P, 1.0, 120.0), _capi.default_fe_params(), _capi.default_reg_params()
+    scans = np.stack([synth.make_scan(R, P, k=k) for k in range(n)])
+    ref = ctx.odometry_host(scans, lp, fe, rp)
+    rp.max_iterations = 100000
+    before = ctx.launch_count
+    got = ctx.odometry_host(scans, lp, fe, rp)
+    launched = ctx.launch_count - before
+    assert launched < 80, launched  # 8 iterations x 5 launches + extraction / build / bookkeeping
+    for a, b in zip(ref, got):
+        assert np.array_equal(a, b)

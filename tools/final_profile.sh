@@ -13,8 +13,8 @@ PY
 # only this library's kernels, first 900 launches (= the whole device-resident phase and the start of the host-buffer
 # phase): profiling the ~10,000 small torch kernels that generate the synthetic scans took 5 minutes in round 1
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv \
-  -k regex:'extract_ring|pack_features|bvh_build|bvh_widen|assoc_knn|assoc_fit|lm_kernel|compact_active|init_pairs|finish_pairs' -c 900 \
-  --log-file gpurun_out/launches_${tag}.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches_${tag}.log 2>&1
+  -k regex:'extract_ring|pack_features|bvh_build|assoc_knn|assoc_fit|lm_kernel|compact_active|init_pairs|finish_pairs|widen_kernel' -c 900 \
+  --log-file gpurun_out/launches_${tag}.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-configs > gpurun_out/ncu_launches_${tag}.log 2>&1
 echo "launch list rc=$? lines=$(wc -l < gpurun_out/launches_${tag}.csv)"
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:'extract_ring|pack_features|bvh_build|assoc_knn|assoc_fit|lm_kernel' --launch-skip 34 --launch-count 10 -f -o gpurun_out/prof_${tag} python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full_${tag}.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:'extract_ring|pack_features|bvh_build|assoc_knn|assoc_fit|lm_kernel' --launch-skip 43 --launch-count 11 -f -o gpurun_out/prof_${tag} python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-configs > gpurun_out/ncu_full_${tag}.log 2>&1
 echo "full capture rc=$? $(ls -la gpurun_out/prof_${tag}.ncu-rep | awk '{print $5}') bytes"

@@ -14,7 +14,8 @@ import csv
 import re
 import sys
 
-OURS = ("extract_ring_kernel", "pack_features_kernel", "bvh_build_kernel", "assoc_knn_kernel", "assoc_fit_kernel",
+OURS = ("extract_ring_kernel", "pack_features_kernel", "bvh_build_smem_kernel", "bvh_build_kernel", "assoc_knn_smem_kernel",
+        "assoc_knn_kernel", "widen_kernel", "assoc_fit_kernel",
         "lm_kernel", "compact_active_kernel", "init_pairs_kernel", "finish_pairs_kernel", "knn_kernel",
         "transform_points_kernel", "big_bbox_kernel", "big_morton_kernel", "big_hist_kernel", "big_scan_kernel",
         "big_scatter_kernel", "big_gather_kernel", "big_topology_kernel", "big_boxes_kernel", "big_header_kernel")
