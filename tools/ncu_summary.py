@@ -83,5 +83,40 @@ def full(path):
               f"{get(d, 'lts__t_sector_hit_rate.pct'):.0f} |")
 
 
+CLASS_OF = {"extract_ring_kernel": ("extract", "scan"), "pack_features_kernel": ("pack", "scan"),
+            "bvh_build_smem_kernel": ("nn_build", "scan"), "bvh_build_kernel": ("nn_build", "scan"),
+            "assoc_knn_smem_kernel": ("knn", "pair"), "assoc_knn_kernel": ("knn", "pair"),
+            "assoc_fit_kernel": ("fit", "pair"), "lm_kernel": ("lm", "pair")}
+
+
+def traffic(path, rings, cols, scans, commit):
+    """profiles/traffic.json from the raw page of the `ncu --set full` capture of ONE step of `scans` scans: DRAM bytes
+    (read + written) of every kernel class per unit of work (scan / registered pair), all launches of the class summed."""
+    import json
+    rows = list(csv.reader(open(path)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    ix = {h: i for i, h in enumerate(hdr)}
+    byte_scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    tot = collections.OrderedDict()
+    for d in data:
+        k = short(d[ix["Kernel Name"]])
+        if k not in CLASS_OF:
+            continue
+        b = sum(num(d[ix[m]]) * byte_scale.get(units[ix[m]], 1.0) for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        tot[CLASS_OF[k][0]] = tot.get(CLASS_OF[k][0], 0.0) + b
+    unit = {c: u for c, u in CLASS_OF.values()}
+    n_units = {"scan": int(scans), "pair": int(scans) - 1}
+    out = {"_note": "DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of each kernel class PER UNIT of work (a scan "
+                    "for extract / pack / nn_build, a registered pair for knn / fit / lm: all launches of the class that "
+                    "touch the unit), from one `ncu --set full --clock-control none` capture of one step of the default "
+                    "`bench.py` command. bench.py turns them into roofline.traffic per launch — only for the shape named "
+                    "here.", "shape": [int(rings), int(cols)], "scans_per_step": int(scans), "commit": commit,
+           "per_unit": {c: tot[c] / n_units[unit[c]] for c in tot}, "unit": {c: unit[c] for c in tot}}
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "traffic":
+        traffic(*sys.argv[2:7])
+    else:
+        {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
