@@ -303,6 +303,16 @@ int loamgpu_multi_odometry_host(loamgpu_multi* m, const void* scans, size_t stri
                                 const loamgpu_reg_params* reg, double* poses, int32_t* termination,
                                 uint32_t* iterations, uint32_t* n_edge, uint32_t* n_planar);
 
+/* TEST HOOK (tests/test_gpu_jacobians.py): the sums ONE evaluation of the on-device Levenberg-Marquardt solve forms for
+ * explicit residual blocks — what associateEdges / associatePlanes hand to Ceres (registration.cpp:52-57, 93-98; functors
+ * registration-inl.h:92-117) — at an arbitrary iterate x (qx qy qz qw tx ty tz of estimate_update): out[0..20] upper
+ * triangle of J^T J (6x6 tangent, loss-corrected), out[21..26] J^T r, out[27] cost, out[28] = 1 if the moment sums of
+ * the inlier planes were used, out[29] = planes left to the streamed part.  mode 0: every record streamed; 1: the
+ * default path of the batched kernel. */
+int loamgpu_debug_problem_eval(loamgpu_ctx* ctx, uint64_t n_edge, const double* edge_p, const double* edge_a,
+                               const double* edge_b, uint64_t n_plane, const double* plane_p, const double* plane_n,
+                               const double* plane_d, const double x[7], int mode, double out[30]);
+
 /* pairs processed per internal chunk by the sequence / batch calls; 0 (default) = automatic: 1024 for
  * device-resident and asynchronous host calls, 256 for synchronous host calls and explicit batches,
  * bounded by a share of the free device memory */

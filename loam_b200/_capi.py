@@ -30,7 +30,7 @@ SYMBOLS = [
     "loamgpu_extract_dewarped", "loamgpu_odometry_host_dewarped", "loamgpu_odometry_device_dewarped",
     "loamgpu_odometry_host_strided", "loamgpu_odometry_host_async_strided", "loamgpu_odometry_device_strided",
     "loamgpu_multi_create", "loamgpu_multi_destroy", "loamgpu_multi_last_error", "loamgpu_multi_device_count",
-    "loamgpu_multi_odometry_host",
+    "loamgpu_multi_odometry_host", "loamgpu_debug_problem_eval",
 ]
 KERNEL_CLASSES = ["extract", "pack", "nn_build", "knn", "lm", "misc", "fit"]
 
@@ -112,6 +112,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         f.argtypes = [vp, vp, C.c_size_t, u64, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.loamgpu_odometry_host_dewarped.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.loamgpu_odometry_device_dewarped.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.loamgpu_debug_problem_eval.argtypes = [vp, u64, vp, vp, vp, u64, vp, vp, vp, vp, C.c_int, vp]
     lib.loamgpu_multi_create.argtypes = [vp, C.c_int, C.POINTER(C.c_void_p)]
     lib.loamgpu_multi_destroy.argtypes = [vp]
     lib.loamgpu_multi_destroy.restype = None
@@ -388,6 +389,26 @@ class Context:
 
     def synchronize(self):
         self._check(self.lib.loamgpu_synchronize(self.h))
+
+    def debug_problem_eval(self, is_plane, P, A, B, x, mode=1):
+        """TEST HOOK: one evaluation of the LM kernel on explicit residual blocks (tests/residual_cases.py layout) at
+        the iterate x.  Returns (H [6,6] = J^T J, g [6] = J^T r, cost, used_moments, planes_streamed)."""
+        k = np.asarray(is_plane) != 0
+        P, A, B = (np.asarray(v, dtype=np.float64).reshape(len(k), 3) for v in (P, A, B))
+        ep, ea, eb = (np.ascontiguousarray(v[~k]) for v in (P, A, B))
+        pp, pn = np.ascontiguousarray(P[k]), np.ascontiguousarray(A[k])
+        pd = np.ascontiguousarray(B[k, 0])
+        xx = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.zeros(30)
+        self._check(self.lib.loamgpu_debug_problem_eval(self.h, len(ep), _ptr(ep), _ptr(ea), _ptr(eb), len(pp), _ptr(pp),
+                                                        _ptr(pn), _ptr(pd), _ptr(xx), int(mode), _ptr(out)))
+        H = np.zeros((6, 6))
+        t = 0
+        for i in range(6):
+            for j in range(i, 6):
+                H[i, j] = H[j, i] = out[t]
+                t += 1
+        return H, out[21:27].copy(), float(out[27]), bool(out[28]), int(out[29])
 
     def odometry_device_ptr(self, scans_ptr: int, n_scans: int, lp, fe, rp, poses_ptr, term_ptr, iters_ptr, ne_ptr,
                             np_ptr, stride: int = 16):

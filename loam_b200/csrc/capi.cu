@@ -88,6 +88,7 @@ struct loamgpu_ctx {
   uint32_t chunk_pairs = 0;  // pairs per internal chunk of the sequence calls; 0 = automatic (pick_chunk)
   int max_smem_optin = 0;
   int morton_queries = 1;  // LOAMGPU_QUERY_ORDER=original switches the k-NN kernel to source-index order (A/B)
+  int lm_moments = 1;      // LOAMGPU_LM_MOMENTS=0: the LM kernel streams every record for every evaluation (round 1)
   uint32_t lm_cluster = 0;          // 0 = automatic (see run_register)
   uint64_t mem_budget = 0;          // bytes the automatic chunk size may plan with (a third of the memory free at creation, <= 24 GB)
   bool staging_unguarded = true;    // scan_in[] was last used outside the event-guarded odometry_host pipeline
@@ -98,7 +99,7 @@ struct loamgpu_ctx {
   DevBuf ring_edge, ring_planar, ring_counts;
   DevBuf edge_idx, planar_idx, edge_pts, planar_pts, feat_counts;
   DevBuf ge_hdr, ge_nodes, ge_sorted, ge_keys, ge_aux, gp_hdr, gp_nodes, gp_sorted, gp_keys, gp_aux;
-  DevBuf ge_quant, gp_quant, leftover;     // compact-record grids per set; pairs left to the general k-NN kernel
+  DevBuf ge_quant, gp_quant, leftover, nc_p, nc_a;     // compact-record grids per set; pairs left to the general k-NN kernel
   DevBuf state, rec_p, rec_a, rec_b, nearest, nn_idx, nn_cnt, active;
   DevBuf big_scratch, misc, motions, out_pose, out_term, out_iters, out_ne, out_np;
   DevBuf det_est, det_upd, det_assoc_n, det_lm_iters, det_lm_cost, init_pose, reg_in;
@@ -347,6 +348,10 @@ int reserve_register(loamgpu_ctx* ctx, uint32_t n_pairs, uint32_t capE, uint32_t
   CU(ctx->ge_quant.reserve(n_sets * sizeof(BvhQuant)));
   CU(ctx->gp_quant.reserve(n_sets * sizeof(BvhQuant)));
   CU(ctx->leftover.reserve(((size_t)n_pairs + 1) * 4));
+  if (ctx->lm_moments) {  // short lists of planes the LM kernel's moment sums do not cover
+    CU(ctx->nc_p.reserve((size_t)n_pairs * kLmNcCap * 32));
+    CU(ctx->nc_a.reserve((size_t)n_pairs * kLmNcCap * 32));
+  }
   CU(ctx->ge_aux.reserve(n_sets * capE * 4));
   CU(ctx->gp_aux.reserve(n_sets * capP * 4));
   CU(ctx->ge_sorted.reserve(n_sets * capE * 32));
@@ -481,6 +486,11 @@ int run_register(loamgpu_ctx* ctx, const RegP& rp, uint32_t n_pairs, uint64_t pa
   la.n_slots = n_slots;
   la.src_offset = src_offset;
   la.rp = rp;
+  if (ctx->lm_moments) {
+    la.nc_p = ctx->nc_p.as<double4>();
+    la.nc_a = ctx->nc_a.as<double4>();
+    la.nc_cap = kLmNcCap;
+  }
   // CTAs per pair in the LM kernel.  Sequence odometry keeps 1 whatever the chunk size (sums are then formed in the
   // same order for every chunking: results do not depend on it; measured: clusters of 2 / 4 are slower on full
   // chunks, 1.04 / 1.34 vs 0.82 ms); explicit single registrations spread the pair over a cluster of 8 CTAs, which
@@ -572,6 +582,7 @@ int loamgpu_create(int device, loamgpu_ctx** out) {
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) c->mem_budget = std::min<uint64_t>(free_b / 3, 24ull << 30);
   }
   if (const char* qo = getenv("LOAMGPU_QUERY_ORDER")) c->morton_queries = strcmp(qo, "original") != 0;
+  if (const char* lmm = getenv("LOAMGPU_LM_MOMENTS")) c->lm_moments = atoi(lmm) != 0;
   if (const char* v = getenv("LOAMGPU_LM_CLUSTER")) {
     const unsigned long cs = strtoul(v, nullptr, 10);
     c->lm_cluster = (cs == 1 || cs == 2 || cs == 4 || cs == 8) ? (uint32_t)cs : 0u;
@@ -587,7 +598,7 @@ void loamgpu_destroy(loamgpu_ctx* c) {
   cudaDeviceSynchronize();
   DevBuf* bufs[] = {&c->scan_in[0], &c->scan_in[1], &c->ring_edge, &c->ring_planar, &c->ring_counts, &c->edge_idx,
                     &c->planar_idx, &c->edge_pts, &c->planar_pts, &c->feat_counts, &c->ge_hdr, &c->ge_nodes,
-                    &c->ge_sorted, &c->ge_keys, &c->ge_aux, &c->gp_hdr, &c->gp_nodes, &c->gp_sorted, &c->gp_keys, &c->gp_aux, &c->ge_quant, &c->gp_quant, &c->leftover, &c->state,
+                    &c->ge_sorted, &c->ge_keys, &c->ge_aux, &c->gp_hdr, &c->gp_nodes, &c->gp_sorted, &c->gp_keys, &c->gp_aux, &c->ge_quant, &c->gp_quant, &c->leftover, &c->nc_p, &c->nc_a, &c->state,
                     &c->rec_p, &c->rec_a, &c->rec_b, &c->nearest, &c->nn_idx, &c->nn_cnt, &c->active, &c->misc, &c->motions, &c->out_pose, &c->out_term,
                     &c->out_iters, &c->out_ne, &c->out_np, &c->det_est, &c->det_upd, &c->det_assoc_n,
                     &c->det_lm_iters, &c->det_lm_cost, &c->init_pose, &c->big_scratch, &c->reg_in};
@@ -1290,6 +1301,65 @@ int loamgpu_knn(loamgpu_ctx* ctx, const double* targets, uint64_t n_t, const dou
   TIMED(LOAMGPU_K_ASSOC, launch_knn(ka, ctx->stream));
   CU(cudaMemcpyAsync(idx_out, didx, (size_t)n_q * k * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(count_out, dcnt, (size_t)n_q * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return LOAMGPU_OK;
+}
+
+// TEST HOOK: one evaluation of the LM kernel on explicit residual blocks (what associateEdges / associatePlanes hand to
+// Ceres, registration.cpp:52-57,93-98) at an arbitrary iterate: out[0..20] upper triangle of J^T J (tangent, loss-
+// corrected), out[21..26] J^T r, out[27] cost, out[28] = 1 if the moment sums were used, out[29] = planes left to the
+// streamed part.  mode 0: streamed evaluation; mode 1: moment path (lm_kernel's default).
+int loamgpu_debug_problem_eval(loamgpu_ctx* ctx, uint64_t n_edge, const double* edge_p, const double* edge_a,
+                               const double* edge_b, uint64_t n_plane, const double* plane_p, const double* plane_n,
+                               const double* plane_d, const double x[7], int mode, double out[30]) {
+  if (!ctx || !x || !out) return LOAMGPU_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  const uint32_t capE = (uint32_t)std::max<uint64_t>(n_edge, 1), capP = (uint32_t)std::max<uint64_t>(n_plane, 1);
+  const size_t cap = (size_t)capE + capP;
+  CU(ctx->rec_p.reserve(cap * 32));
+  CU(ctx->rec_a.reserve(cap * 32));
+  CU(ctx->rec_b.reserve((size_t)capE * 32));
+  CU(ctx->nc_p.reserve((size_t)kLmNcCap * 32));
+  CU(ctx->nc_a.reserve((size_t)kLmNcCap * 32));
+  CU(ctx->feat_counts.reserve(16));
+  CU(ctx->misc.reserve(64 * 8));
+  std::vector<double> hp(cap * 4, 0.0), ha(cap * 4, 0.0), hb((size_t)capE * 4, 0.0);
+  for (uint64_t i = 0; i < n_edge; i++) {
+    for (int k = 0; k < 3; k++) {
+      hp[4 * i + k] = edge_p[3 * i + k];
+      ha[4 * i + k] = edge_a[3 * i + k];
+      hb[4 * i + k] = edge_b[3 * i + k];
+    }
+    hp[4 * i + 3] = 1.0;
+  }
+  for (uint64_t i = 0; i < n_plane; i++) {
+    const size_t r = capE + i;
+    for (int k = 0; k < 3; k++) {
+      hp[4 * r + k] = plane_p[3 * i + k];
+      ha[4 * r + k] = plane_n[3 * i + k];
+    }
+    hp[4 * r + 3] = 2.0;
+    ha[4 * r + 3] = plane_d[i];
+  }
+  const uint32_t counts[4] = {(uint32_t)n_edge, (uint32_t)n_plane, 0, 0};
+  CU(cudaMemcpyAsync(ctx->rec_p.p, hp.data(), hp.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->rec_a.p, ha.data(), ha.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->rec_b.p, hb.data(), hb.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->feat_counts.p, counts, 16, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->misc.p, x, 56, cudaMemcpyHostToDevice, ctx->stream));
+  LmArgs la;
+  memset(&la, 0, sizeof la);
+  la.rec_p = ctx->rec_p.as<double4>();
+  la.rec_a = ctx->rec_a.as<double4>();
+  la.rec_b = ctx->rec_b.as<double4>();
+  la.feat_counts = ctx->feat_counts.as<uint32_t>();
+  la.capE_scan = capE;
+  la.capP_scan = capP;
+  la.nc_p = ctx->nc_p.as<double4>();
+  la.nc_a = ctx->nc_a.as<double4>();
+  la.nc_cap = kLmNcCap;
+  TIMED(LOAMGPU_K_LM, launch_lm_debug_eval(la, ctx->misc.as<double>(), mode, ctx->misc.as<double>() + 8, ctx->stream));
+  CU(cudaMemcpyAsync(out, ctx->misc.as<double>() + 8, 30 * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return LOAMGPU_OK;
 }

@@ -30,6 +30,7 @@ constexpr int kBuildThreads = BUILD_THREADS;  // one CTA per feature set (single
 constexpr int kKnnSmall = 5;     // neighbour counts up to this use the 5-slot register top-k
 constexpr int kKnnRegMax = 8;    // ... up to this the 8-slot one
 constexpr int kKnnMax = 32;      // hard limit on num_*_neighbors
+constexpr uint32_t kLmNcCap = 2048;  // planes per pair the LM kernel's moment sums may leave uncovered (else it streams all)
 
 struct ExtractArgs {
   const unsigned char* pts;     // first scan of this launch
@@ -175,6 +176,10 @@ struct LmArgs {
   uint32_t n_pairs;
   const uint32_t* active;  // see AssocArgs
   uint32_t cluster;        // CTAs (thread-block cluster size, 1..8) sharing one pair
+  // moment path (register.cu: plane_moments_pass): per pair the planes NOT covered by the moment sums; null = stream all
+  double4* nc_p;           // [pair][nc_cap]
+  double4* nc_a;           // [pair][nc_cap]
+  uint32_t nc_cap;
   RegP rp;
   // optional detail (single-pair API): per outer iteration rows
   double* d_iter_est;      // [cap][7]
@@ -184,6 +189,8 @@ struct LmArgs {
   double* d_lm_cost;       // [cap][2]
 };
 cudaError_t launch_lm(const LmArgs& a, uint32_t n_pairs, cudaStream_t st);
+// test hook: the 28 sums (H[21] g[6] cost) of ONE evaluation of pair 0's records at the iterate x (+ 2 status words)
+cudaError_t launch_lm_debug_eval(const LmArgs& a, const double* x_dev, int mode, double* out_dev, cudaStream_t st);
 cudaError_t launch_compact_active(const PairState* st, uint32_t n_pairs, uint32_t* active, cudaStream_t s);
 
 struct KnnArgs {

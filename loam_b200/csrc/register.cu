@@ -833,31 +833,40 @@ struct LmPipe {
   uint32_t eval_no;  // evaluations done by this cluster (same value in every thread of every CTA)
 };
 
+// Where an evaluation streams its residual records from: the pair's edge records and a list of plane records (all of
+// the pair's, or the short list of planes that are not covered by the moment sums below).
+struct LmSrc {
+  const double4* edge_p;
+  const double4* edge_a;
+  const double4* edge_b;
+  uint32_t nE;
+  const double4* plane_p;
+  const double4* plane_a;
+  uint32_t nP;
+};
+
 // thread 0: arm the stage's barrier and issue the bulk copies of tile `tile` (edge tiles first, then plane tiles)
-__device__ __forceinline__ void lm_issue_tile(const double4* __restrict__ rec_p, const double4* __restrict__ rec_a,
-                                              const double4* __restrict__ rec_b, uint32_t nE, uint32_t nP, uint32_t capE,
-                                              uint32_t tilesE, uint32_t tile, LmStage* st, uint64_t* bar) {
+__device__ __forceinline__ void lm_issue_tile(const LmSrc& src, uint32_t tilesE, uint32_t tile, LmStage* st, uint64_t* bar) {
   if (tile < tilesE) {
-    const uint32_t lo = tile * kLmTile, n = min((uint32_t)kLmTile, nE - lo);
+    const uint32_t lo = tile * kLmTile, n = min((uint32_t)kLmTile, src.nE - lo);
     mbar_expect_tx(bar, n * 96u);
-    bulk_g2s(st->p, rec_p + lo, n * 32u, bar);
-    bulk_g2s(st->a, rec_a + lo, n * 32u, bar);
-    bulk_g2s(st->b, rec_b + lo, n * 32u, bar);
+    bulk_g2s(st->p, src.edge_p + lo, n * 32u, bar);
+    bulk_g2s(st->a, src.edge_a + lo, n * 32u, bar);
+    bulk_g2s(st->b, src.edge_b + lo, n * 32u, bar);
   } else {
-    const uint32_t lo = (tile - tilesE) * kLmTile, n = min((uint32_t)kLmTile, nP - lo);
+    const uint32_t lo = (tile - tilesE) * kLmTile, n = min((uint32_t)kLmTile, src.nP - lo);
     mbar_expect_tx(bar, n * 64u);
-    bulk_g2s(st->p, rec_p + capE + lo, n * 32u, bar);
-    bulk_g2s(st->a, rec_a + capE + lo, n * 32u, bar);
+    bulk_g2s(st->p, src.plane_p + lo, n * 32u, bar);
+    bulk_g2s(st->a, src.plane_a + lo, n * 32u, bar);
   }
 }
 
-// Evaluate the whole problem of this pair at x; deterministic fixed-order reduction
+// Evaluate the streamed part of this pair's problem at x; deterministic fixed-order reduction
 // (per-thread strided partial -> warp shuffle tree -> per-warp shared partials summed in warp order).
 template <bool kClustered>
-__device__ void evaluate_problem(const double4* __restrict__ rec_p, const double4* __restrict__ rec_a,
-                                 const double4* __restrict__ rec_b, uint32_t nE, uint32_t nP, uint32_t capE,
-                                 const double* x, double* s_part /*[nwarps][28]*/, double* s_tot /*[28]: H[21] g[6] cost*/,
-                                 double* s_lin /*[kLinDoubles]*/, LmPipe& pipe) {
+__device__ void evaluate_problem(const LmSrc& src, const double* x, double* s_part /*[nwarps][28]*/,
+                                 double* s_tot /*[28]: H[21] g[6] cost*/, double* s_lin /*[kLinDoubles]*/, LmPipe& pipe) {
+  const uint32_t nE = src.nE, nP = src.nP;
   const uint32_t tilesE = (nE + kLmTile - 1) / kLmTile, tilesP = (nP + kLmTile - 1) / kLmTile;
   const uint32_t tiles_all = tilesE + tilesP;
   // this CTA's tiles: global tile rank + j * size, j = 0 .. tiles - 1
@@ -865,8 +874,8 @@ __device__ void evaluate_problem(const double4* __restrict__ rec_p, const double
   const uint32_t g0 = pipe.tile_no;
   if (threadIdx.x == 0) {  // every stage is free here: the previous evaluation consumed all the tiles it issued
     for (uint32_t j = 0; j < min(tiles, (uint32_t)kLmStages); j++)
-      lm_issue_tile(rec_p, rec_a, rec_b, nE, nP, capE, tilesE, pipe.rank + j * pipe.size,
-                    pipe.stages + (g0 + j) % kLmStages, pipe.full + (g0 + j) % kLmStages);
+      lm_issue_tile(src, tilesE, pipe.rank + j * pipe.size, pipe.stages + (g0 + j) % kLmStages,
+                    pipe.full + (g0 + j) % kLmStages);
   }
   __syncthreads();  // the previous evaluation's readers of s_lin are done
   build_linear_maps(x, s_lin);
@@ -904,8 +913,7 @@ __device__ void evaluate_problem(const double4* __restrict__ rec_p, const double
     }
     __syncthreads();  // everyone has read the stage before it is refilled
     if (threadIdx.x == 0 && j + kLmStages < tiles)
-      lm_issue_tile(rec_p, rec_a, rec_b, nE, nP, capE, tilesE, pipe.rank + (j + kLmStages) * pipe.size, st,
-                    pipe.full + sidx);
+      lm_issue_tile(src, tilesE, pipe.rank + (j + kLmStages) * pipe.size, st, pipe.full + sidx);
   }
   pipe.tile_no = g0 + tiles;
   double v[28];
@@ -952,6 +960,227 @@ __device__ void evaluate_problem(const double4* __restrict__ rec_p, const double
     }
   }
   pipe.eval_no++;
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------- moment sums of the inlier planes
+// The LM kernel was HBM-bound on records it re-read for every evaluation (12.3 MB per pair against 1.6 MB algorithmic,
+// profiles/r1_kernels_full_v29.md).  Most residuals are point-to-plane residuals far inside Huber's quadratic region,
+// and for those the sums an evaluation needs are quadratic forms in the iterate with coefficients that do not depend
+// on it:  r_i(x) = | s_i + a_i . phi(x) |  with  s_i = n_i.p_i - d_i  (the signed residual at the identity update),
+// a_i = n_i (x) (p_i, 1)  (12 numbers) and  phi(x) = (rows of M(x) - I | t(x))  (§6: pt = M p + t).  With
+//   A = sum a a^T (12x12; (n n^T) (x) (p~ p~^T): 60 distinct sums),  v = sum a s,  S0 = sum s^2   over such records:
+//   cost = 1/2 (S0 + 2 v.phi + phi^T A phi),   J^T r = D^T (v + A phi),   J^T J = D^T A D,   D = d phi / d delta
+// (the sign of r_i cancels in both products; Huber's corrector is the identity for r^2 <= 1).  A record may be covered
+// only if it stays an inlier at every iterate the solve evaluates: |r_i(x)| <= |s_i| + |M - I|_F |p_i| + |t|, so a
+// plane with |s_i| + kCoreAlpha |p_i| + kCoreTau <= 1 is covered ("core") and an evaluation uses the sums whenever
+// |M - I|_F <= kCoreAlpha and |t| <= kCoreTau (a few centimetres / hundredths of a radian: every LM candidate of a
+// scan-to-scan update); otherwise it streams all records as before.  The first evaluation of a solve (identity)
+// streams every record once, accumulates the sums (split over the two halves of the CTA: 42 + 31 accumulators per
+// thread) and writes the few planes that are not core into a compact list; later evaluations stream the edge records
+// and that list only.  The sums are reduced in a fixed order (thread -> shuffle tree -> warps in order): results are
+// run-to-run identical; they differ from the streamed evaluation by rounding (different summation order).
+constexpr int kMomN = 73;         // A[60] (nn6 index * 10 + pp10 index), v[12] (4 r + c), S0
+constexpr int kMomHalf0 = 42;     // half 0 of the CTA: nn rows 0-2 (30 sums) + v (12); half 1: nn rows 3-5 (30) + S0
+constexpr double kCoreAlpha = 0.02, kCoreTau = 0.2;
+
+__device__ __forceinline__ int mom_nn(int r, int q) {  // index into (n0n0, n0n1, n0n2, n1n1, n1n2, n2n2)
+  const int a = r < q ? r : q, b = r < q ? q : r;
+  return a == 0 ? b : (a == 1 ? 2 + b : 5);
+}
+__device__ __forceinline__ int mom_pp(int c, int e) {  // index into (00,01,02,03,11,12,13,22,23,33), p~3 = 1
+  const int a = c < e ? c : e, b = c < e ? e : c;
+  return a == 0 ? b : (a == 1 ? 3 + b : (a == 2 ? 5 + b : 9));
+}
+__device__ __forceinline__ double mom_A(const double* s_mom, int m, int mp) {  // A[m][m'], m = 4 r + c
+  return s_mom[mom_nn(m >> 2, mp >> 2) * 10 + mom_pp(m & 3, mp & 3)];
+}
+
+// |M(x) - I|_F and |t(x)| of an iterate (M = (1 - 2|u|^2) I + 2 u u^T + 2 w [u]x)
+__device__ __forceinline__ bool moments_valid_at(const double* x) {
+  const double u0 = x[0], u1 = x[1], u2 = x[2], w = x[3];
+  const double dg = -2.0 * (u0 * u0 + u1 * u1 + u2 * u2);
+  const double m[9] = {dg + 2.0 * u0 * u0,           2.0 * u0 * u1 - 2.0 * w * u2, 2.0 * u0 * u2 + 2.0 * w * u1,
+                       2.0 * u1 * u0 + 2.0 * w * u2, dg + 2.0 * u1 * u1,           2.0 * u1 * u2 - 2.0 * w * u0,
+                       2.0 * u2 * u0 - 2.0 * w * u1, 2.0 * u2 * u1 + 2.0 * w * u0, dg + 2.0 * u2 * u2};
+  // (Eigen's rotation formula is v + 2w (u x v) + 2 u x (u x v) whatever |q| is: M - I has no constant term)
+  double f = 0;
+#pragma unroll
+  for (int i = 0; i < 9; i++) f += m[i] * m[i];
+  const double t2 = x[4] * x[4] + x[5] * x[5] + x[6] * x[6];
+  return f <= kCoreAlpha * kCoreAlpha * 0.98 && t2 <= kCoreTau * kCoreTau * 0.98;  // (2 % slack for the roundings)
+}
+
+// First pass of a solve over ALL plane records of the pair (the update is the identity: pt = p): accumulates the moment
+// sums of the core planes into s_mom and writes the other valid planes, in record order, to nc_p / nc_a.  Returns the
+// length of that list, or 0xFFFFFFFF when it does not fit (the solve then streams everything).
+__device__ uint32_t plane_moments_pass(const LmSrc& all, double4* __restrict__ nc_p, double4* __restrict__ nc_a,
+                                       uint32_t nc_cap, double* s_mpart /*[8][kMomHalf0]*/, double* s_mom /*[kMomN]*/,
+                                       uint32_t* s_ncw /*[17]*/, LmPipe& pipe) {
+  LmSrc planes = all;
+  planes.nE = 0;
+  const uint32_t tiles = (all.nP + kLmTile - 1) / kLmTile;
+  const uint32_t g0 = pipe.tile_no;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t half = tid >> 7, u = tid & 127;  // both halves visit every record; each keeps its share of the sums
+  if (tid == 0) {
+    for (uint32_t j = 0; j < min(tiles, (uint32_t)kLmStages); j++)
+      lm_issue_tile(planes, 0, j, pipe.stages + (g0 + j) % kLmStages, pipe.full + (g0 + j) % kLmStages);
+  }
+  double acc[kMomHalf0];
+#pragma unroll
+  for (int i = 0; i < kMomHalf0; i++) acc[i] = 0.0;
+  uint32_t nc_base = 0;
+  bool overflow = false;
+  for (uint32_t j = 0; j < tiles; j++) {
+    const uint32_t g = g0 + j, sidx = g % kLmStages;
+    LmStage* st = pipe.stages + sidx;
+    const uint32_t n_tile = min((uint32_t)kLmTile, all.nP - j * kLmTile);
+    mbar_wait(pipe.full + sidx, (g / kLmStages) & 1u);
+    unsigned ncb[kLmTile / 128];  // per quarter of the tile: this warp's ballot of non-core planes
+#pragma unroll
+    for (int q = 0; q < kLmTile / 128; q++) {
+      const uint32_t slot = q * 128 + u;
+      const bool in = slot < n_tile;
+      const double4 p = in ? st->p[slot] : make_double4(0, 0, 0, 0);
+      const double4 n = st->a[slot];  // (beyond n_tile: stale shared memory, masked by `valid`)
+      const bool valid = p.w != 0.0;
+      const double sd = fma(n.x, p.x, fma(n.y, p.y, n.z * p.z)) - n.w;
+      // |s| + alpha |p| + tau <= 1  without the square root:  alpha^2 |p|^2 <= (1 - tau - |s|)^2, right side >= 0
+      const double room = (1.0 - kCoreTau) - fabs(sd);
+      const double p2 = fma(p.x, p.x, fma(p.y, p.y, p.z * p.z));
+      const bool core = valid && room >= 0.0 && (kCoreAlpha * kCoreAlpha) * p2 <= room * room;
+      ncb[q] = __ballot_sync(0xffffffffu, valid && !core);
+      if (core) {
+        const double pp[10] = {p.x * p.x, p.x * p.y, p.x * p.z, p.x, p.y * p.y, p.y * p.z, p.y, p.z * p.z, p.z, 1.0};
+        if (half == 0) {
+          const double nn[3] = {n.x * n.x, n.x * n.y, n.x * n.z};
+#pragma unroll
+          for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int k = 0; k < 10; k++) acc[i * 10 + k] = fma(nn[i], pp[k], acc[i * 10 + k]);
+          const double ns[3] = {n.x * sd, n.y * sd, n.z * sd};
+          const double pt4[4] = {p.x, p.y, p.z, 1.0};
+#pragma unroll
+          for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) acc[30 + 4 * r + c] = fma(ns[r], pt4[c], acc[30 + 4 * r + c]);
+        } else {
+          const double nn[3] = {n.y * n.y, n.y * n.z, n.z * n.z};
+#pragma unroll
+          for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int k = 0; k < 10; k++) acc[i * 10 + k] = fma(nn[i], pp[k], acc[i * 10 + k]);
+          acc[30] = fma(sd, sd, acc[30]);
+        }
+      }
+    }
+    // compact list of the non-core planes, in record order: quarter-major, then the four warps of half 0, then lanes
+    if (half == 0 && lane == 0) {
+#pragma unroll
+      for (int q = 0; q < kLmTile / 128; q++) s_ncw[q * 4 + warp] = (uint32_t)__popc(ncb[q]);
+    }
+    __syncthreads();
+    {
+      uint32_t total = 0;
+      for (int k = 0; k < 4 * (kLmTile / 128); k++) total += s_ncw[k];
+      if (half == 0 && !overflow) {
+        uint32_t before = 0;
+#pragma unroll
+        for (int q = 0; q < kLmTile / 128; q++) {
+          uint32_t mine = before;
+          for (uint32_t w = 0; w < warp; w++) mine += s_ncw[q * 4 + w];
+          if (ncb[q] & (1u << lane)) {
+            const uint32_t pos = nc_base + mine + (uint32_t)__popc(ncb[q] & ((1u << lane) - 1u));
+            if (pos < nc_cap) {
+              const uint32_t slot = q * 128 + u;
+              nc_p[pos] = st->p[slot];
+              nc_a[pos] = st->a[slot];
+            }
+          }
+          for (uint32_t w = 0; w < 4; w++) before += s_ncw[q * 4 + w];
+        }
+      }
+      nc_base += total;
+      overflow = overflow || nc_base > nc_cap;
+    }
+    __syncthreads();  // everyone has read the stage (and the counts) before it is refilled
+    if (tid == 0 && j + kLmStages < tiles) lm_issue_tile(planes, 0, j + kLmStages, st, pipe.full + sidx);
+  }
+  pipe.tile_no = g0 + tiles;
+  // reduce: shuffle tree per warp, then the four warps of each half in order
+  const int n_mine = half == 0 ? kMomHalf0 : 31;
+#pragma unroll
+  for (int i = 0; i < kMomHalf0; i++) {
+    double t = acc[i];
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+    if (lane == 0 && i < n_mine) s_mpart[warp * kMomHalf0 + i] = t;
+  }
+  // the compact list was written with plain stores and is read next by bulk copies (async proxy, through L2)
+  __threadfence();
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+  __syncthreads();
+  if (tid < kMomN) {
+    // s_mom index -> (half, local index): A rows 0-2 and v live in half 0, A rows 3-5 and S0 in half 1
+    const int h = (tid < 30 || (tid >= 60 && tid < 72)) ? 0 : 1;
+    const int l = tid < 30 ? tid : (tid < 60 ? tid - 30 : (tid < 72 ? 30 + (tid - 60) : 30));
+    double t = 0;
+    for (int w = 0; w < 4; w++) t += s_mpart[(4 * h + w) * kMomHalf0 + l];
+    s_mom[tid] = t;
+  }
+  __syncthreads();
+  return overflow ? 0xFFFFFFFFu : nc_base;
+}
+
+// Adds the covered planes' share of the sums at the iterate whose linear maps are in s_lin (M[9] t[3] B0[9] B1[9] B2[9]).
+__device__ void moment_contrib(const double* __restrict__ s_lin, const double* __restrict__ s_mom,
+                               double* s_scr /*[12 phi][12 w][72 AD]*/, double* s_tot /*[28] +=*/) {
+  const int tid = threadIdx.x;
+  double* phi = s_scr;
+  double* wv = s_scr + 12;
+  double* AD = s_scr + 24;
+  auto D = [&](int m, int j) -> double {  // d phi_m / d delta_j
+    const int r = m >> 2, c = m & 3;
+    if (j < 3) return c < 3 ? s_lin[12 + 9 * j + 3 * r + c] : 0.0;
+    return (c == 3 && r == j - 3) ? 1.0 : 0.0;
+  };
+  if (tid < 12) {
+    const int r = tid >> 2, c = tid & 3;
+    phi[tid] = c < 3 ? s_lin[3 * r + c] - (r == c ? 1.0 : 0.0) : s_lin[9 + r];
+  }
+  __syncthreads();
+  if (tid < 72) {
+    const int m = tid / 6, k = tid % 6;
+    double t = 0;
+    for (int mp = 0; mp < 12; mp++) t = fma(mom_A(s_mom, m, mp), D(mp, k), t);
+    AD[tid] = t;
+  } else if (tid < 84) {
+    const int m = tid - 72;
+    double t = s_mom[60 + m];
+    for (int mp = 0; mp < 12; mp++) t = fma(mom_A(s_mom, m, mp), phi[mp], t);
+    wv[m] = t;
+  }
+  __syncthreads();
+  if (tid < 21) {
+    int i = 0, rem = tid;
+    while (rem >= 6 - i) {
+      rem -= 6 - i;
+      i++;
+    }
+    const int j = i + rem;
+    double t = 0;
+    for (int m = 0; m < 12; m++) t = fma(D(m, i), AD[m * 6 + j], t);
+    s_tot[tid] += t;
+  } else if (tid < 27) {
+    const int j = tid - 21;
+    double t = 0;
+    for (int m = 0; m < 12; m++) t = fma(D(m, j), wv[m], t);
+    s_tot[tid] += t;
+  } else if (tid == 27) {
+    double t = s_mom[72];
+    for (int m = 0; m < 12; m++) t = fma(phi[m], s_mom[60 + m] + wv[m], t);
+    s_tot[27] += 0.5 * t;
+  }
   __syncthreads();
 }
 
@@ -1022,9 +1251,16 @@ __device__ __forceinline__ double norm7(const double* x) {
 
 // One CTA per pair.  Every thread runs the (tiny, uniform) controller redundantly on the reduced sums, so
 // no broadcast of the step is needed between evaluations.
+struct LmMomentScratch {  // shared memory of the moment path (one-CTA-per-pair kernel only)
+  double mom[kMomN];
+  double part[8 * kMomHalf0];
+  double scr[96];
+  uint32_t ncw[17];
+};
+
 template <bool kClustered>
 __device__ void lm_pair(const LmArgs& a, uint32_t pair, double* s_part, double* s_sum /*[2][28]*/, double* s_lin,
-                        LmPipe& pipe) {
+                        LmPipe& pipe, LmMomentScratch* ms) {
   PairState* ps = a.state + pair;
   if (ps->status != -1) return;
   const uint32_t src_slot = (uint32_t)((a.pair0 + pair + a.src_offset) % a.n_slots);
@@ -1048,6 +1284,9 @@ __device__ void lm_pair(const LmArgs& a, uint32_t pair, double* s_part, double* 
   const double4* rec_p = a.rec_p + (size_t)pair * cap_src;
   const double4* rec_a = a.rec_a + (size_t)pair * cap_src;
   const double4* rec_b = a.rec_b + (size_t)pair * a.capE_scan;
+  const LmSrc all{rec_p, rec_a, rec_b, nE, rec_p + a.capE_scan, rec_a + a.capE_scan, nP};
+  LmSrc rest = all;      // what an evaluation streams when the moment sums cover the core planes
+  bool use_mom = false;  // (CTA-uniform)
 
   // ---- Ceres TrustRegionMinimizer, LEVENBERG_MARQUARDT, max_num_iterations = 4, defaults otherwise
   const int max_num_iterations = 4;
@@ -1071,7 +1310,24 @@ __device__ void lm_pair(const LmArgs& a, uint32_t pair, double* s_part, double* 
     long long t_eval = 0, t_all0 = clock64();
     { const long long c0 = clock64();
 #endif
-    evaluate_problem<kClustered>(rec_p, rec_a, rec_b, nE, nP, a.capE_scan, x, s_part, s_sum, s_lin, pipe);
+    if (!kClustered && ms != nullptr && a.nc_p != nullptr && nP > 0) {
+      double4* nc_p = a.nc_p + (size_t)pair * a.nc_cap;
+      double4* nc_a = a.nc_a + (size_t)pair * a.nc_cap;
+      const uint32_t n_nc = plane_moments_pass(all, nc_p, nc_a, a.nc_cap, ms->part, ms->mom, ms->ncw, pipe);
+      if (n_nc != 0xFFFFFFFFu) {
+        use_mom = true;
+        rest.plane_p = nc_p;
+        rest.plane_a = nc_a;
+        rest.nP = n_nc;
+      }
+    }
+    // every evaluation of this solve: the streamed part, plus the closed form of the covered planes
+    auto evaluate = [&](const double* at, double* out) {
+      const bool mom = use_mom && moments_valid_at(at);
+      evaluate_problem<kClustered>(mom ? rest : all, at, s_part, out, s_lin, pipe);
+      if (mom) moment_contrib(s_lin, ms->mom, ms->scr, out);
+    };
+    evaluate(x, s_sum);
 #ifdef LM_TIMING
     t_eval += clock64() - c0; }
 #endif
@@ -1144,7 +1400,7 @@ __device__ void lm_pair(const LmArgs& a, uint32_t pair, double* s_part, double* 
 #ifdef LM_TIMING
       const long long c1 = clock64();
 #endif
-      evaluate_problem<kClustered>(rec_p, rec_a, rec_b, nE, nP, a.capE_scan, cand, s_part, other, s_lin, pipe);
+      evaluate(cand, other);
 #ifdef LM_TIMING
       t_eval += clock64() - c1;
 #endif
@@ -1235,6 +1491,8 @@ __global__ void __launch_bounds__(kLmThreads, kLmMinBlocks) lm_kernel(LmArgs a) 
   __shared__ double s_partial[kClustered ? 2 * 28 : 1];
   __shared__ __align__(16) double s_lin[kLinDoubles];
   __shared__ __align__(8) uint64_t s_full[kLmStages];
+  __shared__ LmMomentScratch s_ms[1];  // (unused by the clustered kernel: 4 KB)
+  static_assert(kLmThreads == 256 && kLmTile == 512, "the moment pass splits a 256-thread CTA in two halves of four warps");
   LmPipe pipe;
   pipe.stages = reinterpret_cast<LmStage*>(lm_smem);
   pipe.full = s_full;
@@ -1254,10 +1512,59 @@ __global__ void __launch_bounds__(kLmThreads, kLmMinBlocks) lm_kernel(LmArgs a) 
   const uint32_t n_act = active_count(a.active, a.n_pairs);
   const uint32_t cluster_id = blockIdx.x / pipe.size, n_clusters = gridDim.x / pipe.size;
   for (uint32_t i = cluster_id; i < n_act; i += n_clusters) {
-    lm_pair<kClustered>(a, active_pair(a.active, i), s_part, s_sum, s_lin, pipe);
+    lm_pair<kClustered>(a, active_pair(a.active, i), s_part, s_sum, s_lin, pipe, kClustered ? nullptr : s_ms);
     __syncthreads();
   }
   if (kClustered) cg::this_cluster().sync();  // nobody leaves while a peer may still read its partial sums
+}
+
+// TEST HOOK (loamgpu_debug_problem_eval): the sums one evaluation of the LM kernel produces for pair 0's records at an
+// arbitrary iterate — through the streamed evaluation (mode 0) or through the moment path (mode 1: first pass over the
+// planes at the identity, then the hybrid evaluation; out[28] = 1 if the moment sums were used at x, out[29] = planes
+// left uncovered).  tests/test_gpu_jacobians.py compares them with torch autograd of the reference's functors.
+__global__ void __launch_bounds__(kLmThreads, kLmMinBlocks) lm_debug_eval_kernel(LmArgs a, const double* x_dev, int mode,
+                                                                                double* out) {
+  extern __shared__ __align__(128) unsigned char lm_smem[];
+  __shared__ double s_part[(kLmThreads / 32) * 28];
+  __shared__ double s_sum[28];
+  __shared__ __align__(16) double s_lin[kLinDoubles];
+  __shared__ __align__(8) uint64_t s_full[kLmStages];
+  __shared__ LmMomentScratch s_ms;
+  LmPipe pipe;
+  pipe.stages = reinterpret_cast<LmStage*>(lm_smem);
+  pipe.full = s_full;
+  pipe.tile_no = 0;
+  pipe.rank = 0;
+  pipe.size = 1;
+  pipe.partial = nullptr;
+  pipe.eval_no = 0;
+  if (threadIdx.x == 0)
+    for (int i = 0; i < kLmStages; i++) mbar_init(s_full + i, 1);
+  __syncthreads();
+  const uint32_t nE = a.feat_counts[0], nP = a.feat_counts[1];
+  const LmSrc all{a.rec_p, a.rec_a, a.rec_b, nE, a.rec_p + a.capE_scan, a.rec_a + a.capE_scan, nP};
+  LmSrc rest = all;
+  double x[7];
+#pragma unroll
+  for (int i = 0; i < 7; i++) x[i] = x_dev[i];
+  bool mom = false;
+  uint32_t n_nc = 0;
+  if (mode == 1 && nP > 0) {
+    n_nc = plane_moments_pass(all, a.nc_p, a.nc_a, a.nc_cap, s_ms.part, s_ms.mom, s_ms.ncw, pipe);
+    if (n_nc != 0xFFFFFFFFu && moments_valid_at(x)) {
+      mom = true;
+      rest.plane_p = a.nc_p;
+      rest.plane_a = a.nc_a;
+      rest.nP = n_nc;
+    }
+  }
+  evaluate_problem<false>(mom ? rest : all, x, s_part, s_sum, s_lin, pipe);
+  if (mom) moment_contrib(s_lin, s_ms.mom, s_ms.scr, s_sum);
+  if (threadIdx.x < 28) out[threadIdx.x] = s_sum[threadIdx.x];
+  if (threadIdx.x == 0) {
+    out[28] = mom ? 1.0 : 0.0;
+    out[29] = (double)n_nc;
+  }
 }
 
 // Rebuilds the list of pairs still iterating (ascending pair index) after an LM launch.
@@ -1490,6 +1797,14 @@ cudaError_t launch_lm(const LmArgs& a, uint32_t n_pairs, cudaStream_t st) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, lm_kernel<true>, a);
+}
+
+cudaError_t launch_lm_debug_eval(const LmArgs& a, const double* x_dev, int mode, double* out_dev, cudaStream_t st) {
+  const size_t smem = (size_t)kLmStages * sizeof(LmStage);
+  cudaError_t err = cudaFuncSetAttribute(lm_debug_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  lm_debug_eval_kernel<<<1, kLmThreads, smem, st>>>(a, x_dev, mode, out_dev);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_compact_active(const PairState* s, uint32_t n_pairs, uint32_t* active, cudaStream_t st) {
