@@ -486,7 +486,7 @@ __host__ __device__ inline size_t sb_smem_bytes(uint32_t cap) {
 
 // grid (sets, kinds): row 0 builds `a0`'s sets, row 1 (when launched) `a1`'s — the edge and the planar sets of the same
 // scans in one launch (short edge CTAs fill in around the long planar ones; one launch less per chunk / call)
-__global__ void __launch_bounds__(kSbThreads, 1) bvh_build_smem_kernel(BvhBuildArgs a0, BvhBuildArgs a1) {
+__global__ void __launch_bounds__(kSbThreads, 1) bvh_build_smem_kernel(BvhBuildArgs a0, BvhBuildArgs a1, uint32_t smem_bytes) {
   const BvhBuildArgs& a = blockIdx.y ? a1 : a0;
   extern __shared__ __align__(16) unsigned char sb_smem[];
   __shared__ double s_red[33];
@@ -498,7 +498,9 @@ __global__ void __launch_bounds__(kSbThreads, 1) bvh_build_smem_kernel(BvhBuildA
   BvhNode* nodes = a.g.nodes + (size_t)set * a.g.pt_cap;
   double4* sorted = a.g.sorted + (size_t)set * a.g.pt_cap;
   const uint32_t tid = threadIdx.x, nthr = kSbThreads, lane = tid & 31, warp = tid >> 5;
-  const size_t capA = ((size_t)a.g.pt_cap + 15) & ~(size_t)15;
+  // (arrays are laid out for the set's own size, not its capacity: what is left of the launch's shared memory holds the
+  // boxes of the big nodes, below)
+  const size_t capA = ((size_t)n + 15) & ~(size_t)15;
   uint32_t* s_code = reinterpret_cast<uint32_t*>(sb_smem);              // [capA] codes: by point, after the sort by position
   uint16_t* s_p0 = reinterpret_cast<uint16_t*>(s_code + capA);          // [capA] sort ping / node: other end of its range
   uint16_t* s_p1 = s_p0 + capA;                                         // [capA] sort pong / node: split position
@@ -719,6 +721,7 @@ __global__ void __launch_bounds__(kSbThreads, 1) bvh_build_smem_kernel(BvhBuildA
   }
   __syncthreads();
 
+  BT_MARK(9);
   // ---- number the big nodes in index order (the root, node 0, is number 0) and list them
   const uint32_t per = (n_int + nthr - 1) / nthr;
   const uint32_t b0 = min(tid * per, n_int), b1 = min(b0 + per, n_int);
@@ -744,6 +747,12 @@ __global__ void __launch_bounds__(kSbThreads, 1) bvh_build_smem_kernel(BvhBuildA
   }
   __syncthreads();
 
+  // Boxes of the big nodes in shared memory (below) when the launch's shared memory has room for 12 bytes per big node
+  // behind the arrays above and the set gets compact records at all; else the level passes through the node records.
+  const size_t box_off = 8 * capA + (3 * capA > 32768 ? 3 * capA : 32768);
+  const bool smem_boxes = a.g.quant != nullptr && n_big <= a.g.pt_cap / 2 && n_big <= (uint32_t)(capA / 2) &&
+                          box_off + 12 * (size_t)n_big <= smem_bytes;
+
   // ---- full range + split searches of the big nodes, one thread per node
   for (uint32_t num = tid; num < n_big; num += nthr) {
     const int i = (int)s_big[num];
@@ -768,11 +777,167 @@ __global__ void __launch_bounds__(kSbThreads, 1) bvh_build_smem_kernel(BvhBuildA
     if (max(i, j) == split + 1) w |= kRightLeaf;
     s_other[i] = (uint16_t)j;
     s_split[i] = (uint16_t)split;
-    nodes[i].split = w;
-    nodes[i].pad = (uint32_t)j;
+    if (!smem_boxes) {  // (the shared-memory box path writes whole node records at its end)
+      nodes[i].split = w;
+      nodes[i].pad = (uint32_t)j;
+    }
   }
   __syncthreads();
   BT_MARK(5);
+
+  // ---- boxes + compact records, shared-memory version.  The level passes of the version below cost an L2 round trip
+  // each (store, barrier, load: ~4.6 k cycles x 20 passes on 14.3 k points, as much as the sort) and the record pass
+  // reads every child box back.  A box on the records' 16-bit grid is 12 bytes: the ~n / 5 big nodes' boxes fit behind
+  // the other arrays, the passes run on shared memory alone, and the records come out bit-identical (quantisation is
+  // monotonic: the union of quantised boxes is the quantised union).  The float boxes the general walk reads are the
+  // grid boxes converted back (outward): at most a cell (extent / 65534) wider than before — boxes only ever steer the
+  // walk, they never decide a result (§5).
+  if (smem_boxes) {
+    uint16_t* s_cid = reinterpret_cast<uint16_t*>(s_code);  // (codes are dead) node -> number
+    uint32_t* s_box = reinterpret_cast<uint32_t*>(sb_smem + box_off);  // [number][axis] lo | hi << 16
+    for (uint32_t num = tid; num < n_big; num += nthr) s_cid[s_big[num]] = (uint16_t)num;
+    BvhRec* recs = reinterpret_cast<BvhRec*>(a.g.keys + (size_t)set * 2 * a.g.pt_cap);
+    const double qorg[3] = {__ldcg(&a.g.quant[set].org[0]), __ldcg(&a.g.quant[set].org[1]), __ldcg(&a.g.quant[set].org[2])};
+    const double qinv = __ldcg(&a.g.quant[set].inv_cell);
+    const double qcell = 1.0 / qinv;
+    __syncthreads();
+    // Per big node (by number): parent's number, sibling's number (0xFFFF: the sibling is leaf-sized) and how many big
+    // children it still waits for.  (s_need overlays the upper half of the dead codes, s_parent / s_sib the readiness
+    // bytes and the tail of the node list: n_big <= n / 2.)
+    uint32_t* s_need = reinterpret_cast<uint32_t*>(s_cid + capA);        // [n_big]
+    uint16_t* s_parent = reinterpret_cast<uint16_t*>(s_ready);           // [n_big]
+    uint16_t* s_sib = s_big + (capA >> 1);                               // [n_big]
+    const uint32_t mine = tid < n_big ? (n_big - tid + nthr - 1) / nthr : 0u;  // (at most 20: n_big < n <= 20,480)
+    uint32_t done = 0;
+    for (uint32_t k = 0; k < mine; k++) {  // pass 1: leaf-sized children straight from their points
+      const uint32_t num = tid + k * nthr;
+      const uint32_t i = s_big[num];
+      const uint32_t o = s_other[i], sp = s_split[i];
+      const uint32_t f = min(i, o), l = max(i, o);
+      uint32_t acc[3] = {0x0000FFFFu, 0x0000FFFFu, 0x0000FFFFu};  // empty: lo 65535, hi 0
+      uint32_t box[6] = {0, 0, 0, 0, 0, 0}, ref[2];
+      uint32_t n_bigc = 0;
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+        const uint32_t cf = c == 0 ? f : sp + 1, cl = c == 0 ? sp : l;
+        if (cl - cf < (uint32_t)kBvhLeaf) {
+          double plo[3] = {CUDART_INF, CUDART_INF, CUDART_INF}, phi[3] = {-CUDART_INF, -CUDART_INF, -CUDART_INF};
+#pragma unroll
+          for (int q = 0; q < kBvhLeaf; q++) {
+            const double4 pt = sorted[min(cf + (uint32_t)q, cl)];
+            plo[0] = fmin(plo[0], pt.x); phi[0] = fmax(phi[0], pt.x);
+            plo[1] = fmin(plo[1], pt.y); phi[1] = fmax(phi[1], pt.y);
+            plo[2] = fmin(plo[2], pt.z); phi[2] = fmax(phi[2], pt.z);
+          }
+          float blo[3], bhi[3];
+#pragma unroll
+          for (int d = 0; d < 3; d++) {
+            blo[d] = __double2float_rd(plo[d]);
+            bhi[d] = __double2float_ru(phi[d]);
+            const double tl = ((double)blo[d] - qorg[d]) * qinv, th = ((double)bhi[d] - qorg[d]) * qinv;
+            const uint32_t ql = (uint32_t)fmin(fmax(floor(tl - 1e-6), 0.0), 65535.0);
+            const uint32_t qh = (uint32_t)fmin(fmax(ceil(th + 1e-6), 0.0), 65535.0);
+            box[3 * c + d] = ql | (qh << 16);
+            acc[d] = min(acc[d] & 0xFFFFu, ql) | (max(acc[d] >> 16, qh) << 16);
+          }
+          if (cf != cl) {  // its node record, for the general walk (split word 0: never expanded)
+            float4* q = reinterpret_cast<float4*>(nodes + sp + c);
+            q[0] = make_float4(blo[0], blo[1], blo[2], 0.f);
+            q[1] = make_float4(bhi[0], bhi[1], bhi[2], 0.f);
+          }
+          ref[c] = kRefLeaf | ((cl - cf) << 24) | cf;
+        } else {
+          ref[c] = (uint32_t)s_cid[sp + c];
+          n_bigc++;
+        }
+      }
+      uint4* dst = reinterpret_cast<uint4*>(recs + num);  // (the halves of big children are filled in at the end)
+      dst[0] = make_uint4(box[0], box[1], box[2], box[3]);
+      dst[1] = make_uint4(box[4], box[5], ref[0], ref[1]);
+#pragma unroll
+      for (int d = 0; d < 3; d++) s_box[3 * num + d] = acc[d];
+      s_need[num] = n_bigc;
+#pragma unroll
+      for (int c = 0; c < 2; c++)
+        if (!(ref[c] & kRefLeaf)) {
+          s_parent[ref[c]] = (uint16_t)num;
+          s_sib[ref[c]] = (ref[c ^ 1] & kRefLeaf) ? (uint16_t)0xFFFFu : (uint16_t)ref[c ^ 1];
+        }
+      if (n_bigc == 0) done |= 1u << k;
+    }
+    __syncthreads();
+    BT_MARK(8);
+    // Walk up: the thread that completes a node's last big child merges the children into the node and goes on to its
+    // parent (shared-memory atomics; the serial chain is the depth of the tree, ~20 steps of ~150 cycles, where
+    // level-synchronous passes paid a barrier and a dozen dependent shared-memory reads per level).  Unions of boxes
+    // are order-independent, so the result does not depend on which thread arrives last.
+    while (done) {
+      const int k = __ffs((int)done) - 1;
+      done &= done - 1;
+      uint32_t cur = tid + (uint32_t)k * nthr;
+      uint32_t b[3] = {s_box[3 * cur], s_box[3 * cur + 1], s_box[3 * cur + 2]};
+      while (cur != 0) {  // (number 0 is the root)
+        const uint32_t par = s_parent[cur], sib = s_sib[cur];
+        __threadfence_block();  // my box before my arrival
+        const uint32_t before = atomicSub(&s_need[par], 1u);
+        if (before != 1u) break;  // the sibling is still open: its thread takes the parent
+        __threadfence_block();
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+          uint32_t pb = s_box[3 * par + d];  // the parent's leaf-sized child, if any (pass 1)
+          pb = min(pb & 0xFFFFu, b[d] & 0xFFFFu) | (max(pb >> 16, b[d] >> 16) << 16);
+          if (sib != 0xFFFFu) {
+            const uint32_t sb = reinterpret_cast<volatile uint32_t*>(s_box)[3 * sib + d];
+            pb = min(pb & 0xFFFFu, sb & 0xFFFFu) | (max(pb >> 16, sb >> 16) << 16);
+          }
+          b[d] = pb;
+          s_box[3 * par + d] = pb;
+        }
+        cur = par;
+      }
+    }
+    __syncthreads();
+    BT_MARK(6);
+    // node records of the big nodes (split word, range end, float box) and the big children's halves of the records
+    for (uint32_t num = tid; num < n_big; num += nthr) {
+      const uint32_t i = s_big[num];
+      const uint32_t o = s_other[i], sp = s_split[i];
+      const uint32_t f = min(i, o), l = max(i, o);
+      uint32_t w = sp;
+      if (f == sp) w |= kLeftLeaf;
+      if (l == sp + 1) w |= kRightLeaf;
+      float blo[3], bhi[3];
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        const uint32_t b = s_box[3 * num + d];
+        blo[d] = __double2float_rd(fma((double)(b & 0xFFFFu), qcell, qorg[d]));
+        bhi[d] = __double2float_ru(fma((double)(b >> 16), qcell, qorg[d]));
+      }
+      float4* q = reinterpret_cast<float4*>(nodes + i);
+      q[0] = make_float4(blo[0], blo[1], blo[2], __uint_as_float(w));
+      q[1] = make_float4(bhi[0], bhi[1], bhi[2], __uint_as_float(o));
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+        const uint32_t cf = c == 0 ? f : sp + 1, cl = c == 0 ? sp : l;
+        if (cl - cf >= (uint32_t)kBvhLeaf) {
+          const uint32_t cn = s_cid[sp + c];
+          uint32_t* dst = recs[num].box + 3 * c;
+          dst[0] = s_box[3 * cn];
+          dst[1] = s_box[3 * cn + 1];
+          dst[2] = s_box[3 * cn + 2];
+        }
+      }
+    }
+    if (tid == 0) a.g.quant[set].n_rec = n_big;
+#ifdef BUILD_TIMING
+    BT_MARK(7);
+    if (tid == 0 && set == 0)
+      printf("BT n %u: bbox %lld morton %lld sort %lld gather %lld topo_sweep %lld topo_big %lld boxes_leaf %lld boxes_up %lld "
+             "n_big %lld compact %lld total %lld\n", n, bt[1] - bt[0], bt[2] - bt[1], bt[3] - bt[2], bt[4] - bt[3],
+             bt[9] - bt[4], bt[5] - bt[9], bt[8] - bt[5], bt[6] - bt[8], (long long)n_big, bt[7] - bt[6], bt[7] - bt[0]);
+#endif
+    return;
+  }
 
   // ---- boxes.  Thread t owns the big nodes numbered t, t + 1024, ...  Pass 1: every big node takes the boxes of its
   // LEAF-SIZED children straight from their points (all loads independent; stored in the child's node record for the
@@ -846,7 +1011,14 @@ __global__ void __launch_bounds__(kSbThreads, 1) bvh_build_smem_kernel(BvhBuildA
     if (!complete) pend |= 1u << k;
   }
   __syncthreads();
+  BT_MARK(8);
+#ifdef BUILD_TIMING
+  uint32_t bt_passes = 0;
+#endif
   for (uint32_t pass = 2; __syncthreads_or(pend != 0); pass++) {
+#ifdef BUILD_TIMING
+    bt_passes = pass;
+#endif
     uint32_t m = pend;
     while (m) {
       const int k = __ffs((int)m) - 1;
@@ -936,9 +1108,9 @@ __global__ void __launch_bounds__(kSbThreads, 1) bvh_build_smem_kernel(BvhBuildA
 #ifdef BUILD_TIMING
   BT_MARK(7);
   if (tid == 0 && set == 0)
-    printf("BT n %u: bbox %lld morton %lld sort %lld gather %lld topology %lld boxes %lld compact %lld total %lld\n", n,
-           bt[1] - bt[0], bt[2] - bt[1], bt[3] - bt[2], bt[4] - bt[3], bt[5] - bt[4], bt[6] - bt[5], bt[7] - bt[6],
-           bt[7] - bt[0]);
+    printf("BT n %u: bbox %lld morton %lld sort %lld gather %lld topology %lld boxes_leaf %lld boxes_levels %lld passes %lld "
+           "n_big %lld compact %lld total %lld\n", n, bt[1] - bt[0], bt[2] - bt[1], bt[3] - bt[2], bt[4] - bt[3],
+           bt[5] - bt[4], bt[8] - bt[5], bt[6] - bt[8], (long long)bt_passes, (long long)n_big, bt[7] - bt[6], bt[7] - bt[0]);
 #endif
 }
 

@@ -1644,11 +1644,17 @@ static bool sb_fits(const BvhBuildArgs& a, int optin) {
   return !legacy && a.g.pt_cap <= kSbMaxPoints && sb_smem_bytes(a.g.pt_cap) + 1024 <= (size_t)optin;
 }
 
-static cudaError_t launch_sb(const BvhBuildArgs& a0, const BvhBuildArgs& a1, uint32_t n_sets, uint32_t kinds, cudaStream_t st) {
-  const size_t smem = std::max(sb_smem_bytes(a0.g.pt_cap), kinds > 1 ? sb_smem_bytes(a1.g.pt_cap) : (size_t)0);
+static cudaError_t launch_sb(const BvhBuildArgs& a0, const BvhBuildArgs& a1, uint32_t n_sets, uint32_t kinds, cudaStream_t st,
+                             int optin) {
+  // one CTA per SM whatever it asks for: take all the shared memory there is — what the sort and the tree arrays of a
+  // set leave free holds the boxes of its big nodes (bvh.cuh)
+  const size_t need = std::max(sb_smem_bytes(a0.g.pt_cap), kinds > 1 ? sb_smem_bytes(a1.g.pt_cap) : (size_t)0);
+  const size_t smem = std::max(need, (size_t)optin - 1024);
   cudaError_t err = cudaFuncSetAttribute(bvh_build_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
-  bvh_build_smem_kernel<<<dim3(n_sets, kinds), kSbThreads, smem, st>>>(a0, a1);
+  // $LOAMGPU_BUILD_GLOBAL_BOXES=1: tell the kernel it has no room for the boxes (A/B and test of its other path)
+  static const bool global_boxes = []() { const char* e = getenv("LOAMGPU_BUILD_GLOBAL_BOXES"); return e && atoi(e) != 0; }();
+  bvh_build_smem_kernel<<<dim3(n_sets, kinds), kSbThreads, smem, st>>>(a0, a1, global_boxes ? 0u : (uint32_t)smem);
   return cudaGetLastError();
 }
 
@@ -1658,7 +1664,7 @@ cudaError_t launch_bvh_build(const BvhBuildArgs& a_in, uint32_t n_sets, cudaStre
   int dev = 0, optin = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  if (sb_fits(a, optin)) return launch_sb(a, a, n_sets, 1, st);
+  if (sb_fits(a, optin)) return launch_sb(a, a, n_sets, 1, st, optin);
   const size_t sort_bytes = (size_t)kRadixBins * kBuildThreads * sizeof(uint32_t);
   // radix counters, reused after the sort for the sorted codes; + one readiness byte per node
   const size_t tree_bytes = std::max(sort_bytes, (size_t)a.g.pt_cap * 4) + a.g.pt_cap + 16;
@@ -1678,7 +1684,7 @@ cudaError_t launch_bvh_build2(const BvhBuildArgs& edge, const BvhBuildArgs& plan
   cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   if (sb_fits(edge, optin) && sb_fits(planar, optin)) {
     if (launches) *launches += 1;
-    return launch_sb(edge, planar, n_sets, 2, st);
+    return launch_sb(edge, planar, n_sets, 2, st, optin);
   }
   if (launches) *launches += 2;
   cudaError_t err = launch_bvh_build(edge, n_sets, st);
