@@ -18,10 +18,6 @@
 #include "common.cuh"
 #include "kernels.h"
 
-#ifndef EXTRACT_WARP_SWEEPS
-#define EXTRACT_WARP_SWEEPS 1
-#endif
-
 namespace loamgpu {
 
 namespace {
@@ -35,10 +31,13 @@ struct Rec {
 
 // Shared memory of one ring: [staging records | P doubles | P mask bytes | mbarrier].  The doubles hold the ranges
 // while the mask is derived and the curvature afterwards; once the curvature is known the staged points are dead and
-// their space holds the selection's walk state (P state bytes, P uint16 pick list, P uint32 neighbour-priority words).
+// their space holds the selection's walk state (two uint32 neighbour-priority words and a uint16 pick-list slot per
+// column, state / validity / candidate bits per 32 columns: 10.4 bytes per column).
 // (Round 1 kept ranges and curvature in separate arrays: 33 KB per 1024-column ring and 6 resident rings per SM; this
 // layout needs 21 KB with packed xyz records, 25 KB with float4 records.)
-__host__ __device__ inline uint32_t walk_bytes(uint32_t P) { return ((P + 15) & ~15u) + 2 * ((P + 1) & ~1u) + 4 * P; }
+__host__ __device__ inline uint32_t walk_bytes(uint32_t P) {  // prio, hp | pick list | state words | valid, candidate bits
+  return 8 * P + 2 * ((P + 3) & ~3u) + 16 * ((P + 31) >> 5);
+}
 __host__ __device__ inline size_t stage_bytes(uint32_t P, uint32_t rec) {
   const size_t a = (size_t)P * rec, b = walk_bytes(P);
   return ((a > b ? a : b) + 15) & ~(size_t)15;
@@ -178,22 +177,61 @@ __device__ __forceinline__ void extract_ring_body(const ExtractArgs& a) {
   // (= the reference's selection order), truncated to max+1, and only the accepted picks invalidate neighbours.
   // Walks run in the reference's order (sector-major, edge before planar) because each sees the mask left by the
   // previous ones, including suppression that spills across a sector boundary (features-inl.h:148-151).
-  uint8_t* st = reinterpret_cast<uint8_t*>(stage);                // walk state per column (the staged points are dead)
-  uint16_t* plist = reinterpret_cast<uint16_t*>(st + ((P + 15) & ~15u));  // columns picked in the current walk
-  uint32_t* hp = reinterpret_cast<uint32_t*>(plist + ((P + 1) & ~1u));    // higher-priority-neighbour bits per column
-  __shared__ uint32_t s_m, s_base[2];
-  if (tid == 0) s_base[0] = s_base[1] = 0;
-  const uint32_t pps = P / S;
+  // Bit-parallel form (round 2; the byte-per-column form of round 1 spent 30 % of the kernel's instructions in the rounds at
+  // 6-8 active lanes and 12 % on the neighbour-priority bits of every walk).  Column states live in 32-column words —
+  // one 64-bit word holds the "open" bits (low half) and the "picked" bits (high half) of 32 columns, so a reader
+  // always sees a consistent pair — and a column's view of its +-(N-1) neighbours is a window of at most 31 bits cut
+  // out of three adjacent words by a funnel shift (bit k of a window = column j - (N-1) + k).  Which neighbours
+  // precede a column in the EDGE order is computed once per ring (prio); the planar order is its complement.  A
+  // round is then two ANDs per column, decided for 32 columns at once and published with one ballot.
   const uint32_t reach = N - 1;
   const size_t ring_id = (size_t)scan * a.R + ring;
+  __shared__ uint32_t s_m, s_base[2];
+  if (reach > 15) {  // only reachable with N >= P (capi.cu: plan_extract), where CHECK 1 leaves no valid column
+    if (tid == 0) a.ring_counts[ring_id * 2 + 0] = a.ring_counts[ring_id * 2 + 1] = 0;
+    return;
+  }
+  const uint32_t W = (P + 31) >> 5;
+  uint32_t* prio = reinterpret_cast<uint32_t*>(stage);                   // [P] neighbours that precede j in the edge order
+  uint32_t* hp = prio + P;                                               // [P] ... that are candidates of this walk and precede j
+  uint16_t* plist = reinterpret_cast<uint16_t*>(hp + P);                 // [P] columns picked in the current walk
+  uint64_t* state = reinterpret_cast<uint64_t*>(plist + ((P + 3) & ~3u));  // [W] open | picked << 32
+  uint32_t* vbits = reinterpret_cast<uint32_t*>(state + W);              // [W] validity mask
+  uint32_t* cbits = vbits + W;                                           // [W] candidates of the current walk
+  const uint32_t lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+  const uint32_t wmask = (2u << (2 * reach)) - 1u;  // 2 (N-1) + 1 window bits
+  const uint32_t self = 1u << reach;
+  auto window = [&](uint32_t prev, uint32_t own, uint32_t next) -> uint32_t {
+    const int pos = (int)lane - (int)reach;
+    return (pos >= 0 ? __funnelshift_r(own, next, pos) : __funnelshift_r(prev, own, 32 + pos)) & wmask;
+  };
+  if (tid == 0) s_base[0] = s_base[1] = 0;
+  for (uint32_t w = warp; w < W; w += nwarps) {
+    const uint32_t j = 32 * w + lane;
+    const uint32_t word = __ballot_sync(0xffffffffu, j < P && mask[j] != 0);
+    if (lane == 0) vbits[w] = word;
+  }
+  for (uint32_t j = tid; j < P; j += nthr) {
+    const double cj = cur[j];
+    uint32_t bits = 0;
+    for (uint32_t n = 1; n <= reach; n++) {
+      if (j >= n && cur[j - n] > cj) bits |= 1u << (reach - n);    // (a left neighbour loses ties: larger index first)
+      if (j + n < P && cur[j + n] >= cj) bits |= 1u << (reach + n);
+    }
+    prio[j] = bits;
+  }
+  __syncthreads();
+  const uint32_t pps = P / S;
   uint32_t* ge = a.ring_edge + ring_id * a.capE_ring;
   uint32_t* gp = a.ring_planar + ring_id * a.capP_ring;
-  enum : uint8_t { kNone = 0, kOpen = 1, kPicked = 2, kDropped = 3 };
+  volatile uint64_t* vstate = state;
   for (uint32_t walk = 0; walk < 2 * S; walk++) {
     const uint32_t sec = walk >> 1;
     const bool planar = (walk & 1u) != 0;
     const uint32_t b = sec * pps, e = (sec == S - 1) ? P : b + pps;
     const uint32_t cap = planar ? a.maxP : a.maxE;  // the walk accepts cap + 1 picks
+    if (b >= e) continue;  // (more sectors than columns)
+    const uint32_t w0 = b >> 5, w1 = (e - 1) >> 5;
     // priority: edge = larger curvature first, ties by larger index (the ascending (c, idx) order walked from the
     // end); planar = smaller curvature first, ties by smaller index
     auto before = [&](uint32_t t, uint32_t j) -> bool {
@@ -201,68 +239,59 @@ __device__ __forceinline__ void extract_ring_body(const ExtractArgs& a) {
       return planar ? (ct < cj || (ct == cj && t < j)) : (ct > cj || (ct == cj && t > j));
     };
     bool any = false;
-    for (uint32_t j = b + tid; j < e; j += nthr) {
-      const double c = cur[j];
-      const bool cand = mask[j] != 0 && (planar ? c < a.planar_thr : c > a.edge_thr);
-      st[j] = cand ? kOpen : kNone;
-      any |= cand;
+    for (uint32_t w = w0 + warp; w <= w1; w += nwarps) {
+      const uint32_t j = 32 * w + lane;
+      const bool in = j >= b && j < e;
+      const double c = in ? cur[j] : 0.0;
+      const bool cand = in && ((vbits[w] >> lane) & 1u) != 0 && (planar ? c < a.planar_thr : c > a.edge_thr);
+      const uint32_t word = __ballot_sync(0xffffffffu, cand);
+      if (lane == 0) {
+        cbits[w] = word;
+        state[w] = (uint64_t)word;
+      }
+      any |= word != 0;
     }
     if (tid == 0) s_m = 0;
     if (!__syncthreads_or(any)) continue;  // no candidate in this walk (uniform: every thread sees the same result)
-    // which of the 2*(N-1) neighbours are candidates of this walk with a higher priority: evaluated once, so the
-    // rounds below only read state bytes (bit 2(n-1) = column j-n, bit 2(n-1)+1 = column j+n)
-    for (uint32_t j = b + tid; j < e; j += nthr) {
-      if (st[j] != kOpen) continue;
-      uint32_t bits = 0;
-      for (uint32_t n = 1; n <= reach; n++) {
-        if (j >= b + n && st[j - n] != kNone && before(j - n, j)) bits |= 1u << (2 * (n - 1));
-        if (j + n < e && st[j + n] != kNone && before(j + n, j)) bits |= 2u << (2 * (n - 1));
-      }
-      hp[j] = bits;
+    for (uint32_t w = w0 + warp; w <= w1; w += nwarps) {
+      const uint32_t j = 32 * w + lane;
+      const uint32_t cw = window(w > w0 ? cbits[w - 1] : 0u, cbits[w], w < w1 ? cbits[w + 1] : 0u);
+      if (j < P) hp[j] = cw & (planar ? ~prio[j] : prio[j]) & ~self;
     }
-    // (hp[j] is only ever read by the thread that wrote it, and st[] is not modified before the first round)
-    // A warp owns runs of 32 consecutive columns, and a candidate only waits on columns within +-(N-1): most
-    // dependency chains never leave the warp.  Those are resolved in warp-local sweeps (one __syncwarp each) and only
-    // chains that cross a warp's span cost a CTA barrier.  Any interleaving gives the same result: a state byte
-    // changes once (open -> picked / dropped) and a stale "open" seen across warps only delays a decision.
+    // (hp[j] is only ever read by the thread that wrote it; cbits is not modified during the walk.)
+    // A warp owns whole state words, and a candidate only waits on columns within +-(N-1): most dependency chains never
+    // leave the word.  Those are resolved in warp-local sweeps on the word in registers and only chains that cross
+    // words cost a CTA barrier.  Any interleaving gives the same result: a column's state changes once (open -> picked /
+    // dropped) and a stale "open" seen across warps only delays a decision.
     for (;;) {
-      bool open_left;
-      for (;;) {
-        open_left = false;
-        bool progress = false;
-        for (uint32_t j = b + tid; j < e; j += nthr) {
-          if (st[j] != kOpen) continue;
-          uint32_t bits = hp[j];
-          bool wait = false, drop = false;
-          for (uint32_t n = 1; bits != 0; n++, bits >>= 2) {
-            if (bits & 1u) {
-              const uint8_t s = st[j - n];
-              drop |= s == kPicked;
-              wait |= s == kOpen;
-            }
-            if (bits & 2u) {
-              const uint8_t s = st[j + n];
-              drop |= s == kPicked;
-              wait |= s == kOpen;
-            }
+      bool open_left = false;
+      for (uint32_t w = w0 + warp; w <= w1; w += nwarps) {
+        uint64_t sw = vstate[w];
+        uint32_t ow = (uint32_t)sw, pw = (uint32_t)(sw >> 32);
+        if (ow == 0) continue;
+        const uint32_t j = 32 * w + lane;
+        const uint32_t h = ((ow >> lane) & 1u) ? hp[j] : 0u;
+        for (;;) {
+          const uint64_t sp = w > w0 ? vstate[w - 1] : 0ull, sn = w < w1 ? vstate[w + 1] : 0ull;
+          const bool my = ((ow >> lane) & 1u) != 0;
+          const uint32_t openwin = window((uint32_t)sp, ow, (uint32_t)sn);
+          const uint32_t pickwin = window((uint32_t)(sp >> 32), pw, (uint32_t)(sn >> 32));
+          const bool drop = my && (pickwin & h) != 0;
+          const bool pick = my && !drop && (openwin & h) == 0;
+          const uint32_t dmask = __ballot_sync(0xffffffffu, drop), kmask = __ballot_sync(0xffffffffu, pick);
+          if ((dmask | kmask) == 0) break;
+          ow &= ~(dmask | kmask);
+          pw |= kmask;
+          if (lane == 0) vstate[w] = (uint64_t)ow | ((uint64_t)pw << 32);
+          if (kmask) {
+            uint32_t at = 0;
+            if (lane == 0) at = atomicAdd(&s_m, (uint32_t)__popc(kmask));
+            at = __shfl_sync(0xffffffffu, at, 0);
+            if (pick) plist[at + (uint32_t)__popc(kmask & ((1u << lane) - 1u))] = (uint16_t)j;
           }
-          if (drop) {
-            st[j] = kDropped;
-            progress = true;
-          } else if (!wait) {
-            st[j] = kPicked;
-            plist[atomicAdd(&s_m, 1u)] = (uint16_t)j;
-            progress = true;
-          } else {
-            open_left = true;
-          }
+          if (ow == 0) break;
         }
-#if EXTRACT_WARP_SWEEPS
-        __syncwarp();
-        if (!(__any_sync(0xffffffffu, progress) && __any_sync(0xffffffffu, open_left))) break;
-#else
-        break;
-#endif
+        open_left |= ow != 0;
       }
       if (!__syncthreads_or(open_left)) break;
     }
@@ -279,9 +308,10 @@ __device__ __forceinline__ void extract_ring_body(const ExtractArgs& a) {
       }
       if (rank > cap) continue;
       (planar ? gp : ge)[base + rank] = ring * P + j;
-      for (uint32_t n = 0; n <= reach; n++) {
-        if (j + n < P) mask[j + n] = 0;
-        if (j >= n) mask[j - n] = 0;
+      const uint32_t lo = j >= reach ? j - reach : 0u, hi = min(j + reach, P - 1);
+      for (uint32_t w = lo >> 5; w <= (hi >> 5); w++) {
+        const uint32_t f = max(lo, 32 * w) - 32 * w, l = min(hi, 32 * w + 31) - 32 * w;  // bits f .. l of word w
+        atomicAnd(&vbits[w], ~((0xFFFFFFFFu >> (31 - l)) & (0xFFFFFFFFu << f)));
       }
     }
     __syncthreads();
