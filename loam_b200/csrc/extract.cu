@@ -18,6 +18,10 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#ifndef EXTRACT_NB_PER_SWEEP
+#define EXTRACT_NB_PER_SWEEP 1
+#endif
+
 namespace loamgpu {
 
 namespace {
@@ -31,12 +35,12 @@ struct Rec {
 
 // Shared memory of one ring: [staging records | P doubles | P mask bytes | mbarrier].  The doubles hold the ranges
 // while the mask is derived and the curvature afterwards; once the curvature is known the staged points are dead and
-// their space holds the selection's walk state (two uint32 neighbour-priority words and a uint16 pick-list slot per
-// column, state / validity / candidate bits per 32 columns: 10.4 bytes per column).
+// their space holds the selection's walk state (a uint32 neighbour-priority word and a 64-bit pick slot per column,
+// a uint16 pick column, state / validity / candidate / threshold bits per 32 columns: 14.75 bytes per column).
 // (Round 1 kept ranges and curvature in separate arrays: 33 KB per 1024-column ring and 6 resident rings per SM; this
 // layout needs 21 KB with packed xyz records, 25 KB with float4 records.)
-__host__ __device__ inline uint32_t walk_bytes(uint32_t P) {  // prio, hp | pick list | state words | valid, candidate bits
-  return 8 * P + 2 * ((P + 3) & ~3u) + 16 * ((P + 31) >> 5);
+__host__ __device__ inline uint32_t walk_bytes(uint32_t P) {  // prio | pick keys | state words | four bit arrays | pick columns
+  return 4 * ((P + 1) & ~1u) + 8 * P + 24 * ((P + 31) >> 5) + 2 * P;
 }
 __host__ __device__ inline size_t stage_bytes(uint32_t P, uint32_t rec) {
   const size_t a = (size_t)P * rec, b = walk_bytes(P);
@@ -192,12 +196,14 @@ __device__ __forceinline__ void extract_ring_body(const ExtractArgs& a) {
     return;
   }
   const uint32_t W = (P + 31) >> 5;
-  uint32_t* prio = reinterpret_cast<uint32_t*>(stage);                   // [P] neighbours that precede j in the edge order
-  uint32_t* hp = prio + P;                                               // [P] ... that are candidates of this walk and precede j
-  uint16_t* plist = reinterpret_cast<uint16_t*>(hp + P);                 // [P] columns picked in the current walk
-  uint64_t* state = reinterpret_cast<uint64_t*>(plist + ((P + 3) & ~3u));  // [W] open | picked << 32
-  uint32_t* vbits = reinterpret_cast<uint32_t*>(state + W);              // [W] validity mask
-  uint32_t* cbits = vbits + W;                                           // [W] candidates of the current walk
+  uint32_t* prio = reinterpret_cast<uint32_t*>(stage);      // [P] neighbours that precede j in the edge order
+  uint64_t* pkey = reinterpret_cast<uint64_t*>(prio + ((P + 1) & ~1u));  // [P] picks of the walk: bits of their curvature
+  uint64_t* state = pkey + P;                               // [W] open | picked << 32
+  uint32_t* vbits = reinterpret_cast<uint32_t*>(state + W); // [W] validity mask (features.cpp:20-68 + accepted picks)
+  uint32_t* cbits = vbits + W;                              // [W] candidates of the current walk
+  uint32_t* ebits = cbits + W;                              // [W] curvature above the edge threshold
+  uint32_t* fbits = ebits + W;                              // [W] curvature below the planar threshold
+  uint16_t* plist = reinterpret_cast<uint16_t*>(fbits + W); // [P] picks of the walk: their columns
   const uint32_t lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
   const uint32_t wmask = (2u << (2 * reach)) - 1u;  // 2 (N-1) + 1 window bits
   const uint32_t self = 1u << reach;
@@ -206,10 +212,17 @@ __device__ __forceinline__ void extract_ring_body(const ExtractArgs& a) {
     return (pos >= 0 ? __funnelshift_r(own, next, pos) : __funnelshift_r(prev, own, 32 + pos)) & wmask;
   };
   if (tid == 0) s_base[0] = s_base[1] = 0;
-  for (uint32_t w = warp; w < W; w += nwarps) {
+  for (uint32_t w = warp; w < W; w += nwarps) {  // per-ring bit words: a walk's candidates are then three ANDs per word
     const uint32_t j = 32 * w + lane;
-    const uint32_t word = __ballot_sync(0xffffffffu, j < P && mask[j] != 0);
-    if (lane == 0) vbits[w] = word;
+    const double c = j < P ? cur[j] : 0.0;
+    const uint32_t vb = __ballot_sync(0xffffffffu, j < P && mask[j] != 0);
+    const uint32_t eb = __ballot_sync(0xffffffffu, j < P && c > a.edge_thr);
+    const uint32_t fb = __ballot_sync(0xffffffffu, j < P && c < a.planar_thr);
+    if (lane == 0) {
+      vbits[w] = vb;
+      ebits[w] = eb;
+      fbits[w] = fb;
+    }
   }
   for (uint32_t j = tid; j < P; j += nthr) {
     const double cj = cur[j];
@@ -232,47 +245,42 @@ __device__ __forceinline__ void extract_ring_body(const ExtractArgs& a) {
     const uint32_t cap = planar ? a.maxP : a.maxE;  // the walk accepts cap + 1 picks
     if (b >= e) continue;  // (more sectors than columns)
     const uint32_t w0 = b >> 5, w1 = (e - 1) >> 5;
-    // priority: edge = larger curvature first, ties by larger index (the ascending (c, idx) order walked from the
-    // end); planar = smaller curvature first, ties by smaller index
-    auto before = [&](uint32_t t, uint32_t j) -> bool {
-      const double ct = cur[t], cj = cur[j];
-      return planar ? (ct < cj || (ct == cj && t < j)) : (ct > cj || (ct == cj && t > j));
-    };
     bool any = false;
-    for (uint32_t w = w0 + warp; w <= w1; w += nwarps) {
-      const uint32_t j = 32 * w + lane;
-      const bool in = j >= b && j < e;
-      const double c = in ? cur[j] : 0.0;
-      const bool cand = in && ((vbits[w] >> lane) & 1u) != 0 && (planar ? c < a.planar_thr : c > a.edge_thr);
-      const uint32_t word = __ballot_sync(0xffffffffu, cand);
-      if (lane == 0) {
-        cbits[w] = word;
-        state[w] = (uint64_t)word;
-      }
+    for (uint32_t w = w0 + tid; w <= w1; w += nthr) {  // candidates: valid, inside the sector, past the walk's threshold
+      const uint32_t f = max(b, 32 * w) - 32 * w, l = min(e - 1, 32 * w + 31) - 32 * w;
+      const uint32_t word = vbits[w] & (planar ? fbits[w] : ebits[w]) & (0xFFFFFFFFu >> (31 - l)) & (0xFFFFFFFFu << f);
+      cbits[w] = word;
+      state[w] = (uint64_t)word;
       any |= word != 0;
     }
     if (tid == 0) s_m = 0;
     if (!__syncthreads_or(any)) continue;  // no candidate in this walk (uniform: every thread sees the same result)
-    for (uint32_t w = w0 + warp; w <= w1; w += nwarps) {
-      const uint32_t j = 32 * w + lane;
-      const uint32_t cw = window(w > w0 ? cbits[w - 1] : 0u, cbits[w], w < w1 ? cbits[w + 1] : 0u);
-      if (j < P) hp[j] = cw & (planar ? ~prio[j] : prio[j]) & ~self;
-    }
-    // (hp[j] is only ever read by the thread that wrote it; cbits is not modified during the walk.)
     // A warp owns whole state words, and a candidate only waits on columns within +-(N-1): most dependency chains never
-    // leave the word.  Those are resolved in warp-local sweeps on the word in registers and only chains that cross
-    // words cost a CTA barrier.  Any interleaving gives the same result: a column's state changes once (open -> picked /
-    // dropped) and a stale "open" seen across warps only delays a decision.
+    // leave the word.  Those are resolved in warp-local sweeps on the word in registers (the neighbouring words are
+    // read once per CTA round) and only chains that cross words cost a CTA barrier.  Any interleaving gives the same
+    // result: a column's state changes once (open -> picked / dropped) and a stale "open" seen across warps only
+    // delays a decision.
     for (;;) {
       bool open_left = false;
       for (uint32_t w = w0 + warp; w <= w1; w += nwarps) {
-        uint64_t sw = vstate[w];
+        const uint64_t sw = vstate[w];
         uint32_t ow = (uint32_t)sw, pw = (uint32_t)(sw >> 32);
         if (ow == 0) continue;
         const uint32_t j = 32 * w + lane;
-        const uint32_t h = ((ow >> lane) & 1u) ? hp[j] : 0u;
+        // neighbours that are candidates of this walk and precede j in its order (priority: edge = larger curvature
+        // first, ties by larger index — the ascending (c, idx) order walked from the end; planar = the complement)
+        uint32_t h = 0;
+        if ((ow >> lane) & 1u) {
+          const uint32_t cw = window(w > w0 ? cbits[w - 1] : 0u, cbits[w], w < w1 ? cbits[w + 1] : 0u);
+          h = cw & (planar ? ~prio[j] : prio[j]) & ~self;
+        }
+#if !EXTRACT_NB_PER_SWEEP
+        const uint64_t sp = w > w0 ? vstate[w - 1] : 0ull, sn = w < w1 ? vstate[w + 1] : 0ull;
+#endif
         for (;;) {
+#if EXTRACT_NB_PER_SWEEP
           const uint64_t sp = w > w0 ? vstate[w - 1] : 0ull, sn = w < w1 ? vstate[w + 1] : 0ull;
+#endif
           const bool my = ((ow >> lane) & 1u) != 0;
           const uint32_t openwin = window((uint32_t)sp, ow, (uint32_t)sn);
           const uint32_t pickwin = window((uint32_t)(sp >> 32), pw, (uint32_t)(sn >> 32));
@@ -282,29 +290,49 @@ __device__ __forceinline__ void extract_ring_body(const ExtractArgs& a) {
           if ((dmask | kmask) == 0) break;
           ow &= ~(dmask | kmask);
           pw |= kmask;
+#if EXTRACT_NB_PER_SWEEP
           if (lane == 0) vstate[w] = (uint64_t)ow | ((uint64_t)pw << 32);
+#endif
           if (kmask) {
             uint32_t at = 0;
             if (lane == 0) at = atomicAdd(&s_m, (uint32_t)__popc(kmask));
             at = __shfl_sync(0xffffffffu, at, 0);
-            if (pick) plist[at + (uint32_t)__popc(kmask & ((1u << lane) - 1u))] = (uint16_t)j;
+            if (pick) {
+              const uint32_t slot = at + (uint32_t)__popc(kmask & ((1u << lane) - 1u));
+              pkey[slot] = (uint64_t)__double_as_longlong(cur[j]);
+              plist[slot] = (uint16_t)j;
+            }
           }
           if (ow == 0) break;
         }
+#if !EXTRACT_NB_PER_SWEEP
+        if (lane == 0) vstate[w] = (uint64_t)ow | ((uint64_t)pw << 32);
+#endif
         open_left |= ow != 0;
       }
       if (!__syncthreads_or(open_left)) break;
     }
-    // rank the picks by priority (one thread per pick, taken from the compact list); accept the first cap + 1;
-    // only those invalidate their neighbours
+    // rank the picks by priority (one thread per pick, taken from the compact list); accept the first cap + 1; only
+    // those invalidate their neighbours.  Curvatures are >= +0 (a sum of squares; NaN is never a candidate), so their
+    // bit patterns order like the doubles: the comparison is integer work, ties go to the index as in `prio`.
     const uint32_t m = s_m;
     const uint32_t base = s_base[planar ? 1 : 0];
     for (uint32_t t = tid; t < m; t += nthr) {
+      const uint64_t kj = pkey[t];
       const uint32_t j = plist[t];
       uint32_t rank = 0;
-      for (uint32_t i = 0; i < m; i++) {
-        const uint32_t o = plist[i];
-        rank += (o != j && before(o, j)) ? 1u : 0u;
+      if (planar) {
+        for (uint32_t i = 0; i < m; i++) {
+          const uint64_t ko = pkey[i];
+          const uint32_t o = plist[i];
+          rank += (ko < kj || (ko == kj && o < j)) ? 1u : 0u;
+        }
+      } else {
+        for (uint32_t i = 0; i < m; i++) {
+          const uint64_t ko = pkey[i];
+          const uint32_t o = plist[i];
+          rank += (ko > kj || (ko == kj && o > j)) ? 1u : 0u;
+        }
       }
       if (rank > cap) continue;
       (planar ? gp : ge)[base + rank] = ring * P + j;
