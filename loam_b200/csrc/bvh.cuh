@@ -130,13 +130,13 @@ __global__ void __launch_bounds__(kBuildThreads, BUILD_MINBLOCKS) bvh_build_kern
   }
   // one scale for all axes (cubic cells); the ordering only has to be spatially coherent, not exact
   const double scale = emax > 0 ? 1023.999 / emax : 0.0;
-  // 16-bit grid of the compact records: origin a margin below the box (float-rounded box corners stay inside),
-  // 65534 cells across the longest axis plus the margins
+  // grid of the compact records: origin a margin below the box (float-rounded box corners stay inside),
+  // kRecCells cells across the longest axis plus the margins
   if (tid == 0 && a.g.quant) {
     double amax = emax;
     for (int d = 0; d < 3; d++) amax = fmax(amax, fmax(fabs(lo[d]), fabs(hi[d])));
     const double qmargin = 1e-6 * amax + 1e-9;
-    const double qinv = 65534.0 / (emax + 2.0 * qmargin);
+    const double qinv = kRecCells / (emax + 2.0 * qmargin);
     BvhQuant q;
     q.org[0] = lo[0] - qmargin;
     q.org[1] = lo[1] - qmargin;
@@ -413,18 +413,18 @@ __global__ void __launch_bounds__(kBuildThreads, BUILD_MINBLOCKS) bvh_build_kern
   const double qinv = __ldcg(&a.g.quant[set].inv_cell);
   auto quant_lo = [&](float v, int d) -> uint32_t {
     const double t = ((double)v - qorg[d]) * qinv;
-    return (uint32_t)fmin(fmax(floor(t - 1e-6), 0.0), 65535.0);
+    return (uint32_t)fmin(fmax(floor(t - 1e-6), 0.0), (double)kRecCellMax);
   };
   auto quant_hi = [&](float v, int d) -> uint32_t {
     const double t = ((double)v - qorg[d]) * qinv;
-    return (uint32_t)fmin(fmax(ceil(t + 1e-6), 0.0), 65535.0);
+    return (uint32_t)fmin(fmax(ceil(t + 1e-6), 0.0), (double)kRecCellMax);
   };
   for (uint32_t i = b0; i < b1; i++) {
     uint32_t f, l;
     node_range(i, f, l);
     if (l - f < (uint32_t)kBvhLeaf) continue;
     const uint32_t sp = __ldcg(&nodes[i].split) & kSplitMask;
-    BvhRec r;
+    uint32_t cbox[2][3], cref[2];
 #pragma unroll
     for (int c = 0; c < 2; c++) {
       const uint32_t cf = c == 0 ? f : sp + 1, cl = c == 0 ? sp : l;
@@ -441,12 +441,14 @@ __global__ void __launch_bounds__(kBuildThreads, BUILD_MINBLOCKS) bvh_build_kern
         chi[0] = vb.x; chi[1] = vb.y; chi[2] = vb.z;
       }
 #pragma unroll
-      for (int d = 0; d < 3; d++) r.box[3 * c + d] = quant_lo(clo[d], d) | (quant_hi(chi[d], d) << 16);
-      r.ref[c] = (cl - cf < (uint32_t)kBvhLeaf) ? (kRefLeaf | ((cl - cf) << 24) | cf) : __ldcg(cid + sp + c);
+      for (int d = 0; d < 3; d++) cbox[c][d] = quant_lo(clo[d], d) | (quant_hi(chi[d], d) << 16);
+      cref[c] = (cl - cf < (uint32_t)kBvhLeaf) ? (kRefLeaf | ((cl - cf) << 24) | cf) : __ldcg(cid + sp + c);
     }
+    uint32_t w6[6];
+    rec_pack_boxes(cbox[0], cbox[1], w6);
     uint4* dst = reinterpret_cast<uint4*>(recs + __ldcg(cid + i));
-    dst[0] = make_uint4(r.box[0], r.box[1], r.box[2], r.box[3]);
-    dst[1] = make_uint4(r.box[4], r.box[5], r.ref[0], r.ref[1]);
+    dst[0] = make_uint4(w6[0], w6[1], w6[2], w6[3]);
+    dst[1] = make_uint4(w6[4], w6[5], cref[0], cref[1]);
   }
   if (tid == 0) a.g.quant[set].n_rec = total;
 #ifdef BUILD_TIMING
@@ -573,7 +575,7 @@ __global__ void __launch_bounds__(kSbThreads, 1) bvh_build_smem_kernel(BvhBuildA
     double amax = emax;
     for (int d = 0; d < 3; d++) amax = fmax(amax, fmax(fabs(lo[d]), fabs(hi[d])));
     const double qmargin = 1e-6 * amax + 1e-9;
-    const double qinv = 65534.0 / (emax + 2.0 * qmargin);
+    const double qinv = kRecCells / (emax + 2.0 * qmargin);
     BvhQuant q;
     q.org[0] = lo[0] - qmargin;
     q.org[1] = lo[1] - qmargin;
@@ -815,7 +817,7 @@ __global__ void __launch_bounds__(kSbThreads, 1) bvh_build_smem_kernel(BvhBuildA
   // reads every child box back.  A box on the records' 16-bit grid is 12 bytes: the ~n / 5 big nodes' boxes fit behind
   // the other arrays, the passes run on shared memory alone, and the records come out bit-identical (quantisation is
   // monotonic: the union of quantised boxes is the quantised union).  The float boxes the general walk reads are the
-  // grid boxes converted back (outward): at most a cell (extent / 65534) wider than before — boxes only ever steer the
+  // grid boxes converted back (outward): at most a cell (extent / 32766) wider than before — boxes only ever steer the
   // walk, they never decide a result (§5).
   if (smem_boxes) {
     uint16_t* s_cid = reinterpret_cast<uint16_t*>(s_code);  // (codes are dead) node -> number
@@ -839,8 +841,8 @@ __global__ void __launch_bounds__(kSbThreads, 1) bvh_build_smem_kernel(BvhBuildA
       const uint32_t i = s_big[num];
       const uint32_t o = s_other[i], sp = s_split[i];
       const uint32_t f = min(i, o), l = max(i, o);
-      uint32_t acc[3] = {0x0000FFFFu, 0x0000FFFFu, 0x0000FFFFu};  // empty: lo 65535, hi 0
-      uint32_t box[6] = {0, 0, 0, 0, 0, 0}, ref[2];
+      uint32_t acc[3] = {0x0000FFFFu, 0x0000FFFFu, 0x0000FFFFu};  // empty: lo above every cell, hi 0
+      uint32_t cbox[2][3] = {{0, 0, 0}, {0, 0, 0}}, ref[2];
       uint32_t n_bigc = 0;
 #pragma unroll
       for (int c = 0; c < 2; c++) {
@@ -860,9 +862,9 @@ __global__ void __launch_bounds__(kSbThreads, 1) bvh_build_smem_kernel(BvhBuildA
             blo[d] = __double2float_rd(plo[d]);
             bhi[d] = __double2float_ru(phi[d]);
             const double tl = ((double)blo[d] - qorg[d]) * qinv, th = ((double)bhi[d] - qorg[d]) * qinv;
-            const uint32_t ql = (uint32_t)fmin(fmax(floor(tl - 1e-6), 0.0), 65535.0);
-            const uint32_t qh = (uint32_t)fmin(fmax(ceil(th + 1e-6), 0.0), 65535.0);
-            box[3 * c + d] = ql | (qh << 16);
+            const uint32_t ql = (uint32_t)fmin(fmax(floor(tl - 1e-6), 0.0), (double)kRecCellMax);
+            const uint32_t qh = (uint32_t)fmin(fmax(ceil(th + 1e-6), 0.0), (double)kRecCellMax);
+            cbox[c][d] = ql | (qh << 16);
             acc[d] = min(acc[d] & 0xFFFFu, ql) | (max(acc[d] >> 16, qh) << 16);
           }
           if (cf != cl) {  // its node record, for the general walk (split word 0: never expanded)
@@ -876,6 +878,8 @@ __global__ void __launch_bounds__(kSbThreads, 1) bvh_build_smem_kernel(BvhBuildA
           n_bigc++;
         }
       }
+      uint32_t box[6];
+      rec_pack_boxes(cbox[0], cbox[1], box);
       uint4* dst = reinterpret_cast<uint4*>(recs + num);  // (the halves of big children are filled in at the end)
       dst[0] = make_uint4(box[0], box[1], box[2], box[3]);
       dst[1] = make_uint4(box[4], box[5], ref[0], ref[1]);
@@ -946,10 +950,13 @@ __global__ void __launch_bounds__(kSbThreads, 1) bvh_build_smem_kernel(BvhBuildA
         const uint32_t cf = c == 0 ? f : sp + 1, cl = c == 0 ? sp : l;
         if (cl - cf >= (uint32_t)kBvhLeaf) {
           const uint32_t cn = s_cid[sp + c];
-          uint32_t* dst = recs[num].box + 3 * c;
-          dst[0] = s_box[3 * cn];
-          dst[1] = s_box[3 * cn + 1];
-          dst[2] = s_box[3 * cn + 2];
+          uint16_t* half = reinterpret_cast<uint16_t*>(recs + num) + c;  // this child's half of each box word
+#pragma unroll
+          for (int d = 0; d < 3; d++) {
+            const uint32_t b = s_box[3 * cn + d];
+            half[2 * d] = (uint16_t)(b & 0xFFFFu);
+            half[6 + 2 * d] = (uint16_t)(0u - (b >> 16));
+          }
         }
       }
     }
@@ -1103,7 +1110,7 @@ __global__ void __launch_bounds__(kSbThreads, 1) bvh_build_smem_kernel(BvhBuildA
     const uint32_t i = s_big[num];
     const uint32_t o = s_other[i], sp = s_split[i];
     const uint32_t f = min(i, o), l = max(i, o);
-    uint32_t box[6], ref[2];
+    uint32_t cbox[2][3], ref[2];
 #pragma unroll
     for (int c = 0; c < 2; c++) {
       const uint32_t cf = c == 0 ? f : sp + 1, cl = c == 0 ? sp : l;
@@ -1119,12 +1126,14 @@ __global__ void __launch_bounds__(kSbThreads, 1) bvh_build_smem_kernel(BvhBuildA
 #pragma unroll
       for (int d = 0; d < 3; d++) {
         const double tl = ((double)blo[d] - qorg[d]) * qinv, th = ((double)bhi[d] - qorg[d]) * qinv;
-        const uint32_t ql = (uint32_t)fmin(fmax(floor(tl - 1e-6), 0.0), 65535.0);
-        const uint32_t qh = (uint32_t)fmin(fmax(ceil(th + 1e-6), 0.0), 65535.0);
-        box[3 * c + d] = ql | (qh << 16);
+        const uint32_t ql = (uint32_t)fmin(fmax(floor(tl - 1e-6), 0.0), (double)kRecCellMax);
+        const uint32_t qh = (uint32_t)fmin(fmax(ceil(th + 1e-6), 0.0), (double)kRecCellMax);
+        cbox[c][d] = ql | (qh << 16);
       }
       ref[c] = (cl - cf < (uint32_t)kBvhLeaf) ? (kRefLeaf | ((cl - cf) << 24) | cf) : (uint32_t)s_cid[sp + c];
     }
+    uint32_t box[6];
+    rec_pack_boxes(cbox[0], cbox[1], box);
     uint4* dst = reinterpret_cast<uint4*>(recs + num);
     dst[0] = make_uint4(box[0], box[1], box[2], box[3]);
     dst[1] = make_uint4(box[4], box[5], ref[0], ref[1]);
@@ -1372,13 +1381,18 @@ __device__ __forceinline__ void knn_bvh(const BvhHdr& h, const BvhNode* __restri
 // The batched association kernel keeps a target set's compact records (common.cuh: BvhRec) in SHARED memory, so a
 // node step costs two LDS.128 (29 cycles) instead of two dependent global loads (L1 hit 32, L2 hit ~250 cycles; 37 % of
 // them missed L1 in the global walk: profiles/r1_kernels_full_v29.md) and the state of a walk is one 32-bit child
-// reference.  Box tests run on the set's 16-bit grid: the query's cell coordinates are rounded outward to integers
-// (below / above), a box corner c is decoded as the float 2^23 + c by OR-ing it into the mantissa of 8388608.0f, and
-// the differences of those integers are exact in fp32.  gap^2 is summed with round-down FMAs and compared with the
-// pruning bound converted to cells^2 and rounded up: a subtree is skipped only when its true distance is strictly
-// above the bound, exactly as in knn_bvh — the results are identical, whatever the tree looks like.
-struct QueryG {  // 2^23 + floor / ceil of the query's cell coordinate, clamped to +-2^22 cells
-  float lo[3], hi[3];
+// reference.  Box tests run on the set's 15-bit grid in integer arithmetic, both children of a record at once: the
+// query's cell coordinates are rounded outward (below / above) and clamped onto the grid, a record word holds the same
+// box corner of both children in its two halves, and per axis
+//     u   = (-hi) + qlo                         VIADDMNMX.S16x2  (max with -32768: a plain 16x2 add)
+//     gap = max(lo + (-qhi), u, 0)              VIADDMNMX.S16x2.RELU
+// give both children's gaps in cells (every difference of two 15-bit cells fits an int16).  gap^2 is summed in 32-bit
+// integers (3 * 32767^2 < 2^32) and compared with the pruning bound converted to cells^2 and rounded up: a subtree is
+// skipped only when its true distance is strictly above the bound, exactly as in knn_bvh — the results are identical,
+// whatever the tree looks like.  (Round 2 first decoded the corners as floats 2^23 + c and took exact float differences:
+// 13 instructions per axis for the two children, 25 % of the kernel's instructions; this form takes 6.)
+struct QueryG {  // per axis, replicated in both halves: lower cell of the query / minus its upper cell
+  uint32_t lo2[3], nhi2[3];
 };
 
 __device__ __forceinline__ void query_grid(const BvhQuant* __restrict__ Q, double qx, double qy, double qz, QueryG& g) {
@@ -1387,26 +1401,29 @@ __device__ __forceinline__ void query_grid(const BvhQuant* __restrict__ Q, doubl
   for (int d = 0; d < 3; d++) {
     const double t = (q[d] - Q->org[d]) * Q->inv_cell;
     const double e = 1e-6 + fabs(t) * 1e-12;  // covers the rounding of t itself
-    // clamping is conservative: a clamped coordinate lies between the true one and every box (cells 0 .. 65535)
-    const double lo = fmin(fmax(floor(t - e), -4194304.0), 4194304.0);
-    const double hi = fmin(fmax(ceil(t + e), -4194304.0), 4194304.0);
-    g.lo[d] = (float)(8388608.0 + lo);  // integers below 2^24: exact
-    g.hi[d] = (float)(8388608.0 + hi);
+    // clamping is conservative: a clamped coordinate lies between the true one and every box (cells 0 .. kRecCellMax)
+    const uint32_t lo = (uint32_t)fmin(fmax(floor(t - e), 0.0), (double)kRecCellMax);
+    const uint32_t hi = (uint32_t)fmin(fmax(ceil(t + e), 0.0), (double)kRecCellMax);
+    g.lo2[d] = lo | (lo << 16);
+    const uint32_t nh = (0u - hi) & 0xFFFFu;
+    g.nhi2[d] = nh | (nh << 16);
   }
 }
 
-// lower bound, in cells^2, of the squared distance from the query to the box packed in (wx, wy, wz)
-__device__ __forceinline__ float rec_lower_bound(uint32_t wx, uint32_t wy, uint32_t wz, const QueryG& g) {
-  const uint32_t w[3] = {wx, wy, wz};
-  float s = 0.f;
+// lower bounds, in cells^2, of the squared distances from the query to the boxes of both children of a record
+__device__ __forceinline__ void rec_lower_bounds(uint32_t lo_x, uint32_t lo_y, uint32_t lo_z, uint32_t nhi_x, uint32_t nhi_y,
+                                                 uint32_t nhi_z, const QueryG& g, uint32_t& sl, uint32_t& sr) {
+  const uint32_t lo[3] = {lo_x, lo_y, lo_z}, nhi[3] = {nhi_x, nhi_y, nhi_z};
+  sl = 0;
+  sr = 0;
 #pragma unroll
   for (int d = 0; d < 3; d++) {
-    const float blo = __uint_as_float(0x4B000000u | (w[d] & 0xFFFFu));  // 2^23 + lo cell
-    const float bhi = __uint_as_float(0x4B000000u | (w[d] >> 16));      // 2^23 + hi cell
-    const float gap = fmax3_nonneg(blo - g.hi[d], g.lo[d] - bhi);      // exact integer differences
-    s = __fmaf_rd(gap, gap, s);
+    const uint32_t u = __viaddmax_s16x2(nhi[d], g.lo2[d], 0x80008000u);   // qlo - hi
+    const uint32_t gap = __viaddmax_s16x2_relu(lo[d], g.nhi2[d], u);      // max(lo - qhi, qlo - hi, 0)
+    const uint32_t gl = gap & 0xFFFFu, gr = gap >> 16;
+    sl += gl * gl;
+    sr += gr * gr;
   }
-  return s;
 }
 
 __device__ __forceinline__ void load_rec_shared(uint32_t saddr, uint4& r0, uint4& r1) {
@@ -1439,7 +1456,9 @@ __device__ __forceinline__ void knn_compact(uint32_t s_recs, uint32_t s_stack, u
   QueryG g;
   query_grid(Q, qx, qy, qz, g);
   const double inv2 = Q->inv_cell2;
-  float bound = __double2float_ru(d2_cut * inv2);  // cells^2; a subtree is pruned when its lower bound > bound
+  // cells^2, rounded up and saturated (the conversion maps +inf and anything above 2^32 - 1 to 2^32 - 1, which no sum of
+  // three squared gaps exceeds); a subtree is pruned when its lower bound > bound
+  uint32_t bound = __double2uint_ru(d2_cut * inv2);
   uint2 st[kBvhStack];                             // pending subtrees: (child reference, lower bound)
   int sp = 0;
 #if KNN_SMEM_STACK
@@ -1466,7 +1485,7 @@ __device__ __forceinline__ void knn_compact(uint32_t s_recs, uint32_t s_stack, u
           else
 #endif
             e = st[sp];
-          if (__uint_as_float(e.y) <= bound) {
+          if (e.y <= bound) {
             cur = e.x;
             have = true;
           }
@@ -1481,14 +1500,14 @@ __device__ __forceinline__ void knn_compact(uint32_t s_recs, uint32_t s_stack, u
         }
 #endif
       } else {
-        uint4 r0, r1;  // (Lx Ly Lz Rx) (Ry Rz refL refR)
+        uint4 r0, r1;  // (lo.x lo.y lo.z nhi.x) (nhi.y nhi.z refL refR)
         load_rec_shared(s_recs + cur * (uint32_t)sizeof(BvhRec), r0, r1);
-        const float dl = rec_lower_bound(r0.x, r0.y, r0.z, g);
-        const float dr = rec_lower_bound(r0.w, r1.x, r1.y, g);
+        uint32_t dl, dr;
+        rec_lower_bounds(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, g, dl, dr);
         const bool right_first = dr < dl;
-        const float dn = right_first ? dr : dl, df = right_first ? dl : dr;
+        const uint32_t dn = right_first ? dr : dl, df = right_first ? dl : dr;
         if (df <= bound) {  // far child stays pending
-          const uint2 e = make_uint2(right_first ? r1.z : r1.w, __float_as_uint(df));
+          const uint2 e = make_uint2(right_first ? r1.z : r1.w, df);
           st[sp] = e;
 #if KNN_SMEM_STACK
           asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(s_stack + (uint32_t)(sp & (KNN_SMEM_STACK - 1)) * kKnnStackPitch),
@@ -1506,7 +1525,7 @@ __device__ __forceinline__ void knn_compact(uint32_t s_recs, uint32_t s_stack, u
     if (!at_leaf) break;  // done
     const uint32_t first = cur & 0x00FFFFFFu;
     scan_leaf<K>(sorted, first, first + ((cur >> 24) & 15u), qx, qy, qz, d2_cut, tk);
-    bound = __double2float_ru(fmin(tk.kth(k), d2_cut) * inv2);
+    bound = __double2uint_ru(fmin(tk.kth(k), d2_cut) * inv2);
     have = false;
   }
 }

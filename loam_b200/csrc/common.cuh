@@ -146,16 +146,28 @@ struct __align__(32) BvhNode {
 };
 // Compact traversal records: what the batched k-NN kernel keeps in SHARED MEMORY while it walks one target set.  One
 // record per internal node that covers more than kBvhLeaf points (~ n / 4.6 of them), holding the boxes of its two
-// children on a 16-bit grid over the set's bounding box (rounded outward: a lower bound stays a lower bound) and what
+// children on a 15-bit grid over the set's bounding box (rounded outward: a lower bound stays a lower bound) and what
 // each child is: another record, or a run of <= kBvhLeaf points of the Morton-sorted copy to scan.  32 bytes per
 // record, so a 64x1024 scan's two sets (2.4 k + 14.3 k points) take ~120 KB.  Written by the build kernel into the
 // (then dead) sort scratch of the set.
 constexpr uint32_t kRefLeaf = 0x80000000u;   // child ref: kRefLeaf | (count - 1) << 24 | first point  /  record index
 constexpr uint32_t kNoRecs = 0xFFFFFFFFu;    // BvhQuant::n_rec of a set without compact records (multi-CTA build, overflow)
 struct __align__(16) BvhRec {
-  uint32_t box[6];  // [axis] child L, [3 + axis] child R: lo | hi << 16 (grid cells)
+  uint32_t lo[3];   // [axis]: lower cell of child L | lower cell of child R << 16
+  uint32_t nhi[3];  // [axis]: minus the upper cell of child L (as int16) | minus the upper cell of child R << 16
   uint32_t ref[2];  // child L, child R
 };
+// Cells are 15-bit (0 .. kRecCellMax) so that every difference of two cell numbers fits an int16: the walk tests both
+// children of a record with the 16x2 SIMD integer instructions of sm_100a (VIADDMNMX.S16x2[.RELU]: two per axis).
+constexpr uint32_t kRecCellMax = 32767u;
+constexpr double kRecCells = 32766.0;  // cells across the longest axis of the set's box (plus the margins)
+// packs the boxes of two children (per axis: lower cell | upper cell << 16) into the record's six box words
+__host__ __device__ inline void rec_pack_boxes(const uint32_t* boxL, const uint32_t* boxR, uint32_t* w6) {
+  for (int d = 0; d < 3; d++) {
+    w6[d] = (boxL[d] & 0xFFFFu) | (boxR[d] << 16);
+    w6[3 + d] = ((0u - (boxL[d] >> 16)) & 0xFFFFu) | ((0u - (boxR[d] >> 16)) << 16);
+  }
+}
 struct BvhQuant {   // grid of one set: cell index of coordinate x on axis d = (x - org[d]) * inv_cell
   double org[3];
   double inv_cell;
