@@ -581,7 +581,12 @@ __device__ __forceinline__ void assoc_fit_pair(const AssocArgs& a, int outer_ite
     double* rec_w = reinterpret_cast<double*>(a.rec_p + rec) + 3;
     const uint32_t li = (uint32_t)__double_as_longlong(*rec_w);
     const int m = (int)a.nn_cnt[rec];
-    const uint32_t* nn = a.nn_idx + rec * (size_t)a.nn_stride;
+    const uint32_t* nn_g = a.nn_idx + rec * (size_t)a.nn_stride;
+    // the neighbour numbers are read before the count is known (slots beyond it hold stale numbers and are not used):
+    // count -> numbers -> points was three dependent round trips per feature, 45 % of the kernel's stall samples
+    uint32_t nn[KMAX];
+#pragma unroll
+    for (int j = 0; j < KMAX; j++) nn[j] = j < (int)a.nn_stride ? nn_g[j] : 0u;
     const int need = is_plane ? a.rp.min_plane : a.rp.min_line;
     if (m >= need && m > 0) {
       const double4* tp = a.ext_target ? (is_plane ? a.tp_pts : a.te_pts)
