@@ -4,7 +4,7 @@
 # usage: bash tools/final_profile.sh <tag>
 tag=${1:-x}
 mkdir -p gpurun_out
-python bench.py --steps 5 --warmup 3 > gpurun_out/bench_${tag}_default.json 2> gpurun_out/bench_${tag}_default.err || { echo "bench failed"; tail -5 gpurun_out/bench_${tag}_default.err; exit 1; }
+python bench.py --steps 20 --warmup 5 > gpurun_out/bench_${tag}_default.json 2> gpurun_out/bench_${tag}_default.err || { echo "bench failed"; tail -5 gpurun_out/bench_${tag}_default.err; exit 1; }
 python - <<PY
 import json
 d=json.loads(open('gpurun_out/bench_${tag}_default.json').read().strip().splitlines()[-1])
