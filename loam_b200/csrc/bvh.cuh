@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(kBuildThreads, BUILD_MINBLOCKS) bvh_build_kern
 
   // ---- compact traversal records (common.cuh: BvhRec).  Internal node i is "big" when it covers more than kBvhLeaf
   // points; big nodes are numbered in index order (the root, node 0, gets record 0) and each writes one record with its
-  // children's boxes on the 16-bit grid.  The records overlay this set's sort scratch, which is dead by now.
+  // children's boxes on the records' grid.  The records overlay this set's sort scratch, which is dead by now.
   BT_MARK(6);
   if (a.g.quant == nullptr || n <= (uint32_t)kBvhLeaf) return;
   __syncthreads();
@@ -814,7 +814,7 @@ __global__ void __launch_bounds__(kSbThreads, 1) bvh_build_smem_kernel(BvhBuildA
 
   // ---- boxes + compact records, shared-memory version.  The level passes of the version below cost an L2 round trip
   // each (store, barrier, load: ~4.6 k cycles x 20 passes on 14.3 k points, as much as the sort) and the record pass
-  // reads every child box back.  A box on the records' 16-bit grid is 12 bytes: the ~n / 5 big nodes' boxes fit behind
+  // reads every child box back.  A box on the records' grid (two 16-bit cell numbers per axis) is 12 bytes: the ~n / 5 big nodes' boxes fit behind
   // the other arrays, the passes run on shared memory alone, and the records come out bit-identical (quantisation is
   // monotonic: the union of quantised boxes is the quantised union).  The float boxes the general walk reads are the
   // grid boxes converted back (outward): at most a cell (extent / 32766) wider than before — boxes only ever steer the
