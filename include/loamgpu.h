@@ -20,8 +20,8 @@
  *   - every entry point opens an NVTX range named after itself (Nsight timelines).
  *
  * Limits the reference does not have (LOAMGPU_ERR_UNSUPPORTED, never a silent fallback):
- *   - one ring is staged in one CTA's shared memory: points_per_line <= ~8,900 (packed xyz floats),
- *     ~7,700 (float4), ~5,700 (doubles) on a B200 (227 KB per SM), and <= 65,535 in any case;
+ *   - one ring is staged in one CTA's shared memory: points_per_line <= ~9,700 (packed xyz floats),
+ *     ~9,200 (float4), ~7,000 (doubles) on a B200 (227 KB per SM), and <= 65,535 in any case;
  *   - num_edge_neighbors, num_plane_neighbors <= 32; neighbor_points <= 16; total points < 2^32;
  *   - the sequence calls take float records of 12 or 16 bytes.
  * Sizes that change the kernels used, not the results: feature sets of up to 20,480 points take the

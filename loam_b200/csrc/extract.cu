@@ -40,7 +40,7 @@ struct Rec {
 // their space holds the selection's walk state (a uint32 neighbour-priority word and a 64-bit pick slot per column,
 // a uint16 pick column, state / validity / candidate / threshold bits per 32 columns: 14.75 bytes per column).
 // (Round 1 kept ranges and curvature in separate arrays: 33 KB per 1024-column ring and 6 resident rings per SM; this
-// layout needs 21 KB with packed xyz records, 25 KB with float4 records.)
+// layout needs 24 KB with packed xyz records (the walk state is larger than the staged ring), 25 KB with float4 records.)
 __host__ __device__ inline uint32_t walk_bytes(uint32_t P) {  // prio | pick keys | state words | four bit arrays | pick columns
   return 4 * ((P + 1) & ~1u) + 8 * P + 24 * ((P + 31) >> 5) + 2 * P;
 }
@@ -357,7 +357,7 @@ __device__ __forceinline__ void extract_ring_body(const ExtractArgs& a) {
 // The plain kernels (what every throughput path runs) and the de-warping ones are separate entry points so that the
 // register budget of one never shapes the other: plain 37-40 registers / 6 CTAs per SM; de-warping (24-byte staging
 // records, 41 KB of shared memory per 1024-column ring) capped for 5.
-// float records: 8 resident rings per SM (32 registers; 21-25 KB of shared memory per 1024-column ring) — measured
+// float records: 8 resident rings per SM (32 registers; 24-25 KB of shared memory per 1024-column ring) — measured
 // 4.04 -> 3.70 ms per 1024 float4 scans against the 40 registers / 6 rings the compiler picks unconstrained; a minimum
 // of 1 lets it take far more registers and runs at 6.4 ms
 template <typename T, int kE>
