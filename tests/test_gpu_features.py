@@ -73,6 +73,28 @@ def test_indices_bit_exact_vs_oracle(ctx, oracle, shape, fe_t):
     assert np.array_equal(ctx.valid_mask(scan, H.to_capi(lp), H.to_capi(fe)), oracle.valid_mask(xyz, lp, fe))
 
 
+@pytest.mark.parametrize("layout,P", [("f32x4", 9000), ("f32x3", 9600), ("f64x3", 6900)])
+def test_largest_rings_that_fit_a_cta(ctx, oracle, layout, P):
+    """One ring is staged in one CTA's shared memory (include/loamgpu.h, limits): rings close to the limit of each
+    record type still give the reference's indices, with a whole SM's shared memory taken by one ring."""
+    R = 2
+    scan = synth.make_scan(R, P, k=3, dropout=0.01)
+    lp, fe = LidarParams(R, P, 1.0, 120.0), FeParams.default()
+    xyz = scan[:, :3].astype(np.float64)
+    eo, po = oracle.extract(xyz, lp, fe)
+    cloud = {"f32x4": scan, "f32x3": np.ascontiguousarray(scan[:, :3]), "f64x3": xyz}[layout]
+    e, p = gpu_extract(ctx, cloud, lp, fe)
+    assert np.array_equal(e, eo) and np.array_equal(p, po)
+
+
+def test_ring_too_long_is_refused_loudly(ctx):
+    R, P = 1, 20000
+    with pytest.raises(_capi.LoamGpuError) as ei:
+        gpu_extract(ctx, np.zeros((R * P, 3), dtype=np.float32), LidarParams(R, P, 1.0, 120.0), FeParams.default())
+    assert ei.value.code == _capi.ERR_UNSUPPORTED
+    assert "shared memory" in str(ei.value)
+
+
 @pytest.mark.parametrize("layout", ["f64x3", "f32x3", "f64x4_strided", "f32_stride20"])
 def test_input_layouts_agree(ctx, oracle, layout):
     R, P = 16, 901  # odd P: f64 ring bytes not 16-aligned -> strided-load path
