@@ -1,9 +1,10 @@
 #!/bin/bash
-# usage (GPU box with 8 GPUs): bash tools/scale_run.sh [tag]  — the driver's 1/2/4/8 scaling launch of our arm (float4 and
+# usage (GPU box with 8 GPUs): bash tools/scale_run.sh [tag] ["list of N"]  — the driver's 1/2/4/8 scaling launch of our arm (float4 and
 # packed-xyz records) with the box's own H2D ceiling (tools/h2d_probe.py) at every N next to it
 tag=${1:-x}
+list=${2:-1 2 4 8}
 mkdir -p gpurun_out
-for n in 1 2 4 8; do
+for n in $list; do
   for pb in 16 12; do
     out=gpurun_out/scale_${tag}_n${n}_pb${pb}.json
     if [ $n -eq 1 ]; then
