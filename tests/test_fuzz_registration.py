@@ -87,3 +87,27 @@ def test_register_fuzz_vs_oracle(ctx, oracle):
         assert H.angular_distance(po[:4], pose[:4]) < H.POSE_TOL_RAD and np.abs(po[4:] - pose[4:]).max() < H.POSE_TOL_M, seed
         checked += do.n_iters
     assert checked > 24
+
+
+def test_batched_walk_fuzz_vs_single_calls(ctx):
+    """>= 16 pairs in one call take the batched shared-memory k-NN walk (compact records, integer box tests); single
+    registrations take the general walk over the float node boxes.  Both must find the same neighbours — on noisy rooms
+    and on quantised / duplicate-riddled sets where equal distances are everywhere and only the index tie-break decides."""
+    rp = H.to_capi(RegParams.default())
+    pairs, inits = [], []
+    for seed in range(20):
+        rng = np.random.RandomState(7000 + seed)
+        ed, pl = random_scene(rng)
+        if seed % 5 == 3:  # quantised coordinates: ties
+            ed, pl = np.round(ed * 8) / 8, np.round(pl * 8) / 8
+        if seed % 5 == 4:  # duplicated points
+            pl = np.concatenate([pl, pl[rng.randint(0, len(pl), len(pl) // 3)]])
+        sTt = np.r_[H.axis_angle(rng.uniform(0, 0.05), rng.normal(size=3)), rng.uniform(-0.06, 0.06, 3)]
+        pairs.append((H.transform(ed, sTt) + rng.normal(0, 0.002, ed.shape),
+                      H.transform(pl, sTt) + rng.normal(0, 0.002, pl.shape), ed, pl))
+        inits.append(IDENT)
+    poses, term, its = ctx.register_pairs(pairs, np.array(inits), rp)
+    for k, pr in enumerate(pairs):
+        single, det = ctx.register(*pr, IDENT, rp, want_detail=True)
+        assert term[k] == det["termination"] and its[k] == det["n_iters"], k
+        assert H.angular_distance(single[:4], poses[k][:4]) < 1e-9 and np.abs(single[4:] - poses[k][4:]).max() < 1e-9, k
