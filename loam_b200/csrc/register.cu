@@ -478,7 +478,10 @@ __global__ void __launch_bounds__(kKnnThreads, KNN_MINBLOCKS) assoc_knn_kernel(A
 // scan) into shared memory once, then its 32 warps pull 32-query chunks of the pair's source features (Morton order)
 // from a shared counter and walk the records there (bvh.cuh: knn_compact).  Pairs whose records do not fit, or whose
 // sets have none, go to a.leftover and are done by the general kernel right after.
-constexpr int kKnnCtaThreads = 1024;
+#ifndef KNN_CTA_THREADS
+#define KNN_CTA_THREADS 1024
+#endif
+constexpr int kKnnCtaThreads = KNN_CTA_THREADS;
 template <int K>
 __global__ void __launch_bounds__(kKnnCtaThreads, 1) assoc_knn_smem_kernel(AssocArgs a, int outer_iter, uint32_t n_slices,
                                                                           uint32_t max_recs) {
