@@ -1150,6 +1150,9 @@ __global__ void __launch_bounds__(kSbThreads, 1) bvh_build_smem_kernel(BvhBuildA
 
 // ============================================================================ exact k-NN (K4)
 
+#ifndef KNN_PTX_INSERT
+#define KNN_PTX_INSERT 1
+#endif
 // K best (d2, id) pairs, sorted ascending, in registers.  insert() is a branch-free shifting network:
 // every lane of a warp executes the same instructions whatever its data.
 template <int K>
@@ -1168,6 +1171,30 @@ struct TopK {
     return da < db || (da == db && ia < ib);
   }
   __device__ __forceinline__ void insert(double dn, uint32_t in) {
+#if KNN_PTX_INSERT
+    if constexpr (K == 5) {
+      // The same network with the comparison chained through predicates: (in < id) -> (dn == d) AND that -> (dn < d) OR
+      // that, three instructions per slot where the compiler's form takes four (a predicate initialisation, the
+      // ordered compare and two predicated compares); the shifts are predicated selects as in the compiler's code.
+      asm("{\n"
+          ".reg .pred q, t, c0, c1, c2, c3, c4;\n"
+          "setp.lt.u32 q, %11, %5;  setp.eq.and.f64 t, %10, %0, q;  setp.lt.or.f64 c0, %10, %0, t;\n"
+          "setp.lt.u32 q, %11, %6;  setp.eq.and.f64 t, %10, %1, q;  setp.lt.or.f64 c1, %10, %1, t;\n"
+          "setp.lt.u32 q, %11, %7;  setp.eq.and.f64 t, %10, %2, q;  setp.lt.or.f64 c2, %10, %2, t;\n"
+          "setp.lt.u32 q, %11, %8;  setp.eq.and.f64 t, %10, %3, q;  setp.lt.or.f64 c3, %10, %3, t;\n"
+          "setp.lt.u32 q, %11, %9;  setp.eq.and.f64 t, %10, %4, q;  setp.lt.or.f64 c4, %10, %4, t;\n"
+          "@c4 selp.f64 %4, %3, %10, c3;  @c4 selp.u32 %9, %8, %11, c3;\n"
+          "@c3 selp.f64 %3, %2, %10, c2;  @c3 selp.u32 %8, %7, %11, c2;\n"
+          "@c2 selp.f64 %2, %1, %10, c1;  @c2 selp.u32 %7, %6, %11, c1;\n"
+          "@c1 selp.f64 %1, %0, %10, c0;  @c1 selp.u32 %6, %5, %11, c0;\n"
+          "@c0 mov.f64 %0, %10;  @c0 mov.u32 %5, %11;\n"
+          "}"
+          : "+d"(d[0]), "+d"(d[1]), "+d"(d[2]), "+d"(d[3]), "+d"(d[4]), "+r"(id[0]), "+r"(id[1]), "+r"(id[2]), "+r"(id[3]),
+            "+r"(id[4])
+          : "d"(dn), "r"(in));
+      return;
+    }
+#endif
     bool c[K];
 #pragma unroll
     for (int i = 0; i < K; i++) c[i] = lt(dn, in, d[i], id[i]);
