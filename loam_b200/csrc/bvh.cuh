@@ -1153,6 +1153,9 @@ __global__ void __launch_bounds__(kSbThreads, 1) bvh_build_smem_kernel(BvhBuildA
 #ifndef KNN_PTX_INSERT
 #define KNN_PTX_INSERT 1
 #endif
+#ifndef KNN_LEAF_LEAN
+#define KNN_LEAF_LEAN 1
+#endif
 // K best (d2, id) pairs, sorted ascending, in registers.  insert() is a branch-free shifting network:
 // every lane of a warp executes the same instructions whatever its data.
 template <int K>
@@ -1283,6 +1286,26 @@ template <int K>
 __device__ __forceinline__ void scan_leaf(const double4* __restrict__ sorted, uint32_t first, uint32_t last, double qx,
                                           double qy, double qz, double d2_cut, TopK<K>& tk) {
   // ---- leaf: fp64 distances in nanoflann's L2_Simple order, branch-free insertion
+#if KNN_LEAF_LEAN
+  // All kBvhLeaf records behind `first` are loaded from one base address (immediate offsets; slots beyond `last` read
+  // the following points of the sorted copy, or the padding behind the last set — capi.cu reserves it — and are
+  // discarded).  Candidates beyond d2_cut are not filtered here: they can only sit behind the true neighbours in the
+  // list (the cut is a distance within which k points exist, or the radius that radius_count() applies afterwards),
+  // and the pruning bound is min(k-th, d2_cut) either way — same result, two instructions less per slot.
+  (void)d2_cut;
+  const double4* base = sorted + first;
+  const uint32_t cnt = last - first;
+#pragma unroll
+  for (int j = 0; j < kBvhLeaf; j++) {
+    const double4 t = load_point(base + j);
+    double d2 = sqdist(qx, qy, qz, t.x, t.y, t.z);
+    uint32_t id = (uint32_t)__double_as_longlong(t.w);
+    const bool ok = (uint32_t)j <= cnt;
+    d2 = ok ? d2 : CUDART_INF;
+    id = ok ? id : 0xFFFFFFFFu;
+    tk.insert(d2, id);
+  }
+#else
 #pragma unroll
   for (int j = 0; j < kBvhLeaf; j++) {
     const uint32_t p = first + j;
@@ -1294,6 +1317,7 @@ __device__ __forceinline__ void scan_leaf(const double4* __restrict__ sorted, ui
     id = ok ? id : 0xFFFFFFFFu;
     tk.insert(d2, id);
   }
+#endif
 }
 
 // Exact k nearest neighbours of (qx,qy,qz) among the points of one set, restricted to candidates that can pass the

@@ -354,8 +354,9 @@ int reserve_register(loamgpu_ctx* ctx, uint32_t n_pairs, uint32_t capE, uint32_t
   }
   CU(ctx->ge_aux.reserve(n_sets * capE * 4));
   CU(ctx->gp_aux.reserve(n_sets * capP * 4));
-  CU(ctx->ge_sorted.reserve(n_sets * capE * 32));
-  CU(ctx->gp_sorted.reserve(n_sets * capP * 32));
+  // (+ kBvhLeaf records: a leaf scan loads whole groups of kBvhLeaf records behind a leaf's first point)
+  CU(ctx->ge_sorted.reserve(n_sets * capE * 32 + kBvhLeaf * 32));
+  CU(ctx->gp_sorted.reserve(n_sets * capP * 32 + kBvhLeaf * 32));
   CU(ctx->ge_keys.reserve(n_sets * capE * 16));
   CU(ctx->gp_keys.reserve(n_sets * capP * 16));
   CU(ctx->nn_idx.reserve((size_t)n_pairs * (capE + capP) * nn_stride * 4));
@@ -401,7 +402,7 @@ int build_map(loamgpu_ctx* ctx, loamgpu_map* m) {
     const size_t cap = (size_t)std::max<uint64_t>(m->n[kind], 1);
     CU(m->hdr[kind].reserve(sizeof(BvhHdr)));
     CU(m->nodes[kind].reserve(cap * sizeof(BvhNode)));
-    CU(m->sorted[kind].reserve(cap * 32));
+    CU(m->sorted[kind].reserve(cap * 32 + kBvhLeaf * 32));
     CU(m->keys[kind].reserve(cap * 16));
     ProfScope ps(ctx, LOAMGPU_K_GRID);
     ctx->launches--;  // the launcher counts its own kernels
