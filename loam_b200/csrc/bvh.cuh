@@ -1512,44 +1512,22 @@ __device__ __forceinline__ void knn_compact(uint32_t s_recs, uint32_t s_stack, u
   uint32_t bound = __double2uint_ru(d2_cut * inv2);
   uint2 st[kBvhStack];                             // pending subtrees: (child reference, lower bound)
   int sp = 0;
-#if KNN_SMEM_STACK
-  int ring_lo = 0;  // entries [ring_lo, sp) are intact in the shared-memory ring
-#else
-  (void)s_stack;
-#endif
+  (void)s_stack;  // (the shared-memory stack ring of §10b was measured out; the parameter stays for the flag's layout)
+  // The state of the walk is ONE word: a record number, a leaf reference (kRefLeaf set), kWalkPop (take the next
+  // pending subtree) or kWalkDone (kRefLeaf set too, so the node loop ends on it like on a leaf).  (Separate
+  // have / done / at-leaf flags cost a handful of byte-juggling instructions per step of the node loop.)
+  constexpr uint32_t kWalkPop = 0x7FFFFFFFu, kWalkDone = 0xFFFFFFFFu;
   uint32_t cur = n_pts > (uint32_t)kBvhLeaf ? 0u : (kRefLeaf | ((n_pts - 1u) << 24));
-  bool have = true, done = false;
   while (true) {
-    bool at_leaf = false;
-    while (!done && !at_leaf) {
-      if (!have) {
+    while (!(cur & kRefLeaf)) {
+      if (cur == kWalkPop) {
         if (sp == 0) {
-          done = true;
+          cur = kWalkDone;
         } else {
           --sp;
-          uint2 e;
-#if KNN_SMEM_STACK
-          if (sp >= ring_lo)
-            asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];"
-                         : "=r"(e.x), "=r"(e.y)
-                         : "r"(s_stack + (uint32_t)(sp & (KNN_SMEM_STACK - 1)) * kKnnStackPitch));
-          else
-#endif
-            e = st[sp];
-          if (e.y <= bound) {
-            cur = e.x;
-            have = true;
-          }
+          const uint2 e = st[sp];
+          if (e.y <= bound) cur = e.x;
         }
-      } else if (cur & kRefLeaf) {
-        at_leaf = true;
-#if KNN_PREFETCH
-        {  // the leaf's points are needed once every lane of the warp stands on a leaf: start fetching them now
-          const char* p = reinterpret_cast<const char*>(sorted + (cur & 0x00FFFFFFu));
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 128));
-        }
-#endif
       } else {
         uint4 r0, r1;  // (lo.x lo.y lo.z nhi.x) (nhi.y nhi.z refL refR)
         load_rec_shared(s_recs + cur * (uint32_t)sizeof(BvhRec), r0, r1);
@@ -1558,26 +1536,17 @@ __device__ __forceinline__ void knn_compact(uint32_t s_recs, uint32_t s_stack, u
         const bool right_first = dr < dl;
         const uint32_t dn = right_first ? dr : dl, df = right_first ? dl : dr;
         if (df <= bound) {  // far child stays pending
-          const uint2 e = make_uint2(right_first ? r1.z : r1.w, df);
-          st[sp] = e;
-#if KNN_SMEM_STACK
-          asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(s_stack + (uint32_t)(sp & (KNN_SMEM_STACK - 1)) * kKnnStackPitch),
-                       "r"(e.x), "r"(e.y));
-          ring_lo = max(min(ring_lo, sp), sp - (KNN_SMEM_STACK - 1));
-#endif
+          st[sp] = make_uint2(right_first ? r1.z : r1.w, df);
           sp++;
         }
-        if (dn <= bound)
-          cur = right_first ? r1.w : r1.z;
-        else
-          have = false;
+        cur = dn <= bound ? (right_first ? r1.w : r1.z) : kWalkPop;
       }
     }
-    if (!at_leaf) break;  // done
+    if (cur == kWalkDone) break;
     const uint32_t first = cur & 0x00FFFFFFu;
     scan_leaf<K>(sorted, first, first + ((cur >> 24) & 15u), qx, qy, qz, d2_cut, tk);
     bound = __double2uint_ru(fmin(tk.kth(k), d2_cut) * inv2);
-    have = false;
+    cur = kWalkPop;
   }
 }
 
