@@ -49,6 +49,20 @@ __host__ __device__ inline size_t stage_bytes(uint32_t P, uint32_t rec) {
   return ((a > b ? a : b) + 15) & ~(size_t)15;
 }
 
+// 0xFFFFFFFF if (ka, ia) < (kb, ib) lexicographically, else 0: the borrow of the 96-bit subtraction (ka:ia) - (kb:ib),
+// three carry-chained subtractions instead of a 64-bit compare, an equality test and an index compare.
+__device__ __forceinline__ uint32_t lex_less(uint64_t ka, uint32_t ia, uint64_t kb, uint32_t ib) {
+  uint32_t r;
+  asm("{\n.reg .u32 t;\n"
+      "sub.cc.u32 t, %1, %2;\n"
+      "subc.cc.u32 t, %3, %4;\n"
+      "subc.cc.u32 t, %5, %6;\n"
+      "subc.u32 %0, 0, 0;\n}"
+      : "=r"(r)
+      : "r"(ia), "r"(ib), "r"((uint32_t)ka), "r"((uint32_t)kb), "r"((uint32_t)(ka >> 32)), "r"((uint32_t)(kb >> 32)));
+  return r;
+}
+
 // T = scalar type of the staged ring (what the arithmetic widens from), TIn = scalar type of the caller's records.
 // They differ only for de-warping float input: the moved points are not float-representable, so the ring is staged
 // as doubles.
@@ -324,17 +338,9 @@ __device__ __forceinline__ void extract_ring_body(const ExtractArgs& a) {
       const uint32_t j = plist[t];
       uint32_t rank = 0;
       if (planar) {
-        for (uint32_t i = 0; i < m; i++) {
-          const uint64_t ko = pkey[i];
-          const uint32_t o = plist[i];
-          rank += (ko < kj || (ko == kj && o < j)) ? 1u : 0u;
-        }
+        for (uint32_t i = 0; i < m; i++) rank -= lex_less(pkey[i], plist[i], kj, j);
       } else {
-        for (uint32_t i = 0; i < m; i++) {
-          const uint64_t ko = pkey[i];
-          const uint32_t o = plist[i];
-          rank += (ko > kj || (ko == kj && o > j)) ? 1u : 0u;
-        }
+        for (uint32_t i = 0; i < m; i++) rank -= lex_less(kj, j, pkey[i], plist[i]);
       }
       if (rank > cap) continue;
       (planar ? gp : ge)[base + rank] = ring * P + j;
